@@ -1,0 +1,187 @@
+/* mdm_b200.h — C-ABI of libmdm_b200.so: the sm_100a kernels behind the MoE motion-denoiser hot path.
+ *
+ * Drop-in boundary for ltdoanh2004/MotionDiffusion-MoE (reference paths are relative to
+ * text2motion/ in that repository).  The reference has no FFI of its own — its hot path is torch
+ * eager — so each entry point below names the reference Python code it replaces.  Conventions:
+ *   - every function returns an int status (MDM_OK == 0); no allocation, no host synchronisation;
+ *   - all pointers are device pointers, tensors are row-major and contiguous unless an `ld` is given;
+ *   - `dt` selects the activation/operand element type of `void*` buffers: MDM_F32 or MDM_BF16;
+ *     the residual stream, LayerNorm/softmax statistics and all accumulators are always fp32;
+ *   - the last argument is the CUDA stream (cudaStream_t passed as void*).
+ * The Python host (motiondiffusion_moe_b200/) binds these with ctypes; INTEGRATION.md shows the stub.
+ */
+#ifndef MDM_B200_H
+#define MDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MDM_API __attribute__((visibility("default")))
+#else
+#define MDM_API
+#endif
+
+#define MDM_OK 0
+#define MDM_ERR_ARG 1
+#define MDM_ERR_CUDA 2
+#define MDM_ERR_UNSUPPORTED 3
+
+#define MDM_F32 0
+#define MDM_BF16 1
+
+#define MDM_ACT_NONE 0
+#define MDM_ACT_GELU 1    /* exact erf GELU, nn.GELU() default */
+#define MDM_ACT_SILU 2
+#define MDM_ACT_EXPFEAT 3 /* exp(clamp(v,-15,15))*0.1, models/fast_attention.py:58-66 */
+
+/* GEMM epilogue:  out = alpha * act(acc + bias[n]) * rowscale[m] * rowmask[m] + beta * resid[m'][n],
+ * m' = m % resid_mod when resid_mod > 0 (positional embedding), else m. */
+typedef struct MdmGemmEpi {
+  const float* bias;
+  const float* rowscale;
+  const float* rowmask;
+  const float* resid;
+  int ld_resid;
+  int resid_mod;
+  float alpha, beta;
+  int act;
+  float* out_f32;
+  int ld_f32;
+  void* out_bf16; /* bf16 output (tensor-core GEMM only) */
+  int ld_bf16;
+  int bf16_pre_resid; /* 1: the bf16 output omits the residual term */
+} MdmGemmEpi;
+
+/* One 128-row tile of a grouped GEMM: rows [a_row0, a_row0+128) of A times the weight rows starting
+ * at w_row0, written to rows [c_row0, c_row0+rows_valid) of C.  bias is indexed bias[w_row0 + n]. */
+typedef struct MdmMTile { int a_row0, c_row0, w_row0, rows_valid; } MdmMTile;
+
+/* Fused row pipeline (one warp per row of D elements):
+ *   v = in;                         out0_a  = cast(v)
+ *   v = LN(v; ln1_w, ln1_b);        if l2norm: v = v / max(||v||, 1e-12) * sqrt(D)
+ *                                   out1_f32 / out1_a = v
+ *   v = LN(v; ln2_w, ln2_b);        if film: v = v * (1 + scale[b]) + shift[b],  b = row / rows_per_seq
+ *   if silu: v = silu(v);           out2_f32 / out2_a = v
+ * Stages with null weights are skipped.  Replaces nn.LayerNorm / F.normalize / StylizationBlock's
+ * FiLM+SiLU (models/stylization.py:29-30, models/fast_attention.py:142,169-172,210,225,248). */
+typedef struct MdmRowOp {
+  const void* in;
+  int in_dt;
+  const float *ln1_w, *ln1_b;
+  int l2norm;
+  float* out1_f32;
+  void* out1_a;
+  const float *ln2_w, *ln2_b;
+  const float* film; /* [n_seq, 2*D]: scale | shift */
+  int rows_per_seq;
+  int silu;
+  float* out2_f32;
+  void* out2_a;
+  void* out0_a;
+} MdmRowOp;
+
+/* ---- GEMMs: every nn.Linear, expert FFN and k=2,s=2 (transposed) conv of the path ------------- */
+/* C = epi(A[rows,K] * W[N,K]^T), bf16 operands, tcgen05/TMEM/TMA.  mtiles == NULL: plain GEMM over
+ * M rows.  Otherwise grouped: num_m_tiles entries (or *num_m_tiles_dev if non-NULL, device int).
+ * a_rows / w_rows are the total row counts of the A and W allocations (TMA bounds).
+ * Replaces F.linear at e.g. models/switch_moe.py:19-25,53,104; models/fast_attention.py:145-147,165. */
+MDM_API int mdm_gemm_bf16(const void* A, int lda, long a_rows, const void* W, int ldw, long w_rows,
+                          int M, int N, int K, const void* mtiles, int num_m_tiles,
+                          const int* num_m_tiles_dev, const MdmGemmEpi* epi, int max_ctas, void* stream);
+/* Same contract, fp32 operands, CUDA-core FMA (the reference's fp32 precision mode). */
+MDM_API int mdm_gemm_f32(const float* A, int lda, long a_rows, const float* W, int ldw, long w_rows,
+                         int M, int N, int K, const void* mtiles, int num_m_tiles,
+                         const int* num_m_tiles_dev, const MdmGemmEpi* epi, void* stream);
+
+/* ---- row-wise normalisation / FiLM ----------------------------------------------------------- */
+MDM_API int mdm_rowop(const MdmRowOp* op, long rows, int D, int out_dt, void* stream);
+
+/* ---- FastAttention core, models/fast_attention.py:29-92 (PerformerSelfAttention :155-160) ----
+ * qkv: [B*T, 3*H*hd] (q | k | v, already multiplied by nothing: the 0.1 pre-scale of :155-157 is
+ * applied inside).  P: [hd, M] fp32 projection_matrix.  norm_w/b: the shared LayerNorm(hd).
+ * length[b]: frames t >= length[b] have their key features zeroed (:69-74).  out: [B*T, H*hd]. */
+MDM_API int mdm_fastattn(const void* qkv, int dt, const float* P, const float* norm_w,
+                         const float* norm_b, const int64_t* length, int length_shift, int B, int H,
+                         int T, int hd, int M, void* out, void* stream);
+
+/* ---- LinearTemporalCrossAttention, models/fast_attention.py:242-253 --------------------------- */
+/* Text side (step-invariant): ctx[b,h,d,l] = sum_n softmax_n(k[b,n,h,d]) * v[b,n,h,l], n < nt[b].
+ * k, v: [B, Nt_max, H*hd] of type dt; ctx fp32. */
+MDM_API int mdm_lincross_ctx(const void* k, const void* v, int dt, const int* nt, int B, int Nt_max,
+                             int H, int hd, float* ctx, void* stream);
+/* Motion side: y[t,h,:] = softmax_hd(q[t,h,:]) @ ctx[b,h]. */
+MDM_API int mdm_lincross_apply(const void* q, int dt, const float* ctx, int B, int T, int H, int hd,
+                               void* y, void* stream);
+
+/* ---- MemoryEfficientCrossAttentionBlock core, models/fast_attention.py:305-325 ----------------
+ * o[t,h,:] = softmax_n(q[t,h,:]·k[b,n,h,:] * hd^-0.5) @ v[b,n,h,:], n < nt[b] (Nt_max <= 96). */
+MDM_API int mdm_softmax_cross(const void* q, const void* k, const void* v, int dt, const int* nt,
+                              int B, int T, int Nt_max, int H, int hd, void* o, void* stream);
+
+/* ---- SwitchMoELayer x NB branches, models/switch_moe.py:44-111, models/multi_branch.py:52-61 ---
+ * Gate: per token and branch b: h = LN_b(x); probs = softmax(h Wg_b^T + bg_b) (fp32, ATen order);
+ * (vals, idx) = top-k(probs) with torch.topk's CUDA tie order.  Writes idx [N,NB,K] int32, vals
+ * [N,NB,K] fp32, LN statistics stats [N,2] (mean, rstd) and per-block histograms / importance
+ * partial sums: blk_hist [nblk, 2, NB*E] (0: all K slots, 1: top-1 only), blk_imp [nblk, NB*E],
+ * nblk = ceil(N/128).  K must be 2 (the reference hard-codes top-2). */
+MDM_API int mdm_moe_gate(const float* x, long N, int D, int NB, int E, int K, const float* ln_w,
+                         const float* ln_b, const float* gate_w, const float* gate_b, int* idx,
+                         float* vals, float* stats, int* blk_hist, float* blk_imp, void* stream);
+/* Scan: expert segment offsets (each padded to 128 rows), per-block bases, the two grouped-GEMM tile
+ * tables (up: w_row0 = g*F, down: w_row0 = g*D), the tile count, and the usage / importance
+ * counters (expert_usage, expert_importance buffers of switch_moe.py:32-34,72-92), updated in place. */
+MDM_API int mdm_moe_scan(const int* blk_hist, const float* blk_imp, const int* idx, long N, int NB,
+                         int E, int K, int F, int D, int* blk_base, int* seg_offsets, void* tiles_up,
+                         void* tiles_down, int* num_tiles, float* usage, float* importance,
+                         void* stream);
+/* Permute: writes LN_b(x[token]) to its expert-sorted row of xp (type dt), the row position perm
+ * [N,NB,K] and rowscale[pos] = vals / NB. */
+MDM_API int mdm_moe_permute(const float* x, long N, int D, int NB, int E, int K, const float* ln_w,
+                            const float* ln_b, const int* idx, const float* vals, const float* stats,
+                            const int* blk_base, const int* seg_offsets, void* xp, int dt, int* perm,
+                            float* rowscale, void* stream);
+/* Combine + FiLM: m = sum over the NB*K expert rows of a token (already scaled by vals/NB), then
+ * out = silu(LN(m; ln_w, ln_b) * (1 + scale[b]) + shift[b])  (multi_branch.py:57-60 +
+ * stylization.py:29-30, up to its out Linear). */
+MDM_API int mdm_moe_combine_film(const void* yp, int dt, const int* perm, long N, int D, int NBK,
+                                 const float* ln_w, const float* ln_b, const float* film,
+                                 int rows_per_seq, void* out, void* stream);
+/* softmax + top-k alone on given logits [N,E] (parity probe for routing; same device code as the
+ * fused gate).  idx64 int64 [N,K], vals/probs fp32. */
+MDM_API int mdm_softmax_topk(const float* logits, long N, int E, int K, float* probs, int64_t* idx64,
+                             float* vals, void* stream);
+
+/* ---- small per-sequence ops of MotionTransformer.forward, models/transformer.py:318-329 ------- */
+/* Sinusoidal timestep embedding, models/time.py:15-26: [cos | sin](t * exp(-ln(1e4) i / (D/2))). */
+MDM_API int mdm_timestep_embedding(const int64_t* t, int B, int D, void* out, int dt, void* stream);
+/* GatedFusion mix, models/gate.py:18-19: out = sigmoid(t + x) * t + (1 - sigmoid(t + x)) * x. */
+MDM_API int mdm_gated_mix(const float* t, const float* x, long n, void* out, int dt, void* stream);
+/* x[rows, F] fp32 -> [rows, ld_out] of type dt, zero padded (operand of joint_embed, :324). */
+MDM_API int mdm_pad_cast(const float* x, long rows, int F, void* out, int ld_out, int dt, void* stream);
+
+/* ---- GaussianDiffusion, models/gaussian_diffusion.py ------------------------------------------ */
+/* One classifier-free-guidance DDPM update (p_sample_with_cfg, :1042-1098) after the two model
+ * evaluations: per element, with the fp32 table entries of timestep t[b]:
+ *   x0_c = c_recip*x - c_recipm1*eps_c ; x0_u likewise ; x0 = x0_u + s*(x0_c - x0_u)
+ *   mean = coef1*x0 + coef2*x ; x_prev = mean + (t != 0) * exp(0.5*logvar) * noise
+ * tables: [5, n_steps] fp32 rows = sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod,
+ * posterior_mean_coef1, posterior_mean_coef2, posterior_log_variance_clipped.
+ * clip != 0 clamps each branch's x0 to [-1, 1] (clip_denoised). */
+MDM_API int mdm_cfg_update(const float* x, const float* eps_c, const float* eps_u, const float* noise,
+                           const int64_t* t, const float* tables, int n_steps, float cfg_scale,
+                           int clip, int B, long per_sample, float* x_prev, float* x0, void* stream);
+/* q_sample, :449-460: x_t = sqrt_ac[t]*x0 + sqrt_1mac[t]*noise.  tables2: [2, n_steps]. */
+MDM_API int mdm_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tables2,
+                         int n_steps, int B, long per_sample, float* x_t, void* stream);
+
+MDM_API int mdm_num_sms(void);
+MDM_API const char* mdm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDM_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes binding of libmdm_b200.so (the C-ABI declared in include/mdm_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmdm_b200.so")
+
+MDM_F32, MDM_BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_SILU, ACT_EXPFEAT = 0, 1, 2, 3
+
+_ERR = {1: "invalid argument", 2: "CUDA error", 3: "unsupported configuration"}
+
+
+class MdmError(RuntimeError):
+    pass
+
+
+class GemmEpi(C.Structure):
+    _fields_ = [
+        ("bias", C.c_void_p), ("rowscale", C.c_void_p), ("rowmask", C.c_void_p),
+        ("resid", C.c_void_p), ("ld_resid", C.c_int), ("resid_mod", C.c_int),
+        ("alpha", C.c_float), ("beta", C.c_float), ("act", C.c_int),
+        ("out_f32", C.c_void_p), ("ld_f32", C.c_int),
+        ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int), ("bf16_pre_resid", C.c_int),
+    ]
+
+
+class RowOp(C.Structure):
+    _fields_ = [
+        ("inp", C.c_void_p), ("in_dt", C.c_int),
+        ("ln1_w", C.c_void_p), ("ln1_b", C.c_void_p), ("l2norm", C.c_int),
+        ("out1_f32", C.c_void_p), ("out1_a", C.c_void_p),
+        ("ln2_w", C.c_void_p), ("ln2_b", C.c_void_p),
+        ("film", C.c_void_p), ("rows_per_seq", C.c_int), ("silu", C.c_int),
+        ("out2_f32", C.c_void_p), ("out2_a", C.c_void_p), ("out0_a", C.c_void_p),
+    ]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_long, C.c_float
+
+_SIGS = {
+    "mdm_gemm_bf16": [_P, _I, _L, _P, _I, _L, _I, _I, _I, _P, _I, _P, C.POINTER(GemmEpi), _I, _P],
+    "mdm_gemm_f32": [_P, _I, _L, _P, _I, _L, _I, _I, _I, _P, _I, _P, C.POINTER(GemmEpi), _P],
+    "mdm_rowop": [C.POINTER(RowOp), _L, _I, _I, _P],
+    "mdm_fastattn": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "mdm_lincross_ctx": [_P, _P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "mdm_lincross_apply": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "mdm_softmax_cross": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P],
+    "mdm_moe_gate": [_P, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "mdm_moe_scan": [_P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    "mdm_moe_permute": [_P, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
+    "mdm_moe_combine_film": [_P, _I, _P, _L, _I, _I, _P, _P, _P, _I, _P, _P],
+    "mdm_softmax_topk": [_P, _L, _I, _I, _P, _P, _P, _P],
+    "mdm_timestep_embedding": [_P, _I, _I, _P, _I, _P],
+    "mdm_gated_mix": [_P, _P, _L, _P, _I, _P],
+    "mdm_pad_cast": [_P, _L, _I, _P, _I, _I, _P],
+    "mdm_cfg_update": [_P, _P, _P, _P, _P, _P, _I, _F, _I, _I, _L, _P, _P, _P],
+    "mdm_q_sample": [_P, _P, _P, _P, _I, _I, _L, _P, _P],
+    "mdm_num_sms": [],
+}
+
+_lib = None
+
+
+def load():
+    """Load the library once; raise (never fall back) if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MdmError(
+            "libmdm_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; "
+            "g.build()'` or `python -m motiondiffusion_moe_b200.build`. There is no CPU fallback."
+            % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: loud by design
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.mdm_version.restype = C.c_char_p
+    lib.mdm_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        raise MdmError("%s failed: %s (status %d)" % (what, _ERR.get(status, "unknown"), status))
+
+
+def exported_symbols():
+    return list(_SIGS.keys()) + ["mdm_version"]

@@ -1,0 +1,9 @@
+// Library-level entry points.
+#include "common.cuh"
+extern "C" MDM_API int mdm_num_sms(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+extern "C" MDM_API const char* mdm_version(void) { return "mdm_b200 0.1 (sm_100a)"; }

@@ -1,0 +1,373 @@
+// MoE routing path of MoEMultiBranchFFN / SwitchMoELayer
+// (reference: models/multi_branch.py:52-61, models/switch_moe.py:44-111).
+//
+//   gate     per token, per branch: LN -> gate GEMV (D -> E) -> softmax (ATen arithmetic order) ->
+//            top-2 with torch.topk's CUDA tie order; per-128-token-block histograms (warp-private
+//            counters, no atomics => deterministic).
+//   scan     one CTA: expert segment offsets padded to the 128-row GEMM tile, per-block bases, the
+//            grouped-GEMM tile tables, the usage / importance counters.  No host synchronisation.
+//   permute  expert-sorted copy of the LN'd rows (ballot/match ranks inside a block), row scales.
+//   combine  gathers the NB*K expert rows of a token, sums them, and applies the FiLM of the
+//            following StylizationBlock (its LN, scale/shift and SiLU).
+// All four are HBM-bound; algorithmic bytes per token (D elements, s = sizeof activation):
+//   gate 4D (read x) ; permute 4D + NB*K*D*s ; combine NB*K*D*s + D*s.
+#include "common.cuh"
+#include "rowmath.cuh"
+
+namespace {
+
+constexpr int TOK_PER_BLK = 128;
+constexpr int MAX_G = 32;   // NB * E groups
+constexpr int MAX_E = 16;
+
+// softmax over E logits with ATen's softmax_warp_forward arithmetic (max-subtract, expf, butterfly
+// xor-shuffle sum over next_pow2(E) lanes, IEEE divide), then top-2 with the tie order of
+// torch.topk on CUDA: lowest indices are selected first; equal values are emitted higher index first.
+__device__ __forceinline__ void softmax_top2(const float* logits, int E, float* probs, int& i0, int& i1,
+                                             float& v0, float& v1) {
+  float mx = logits[0];
+  for (int e = 1; e < E; ++e) mx = fmaxf(mx, logits[e]);
+  int P2 = 1;
+  while (P2 < E) P2 <<= 1;
+  float ex[MAX_E], red[MAX_E];
+  for (int e = 0; e < P2; ++e) {
+    ex[e] = e < E ? expf(logits[e] - mx) : 0.f;
+    red[e] = ex[e];
+  }
+  for (int off = P2 >> 1; off > 0; off >>= 1) {
+    float nxt[MAX_E];
+    for (int e = 0; e < P2; ++e) nxt[e] = red[e] + red[e ^ off];
+    for (int e = 0; e < P2; ++e) red[e] = nxt[e];
+  }
+  const float sum = red[0];
+  for (int e = 0; e < E; ++e) probs[e] = ex[e] / sum;
+  int a = 0;
+  for (int e = 1; e < E; ++e)
+    if (probs[e] > probs[a]) a = e;
+  int b = (a == 0) ? 1 : 0;
+  for (int e = 0; e < E; ++e)
+    if (e != a && probs[e] > probs[b]) b = e;
+  if (probs[a] == probs[b]) { i0 = b; i1 = a; }  // b > a here: tie => higher index first
+  else { i0 = a; i1 = b; }
+  v0 = probs[i0];
+  v1 = probs[i1];
+}
+
+template <int VPT>
+__global__ void __launch_bounds__(256)
+moe_gate_kernel(const float* __restrict__ x, long N, int D, int NB, int E, const float* __restrict__ ln_w,
+                const float* __restrict__ ln_b, const float* __restrict__ gate_w,
+                const float* __restrict__ gate_b, int* __restrict__ idx, float* __restrict__ vals,
+                float* __restrict__ stats, int* __restrict__ blk_hist, float* __restrict__ blk_imp) {
+  extern __shared__ float sm[];
+  float* gw = sm;                                   // [NB*E][D]
+  __shared__ int w_all[8][MAX_G], w_top1[8][MAX_G];
+  __shared__ float w_imp[8][MAX_G];
+  const int G = NB * E;
+  for (int i = threadIdx.x; i < G * D; i += 256) gw[i] = gate_w[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int cnt_all = 0, cnt_top1 = 0;  // lane g owns group g
+  float imp = 0.f;
+  const long tok0 = (long)blockIdx.x * TOK_PER_BLK + warp * 16;
+  for (int it = 0; it < 16; ++it) {
+    const long tok = tok0 + it;
+    if (tok >= N) break;
+    float v[VPT];
+    load_row<VPT, float>(x + tok * D, lane, v);
+    float mean, rstd;
+    row_stats<VPT>(v, D, mean, rstd);
+    if (lane == 0) { stats[tok * 2] = mean; stats[tok * 2 + 1] = rstd; }
+    for (int br = 0; br < NB; ++br) {
+      float hrow[VPT];
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) hrow[i] = v[i];
+      affine_row<VPT>(hrow, mean, rstd, ln_w + br * D, ln_b + br * D, lane);
+      float logits[MAX_E];
+      for (int e = 0; e < E; ++e) {
+        const float* wr = gw + (br * E + e) * D;
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT / 4; ++j) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wr + (j * 32 + lane) * 4);
+          a = fmaf(hrow[4 * j], w4.x, a);
+          a = fmaf(hrow[4 * j + 1], w4.y, a);
+          a = fmaf(hrow[4 * j + 2], w4.z, a);
+          a = fmaf(hrow[4 * j + 3], w4.w, a);
+        }
+        logits[e] = warp_sum(a) + gate_b[br * E + e];
+      }
+      float probs[MAX_E];
+      int i0, i1;
+      float v0, v1;
+      softmax_top2(logits, E, probs, i0, i1, v0, v1);
+      if (lane == 0) {
+        const long o = (tok * NB + br) * 2;
+        idx[o] = i0; idx[o + 1] = i1;
+        vals[o] = v0; vals[o + 1] = v1;
+      }
+      const int g0 = br * E + i0, g1 = br * E + i1;
+      if (lane == g0) { cnt_all++; cnt_top1++; imp += v0; }
+      if (lane == g1) { cnt_all++; imp += v1; }
+    }
+  }
+  w_all[warp][lane] = cnt_all;
+  w_top1[warp][lane] = cnt_top1;
+  w_imp[warp][lane] = imp;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    int a = 0, t1 = 0;
+    float im = 0.f;
+    for (int w = 0; w < 8; ++w) { a += w_all[w][threadIdx.x]; t1 += w_top1[w][threadIdx.x]; im += w_imp[w][threadIdx.x]; }
+    blk_hist[((long)blockIdx.x * 2) * G + threadIdx.x] = a;
+    blk_hist[((long)blockIdx.x * 2 + 1) * G + threadIdx.x] = t1;
+    blk_imp[(long)blockIdx.x * G + threadIdx.x] = im;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+moe_scan_kernel(const int* __restrict__ blk_hist, const float* __restrict__ blk_imp, int nblk, int G, int E,
+                int F, int D, int* __restrict__ blk_base, int* __restrict__ seg_offsets,
+                MTile* __restrict__ tiles_up, MTile* __restrict__ tiles_down, int* __restrict__ num_tiles,
+                float* __restrict__ usage, float* __restrict__ importance) {
+  const int g = threadIdx.x;
+  int total = 0, top1 = 0;
+  float imp = 0.f;
+  if (g < G) {
+    for (int b = 0; b < nblk; ++b) {
+      blk_base[(long)b * G + g] = total;
+      total += blk_hist[((long)b * 2) * G + g];
+      top1 += blk_hist[((long)b * 2 + 1) * G + g];
+      imp += blk_imp[(long)b * G + g];
+    }
+    if (usage) usage[g] += (float)top1;
+    if (importance) importance[g] += imp;
+  }
+  const int padded = g < G ? ((total + 127) / 128) * 128 : 0;
+  // exclusive scan of padded sizes across the warp
+  int incl = padded;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (g >= o) incl += n;
+  }
+  const int off = incl - padded;
+  if (g < G) {
+    seg_offsets[g] = off;
+    const int ntile = padded / 128, tile0 = off / 128;
+    for (int i = 0; i < ntile; ++i) {
+      const int rows = min(128, total - i * 128);
+      MTile u; u.a_row0 = off + i * 128; u.c_row0 = u.a_row0; u.w_row0 = g * F; u.rows_valid = rows;
+      MTile d = u; d.w_row0 = g * D;
+      tiles_up[tile0 + i] = u;
+      tiles_down[tile0 + i] = d;
+    }
+  }
+  const int all = __shfl_sync(0xffffffffu, incl, 31);
+  if (g == 0) { seg_offsets[G] = all; *num_tiles = all / 128; }
+}
+
+template <int VPT, typename TO>
+__global__ void __launch_bounds__(256)
+moe_permute_kernel(const float* __restrict__ x, long N, int D, int NB, int E, const float* __restrict__ ln_w,
+                   const float* __restrict__ ln_b, const int* __restrict__ idx, const float* __restrict__ vals,
+                   const float* __restrict__ stats, const int* __restrict__ blk_base,
+                   const int* __restrict__ seg_offsets, TO* __restrict__ xp, int* __restrict__ perm,
+                   float* __restrict__ rowscale) {
+  // pairs of a block: p = token_local * NBK + slot, NBK = NB*2; 32 pairs per segment
+  __shared__ int seg_cnt[16][MAX_G];
+  __shared__ int pos_s[TOK_PER_BLK * 4];
+  const int G = NB * E, NBK = NB * 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npairs = TOK_PER_BLK * NBK;           // <= 512
+  const int nseg = npairs / 32;                   // <= 16
+  for (int i = threadIdx.x; i < 16 * MAX_G; i += 256) (&seg_cnt[0][0])[i] = 0;
+  __syncthreads();
+  const long tok_blk0 = (long)blockIdx.x * TOK_PER_BLK;
+  int my_g[2], my_rank[2];
+  for (int r = 0; r < 2; ++r) {
+    const int seg = warp * 2 + r;
+    my_g[r] = -1; my_rank[r] = 0;
+    if (seg < nseg) {
+      const int p = seg * 32 + lane;
+      const long tok = tok_blk0 + p / NBK;
+      const int slot = p % NBK;
+      int g = -1;
+      if (tok < N) g = (slot >> 1) * E + idx[tok * NBK + slot];
+      const unsigned peers = __match_any_sync(0xffffffffu, g);
+      my_g[r] = g;
+      my_rank[r] = __popc(peers & ((1u << lane) - 1u));
+      if (g >= 0 && my_rank[r] == 0) seg_cnt[seg][g] = __popc(peers);
+    }
+  }
+  __syncthreads();
+  for (int r = 0; r < 2; ++r) {
+    const int seg = warp * 2 + r;
+    if (seg < nseg && my_g[r] >= 0) {
+      const int g = my_g[r];
+      int base = 0;
+      for (int s = 0; s < seg; ++s) base += seg_cnt[s][g];
+      const int p = seg * 32 + lane;
+      const long tok = tok_blk0 + p / NBK;
+      const int slot = p % NBK;
+      const int pos = seg_offsets[g] + blk_base[(long)blockIdx.x * G + g] + base + my_rank[r];
+      pos_s[p] = pos;
+      perm[tok * NBK + slot] = pos;
+      rowscale[pos] = vals[tok * NBK + slot] / (float)NB;
+    }
+  }
+  __syncthreads();
+  for (int it = 0; it < 16; ++it) {
+    const int tl = warp * 16 + it;
+    const long tok = tok_blk0 + tl;
+    if (tok >= N) break;
+    float v[VPT];
+    load_row<VPT, float>(x + tok * D, lane, v);
+    const float mean = stats[tok * 2], rstd = stats[tok * 2 + 1];
+    for (int br = 0; br < NB; ++br) {
+      float hrow[VPT];
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) hrow[i] = v[i];
+      affine_row<VPT>(hrow, mean, rstd, ln_w + br * D, ln_b + br * D, lane);
+      store_row<VPT, TO>(xp + (long)pos_s[tl * NBK + br * 2] * D, lane, hrow);
+      store_row<VPT, TO>(xp + (long)pos_s[tl * NBK + br * 2 + 1] * D, lane, hrow);
+    }
+  }
+}
+
+template <int VPT, typename TI>
+__global__ void __launch_bounds__(256)
+moe_combine_film_kernel(const TI* __restrict__ yp, const int* __restrict__ perm, long N, int D, int NBK,
+                        const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                        const float* __restrict__ film, int rows_per_seq, TI* __restrict__ out) {
+  const long tok = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= N) return;
+  const int lane = threadIdx.x & 31;
+  float acc[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) acc[i] = 0.f;
+  for (int br = 0; br < NBK / 2; ++br) {
+    float a[VPT], b[VPT];
+    load_row<VPT, TI>(yp + (long)perm[tok * NBK + br * 2] * D, lane, a);
+    load_row<VPT, TI>(yp + (long)perm[tok * NBK + br * 2 + 1] * D, lane, b);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) acc[i] += a[i] + b[i];
+  }
+  layernorm_row<VPT>(acc, ln_w, ln_b, lane, D);
+  film_row<VPT>(acc, film + (tok / rows_per_seq) * 2 * D, lane, D);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) acc[i] = silu_f(acc[i]);
+  store_row<VPT, TI>(out + tok * D, lane, acc);
+}
+
+__global__ void softmax_topk_kernel(const float* __restrict__ logits, long N, int E, float* __restrict__ probs,
+                                    int64_t* __restrict__ idx64, float* __restrict__ vals) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float l[MAX_E], p[MAX_E];
+  for (int e = 0; e < E; ++e) l[e] = logits[i * E + e];
+  int i0, i1;
+  float v0, v1;
+  softmax_top2(l, E, p, i0, i1, v0, v1);
+  if (probs)
+    for (int e = 0; e < E; ++e) probs[i * E + e] = p[e];
+  idx64[i * 2] = i0; idx64[i * 2 + 1] = i1;
+  vals[i * 2] = v0; vals[i * 2 + 1] = v1;
+}
+
+}  // namespace
+
+#define VPT_SWITCH(D, ...)               \
+  switch (D) {                           \
+    case 128: { constexpr int V = 4; __VA_ARGS__; break; }  \
+    case 256: { constexpr int V = 8; __VA_ARGS__; break; }  \
+    case 512: { constexpr int V = 16; __VA_ARGS__; break; } \
+    case 1024: { constexpr int V = 32; __VA_ARGS__; break; }\
+    default: return MDM_ERR_UNSUPPORTED; \
+  }
+
+extern "C" MDM_API int mdm_moe_gate(const float* x, long N, int D, int NB, int E, int K, const float* ln_w,
+                                    const float* ln_b, const float* gate_w, const float* gate_b, int* idx,
+                                    float* vals, float* stats, int* blk_hist, float* blk_imp, void* stream) {
+  if (!x || !ln_w || !ln_b || !gate_w || !gate_b || !idx || !vals || !stats || !blk_hist || !blk_imp)
+    return MDM_ERR_ARG;
+  if (K != 2 || E < 2 || E > MAX_E || NB * E > MAX_G || NB < 1) return MDM_ERR_UNSUPPORTED;
+  if (N == 0) return MDM_OK;
+  const int nblk = (int)((N + TOK_PER_BLK - 1) / TOK_PER_BLK);
+  const size_t smem = sizeof(float) * (size_t)NB * E * D;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VPT_SWITCH(D, {
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(moe_gate_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return MDM_ERR_CUDA;
+    moe_gate_kernel<V><<<nblk, 256, smem, st>>>(x, N, D, NB, E, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
+                                                 blk_hist, blk_imp);
+  });
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_moe_scan(const int* blk_hist, const float* blk_imp, const int* idx, long N, int NB,
+                                    int E, int K, int F, int D, int* blk_base, int* seg_offsets,
+                                    void* tiles_up, void* tiles_down, int* num_tiles, float* usage,
+                                    float* importance, void* stream) {
+  (void)idx;
+  if (!blk_hist || !blk_imp || !blk_base || !seg_offsets || !tiles_up || !tiles_down || !num_tiles)
+    return MDM_ERR_ARG;
+  if (K != 2 || NB * E > MAX_G) return MDM_ERR_UNSUPPORTED;
+  const int nblk = (int)((N + TOK_PER_BLK - 1) / TOK_PER_BLK);
+  moe_scan_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      blk_hist, blk_imp, nblk, NB * E, E, F, D, blk_base, seg_offsets, reinterpret_cast<MTile*>(tiles_up),
+      reinterpret_cast<MTile*>(tiles_down), num_tiles, usage, importance);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_moe_permute(const float* x, long N, int D, int NB, int E, int K, const float* ln_w,
+                                       const float* ln_b, const int* idx, const float* vals, const float* stats,
+                                       const int* blk_base, const int* seg_offsets, void* xp, int dt,
+                                       int* perm, float* rowscale, void* stream) {
+  if (!x || !idx || !vals || !stats || !blk_base || !seg_offsets || !xp || !perm || !rowscale) return MDM_ERR_ARG;
+  if (K != 2 || NB < 1 || NB > 2 || NB * E > MAX_G) return MDM_ERR_UNSUPPORTED;
+  if (N == 0) return MDM_OK;
+  const int nblk = (int)((N + TOK_PER_BLK - 1) / TOK_PER_BLK);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VPT_SWITCH(D, {
+    if (dt == MDM_F32)
+      moe_permute_kernel<V, float><<<nblk, 256, 0, st>>>(x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
+                                                          seg_offsets, reinterpret_cast<float*>(xp), perm, rowscale);
+    else
+      moe_permute_kernel<V, bf16><<<nblk, 256, 0, st>>>(x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
+                                                         seg_offsets, reinterpret_cast<bf16*>(xp), perm, rowscale);
+  });
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_moe_combine_film(const void* yp, int dt, const int* perm, long N, int D, int NBK,
+                                            const float* ln_w, const float* ln_b, const float* film,
+                                            int rows_per_seq, void* out, void* stream) {
+  if (!yp || !perm || !ln_w || !ln_b || !film || !out || rows_per_seq <= 0) return MDM_ERR_ARG;
+  if (NBK < 2 || (NBK & 1)) return MDM_ERR_UNSUPPORTED;
+  if (N == 0) return MDM_OK;
+  const unsigned grid = (unsigned)((N + 7) / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VPT_SWITCH(D, {
+    if (dt == MDM_F32)
+      moe_combine_film_kernel<V, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(yp), perm, N, D, NBK,
+                                                               ln_w, ln_b, film, rows_per_seq,
+                                                               reinterpret_cast<float*>(out));
+    else
+      moe_combine_film_kernel<V, bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(yp), perm, N, D, NBK,
+                                                              ln_w, ln_b, film, rows_per_seq,
+                                                              reinterpret_cast<bf16*>(out));
+  });
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_softmax_topk(const float* logits, long N, int E, int K, float* probs, int64_t* idx64,
+                                        float* vals, void* stream) {
+  if (!logits || !idx64 || !vals) return MDM_ERR_ARG;
+  if (K != 2 || E < 2 || E > MAX_E) return MDM_ERR_UNSUPPORTED;
+  if (N == 0) return MDM_OK;
+  softmax_topk_kernel<<<(unsigned)((N + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, N, E, probs, idx64, vals);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
