@@ -51,9 +51,9 @@ typedef struct MdmGemmEpi {
   int act;
   float* out_f32;
   int ld_f32;
-  void* out_bf16; /* bf16 output (tensor-core GEMM only) */
+  void* out_bf16; /* secondary output in the operand type: bf16 (mdm_gemm_bf16) / fp32 (mdm_gemm_f32) */
   int ld_bf16;
-  int bf16_pre_resid; /* 1: the bf16 output omits the residual term */
+  int bf16_pre_resid; /* 1: the secondary output omits the residual term */
 } MdmGemmEpi;
 
 /* One 128-row tile of a grouped GEMM: rows [a_row0, a_row0+128) of A times the weight rows starting

@@ -1,0 +1,9 @@
+"""motiondiffusion_moe_b200 — B200-native MoE motion denoiser + CFG sampler (drop-in for the hot path of
+ltdoanh2004/MotionDiffusion-MoE).  Python host code over a C-ABI CUDA library (include/mdm_b200.h)."""
+from ._lib import MdmError, load as load_library, LIB_PATH  # noqa: F401
+from .transformer import MotionTransformer, TextContext  # noqa: F401
+from .gaussian_diffusion import (GaussianDiffusion, get_named_beta_schedule, ModelMeanType, ModelVarType,  # noqa: F401
+                                 LossType)
+
+__all__ = ["MotionTransformer", "TextContext", "GaussianDiffusion", "get_named_beta_schedule", "ModelMeanType",
+           "ModelVarType", "LossType", "MdmError", "load_library"]

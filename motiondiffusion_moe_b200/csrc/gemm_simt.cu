@@ -81,8 +81,11 @@ gemm_f32_kernel(const float* __restrict__ A, int lda, long a_rows, const float* 
       float v = acc[i][j];
       if (epi.bias) v += epi.bias[w_row0 + n];
       v = apply_act(v, epi.act) * scale;
+      float* out2 = reinterpret_cast<float*>(epi.out_bf16);  // operand-typed secondary output: fp32 here
+      if (out2 && epi.bf16_pre_resid) out2[m * epi.ld_bf16 + n] = v;
       if (resid_row) v += epi.beta * resid_row[n];
       if (epi.out_f32) epi.out_f32[m * epi.ld_f32 + n] = v;
+      if (out2 && !epi.bf16_pre_resid) out2[m * epi.ld_bf16 + n] = v;
     }
   }
 }
@@ -94,7 +97,6 @@ extern "C" MDM_API int mdm_gemm_f32(const float* A, int lda, long a_rows, const 
                                     int num_m_tiles, const int* num_m_tiles_dev, const MdmGemmEpi* epi,
                                     void* stream) {
   if (!A || !W || !epi || M < 0 || N <= 0 || K <= 0) return MDM_ERR_ARG;
-  if (epi->out_bf16) return MDM_ERR_ARG;
   if (!mtiles) num_m_tiles = (M + 127) / 128;
   if (num_m_tiles <= 0) return MDM_OK;
   dim3 grid((N + TN - 1) / TN, num_m_tiles * 2);

@@ -1,0 +1,233 @@
+"""GaussianDiffusion — drop-in for the sampling / q-sample surface of the reference
+(text2motion/models/gaussian_diffusion.py:375-1141) that the trainer uses
+(trainers/ddpm_trainer.py:43-50,161): linear-beta DDPM, epsilon prediction, FIXED_SMALL variance,
+classifier-free guidance.
+
+What is B200-native here: the conditional and unconditional branches of p_sample_with_cfg run as ONE
+batched MotionTransformer forward (2B sequences, per-sequence text lengths), the whole
+eps -> x0 -> guidance -> posterior mean -> noise update is one kernel (mdm_cfg_update) with fp32 schedule
+tables resident on the device, the text-side projections are computed once per loop, and the 1000-step
+loop replays a CUDA graph of the step.
+"""
+import enum
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import MdmError
+
+
+class ModelMeanType(enum.Enum):      # gaussian_diffusion.py:346-352
+    PREVIOUS_X = enum.auto()
+    START_X = enum.auto()
+    EPSILON = enum.auto()
+
+
+class ModelVarType(enum.Enum):       # :355-362
+    LEARNED = enum.auto()
+    FIXED_SMALL = enum.auto()
+    FIXED_LARGE = enum.auto()
+    LEARNED_RANGE = enum.auto()
+
+
+class LossType(enum.Enum):           # :365-372
+    MSE = enum.auto()
+    RESCALED_MSE = enum.auto()
+    KL = enum.auto()
+    RESCALED_KL = enum.auto()
+
+
+def get_named_beta_schedule(schedule_name, num_diffusion_timesteps):
+    """gaussian_diffusion.py:19-55 (float64)."""
+    n = num_diffusion_timesteps
+    if schedule_name == "linear":
+        scale = 1000 / n
+        return np.linspace(scale * 0.0001, scale * 0.02, n, dtype=np.float64)
+    if schedule_name == "cosine":
+        f = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+        return np.array([min(1 - f((i + 1) / n) / f(i / n), 0.999) for i in range(n)], dtype=np.float64)
+    if schedule_name == "sqrt":
+        a = np.linspace(1.0, 0.0, n, dtype=np.float64)
+        b = 1 - a ** 2
+        b = (b - b.min()) / (b.max() - b.min())
+        return b * (0.02 - 0.0001) + 0.0001
+    raise NotImplementedError("unknown beta schedule: %s" % schedule_name)
+
+
+class GaussianDiffusion:
+    def __init__(self, *, betas, model_mean_type=ModelMeanType.EPSILON, model_var_type=ModelVarType.FIXED_SMALL,
+                 loss_type=LossType.MSE, rescale_timesteps=False, cfg_scale=7.5):
+        self.model_mean_type = model_mean_type
+        self.model_var_type = model_var_type
+        self.loss_type = loss_type
+        self.rescale_timesteps = rescale_timesteps
+        self.cfg_scale = cfg_scale
+        betas = np.array(betas, dtype=np.float64)                     # :396-431
+        assert betas.ndim == 1 and (betas > 0).all() and (betas <= 1).all()
+        self.betas = betas
+        self.num_timesteps = int(betas.shape[0])
+        alphas = 1.0 - betas
+        self.alphas_cumprod = np.cumprod(alphas, axis=0)
+        self.alphas_cumprod_prev = np.append(1.0, self.alphas_cumprod[:-1])
+        self.sqrt_alphas_cumprod = np.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - self.alphas_cumprod)
+        self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
+        self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
+        self.posterior_variance = betas * (1.0 - self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_log_variance_clipped = np.log(np.append(self.posterior_variance[1], self.posterior_variance[1:]))
+        self.posterior_mean_coef1 = betas * np.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - self.alphas_cumprod)
+        self._dev_tables = {}
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ device tables
+    def _tables(self, device):
+        """fp32 copies of the float64 tables (the reference gathers then .float(): :338), uploaded once."""
+        key = str(device)
+        if key not in self._dev_tables:
+            step = np.stack([self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
+                             self.posterior_mean_coef1, self.posterior_mean_coef2,
+                             self.posterior_log_variance_clipped]).astype(np.float32)
+            q = np.stack([self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod]).astype(np.float32)
+            self._dev_tables[key] = (torch.from_numpy(step).to(device).contiguous(),
+                                     torch.from_numpy(q).to(device).contiguous())
+        return self._dev_tables[key]
+
+    def _check_supported(self):
+        if self.model_mean_type != ModelMeanType.EPSILON or self.model_var_type != ModelVarType.FIXED_SMALL:
+            raise NotImplementedError("the CUDA sampler implements the trainer's configuration only: "
+                                      "EPSILON mean, FIXED_SMALL variance (trainers/ddpm_trainer.py:43-50)")
+        if self.rescale_timesteps:
+            raise NotImplementedError("rescale_timesteps=True is not used by the reference trainer")
+
+    # ------------------------------------------------------------------ q(x_t | x_0)
+    def q_sample(self, x_start, t, noise=None):
+        """:449-460."""
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        assert noise.shape == x_start.shape
+        _, q = self._tables(x_start.device)
+        out = torch.empty_like(x_start, dtype=torch.float32)
+        ops.q_sample(x_start.float().contiguous(), noise.float().contiguous(), t.to(torch.int64).contiguous(), q,
+                     self.num_timesteps, out)
+        return out
+
+    # ------------------------------------------------------------------ CFG sampling
+    def _cfg_inputs(self, model, B, model_kwargs, device):
+        """Conditional + unconditional text batched as 2B sequences with per-sequence token counts.
+        The unconditional branch is text="" with xf_* re-encoded (:1059-1062)."""
+        if model_kwargs is None or "text" not in model_kwargs:
+            raise KeyError("text")                                     # reference: model_kwargs["text"], :1060
+        xf_proj, xf_out = model_kwargs.get("xf_proj"), model_kwargs.get("xf_out")
+        if xf_proj is None or xf_out is None:
+            xf_proj, xf_out = model.encode_text(model_kwargs["text"], device)
+        u_proj, u_out = model.encode_text([""] * len(model_kwargs["text"]), device)
+        nc, nu = xf_out.shape[1], u_out.shape[1]
+        nmax = max(nc, nu)
+        Dt = xf_out.shape[2]
+        xo = torch.zeros(2 * B, nmax, Dt, device=device, dtype=torch.float32)
+        xo[:B, :nc] = xf_out
+        xo[B:, :nu] = u_out
+        xp = torch.cat([xf_proj.float(), u_proj.float()])
+        nt = torch.cat([torch.full((B,), nc, dtype=torch.int32, device=device),
+                        torch.full((B,), nu, dtype=torch.int32, device=device)])
+        return model.prepare_text(xp, xo, nt)
+
+    def _cfg_step(self, model, ctx, x, t, length2, noise, cfg_scale, clip, x_out, x0_out):
+        B = x.shape[0]
+        eps = model(torch.cat([x, x]), torch.cat([t, t]), length2, text_ctx=ctx)
+        step, _ = self._tables(x.device)
+        ops.cfg_update(x, eps[:B], eps[B:], noise, t, step, self.num_timesteps, cfg_scale, clip, x_out, x0_out)
+
+    def p_sample_with_cfg(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None,
+                          cfg_scale=7.5, noise=None, text_ctx=None):
+        """:1042-1098.  `noise` (optional) replaces the internal torch.randn_like(x) draw."""
+        self._check_supported()
+        if denoised_fn is not None:
+            raise NotImplementedError("denoised_fn is not supported by the fused CFG update")
+        if model_kwargs is None:
+            model_kwargs = {}
+        B = x.shape[0]
+        x = x.float().contiguous()
+        t = t.to(torch.int64).contiguous()
+        assert t.shape == (B,)
+        ctx = text_ctx if text_ctx is not None else self._cfg_inputs(model, B, model_kwargs, x.device)
+        length = model_kwargs["length"].reshape(-1).to(torch.int64)
+        if noise is None:
+            noise = torch.randn_like(x)                                # :1094
+        sample, x0 = torch.empty_like(x), torch.empty_like(x)
+        self._cfg_step(model, ctx, x, t, torch.cat([length, length]), noise.float().contiguous(), cfg_scale,
+                       clip_denoised, sample, x0)
+        return {"sample": sample, "pred_xstart": x0}
+
+    def p_sample_loop_with_cfg(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
+                               model_kwargs=None, device=None, progress=False, cfg_scale=7.5, *,
+                               use_cuda_graph=True, num_steps=None, step_noise=None):
+        """:1100-1141.  Extra keyword-only arguments: use_cuda_graph (replay one captured step),
+        num_steps (run only the first num_steps of the num_timesteps reverse steps: benchmarking),
+        step_noise (callable t -> noise tensor, for parity tests with injected noise)."""
+        self._check_supported()
+        if denoised_fn is not None:
+            raise NotImplementedError("denoised_fn is not supported by the fused CFG update")
+        if device is None:
+            device = next(model.parameters()).device
+        B = shape[0]
+        x = (torch.randn(*shape, device=device) if noise is None else noise.to(device).float()).contiguous().clone()
+        ctx = self._cfg_inputs(model, B, model_kwargs, device)
+        length = model_kwargs["length"].reshape(-1).to(device=device, dtype=torch.int64)
+        length2 = torch.cat([length, length]).contiguous()
+        t_buf = torch.zeros(B, dtype=torch.int64, device=device)
+        nz = torch.empty_like(x)
+        steps = list(reversed(range(self.num_timesteps)))
+        if num_steps is not None:
+            steps = steps[:num_steps]
+        if progress:
+            from tqdm.auto import tqdm
+            steps = tqdm(steps, desc="Sampling")
+        graph = None
+        for i, ts in enumerate(steps):
+            t_buf.fill_(ts)
+            if step_noise is not None:
+                nz.copy_(step_noise(ts))
+            else:
+                nz.normal_()                                           # == torch.randn_like(x), :1094
+            if not use_cuda_graph:
+                self._cfg_step(model, ctx, x, t_buf, length2, nz, cfg_scale, clip_denoised, x, None)
+            elif graph is None and i == 0:
+                # first step eagerly (warms workspaces and lazy state), then capture the step once
+                self._cfg_step(model, ctx, x, t_buf, length2, nz, cfg_scale, clip_denoised, x, None)
+                torch.cuda.synchronize(device)
+                graph = torch.cuda.CUDAGraph()
+                keep_x, keep_c = x.clone(), model._packed["usage"].clone(),
+                keep_i = model._packed["importance"].clone()
+                with torch.cuda.graph(graph):
+                    self._cfg_step(model, ctx, x, t_buf, length2, nz, cfg_scale, clip_denoised, x, None)
+                # capture does not execute; restore nothing but be explicit about state
+                x.copy_(keep_x)
+                model._packed["usage"].copy_(keep_c)
+                model._packed["importance"].copy_(keep_i)
+            else:
+                graph.replay()
+        return x
+
+    # ------------------------------------------------------------------ training losses (forward value)
+    def training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
+        """:923-992, MSE branch, forward values only: {"mse","target","pred","moe_loss"}.
+        The backward kernels of the training step (BASELINE.json configs[4]) are not built yet, so
+        the returned tensors carry no autograd graph."""
+        self._check_supported()
+        if self.loss_type not in (LossType.MSE, LossType.RESCALED_MSE):
+            raise NotImplementedError(self.loss_type)
+        if model_kwargs is None:
+            model_kwargs = {}
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        x_t = self.q_sample(x_start, t, noise=noise)
+        model.reset_all_moe_counters(model)                           # :935
+        out = model(x_t, t, **model_kwargs)                           # :950
+        assert out.shape == noise.shape == x_start.shape
+        terms = {"mse": ((noise - out) ** 2).mean(dim=list(range(1, out.dim()))).view(-1),
+                 "target": noise, "pred": out, "moe_loss": 0.0 + model.get_moe_loss(model)}
+        return terms

@@ -1,0 +1,170 @@
+"""Thin Python wrappers over the C-ABI (include/mdm_b200.h).  torch is used only for device memory
+and the current stream; every computation below runs in libmdm_b200.so.  No fallbacks."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_GELU, ACT_SILU, ACT_EXPFEAT, MDM_F32, MDM_BF16  # noqa: F401
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return MDM_F32
+    if t.dtype == torch.bfloat16:
+        return MDM_BF16
+    raise _lib.MdmError("unsupported dtype %s" % t.dtype)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MdmError("mdm_b200 kernels need CUDA tensors; there is no CPU path")
+
+
+def gemm(A, W, bias=None, *, act=ACT_NONE, alpha=1.0, beta=0.0, resid=None, resid_mod=0, rowscale=None,
+         rowmask=None, out_f32=None, out_a=None, a_pre_resid=False, N=None, M=None, tiles=None,
+         num_tiles=0, num_tiles_dev=None, a_rows=None, w_rows=None):
+    """C = epi(A @ W^T).  A [rows,K] (row stride may exceed K), W [w_rows,K]; both bf16 (tcgen05 path)
+    or both fp32.  out_f32: fp32 output; out_a: secondary output in the operand dtype."""
+    _req_cuda(A, W)
+    lib = _lib.load()
+    K = A.shape[1]
+    M = A.shape[0] if M is None else M
+    N = W.shape[0] if N is None else N
+    e = _lib.GemmEpi()
+    e.bias, e.rowscale, e.rowmask, e.resid = _ptr(bias), _ptr(rowscale), _ptr(rowmask), _ptr(resid)
+    e.ld_resid = resid.stride(0) if resid is not None else 0
+    e.resid_mod = resid_mod
+    e.alpha, e.beta, e.act = alpha, beta, act
+    if out_f32 is not None:
+        e.out_f32, e.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    if out_a is not None:
+        e.out_bf16, e.ld_bf16 = out_a.data_ptr(), out_a.stride(0)
+    e.bf16_pre_resid = 1 if a_pre_resid else 0
+    a_rows = A.shape[0] if a_rows is None else a_rows
+    w_rows = W.shape[0] if w_rows is None else w_rows
+    if A.dtype == torch.bfloat16:
+        st = lib.mdm_gemm_bf16(A.data_ptr(), A.stride(0), a_rows, W.data_ptr(), W.stride(0), w_rows, M, N, K,
+                               _ptr(tiles), num_tiles, _ptr(num_tiles_dev), C.byref(e), 0, _stream())
+    else:
+        st = lib.mdm_gemm_f32(A.data_ptr(), A.stride(0), a_rows, W.data_ptr(), W.stride(0), w_rows, M, N, K,
+                              _ptr(tiles), num_tiles, _ptr(num_tiles_dev), C.byref(e), _stream())
+    _lib.check(st, "mdm_gemm")
+
+
+def rowop(x, rows, D, out_dt, *, ln1=None, l2norm=False, out1_f32=None, out1_a=None, ln2=None, film=None,
+          rows_per_seq=0, silu=False, out2_f32=None, out2_a=None, out0_a=None):
+    _req_cuda(x)
+    op = _lib.RowOp()
+    op.inp, op.in_dt = x.data_ptr(), _dt(x)
+    if ln1 is not None:
+        op.ln1_w, op.ln1_b = ln1[0].data_ptr(), ln1[1].data_ptr()
+    op.l2norm = 1 if l2norm else 0
+    op.out1_f32, op.out1_a = _ptr(out1_f32), _ptr(out1_a)
+    if ln2 is not None:
+        op.ln2_w, op.ln2_b = ln2[0].data_ptr(), ln2[1].data_ptr()
+    op.film, op.rows_per_seq, op.silu = _ptr(film), rows_per_seq, 1 if silu else 0
+    op.out2_f32, op.out2_a, op.out0_a = _ptr(out2_f32), _ptr(out2_a), _ptr(out0_a)
+    _lib.check(_lib.load().mdm_rowop(C.byref(op), rows, D, out_dt, _stream()), "mdm_rowop")
+
+
+def fastattn(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out):
+    _req_cuda(qkv, P, out)
+    _lib.check(_lib.load().mdm_fastattn(qkv.data_ptr(), _dt(qkv), P.data_ptr(), norm_w.data_ptr(),
+                                        norm_b.data_ptr(), _ptr(length), length_shift, B, H, T, hd, P.shape[1],
+                                        out.data_ptr(), _stream()), "mdm_fastattn")
+
+
+def lincross_ctx(k, v, nt, B, Nt_max, H, hd, ctx):
+    _lib.check(_lib.load().mdm_lincross_ctx(k.data_ptr(), v.data_ptr(), _dt(k), _ptr(nt), B, Nt_max, H, hd,
+                                            ctx.data_ptr(), _stream()), "mdm_lincross_ctx")
+
+
+def lincross_apply(q, ctx, B, T, H, hd, y):
+    _lib.check(_lib.load().mdm_lincross_apply(q.data_ptr(), _dt(q), ctx.data_ptr(), B, T, H, hd, y.data_ptr(),
+                                              _stream()), "mdm_lincross_apply")
+
+
+def softmax_cross(q, k, v, nt, B, T, Nt_max, H, hd, o):
+    _lib.check(_lib.load().mdm_softmax_cross(q.data_ptr(), k.data_ptr(), v.data_ptr(), _dt(q), _ptr(nt), B, T,
+                                             Nt_max, H, hd, o.data_ptr(), _stream()), "mdm_softmax_cross")
+
+
+def moe_gate(x, N, D, NB, E, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp):
+    _lib.check(_lib.load().mdm_moe_gate(x.data_ptr(), N, D, NB, E, 2, ln_w.data_ptr(), ln_b.data_ptr(),
+                                        gate_w.data_ptr(), gate_b.data_ptr(), idx.data_ptr(), vals.data_ptr(),
+                                        stats.data_ptr(), blk_hist.data_ptr(), blk_imp.data_ptr(), _stream()),
+               "mdm_moe_gate")
+
+
+def moe_scan(blk_hist, blk_imp, idx, N, NB, E, F, D, blk_base, seg_offsets, tiles_up, tiles_down, num_tiles,
+             usage, importance):
+    _lib.check(_lib.load().mdm_moe_scan(blk_hist.data_ptr(), blk_imp.data_ptr(), idx.data_ptr(), N, NB, E, 2, F,
+                                        D, blk_base.data_ptr(), seg_offsets.data_ptr(), tiles_up.data_ptr(),
+                                        tiles_down.data_ptr(), num_tiles.data_ptr(), _ptr(usage),
+                                        _ptr(importance), _stream()), "mdm_moe_scan")
+
+
+def moe_permute(x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base, seg_offsets, xp, perm, rowscale):
+    _lib.check(_lib.load().mdm_moe_permute(x.data_ptr(), N, D, NB, E, 2, ln_w.data_ptr(), ln_b.data_ptr(),
+                                           idx.data_ptr(), vals.data_ptr(), stats.data_ptr(), blk_base.data_ptr(),
+                                           seg_offsets.data_ptr(), xp.data_ptr(), _dt(xp), perm.data_ptr(),
+                                           rowscale.data_ptr(), _stream()), "mdm_moe_permute")
+
+
+def moe_combine_film(yp, perm, N, D, NBK, ln_w, ln_b, film, rows_per_seq, out):
+    _lib.check(_lib.load().mdm_moe_combine_film(yp.data_ptr(), _dt(yp), perm.data_ptr(), N, D, NBK,
+                                                ln_w.data_ptr(), ln_b.data_ptr(), film.data_ptr(), rows_per_seq,
+                                                out.data_ptr(), _stream()), "mdm_moe_combine_film")
+
+
+def softmax_topk(logits):
+    """Routing probe: (probs, idx int64 [N,2], vals) with the fused gate's device code."""
+    _req_cuda(logits)
+    N, E = logits.shape
+    probs = torch.empty_like(logits)
+    idx = torch.empty(N, 2, dtype=torch.int64, device=logits.device)
+    vals = torch.empty(N, 2, dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.load().mdm_softmax_topk(logits.data_ptr(), N, E, 2, probs.data_ptr(), idx.data_ptr(),
+                                            vals.data_ptr(), _stream()), "mdm_softmax_topk")
+    return probs, idx, vals
+
+
+def timestep_embedding(t, B, D, out):
+    _lib.check(_lib.load().mdm_timestep_embedding(t.data_ptr(), B, D, out.data_ptr(), _dt(out), _stream()),
+               "mdm_timestep_embedding")
+
+
+def gated_mix(t, x, out):
+    _lib.check(_lib.load().mdm_gated_mix(t.data_ptr(), x.data_ptr(), t.numel(), out.data_ptr(), _dt(out),
+                                         _stream()), "mdm_gated_mix")
+
+
+def pad_cast(x, rows, F, out):
+    _lib.check(_lib.load().mdm_pad_cast(x.data_ptr(), rows, F, out.data_ptr(), out.stride(0), _dt(out), _stream()),
+               "mdm_pad_cast")
+
+
+def cfg_update(x, eps_c, eps_u, noise, t, tables, n_steps, cfg_scale, clip, x_prev, x0=None):
+    _req_cuda(x, eps_c, eps_u, noise, t, tables, x_prev)
+    B = x.shape[0]
+    _lib.check(_lib.load().mdm_cfg_update(x.data_ptr(), eps_c.data_ptr(), eps_u.data_ptr(), noise.data_ptr(),
+                                          t.data_ptr(), tables.data_ptr(), n_steps, float(cfg_scale),
+                                          1 if clip else 0, B, x.numel() // B, x_prev.data_ptr(), _ptr(x0),
+                                          _stream()), "mdm_cfg_update")
+
+
+def q_sample(x0, noise, t, tables2, n_steps, x_t):
+    _req_cuda(x0, noise, t, tables2, x_t)
+    B = x0.shape[0]
+    _lib.check(_lib.load().mdm_q_sample(x0.data_ptr(), noise.data_ptr(), t.data_ptr(), tables2.data_ptr(), n_steps,
+                                        B, x0.numel() // B, x_t.data_ptr(), _stream()), "mdm_q_sample")
