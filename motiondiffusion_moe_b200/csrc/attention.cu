@@ -7,6 +7,11 @@
 // (one column per thread).  Activations are read/written as fp32 or bf16.
 #include "common.cuh"
 
+// tensor-core (mma.sync) kernel for the bf16 path, attention_tc.cu
+int mdm_fastattn_tc(const void* qkv, const float* P, const float* norm_w, const float* norm_b,
+                    const int64_t* length, int length_shift, int B, int H, int T, int hd, int M, void* out,
+                    cudaStream_t st);
+
 namespace {
 
 constexpr int AT = 128;  // threads per CTA == max(hd, M)
@@ -360,6 +365,10 @@ extern "C" MDM_API int mdm_fastattn(const void* qkv, int dt, const float* P, con
   if (B * H == 0 || T == 0) return MDM_OK;
   const size_t smem = sizeof(float) * ((size_t)hd * M + 3 * TC * hd + 2 * M * TC + TC * 4);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dt == MDM_BF16) {
+    const int r = mdm_fastattn_tc(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, M, out, st);
+    if (r != MDM_ERR_UNSUPPORTED) return r;  // otherwise: shape outside the tensor-core kernel
+  }
   if (dt == MDM_F32) {
     if (set_smem(fastattn_kernel<float>, smem)) return MDM_ERR_CUDA;
     fastattn_kernel<float><<<B * H, AT, smem, st>>>(reinterpret_cast<const float*>(qkv), P, norm_w, norm_b,

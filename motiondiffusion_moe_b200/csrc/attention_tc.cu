@@ -1,0 +1,297 @@
+// Tensor-core attention cores for the bf16 path (reference: models/fast_attention.py).
+//
+// mdm_fastattn (bf16): FastAttention.forward :29-92 fused into ONE kernel per call, one CTA per
+// (sequence, head).  HBM traffic = read q,k,v + write out (4*N*D*2 bytes); everything else stays
+// in shared memory / registers:
+//   S1  LayerNorm(hd) (+ L2 norm for q,k) of the 0.1-scaled rows            -> Qs, Ks, Vs (bf16)
+//   S2  feature maps  exp(clamp(X . P, +-15)) * 0.1 (key rows masked)       -> in place in Qs, Ks
+//   S2b den[t] = max(sum_m q'[t,m] k'[t,m], 1e-6)
+//   S3  kv = (K'^T V) * 0.1            [M x hd], accumulated over T        -> bf16 over P's smem
+//   S4  out = LN( (Q' kv) * 0.1 / den )                                     -> staged, coalesced store
+// The three matrix products use mma.sync.m16n8k16 (bf16 in, fp32 accumulate) fed by ldmatrix from
+// padded (conflict-free) shared-memory tiles.  They are small per-(b,h) products (<= 208x128x128),
+// which is why they live here rather than in the tcgen05 GEMM.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(256, 1)
+fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, const float* __restrict__ nw,
+                   const float* __restrict__ nb, const int64_t* __restrict__ length, int length_shift, int H,
+                   int T, int Tp, bf16* __restrict__ out) {
+  constexpr int LDS = HD + 8;   // padded row pitch (elements): 16-byte row shift => conflict-free ldmatrix
+  constexpr int EPL = HD / 32;  // elements per lane in the row passes
+  constexpr int KS = HD / 16;   // k-steps over hd (== M)
+  constexpr int NT = HD / 8;    // 8-wide n-tiles over hd (== M)
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem);
+  bf16* Ks = Qs + Tp * LDS;
+  bf16* Vs = Ks + Tp * LDS;
+  bf16* Ps = Vs + Tp * LDS;                         // P^T [m][n], later kv [m][n]
+  float* den_s = reinterpret_cast<float*>(Ps + HD * LDS);
+  float* nw_s = den_s + Tp;
+  float* nb_s = nw_s + HD;
+
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int D = H * HD;
+  const int len = length ? (int)min((long)T, (long)(length[b] >> length_shift)) : T;
+  const int nstrips = Tp / 16;
+
+  // ---- S0: P^T as bf16, LN affine
+  for (int i = tid; i < HD * HD; i += 256) {
+    const int n = i / HD, m = i - n * HD;
+    Ps[m * LDS + n] = __float2bfloat16_rn(P[i]);
+  }
+  for (int i = tid; i < HD; i += 256) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }
+  __syncthreads();
+
+  // ---- S1: per-row LayerNorm (+ L2 norm) of 0.1*q, 0.1*k, 0.1*v
+  for (int t = warp; t < Tp; t += 8) {
+    bf16* dst[3] = {Qs + t * LDS, Ks + t * LDS, Vs + t * LDS};
+    if (t < T) {
+      const bf16* row = qkv + ((long)(b * T + t)) * 3 * D + h * HD + lane * EPL;
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        float x[EPL];
+        if (EPL == 4) {
+          const uint2 raw = *reinterpret_cast<const uint2*>(row + w * D);
+          const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+          const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+          x[0] = __low2float(p0); x[1] = __high2float(p0); x[2 % EPL] = __low2float(p1); x[3 % EPL] = __high2float(p1);
+        } else {
+          const uint32_t raw = *reinterpret_cast<const uint32_t*>(row + w * D);
+          const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw);
+          x[0] = __low2float(p0); x[1] = __high2float(p0);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) { x[i] *= 0.1f; s += x[i]; }
+        const float mean = warp_sum(s) / (float)HD;
+        float q2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) { const float d = x[i] - mean; q2 = fmaf(d, d, q2); }
+        const float rstd = rsqrtf(warp_sum(q2) / (float)HD + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) x[i] = (x[i] - mean) * rstd * nw_s[lane * EPL + i] + nb_s[lane * EPL + i];
+        if (w < 2) {  // F.normalize for q and k
+          float n2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) n2 = fmaf(x[i], x[i], n2);
+          const float denom = fmaxf(sqrtf(warp_sum(n2)), 1e-12f);
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) x[i] = x[i] / denom;
+        }
+        if (EPL == 4) {
+          uint2 pk;
+          pk.x = pack_bf16(x[0], x[1]);
+          pk.y = pack_bf16(x[2 % EPL], x[3 % EPL]);
+          *reinterpret_cast<uint2*>(dst[w] + lane * EPL) = pk;
+        } else {
+          *reinterpret_cast<uint32_t*>(dst[w] + lane * EPL) = pack_bf16(x[0], x[1]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int w = 0; w < 3; ++w)
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) dst[w][lane * EPL + i] = __float2bfloat16_rn(0.f);
+    }
+  }
+  __syncthreads();
+
+  // ---- S2: feature maps in place: X' = exp(clamp(X . P)) * 0.1 ; key rows t >= len are zeroed
+  for (int job = warp; job < 2 * nstrips; job += 8) {
+    const bool isK = job >= nstrips;
+    bf16* X = isK ? Ks : Qs;
+    const int r0 = (isK ? job - nstrips : job) * 16;
+    uint32_t a[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+      ldsm_x4(a[ks], X + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
+    __syncwarp();
+    const bool live0 = !isK || (r0 + g) < len, live1 = !isK || (r0 + g + 8) < len;
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bb[4];
+        ldsm_x4(bb, Ps + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
+        mma16816(c[0], a[ks], bb[0], bb[1]);
+        mma16816(c[1], a[ks], bb[2], bb[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = np * 16 + j * 8 + 2 * tq;
+        float f[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] = expf(fminf(fmaxf(c[j][i], -15.f), 15.f)) * 0.1f;
+        *reinterpret_cast<uint32_t*>(X + (r0 + g) * LDS + col) = live0 ? pack_bf16(f[0], f[1]) : 0u;
+        *reinterpret_cast<uint32_t*>(X + (r0 + g + 8) * LDS + col) = live1 ? pack_bf16(f[2], f[3]) : 0u;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- S2b: per-frame denominator (same-t product, fast_attention.py:81-82)
+  for (int t = warp; t < Tp; t += 8) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i)
+      s = fmaf(__bfloat162float(Qs[t * LDS + lane * EPL + i]), __bfloat162float(Ks[t * LDS + lane * EPL + i]), s);
+    s = warp_sum(s);
+    if (lane == 0) den_s[t] = fmaxf(s, 1e-6f);
+  }
+
+  // ---- S3: kv[m][n] = 0.1 * sum_t K'[t][m] V[t][n]
+  constexpr int MS = HD / 16;        // 16-row m-strips
+  constexpr int NSPLIT = 8 / MS;     // warps per m-strip
+  constexpr int NCOLS = HD / NSPLIT; // columns per warp
+  constexpr int NTW = NCOLS / 8;
+  {
+    const int m0 = (warp % MS) * 16, n00 = (warp / MS) * NCOLS;
+    float acc[NTW][4];
+#pragma unroll
+    for (int i = 0; i < NTW; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int ks = 0; ks < nstrips; ++ks) {
+      const int k0 = ks * 16;
+      uint32_t a[4];
+      ldsm_x4_t(a, Ks + (k0 + (lane & 7) + (lane >> 4) * 8) * LDS + m0 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+      for (int np = 0; np < NTW / 2; ++np) {
+        uint32_t bb[4];
+        ldsm_x4_t(bb, Vs + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + n00 + np * 16 + (lane >> 4) * 8);
+        mma16816(acc[2 * np], a, bb[0], bb[1]);
+        mma16816(acc[2 * np + 1], a, bb[2], bb[3]);
+      }
+    }
+    // P^T is dead (all S2 reads finished before the barrier above): overwrite it with kv
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      const int col = n00 + nt * 8 + 2 * tq;
+      *reinterpret_cast<uint32_t*>(Ps + (m0 + g) * LDS + col) = pack_bf16(acc[nt][0] * 0.1f, acc[nt][1] * 0.1f);
+      *reinterpret_cast<uint32_t*>(Ps + (m0 + g + 8) * LDS + col) = pack_bf16(acc[nt][2] * 0.1f, acc[nt][3] * 0.1f);
+    }
+  }
+  __syncthreads();
+
+  // ---- S4: out = LN((Q' kv) * 0.1 / den), staged in the strip's own Qs rows, then coalesced store
+  for (int strip = warp; strip < nstrips; strip += 8) {
+    const int r0 = strip * 16;
+    uint32_t a[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+      ldsm_x4(a[ks], Qs + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bb[4];
+        ldsm_x4_t(bb, Ps + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8);
+        mma16816(acc[2 * np], a[ks], bb[0], bb[1]);
+        mma16816(acc[2 * np + 1], a[ks], bb[2], bb[3]);
+      }
+    }
+    const float d0 = den_s[r0 + g], d1 = den_s[r0 + g + 8];
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      acc[nt][0] = (acc[nt][0] * 0.1f) / d0; acc[nt][1] = (acc[nt][1] * 0.1f) / d0;
+      acc[nt][2] = (acc[nt][2] * 0.1f) / d1; acc[nt][3] = (acc[nt][3] * 0.1f) / d1;
+      s0 += acc[nt][0] + acc[nt][1];
+      s1 += acc[nt][2] + acc[nt][3];
+    }
+    const float mean0 = quad_sum(s0) / (float)HD, mean1 = quad_sum(s1) / (float)HD;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float d;
+      d = acc[nt][0] - mean0; q0 = fmaf(d, d, q0);
+      d = acc[nt][1] - mean0; q0 = fmaf(d, d, q0);
+      d = acc[nt][2] - mean1; q1 = fmaf(d, d, q1);
+      d = acc[nt][3] - mean1; q1 = fmaf(d, d, q1);
+    }
+    const float rstd0 = rsqrtf(quad_sum(q0) / (float)HD + 1e-5f);
+    const float rstd1 = rsqrtf(quad_sum(q1) / (float)HD + 1e-5f);
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = nt * 8 + 2 * tq;
+      const float w0 = nw_s[col], w1 = nw_s[col + 1], b0 = nb_s[col], b1 = nb_s[col + 1];
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g) * LDS + col) =
+          pack_bf16((acc[nt][0] - mean0) * rstd0 * w0 + b0, (acc[nt][1] - mean0) * rstd0 * w1 + b1);
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g + 8) * LDS + col) =
+          pack_bf16((acc[nt][2] - mean1) * rstd1 * w0 + b0, (acc[nt][3] - mean1) * rstd1 * w1 + b1);
+    }
+    __syncwarp();
+    constexpr int CPR = HD / 8;  // 16-byte chunks per row
+    for (int i = lane; i < 16 * CPR; i += 32) {
+      const int r = i / CPR, c = i - r * CPR;
+      if (r0 + r < T)
+        *reinterpret_cast<uint4*>(out + ((long)(b * T + r0 + r)) * D + h * HD + c * 8) =
+            *reinterpret_cast<const uint4*>(Qs + (r0 + r) * LDS + c * 8);
+    }
+  }
+}
+
+template <int HD>
+int launch_fastattn(const bf16* qkv, const float* P, const float* nw, const float* nb, const int64_t* length,
+                    int shift, int B, int H, int T, bf16* out, cudaStream_t st) {
+  const int Tp = (T + 15) / 16 * 16;
+  const size_t smem = (size_t)(3 * Tp + HD) * (HD + 8) * 2 + sizeof(float) * (Tp + 2 * HD);
+  if (smem > 227 * 1024) return MDM_ERR_UNSUPPORTED;
+  static size_t attr = 0;
+  if (smem > attr) {
+    if (cudaFuncSetAttribute(fastattn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return MDM_ERR_CUDA;
+    attr = smem;
+  }
+  fastattn_tc_kernel<HD><<<B * H, 256, smem, st>>>(qkv, P, nw, nb, length, shift, H, T, Tp, out);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+}  // namespace
+
+// Returns MDM_ERR_UNSUPPORTED when the shape does not fit this kernel (the caller then uses the
+// generic fp32-compute kernel of attention.cu).
+int mdm_fastattn_tc(const void* qkv, const float* P, const float* norm_w, const float* norm_b,
+                    const int64_t* length, int length_shift, int B, int H, int T, int hd, int M, void* out,
+                    cudaStream_t st) {
+  if (M != hd) return MDM_ERR_UNSUPPORTED;
+  const bf16* q = reinterpret_cast<const bf16*>(qkv);
+  bf16* o = reinterpret_cast<bf16*>(out);
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(o) & 15)) return MDM_ERR_UNSUPPORTED;
+  if (hd == 128) return launch_fastattn<128>(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, st);
+  if (hd == 64) return launch_fastattn<64>(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, st);
+  return MDM_ERR_UNSUPPORTED;
+}

@@ -30,12 +30,28 @@ def _req_cuda(*ts):
             raise _lib.MdmError("mdm_b200 kernels need CUDA tensors; there is no CPU path")
 
 
+def _c(*ts):
+    """The C-ABI takes raw pointers: every tensor must be CUDA and dense row-major."""
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.MdmError("mdm_b200 kernels need CUDA tensors; there is no CPU path")
+        if not t.is_contiguous():
+            raise _lib.MdmError("non-contiguous tensor (shape %s, strides %s) passed to a raw-pointer kernel"
+                                % (tuple(t.shape), t.stride()))
+
+
 def gemm(A, W, bias=None, *, act=ACT_NONE, alpha=1.0, beta=0.0, resid=None, resid_mod=0, rowscale=None,
          rowmask=None, out_f32=None, out_a=None, a_pre_resid=False, N=None, M=None, tiles=None,
          num_tiles=0, num_tiles_dev=None, a_rows=None, w_rows=None):
     """C = epi(A @ W^T).  A [rows,K] (row stride may exceed K), W [w_rows,K]; both bf16 (tcgen05 path)
     or both fp32.  out_f32: fp32 output; out_a: secondary output in the operand dtype."""
-    _req_cuda(A, W)
+    _req_cuda(A, W, out_f32, out_a, resid)
+    _c(bias, rowscale, rowmask, tiles, num_tiles_dev)
+    for t_ in (A, W, out_f32, out_a, resid):
+        if t_ is not None and (t_.dim() != 2 or t_.stride(1) != 1):
+            raise _lib.MdmError("GEMM operands/outputs must be 2-D with unit inner stride")
     lib = _lib.load()
     K = A.shape[1]
     M = A.shape[0] if M is None else M
@@ -63,7 +79,10 @@ def gemm(A, W, bias=None, *, act=ACT_NONE, alpha=1.0, beta=0.0, resid=None, resi
 
 def rowop(x, rows, D, out_dt, *, ln1=None, l2norm=False, out1_f32=None, out1_a=None, ln2=None, film=None,
           rows_per_seq=0, silu=False, out2_f32=None, out2_a=None, out0_a=None):
-    _req_cuda(x)
+    _c(x, out1_f32, out1_a, out2_f32, out2_a, out0_a, film)
+    for pair in (ln1, ln2):
+        if pair is not None:
+            _c(*pair)
     op = _lib.RowOp()
     op.inp, op.in_dt = x.data_ptr(), _dt(x)
     if ln1 is not None:
@@ -78,28 +97,32 @@ def rowop(x, rows, D, out_dt, *, ln1=None, l2norm=False, out1_f32=None, out1_a=N
 
 
 def fastattn(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out):
-    _req_cuda(qkv, P, out)
+    _c(qkv, P, norm_w, norm_b, length, out)
     _lib.check(_lib.load().mdm_fastattn(qkv.data_ptr(), _dt(qkv), P.data_ptr(), norm_w.data_ptr(),
                                         norm_b.data_ptr(), _ptr(length), length_shift, B, H, T, hd, P.shape[1],
                                         out.data_ptr(), _stream()), "mdm_fastattn")
 
 
 def lincross_ctx(k, v, nt, B, Nt_max, H, hd, ctx):
+    _c(k, v, nt, ctx)
     _lib.check(_lib.load().mdm_lincross_ctx(k.data_ptr(), v.data_ptr(), _dt(k), _ptr(nt), B, Nt_max, H, hd,
                                             ctx.data_ptr(), _stream()), "mdm_lincross_ctx")
 
 
 def lincross_apply(q, ctx, B, T, H, hd, y):
+    _c(q, ctx, y)
     _lib.check(_lib.load().mdm_lincross_apply(q.data_ptr(), _dt(q), ctx.data_ptr(), B, T, H, hd, y.data_ptr(),
                                               _stream()), "mdm_lincross_apply")
 
 
 def softmax_cross(q, k, v, nt, B, T, Nt_max, H, hd, o):
+    _c(q, k, v, nt, o)
     _lib.check(_lib.load().mdm_softmax_cross(q.data_ptr(), k.data_ptr(), v.data_ptr(), _dt(q), _ptr(nt), B, T,
                                              Nt_max, H, hd, o.data_ptr(), _stream()), "mdm_softmax_cross")
 
 
 def moe_gate(x, N, D, NB, E, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp):
+    _c(x, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp)
     _lib.check(_lib.load().mdm_moe_gate(x.data_ptr(), N, D, NB, E, 2, ln_w.data_ptr(), ln_b.data_ptr(),
                                         gate_w.data_ptr(), gate_b.data_ptr(), idx.data_ptr(), vals.data_ptr(),
                                         stats.data_ptr(), blk_hist.data_ptr(), blk_imp.data_ptr(), _stream()),
@@ -108,6 +131,7 @@ def moe_gate(x, N, D, NB, E, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_h
 
 def moe_scan(blk_hist, blk_imp, idx, N, NB, E, F, D, blk_base, seg_offsets, tiles_up, tiles_down, num_tiles,
              usage, importance):
+    _c(blk_hist, blk_imp, idx, blk_base, seg_offsets, tiles_up, tiles_down, num_tiles, usage, importance)
     _lib.check(_lib.load().mdm_moe_scan(blk_hist.data_ptr(), blk_imp.data_ptr(), idx.data_ptr(), N, NB, E, 2, F,
                                         D, blk_base.data_ptr(), seg_offsets.data_ptr(), tiles_up.data_ptr(),
                                         tiles_down.data_ptr(), num_tiles.data_ptr(), _ptr(usage),
@@ -115,6 +139,7 @@ def moe_scan(blk_hist, blk_imp, idx, N, NB, E, F, D, blk_base, seg_offsets, tile
 
 
 def moe_permute(x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base, seg_offsets, xp, perm, rowscale):
+    _c(x, ln_w, ln_b, idx, vals, stats, blk_base, seg_offsets, xp, perm, rowscale)
     _lib.check(_lib.load().mdm_moe_permute(x.data_ptr(), N, D, NB, E, 2, ln_w.data_ptr(), ln_b.data_ptr(),
                                            idx.data_ptr(), vals.data_ptr(), stats.data_ptr(), blk_base.data_ptr(),
                                            seg_offsets.data_ptr(), xp.data_ptr(), _dt(xp), perm.data_ptr(),
@@ -122,6 +147,7 @@ def moe_permute(x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base, seg_offs
 
 
 def moe_combine_film(yp, perm, N, D, NBK, ln_w, ln_b, film, rows_per_seq, out):
+    _c(yp, perm, ln_w, ln_b, film, out)
     _lib.check(_lib.load().mdm_moe_combine_film(yp.data_ptr(), _dt(yp), perm.data_ptr(), N, D, NBK,
                                                 ln_w.data_ptr(), ln_b.data_ptr(), film.data_ptr(), rows_per_seq,
                                                 out.data_ptr(), _stream()), "mdm_moe_combine_film")
@@ -129,7 +155,7 @@ def moe_combine_film(yp, perm, N, D, NBK, ln_w, ln_b, film, rows_per_seq, out):
 
 def softmax_topk(logits):
     """Routing probe: (probs, idx int64 [N,2], vals) with the fused gate's device code."""
-    _req_cuda(logits)
+    _c(logits)
     N, E = logits.shape
     probs = torch.empty_like(logits)
     idx = torch.empty(N, 2, dtype=torch.int64, device=logits.device)
@@ -140,22 +166,26 @@ def softmax_topk(logits):
 
 
 def timestep_embedding(t, B, D, out):
+    _c(t, out)
     _lib.check(_lib.load().mdm_timestep_embedding(t.data_ptr(), B, D, out.data_ptr(), _dt(out), _stream()),
                "mdm_timestep_embedding")
 
 
 def gated_mix(t, x, out):
+    _c(t, x, out)
     _lib.check(_lib.load().mdm_gated_mix(t.data_ptr(), x.data_ptr(), t.numel(), out.data_ptr(), _dt(out),
                                          _stream()), "mdm_gated_mix")
 
 
 def pad_cast(x, rows, F, out):
+    _c(x)
+    _req_cuda(out)
     _lib.check(_lib.load().mdm_pad_cast(x.data_ptr(), rows, F, out.data_ptr(), out.stride(0), _dt(out), _stream()),
                "mdm_pad_cast")
 
 
 def cfg_update(x, eps_c, eps_u, noise, t, tables, n_steps, cfg_scale, clip, x_prev, x0=None):
-    _req_cuda(x, eps_c, eps_u, noise, t, tables, x_prev)
+    _c(x, eps_c, eps_u, noise, t, tables, x_prev, x0)
     B = x.shape[0]
     _lib.check(_lib.load().mdm_cfg_update(x.data_ptr(), eps_c.data_ptr(), eps_u.data_ptr(), noise.data_ptr(),
                                           t.data_ptr(), tables.data_ptr(), n_steps, float(cfg_scale),
@@ -164,7 +194,7 @@ def cfg_update(x, eps_c, eps_u, noise, t, tables, n_steps, cfg_scale, clip, x_pr
 
 
 def q_sample(x0, noise, t, tables2, n_steps, x_t):
-    _req_cuda(x0, noise, t, tables2, x_t)
+    _c(x0, noise, t, tables2, x_t)
     B = x0.shape[0]
     _lib.check(_lib.load().mdm_q_sample(x0.data_ptr(), noise.data_ptr(), t.data_ptr(), tables2.data_ptr(), n_steps,
                                         B, x0.numel() // B, x_t.data_ptr(), _stream()), "mdm_q_sample")
