@@ -71,56 +71,96 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
   for (int i = tid; i < HD; i += 256) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }
   __syncthreads();
 
-  // ---- S1: per-row LayerNorm (+ L2 norm) of 0.1*q, 0.1*k, 0.1*v
-  for (int t = warp; t < Tp; t += 8) {
-    bf16* dst[3] = {Qs + t * LDS, Ks + t * LDS, Vs + t * LDS};
-    if (t < T) {
-      const bf16* row = qkv + ((long)(b * T + t)) * 3 * D + h * HD + lane * EPL;
+  // ---- S1: per-row LayerNorm (+ L2 norm) of 0.1*q, 0.1*k, 0.1*v.  Two rows x three tensors are
+  // normalised together so that six independent shuffle-reduction chains are in flight per warp.
+  {
+    float wv[EPL], bv[EPL];
 #pragma unroll
-      for (int w = 0; w < 3; ++w) {
-        float x[EPL];
-        if (EPL == 4) {
-          const uint2 raw = *reinterpret_cast<const uint2*>(row + w * D);
-          const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-          const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-          x[0] = __low2float(p0); x[1] = __high2float(p0); x[2 % EPL] = __low2float(p1); x[3 % EPL] = __high2float(p1);
-        } else {
-          const uint32_t raw = *reinterpret_cast<const uint32_t*>(row + w * D);
-          const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw);
-          x[0] = __low2float(p0); x[1] = __high2float(p0);
-        }
-        float s = 0.f;
+    for (int i = 0; i < EPL; ++i) { wv[i] = nw_s[lane * EPL + i]; bv[i] = nb_s[lane * EPL + i]; }
+    for (int t0 = warp * 2; t0 < Tp; t0 += 16) {
+      float x[6][EPL];
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) { x[i] *= 0.1f; s += x[i]; }
-        const float mean = warp_sum(s) / (float)HD;
-        float q2 = 0.f;
+      for (int rr = 0; rr < 2; ++rr) {
+        const int t = t0 + rr;
+        const bf16* row = qkv + ((long)(b * T + min(t, T - 1))) * 3 * D + h * HD + lane * EPL;
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) { const float d = x[i] - mean; q2 = fmaf(d, d, q2); }
-        const float rstd = rsqrtf(warp_sum(q2) / (float)HD + 1e-5f);
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) x[i] = (x[i] - mean) * rstd * nw_s[lane * EPL + i] + nb_s[lane * EPL + i];
-        if (w < 2) {  // F.normalize for q and k
-          float n2 = 0.f;
-#pragma unroll
-          for (int i = 0; i < EPL; ++i) n2 = fmaf(x[i], x[i], n2);
-          const float denom = fmaxf(sqrtf(warp_sum(n2)), 1e-12f);
-#pragma unroll
-          for (int i = 0; i < EPL; ++i) x[i] = x[i] / denom;
-        }
-        if (EPL == 4) {
-          uint2 pk;
-          pk.x = pack_bf16(x[0], x[1]);
-          pk.y = pack_bf16(x[2 % EPL], x[3 % EPL]);
-          *reinterpret_cast<uint2*>(dst[w] + lane * EPL) = pk;
-        } else {
-          *reinterpret_cast<uint32_t*>(dst[w] + lane * EPL) = pack_bf16(x[0], x[1]);
+        for (int w = 0; w < 3; ++w) {
+          if (EPL == 4) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(row + w * D);
+            const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+            const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+            x[rr * 3 + w][0] = __low2float(p0); x[rr * 3 + w][1] = __high2float(p0);
+            x[rr * 3 + w][2 % EPL] = __low2float(p1); x[rr * 3 + w][3 % EPL] = __high2float(p1);
+          } else {
+            const uint32_t raw = *reinterpret_cast<const uint32_t*>(row + w * D);
+            const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw);
+            x[rr * 3 + w][0] = __low2float(p0); x[rr * 3 + w][1] = __high2float(p0);
+          }
         }
       }
-    } else {
+      float red[6];
 #pragma unroll
-      for (int w = 0; w < 3; ++w)
+      for (int c = 0; c < 6; ++c) {
+        red[c] = 0.f;
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) dst[w][lane * EPL + i] = __float2bfloat16_rn(0.f);
+        for (int i = 0; i < EPL; ++i) { x[c][i] *= 0.1f; red[c] += x[c][i]; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) red[c] += __shfl_xor_sync(0xffffffffu, red[c], o);
+      float mean[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        mean[c] = red[c] / (float)HD;
+        red[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) { const float d = x[c][i] - mean[c]; red[c] = fmaf(d, d, red[c]); }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) red[c] += __shfl_xor_sync(0xffffffffu, red[c], o);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const float rstd = rsqrtf(red[c] / (float)HD + 1e-5f);
+        red[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+          x[c][i] = (x[c][i] - mean[c]) * rstd * wv[i] + bv[i];
+          red[c] = fmaf(x[c][i], x[c][i], red[c]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) red[c] += __shfl_xor_sync(0xffffffffu, red[c], o);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int t = t0 + rr;
+        bf16* dst[3] = {Qs + t * LDS, Ks + t * LDS, Vs + t * LDS};
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const int c = rr * 3 + w;
+          if (w < 2) {  // F.normalize for q and k
+            const float denom = fmaxf(sqrtf(red[c]), 1e-12f);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) x[c][i] = x[c][i] / denom;
+          }
+          if (t >= T) {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) x[c][i] = 0.f;
+          }
+          if (EPL == 4) {
+            uint2 pk;
+            pk.x = pack_bf16(x[c][0], x[c][1]);
+            pk.y = pack_bf16(x[c][2 % EPL], x[c][3 % EPL]);
+            *reinterpret_cast<uint2*>(dst[w] + lane * EPL) = pk;
+          } else {
+            *reinterpret_cast<uint32_t*>(dst[w] + lane * EPL) = pack_bf16(x[c][0], x[c][1]);
+          }
+        }
+      }
     }
   }
   __syncthreads();
@@ -130,31 +170,31 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
     const bool isK = job >= nstrips;
     bf16* X = isK ? Ks : Qs;
     const int r0 = (isK ? job - nstrips : job) * 16;
-    uint32_t a[KS][4];
+    float c[NT][4];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-      ldsm_x4(a[ks], X + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
-    __syncwarp();
-    const bool live0 = !isK || (r0 + g) < len, live1 = !isK || (r0 + g + 8) < len;
+    for (int i = 0; i < NT; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
 #pragma unroll
-    for (int np = 0; np < NT / 2; ++np) {
-      float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(a, X + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
+      for (int np = 0; np < NT / 2; ++np) {
         uint32_t bb[4];
         ldsm_x4(bb, Ps + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
-        mma16816(c[0], a[ks], bb[0], bb[1]);
-        mma16816(c[1], a[ks], bb[2], bb[3]);
+        mma16816(c[2 * np], a, bb[0], bb[1]);
+        mma16816(c[2 * np + 1], a, bb[2], bb[3]);
       }
+    }
+    __syncwarp();  // every A fragment of this strip is in registers: the rows may now be overwritten
+    const bool live0 = !isK || (r0 + g) < len, live1 = !isK || (r0 + g + 8) < len;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int col = np * 16 + j * 8 + 2 * tq;
-        float f[4];
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = nt * 8 + 2 * tq;
+      float f[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) f[i] = expf(fminf(fmaxf(c[j][i], -15.f), 15.f)) * 0.1f;
-        *reinterpret_cast<uint32_t*>(X + (r0 + g) * LDS + col) = live0 ? pack_bf16(f[0], f[1]) : 0u;
-        *reinterpret_cast<uint32_t*>(X + (r0 + g + 8) * LDS + col) = live1 ? pack_bf16(f[2], f[3]) : 0u;
-      }
+      for (int i = 0; i < 4; ++i) f[i] = expf(fminf(fmaxf(c[nt][i], -15.f), 15.f)) * 0.1f;
+      *reinterpret_cast<uint32_t*>(X + (r0 + g) * LDS + col) = live0 ? pack_bf16(f[0], f[1]) : 0u;
+      *reinterpret_cast<uint32_t*>(X + (r0 + g + 8) * LDS + col) = live1 ? pack_bf16(f[2], f[3]) : 0u;
     }
   }
   __syncthreads();
@@ -204,21 +244,19 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
   // ---- S4: out = LN((Q' kv) * 0.1 / den), staged in the strip's own Qs rows, then coalesced store
   for (int strip = warp; strip < nstrips; strip += 8) {
     const int r0 = strip * 16;
-    uint32_t a[KS][4];
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-      ldsm_x4(a[ks], Qs + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
     float acc[NT][4];
 #pragma unroll
     for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 #pragma unroll
-    for (int np = 0; np < NT / 2; ++np) {
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(a, Qs + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
+      for (int np = 0; np < NT / 2; ++np) {
         uint32_t bb[4];
         ldsm_x4_t(bb, Ps + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8);
-        mma16816(acc[2 * np], a[ks], bb[0], bb[1]);
-        mma16816(acc[2 * np + 1], a[ks], bb[2], bb[3]);
+        mma16816(acc[2 * np], a, bb[0], bb[1]);
+        mma16816(acc[2 * np + 1], a, bb[2], bb[3]);
       }
     }
     const float d0 = den_s[r0 + g], d1 = den_s[r0 + g + 8];

@@ -7,7 +7,7 @@
 // this one kernel family.  Persistent, warp-specialised:
 //   warp 0 lane 0 : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma 128 x BN x 16, fp32 accumulate in TMEM, 2 stages)
-//   warps 2..5    : epilogue       (tcgen05.ld -> bias/act/scale/residual -> global)
+//   warps 2..9    : epilogue       (tcgen05.ld -> bias/act/scale -> (smem transpose) -> residual -> global)
 // Grouped mode (MoE experts, stacked FiLM MLPs): an MTile table maps each 128-row tile to its
 // A rows, C rows and weight rows; the table and its length may be produced on the device.
 #include "common.cuh"
@@ -17,17 +17,53 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int STAGE_T_BYTES = 32 * 32 * 4;  // per-warp 32x32 fp32 transpose buffer
 
 template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = TR_OFFSET + NUM_EPI_WARPS * STAGE_T_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024 align slack
 };
 
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) on
+// the MUFU rcp / ex2 units: ~14 issue slots instead of erff's ~50, so that the epilogue of a K=512
+// GEMM stays under its MMA time.  Max abs deviation from the exact erf GELU: 4.5e-7 (bf16 ulp at 1 is 7.8e-3).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float silu_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-x * 1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+__device__ __forceinline__ float act_fast(float v, int act) {
+  if (act == MDM_ACT_GELU) return gelu_fast(v);
+  if (act == MDM_ACT_SILU) return silu_fast(v);
+  if (act == MDM_ACT_EXPFEAT) return expf(fminf(fmaxf(v, -15.f), 15.f)) * 0.1f;
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -56,8 +92,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4);
-    mbar_init(&tmem_empty[1], 4);
+    mbar_init(&tmem_empty[0], NUM_EPI_WARPS);
+    mbar_init(&tmem_empty[1], NUM_EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);
@@ -122,8 +158,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------------------ epilogue
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------ epilogue (8 warps)
+    // warp -> TMEM lane quadrant (warp & 3) x unit parity ((warp-2) >> 2): two warps share a
+    // quadrant and take alternate column units.  Accumulators arrive with lane == row; bias,
+    // activation and row scale are applied in that layout, then the 32-row block is transposed
+    // through a 4 KB XOR-swizzled shared-memory buffer with 128-bit accesses so that every global
+    // access (residual load, fp32 / bf16 store) is a full 128-byte row segment:
+    //   read phase: lane -> (row = 4*i + lane/8, 16-byte chunk = lane%8), i = 0..7.
+    const int quad = warp & 3;
+    const int cpar = (warp - 2) >> 2;
+    uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - 2) * 256;  // 32 rows x 8 chunks
+    const bool f32_path = (epi.out_f32 != nullptr) || (epi.resid != nullptr);
+    const int rsub = lane >> 3, ch = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -143,27 +189,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float rs = (epi.rowscale && row_ok) ? epi.rowscale[m] : 1.0f;
       const float rm = (epi.rowmask && row_ok) ? epi.rowmask[m] : 1.0f;
       const float scale = rs * rm * epi.alpha;
-      const float* resid_row = nullptr;
-      if (epi.resid && row_ok) {
-        const long rr = epi.resid_mod > 0 ? (m % epi.resid_mod) : m;
-        resid_row = epi.resid + rr * epi.ld_resid;
-      }
+      const int rmax = min(32, rows_valid - quad * 32);   // valid rows of this warp's 32-row block
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = nt * BN + c * 32;
-        if (n0 >= N) break;
+      // per-tile base pointers; in-tile offsets stay 32-bit
+      const long blk_row0 = (long)c_row0 + quad * 32;
+      float* of_blk = epi.out_f32 ? epi.out_f32 + blk_row0 * epi.ld_f32 : nullptr;
+      bf16* ob_blk = epi.out_bf16 ? reinterpret_cast<bf16*>(epi.out_bf16) + blk_row0 * epi.ld_bf16 : nullptr;
+      const float* rs_blk = (epi.resid && epi.resid_mod <= 0) ? epi.resid + blk_row0 * epi.ld_resid : epi.resid;
+      const int rmod_base = epi.resid_mod > 0 ? (int)(blk_row0 % epi.resid_mod) : 0;
+
+      auto load_chunk = [&](int c, int n0, float (&v)[32]) {
         uint32_t raw[32];
         tmem_ld32(t_addr + c * 32, raw);
         tmem_ld_wait();
-        if (!row_ok) continue;
-        const bool full = (n0 + 32 <= N);
-        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         if (epi.bias) {
           const float* bp = epi.bias + w_row0 + n0;
-          if (full) {
+          if (n0 + 32 <= N) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
@@ -177,77 +220,137 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (epi.act != MDM_ACT_NONE) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], epi.act);
+          for (int j = 0; j < 32; ++j) v[j] = act_fast(v[j], epi.act);
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= scale;
+      };
 
-        if (epi.out_bf16 && epi.bf16_pre_resid) {
-          bf16* op = reinterpret_cast<bf16*>(epi.out_bf16) + m * epi.ld_bf16 + n0;
-          if (full && (epi.ld_bf16 & 7) == 0) {
+      if (f32_path) {
+        const bool vec_ok = ((epi.ld_f32 & 3) == 0 || !epi.out_f32) && ((epi.ld_resid & 3) == 0 || !epi.resid) &&
+                            ((epi.ld_bf16 & 3) == 0 || !epi.out_bf16);
+#pragma unroll 1
+        for (int c = cpar; c < BN / 32; c += 2) {
+          const int n0 = nt * BN + c * 32;
+          if (n0 >= N) break;
+          const int n = n0 + ch * 4;                        // this lane's 4 columns in the read phase
+          const bool cvec = vec_ok && (n + 4 <= N);
+          // residual prefetch (volatile: issued here, ahead of the TMEM load and the math)
+          float4 res[8];
+          if (epi.resid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-              pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(op + j) = pk;
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + rsub;
+              res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < rmax) {
+                const int rr_ = epi.resid_mod > 0 ? (rmod_base + row) % epi.resid_mod : row;
+                const float* rp = rs_blk + (long)rr_ * epi.ld_resid + n;
+                if (cvec) {
+                  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                               : "=f"(res[i].x), "=f"(res[i].y), "=f"(res[i].z), "=f"(res[i].w) : "l"(rp));
+                } else {
+                  if (n < N) res[i].x = __ldg(rp);
+                  if (n + 1 < N) res[i].y = __ldg(rp + 1);
+                  if (n + 2 < N) res[i].z = __ldg(rp + 2);
+                  if (n + 3 < N) res[i].w = __ldg(rp + 3);
+                }
+              }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < N) op[j] = __float2bfloat16_rn(v[j]);
           }
-        }
-        if (resid_row) {
-          const float* rp = resid_row + n0;
-          if (full && (epi.ld_resid & 3) == 0) {
+          float v[32];
+          load_chunk(c, n0, v);
+          float4* trf = reinterpret_cast<float4*>(tr);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-              v[j] += epi.beta * r4.x; v[j + 1] += epi.beta * r4.y;
-              v[j + 2] += epi.beta * r4.z; v[j + 3] += epi.beta * r4.w;
+          for (int c8 = 0; c8 < 8; ++c8)
+            trf[lane * 8 + (c8 ^ (lane & 7))] = make_float4(v[4 * c8], v[4 * c8 + 1], v[4 * c8 + 2], v[4 * c8 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + rsub;
+            float4 x = trf[row * 8 + (ch ^ (row & 7))];
+            if (row < rmax && n < N) {
+              bf16* ob = ob_blk ? ob_blk + row * epi.ld_bf16 + n : nullptr;
+              float* of = of_blk ? of_blk + row * epi.ld_f32 + n : nullptr;
+              if (ob && epi.bf16_pre_resid) {
+                if (cvec) {
+                  uint2 pk; pk.x = pack2(x.x, x.y); pk.y = pack2(x.z, x.w);
+                  *reinterpret_cast<uint2*>(ob) = pk;
+                } else {
+                  ob[0] = __float2bfloat16_rn(x.x);
+                  if (n + 1 < N) ob[1] = __float2bfloat16_rn(x.y);
+                  if (n + 2 < N) ob[2] = __float2bfloat16_rn(x.z);
+                  if (n + 3 < N) ob[3] = __float2bfloat16_rn(x.w);
+                }
+              }
+              if (epi.resid) {
+                x.x = fmaf(epi.beta, res[i].x, x.x); x.y = fmaf(epi.beta, res[i].y, x.y);
+                x.z = fmaf(epi.beta, res[i].z, x.z); x.w = fmaf(epi.beta, res[i].w, x.w);
+              }
+              if (of) {
+                if (cvec) {
+                  *reinterpret_cast<float4*>(of) = x;
+                } else {
+                  of[0] = x.x;
+                  if (n + 1 < N) of[1] = x.y;
+                  if (n + 2 < N) of[2] = x.z;
+                  if (n + 3 < N) of[3] = x.w;
+                }
+              }
+              if (ob && !epi.bf16_pre_resid) {
+                if (cvec) {
+                  uint2 pk; pk.x = pack2(x.x, x.y); pk.y = pack2(x.z, x.w);
+                  *reinterpret_cast<uint2*>(ob) = pk;
+                } else {
+                  ob[0] = __float2bfloat16_rn(x.x);
+                  if (n + 1 < N) ob[1] = __float2bfloat16_rn(x.y);
+                  if (n + 2 < N) ob[2] = __float2bfloat16_rn(x.z);
+                  if (n + 3 < N) ob[3] = __float2bfloat16_rn(x.w);
+                }
+              }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < N) v[j] += epi.beta * rp[j];
           }
+          __syncwarp();
         }
-        if (epi.out_f32) {
-          float* op = epi.out_f32 + m * epi.ld_f32 + n0;
-          if (full && (epi.ld_f32 & 3) == 0) {
+      } else if (ob_blk) {
+        // bf16-only output: 64-column units (two TMEM chunks), staged as bf16 (128 bytes per row)
+        const bool vec_ok = (epi.ld_bf16 & 7) == 0;
+#pragma unroll 1
+        for (int u = cpar; u < BN / 64; u += 2) {
+          const int n0 = nt * BN + u * 64;
+          if (n0 >= N) break;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
+          for (int hh = 0; hh < 2; ++hh) {
+            if (n0 + hh * 32 < N) {
+              float v[32];
+              load_chunk(u * 2 + hh, n0 + hh * 32, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < N) op[j] = v[j];
-          }
-        }
-        if (epi.out_bf16 && !epi.bf16_pre_resid) {
-          bf16* op = reinterpret_cast<bf16*>(epi.out_bf16) + m * epi.ld_bf16 + n0;
-          if (full && (epi.ld_bf16 & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-              pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(op + j) = pk;
+              for (int c4 = 0; c4 < 4; ++c4) {
+                uint4 pk;
+                pk.x = pack2(v[8 * c4], v[8 * c4 + 1]); pk.y = pack2(v[8 * c4 + 2], v[8 * c4 + 3]);
+                pk.z = pack2(v[8 * c4 + 4], v[8 * c4 + 5]); pk.w = pack2(v[8 * c4 + 6], v[8 * c4 + 7]);
+                tr[lane * 8 + ((hh * 4 + c4) ^ (lane & 7))] = pk;
+              }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < N) op[j] = __float2bfloat16_rn(v[j]);
           }
+          __syncwarp();
+          const int n = n0 + ch * 8;   // this lane's 8 columns in the read phase
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + rsub;
+            const uint4 w = tr[row * 8 + (ch ^ (row & 7))];
+            if (row < rmax && n < N) {
+              bf16* ob = ob_blk + row * epi.ld_bf16 + n;
+              if (vec_ok && n + 8 <= N) {
+                *reinterpret_cast<uint4*>(ob) = w;
+              } else {
+                const bf16* e = reinterpret_cast<const bf16*>(&w);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (n + j < N) ob[j] = e[j];
+              }
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -344,7 +447,14 @@ extern "C" MDM_API int mdm_gemm_bf16(const void* A, int lda, long a_rows, const 
   if (num_m_tiles == 0 && !num_m_tiles_dev) return MDM_OK;
   const int sms = num_sms();
   if (max_ctas <= 0 || max_ctas > sms) max_ctas = sms;
-  const bool wide = N > 128;
+  // tile width: 256 columns unless N is small or the 256-wide tiling leaves the last wave mostly idle
+  bool wide = N > 128;
+  if (wide && !num_m_tiles_dev) {
+    const long t256 = (long)num_m_tiles * ((N + 255) / 256), t128 = (long)num_m_tiles * ((N + 127) / 128);
+    const double e256 = (double)t256 / (double)(((t256 + max_ctas - 1) / max_ctas) * max_ctas);
+    const double e128 = (double)t128 / (double)(((t128 + max_ctas - 1) / max_ctas) * max_ctas);
+    if (e128 > e256 + 0.12) wide = false;
+  }
   CUtensorMap ta, tb;
   if (!make_map(&ta, A, a_rows, K, lda, BM)) return MDM_ERR_CUDA;
   if (!make_map(&tb, W, w_rows, K, ldw, wide ? 256 : 128)) return MDM_ERR_CUDA;

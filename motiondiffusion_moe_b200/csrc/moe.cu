@@ -23,67 +23,108 @@ constexpr int MAX_E = 16;
 // softmax over E logits with ATen's softmax_warp_forward arithmetic (max-subtract, expf, butterfly
 // xor-shuffle sum over next_pow2(E) lanes, IEEE divide), then top-2 with the tie order of
 // torch.topk on CUDA: lowest indices are selected first; equal values are emitted higher index first.
-__device__ __forceinline__ void softmax_top2(const float* logits, int E, float* probs, int& i0, int& i1,
+// E is a compile-time power of two so that everything stays in registers.
+template <int E>
+__device__ __forceinline__ void softmax_top2(const float (&logits)[E], float (&probs)[E], int& i0, int& i1,
                                              float& v0, float& v1) {
   float mx = logits[0];
+#pragma unroll
   for (int e = 1; e < E; ++e) mx = fmaxf(mx, logits[e]);
-  int P2 = 1;
-  while (P2 < E) P2 <<= 1;
-  float ex[MAX_E], red[MAX_E];
-  for (int e = 0; e < P2; ++e) {
-    ex[e] = e < E ? expf(logits[e] - mx) : 0.f;
-    red[e] = ex[e];
-  }
-  for (int off = P2 >> 1; off > 0; off >>= 1) {
-    float nxt[MAX_E];
-    for (int e = 0; e < P2; ++e) nxt[e] = red[e] + red[e ^ off];
-    for (int e = 0; e < P2; ++e) red[e] = nxt[e];
+  float ex[E], red[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) { ex[e] = expf(logits[e] - mx); red[e] = ex[e]; }
+#pragma unroll
+  for (int off = E >> 1; off > 0; off >>= 1) {
+    float nxt[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) nxt[e] = red[e] + red[e ^ off];
+#pragma unroll
+    for (int e = 0; e < E; ++e) red[e] = nxt[e];
   }
   const float sum = red[0];
+#pragma unroll
   for (int e = 0; e < E; ++e) probs[e] = ex[e] / sum;
   int a = 0;
+  float pa = probs[0];
+#pragma unroll
   for (int e = 1; e < E; ++e)
-    if (probs[e] > probs[a]) a = e;
-  int b = (a == 0) ? 1 : 0;
+    if (probs[e] > pa) { a = e; pa = probs[e]; }
+  int b = -1;
+  float pb = -1.f;
+#pragma unroll
   for (int e = 0; e < E; ++e)
-    if (e != a && probs[e] > probs[b]) b = e;
-  if (probs[a] == probs[b]) { i0 = b; i1 = a; }  // b > a here: tie => higher index first
-  else { i0 = a; i1 = b; }
-  v0 = probs[i0];
-  v1 = probs[i1];
+    if (e != a && probs[e] > pb) { b = e; pb = probs[e]; }
+  if (pa == pb) { i0 = b; i1 = a; v0 = pb; v1 = pa; }  // b > a here: tie => higher index first
+  else { i0 = a; i1 = b; v0 = pa; v1 = pb; }
 }
 
-template <int VPT>
+// Sum GP per-lane partial values across the warp: after the call lane l holds (in p[0]) the total of
+// value index l >> (5 - log2(GP)).  GP-1 + (5 - log2 GP) shuffles instead of 5*GP.
+template <int GP>
+__device__ __forceinline__ void warp_reduce_scatter(float (&p)[GP], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = GP; n > 1; n >>= 1, off >>= 1) {
+    const int half = n >> 1;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? p[i] : p[i + half];
+      const float keep = upper ? p[i + half] : p[i];
+      p[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) p[0] += __shfl_xor_sync(0xffffffffu, p[0], off);
+}
+
+template <int VPT, int E, int NB>
 __global__ void __launch_bounds__(256)
-moe_gate_kernel(const float* __restrict__ x, long N, int D, int NB, int E, const float* __restrict__ ln_w,
+moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restrict__ ln_w,
                 const float* __restrict__ ln_b, const float* __restrict__ gate_w,
                 const float* __restrict__ gate_b, int* __restrict__ idx, float* __restrict__ vals,
                 float* __restrict__ stats, int* __restrict__ blk_hist, float* __restrict__ blk_imp) {
+  constexpr int G = NB * E;
+  constexpr int LG = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : (G == 4) ? 2 : 1;
   extern __shared__ float sm[];
-  float* gw = sm;                                   // [NB*E][D]
+  float* gw = sm;               // [G][D] gate weights
+  float* lw = gw + G * D;       // [NB][D] LayerNorm weight
+  float* lb = lw + NB * D;      // [NB][D] LayerNorm bias
   __shared__ int w_all[8][MAX_G], w_top1[8][MAX_G];
   __shared__ float w_imp[8][MAX_G];
-  const int G = NB * E;
   for (int i = threadIdx.x; i < G * D; i += 256) gw[i] = gate_w[i];
+  for (int i = threadIdx.x; i < NB * D; i += 256) { lw[i] = ln_w[i]; lb[i] = ln_b[i]; }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int cnt_all = 0, cnt_top1 = 0;  // lane g owns group g
   float imp = 0.f;
   const long tok0 = (long)blockIdx.x * TOK_PER_BLK + warp * 16;
+  float nxt[VPT];
+  if (tok0 < N) load_row<VPT, float>(x + tok0 * D, lane, nxt);
   for (int it = 0; it < 16; ++it) {
     const long tok = tok0 + it;
     if (tok >= N) break;
     float v[VPT];
-    load_row<VPT, float>(x + tok * D, lane, v);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) v[i] = nxt[i];
+    if (it + 1 < 16 && tok + 1 < N) load_row<VPT, float>(x + (tok + 1) * D, lane, nxt);  // prefetch
     float mean, rstd;
     row_stats<VPT>(v, D, mean, rstd);
     if (lane == 0) { stats[tok * 2] = mean; stats[tok * 2 + 1] = rstd; }
+    float part[G];
+#pragma unroll
     for (int br = 0; br < NB; ++br) {
       float hrow[VPT];
 #pragma unroll
-      for (int i = 0; i < VPT; ++i) hrow[i] = v[i];
-      affine_row<VPT>(hrow, mean, rstd, ln_w + br * D, ln_b + br * D, lane);
-      float logits[MAX_E];
+      for (int j = 0; j < VPT / 4; ++j) {
+        const float4 w4 = *reinterpret_cast<const float4*>(lw + br * D + (j * 32 + lane) * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(lb + br * D + (j * 32 + lane) * 4);
+        hrow[4 * j] = (v[4 * j] - mean) * rstd * w4.x + b4.x;
+        hrow[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * w4.y + b4.y;
+        hrow[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * w4.z + b4.z;
+        hrow[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * w4.w + b4.w;
+      }
+#pragma unroll
       for (int e = 0; e < E; ++e) {
         const float* wr = gw + (br * E + e) * D;
         float a = 0.f;
@@ -95,16 +136,23 @@ moe_gate_kernel(const float* __restrict__ x, long N, int D, int NB, int E, const
           a = fmaf(hrow[4 * j + 2], w4.z, a);
           a = fmaf(hrow[4 * j + 3], w4.w, a);
         }
-        logits[e] = warp_sum(a) + gate_b[br * E + e];
+        part[br * E + e] = a;
       }
-      float probs[MAX_E];
+    }
+    warp_reduce_scatter<G>(part, lane);   // lane (g << (5-LG)) now holds the dot product of group g
+#pragma unroll
+    for (int br = 0; br < NB; ++br) {
+      float logits[E], probs[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        logits[e] = __shfl_sync(0xffffffffu, part[0], (br * E + e) << (5 - LG)) + __ldg(gate_b + br * E + e);
       int i0, i1;
       float v0, v1;
-      softmax_top2(logits, E, probs, i0, i1, v0, v1);
+      softmax_top2<E>(logits, probs, i0, i1, v0, v1);
       if (lane == 0) {
         const long o = (tok * NB + br) * 2;
-        idx[o] = i0; idx[o + 1] = i1;
-        vals[o] = v0; vals[o + 1] = v1;
+        *reinterpret_cast<int2*>(idx + o) = make_int2(i0, i1);
+        *reinterpret_cast<float2*>(vals + o) = make_float2(v0, v1);
       }
       const int g0 = br * E + i0, g1 = br * E + i1;
       if (lane == g0) { cnt_all++; cnt_top1++; imp += v0; }
@@ -260,17 +308,21 @@ moe_combine_film_kernel(const TI* __restrict__ yp, const int* __restrict__ perm,
   store_row<VPT, TI>(out + tok * D, lane, acc);
 }
 
-__global__ void softmax_topk_kernel(const float* __restrict__ logits, long N, int E, float* __restrict__ probs,
+template <int E>
+__global__ void softmax_topk_kernel(const float* __restrict__ logits, long N, float* __restrict__ probs,
                                     int64_t* __restrict__ idx64, float* __restrict__ vals) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  float l[MAX_E], p[MAX_E];
+  float l[E], p[E];
+#pragma unroll
   for (int e = 0; e < E; ++e) l[e] = logits[i * E + e];
   int i0, i1;
   float v0, v1;
-  softmax_top2(l, E, p, i0, i1, v0, v1);
-  if (probs)
+  softmax_top2<E>(l, p, i0, i1, v0, v1);
+  if (probs) {
+#pragma unroll
     for (int e = 0; e < E; ++e) probs[i * E + e] = p[e];
+  }
   idx64[i * 2] = i0; idx64[i * 2 + 1] = i1;
   vals[i * 2] = v0; vals[i * 2 + 1] = v1;
 }
@@ -286,6 +338,33 @@ __global__ void softmax_topk_kernel(const float* __restrict__ logits, long N, in
     default: return MDM_ERR_UNSUPPORTED; \
   }
 
+template <int VPT, int E, int NB>
+int launch_gate(const float* x, long N, int D, const float* ln_w, const float* ln_b, const float* gate_w,
+                const float* gate_b, int* idx, float* vals, float* stats, int* blk_hist, float* blk_imp,
+                cudaStream_t st) {
+  const int nblk = (int)((N + TOK_PER_BLK - 1) / TOK_PER_BLK);
+  const size_t smem = sizeof(float) * ((size_t)NB * E * D + 2 * (size_t)NB * D);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+          cudaSuccess)
+    return MDM_ERR_CUDA;
+  moe_gate_kernel<VPT, E, NB><<<nblk, 256, smem, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
+                                                         blk_hist, blk_imp);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+template <int VPT>
+int gate_dispatch(int NB, int E, const float* x, long N, int D, const float* ln_w, const float* ln_b,
+                  const float* gate_w, const float* gate_b, int* idx, float* vals, float* stats, int* blk_hist,
+                  float* blk_imp, cudaStream_t st) {
+#define GATE_CASE(e, nb) \
+  if (E == e && NB == nb) return launch_gate<VPT, e, nb>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st);
+  GATE_CASE(2, 1) GATE_CASE(4, 1) GATE_CASE(8, 1) GATE_CASE(16, 1)
+  GATE_CASE(2, 2) GATE_CASE(4, 2) GATE_CASE(8, 2) GATE_CASE(16, 2)
+#undef GATE_CASE
+  return MDM_ERR_UNSUPPORTED;  // the expert count must be a power of two <= 16 (reference uses 4 / 8)
+}
+
 extern "C" MDM_API int mdm_moe_gate(const float* x, long N, int D, int NB, int E, int K, const float* ln_w,
                                     const float* ln_b, const float* gate_w, const float* gate_b, int* idx,
                                     float* vals, float* stats, int* blk_hist, float* blk_imp, void* stream) {
@@ -293,17 +372,14 @@ extern "C" MDM_API int mdm_moe_gate(const float* x, long N, int D, int NB, int E
     return MDM_ERR_ARG;
   if (K != 2 || E < 2 || E > MAX_E || NB * E > MAX_G || NB < 1) return MDM_ERR_UNSUPPORTED;
   if (N == 0) return MDM_OK;
-  const int nblk = (int)((N + TOK_PER_BLK - 1) / TOK_PER_BLK);
-  const size_t smem = sizeof(float) * (size_t)NB * E * D;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  VPT_SWITCH(D, {
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(moe_gate_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return MDM_ERR_CUDA;
-    moe_gate_kernel<V><<<nblk, 256, smem, st>>>(x, N, D, NB, E, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
-                                                 blk_hist, blk_imp);
-  });
-  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+  switch (D) {
+    case 128: return gate_dispatch<4>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st);
+    case 256: return gate_dispatch<8>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st);
+    case 512: return gate_dispatch<16>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st);
+    case 1024: return gate_dispatch<32>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st);
+    default: return MDM_ERR_UNSUPPORTED;
+  }
 }
 
 extern "C" MDM_API int mdm_moe_scan(const int* blk_hist, const float* blk_imp, const int* idx, long N, int NB,
@@ -365,9 +441,16 @@ extern "C" MDM_API int mdm_moe_combine_film(const void* yp, int dt, const int* p
 extern "C" MDM_API int mdm_softmax_topk(const float* logits, long N, int E, int K, float* probs, int64_t* idx64,
                                         float* vals, void* stream) {
   if (!logits || !idx64 || !vals) return MDM_ERR_ARG;
-  if (K != 2 || E < 2 || E > MAX_E) return MDM_ERR_UNSUPPORTED;
+  if (K != 2) return MDM_ERR_UNSUPPORTED;
   if (N == 0) return MDM_OK;
-  softmax_topk_kernel<<<(unsigned)((N + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, N, E, probs, idx64, vals);
+  const unsigned grid = (unsigned)((N + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (E) {
+    case 2: softmax_topk_kernel<2><<<grid, 256, 0, st>>>(logits, N, probs, idx64, vals); break;
+    case 4: softmax_topk_kernel<4><<<grid, 256, 0, st>>>(logits, N, probs, idx64, vals); break;
+    case 8: softmax_topk_kernel<8><<<grid, 256, 0, st>>>(logits, N, probs, idx64, vals); break;
+    case 16: softmax_topk_kernel<16><<<grid, 256, 0, st>>>(logits, N, probs, idx64, vals); break;
+    default: return MDM_ERR_UNSUPPORTED;
+  }
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }

@@ -17,6 +17,10 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     net(x, t, length, text_ctx=ctx)
     torch.cuda.synchronize()
+import json
+evs = [(e.time_range.start, e.name, e.time_range.elapsed_us()) for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort()
+json.dump([(n[:80], d) for _, n, d in evs], open("gpurun_out/timeline.json", "w"))
 rows = []
 for ev in prof.key_averages():
     dt = getattr(ev, "device_time_total", None) or getattr(ev, "cuda_time_total", 0)
