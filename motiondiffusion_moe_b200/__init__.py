@@ -2,8 +2,8 @@
 ltdoanh2004/MotionDiffusion-MoE).  Python host code over a C-ABI CUDA library (include/mdm_b200.h)."""
 from ._lib import MdmError, load as load_library, LIB_PATH  # noqa: F401
 from .transformer import MotionTransformer, TextContext  # noqa: F401
-from .gaussian_diffusion import (GaussianDiffusion, get_named_beta_schedule, ModelMeanType, ModelVarType,  # noqa: F401
-                                 LossType)
+from .gaussian_diffusion import (GaussianDiffusion, CFGStepper, get_named_beta_schedule, ModelMeanType,  # noqa: F401
+                                 ModelVarType, LossType)
 
-__all__ = ["MotionTransformer", "TextContext", "GaussianDiffusion", "get_named_beta_schedule", "ModelMeanType",
+__all__ = ["MotionTransformer", "TextContext", "GaussianDiffusion", "CFGStepper", "get_named_beta_schedule", "ModelMeanType",
            "ModelVarType", "LossType", "MdmError", "load_library"]

@@ -86,7 +86,11 @@ def load():
     return lib
 
 
+LAUNCHES = [0]   # kernels launched through this binding (every C-ABI compute call launches exactly one)
+
+
 def check(status, what):
+    LAUNCHES[0] += 1
     if status != 0:
         raise MdmError("%s failed: %s (status %d)" % (what, _ERR.get(status, "unknown"), status))
 

@@ -141,6 +141,12 @@ class GaussianDiffusion:
         step, _ = self._tables(x.device)
         ops.cfg_update(x, eps[:B], eps[B:], noise, t, step, self.num_timesteps, cfg_scale, clip, x_out, x0_out)
 
+    def make_cfg_stepper(self, model, shape, model_kwargs, cfg_scale=7.5, clip_denoised=True, device=None,
+                         use_cuda_graph=True):
+        """Static-shape CFG step runner: text context prepared once, device buffers allocated once and
+        (optionally) the whole step (batched cond+uncond forward + update) captured in a CUDA graph."""
+        return CFGStepper(self, model, shape, model_kwargs, cfg_scale, clip_denoised, device, use_cuda_graph)
+
     def p_sample_with_cfg(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None,
                           cfg_scale=7.5, noise=None, text_ctx=None):
         """:1042-1098.  `noise` (optional) replaces the internal torch.randn_like(x) draw."""
@@ -158,8 +164,8 @@ class GaussianDiffusion:
         if noise is None:
             noise = torch.randn_like(x)                                # :1094
         sample, x0 = torch.empty_like(x), torch.empty_like(x)
-        self._cfg_step(model, ctx, x, t, torch.cat([length, length]), noise.float().contiguous(), cfg_scale,
-                       clip_denoised, sample, x0)
+        self._cfg_step(model, ctx, x, t, torch.cat([length, length]).contiguous(), noise.float().contiguous(),
+                       cfg_scale, clip_denoised, sample, x0)
         return {"sample": sample, "pred_xstart": x0}
 
     def p_sample_loop_with_cfg(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
@@ -173,44 +179,17 @@ class GaussianDiffusion:
             raise NotImplementedError("denoised_fn is not supported by the fused CFG update")
         if device is None:
             device = next(model.parameters()).device
-        B = shape[0]
-        x = (torch.randn(*shape, device=device) if noise is None else noise.to(device).float()).contiguous().clone()
-        ctx = self._cfg_inputs(model, B, model_kwargs, device)
-        length = model_kwargs["length"].reshape(-1).to(device=device, dtype=torch.int64)
-        length2 = torch.cat([length, length]).contiguous()
-        t_buf = torch.zeros(B, dtype=torch.int64, device=device)
-        nz = torch.empty_like(x)
+        st = CFGStepper(self, model, shape, model_kwargs, cfg_scale, clip_denoised, device, use_cuda_graph)
+        st.x.copy_(torch.randn(*shape, device=device) if noise is None else noise.to(device).float())
         steps = list(reversed(range(self.num_timesteps)))
         if num_steps is not None:
             steps = steps[:num_steps]
         if progress:
             from tqdm.auto import tqdm
             steps = tqdm(steps, desc="Sampling")
-        graph = None
-        for i, ts in enumerate(steps):
-            t_buf.fill_(ts)
-            if step_noise is not None:
-                nz.copy_(step_noise(ts))
-            else:
-                nz.normal_()                                           # == torch.randn_like(x), :1094
-            if not use_cuda_graph:
-                self._cfg_step(model, ctx, x, t_buf, length2, nz, cfg_scale, clip_denoised, x, None)
-            elif graph is None and i == 0:
-                # first step eagerly (warms workspaces and lazy state), then capture the step once
-                self._cfg_step(model, ctx, x, t_buf, length2, nz, cfg_scale, clip_denoised, x, None)
-                torch.cuda.synchronize(device)
-                graph = torch.cuda.CUDAGraph()
-                keep_x, keep_c = x.clone(), model._packed["usage"].clone(),
-                keep_i = model._packed["importance"].clone()
-                with torch.cuda.graph(graph):
-                    self._cfg_step(model, ctx, x, t_buf, length2, nz, cfg_scale, clip_denoised, x, None)
-                # capture does not execute; restore nothing but be explicit about state
-                x.copy_(keep_x)
-                model._packed["usage"].copy_(keep_c)
-                model._packed["importance"].copy_(keep_i)
-            else:
-                graph.replay()
-        return x
+        for ts in steps:
+            st.step(ts, None if step_noise is None else step_noise(ts))
+        return st.x.clone()
 
     # ------------------------------------------------------------------ training losses (forward value)
     def training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
@@ -231,3 +210,58 @@ class GaussianDiffusion:
         terms = {"mse": ((noise - out) ** 2).mean(dim=list(range(1, out.dim()))).view(-1),
                  "target": noise, "pred": out, "moe_loss": 0.0 + model.get_moe_loss(model)}
         return terms
+
+
+class CFGStepper:
+    """One reverse-diffusion step x_t -> x_{t-1} with classifier-free guidance on static device buffers.
+
+    `x` is updated in place by `step(t)`.  With use_cuda_graph the step is captured once (after one
+    eager warm-up step on scratch data, so lazily created workspaces exist) and replayed afterwards."""
+
+    def __init__(self, diffusion, model, shape, model_kwargs, cfg_scale=7.5, clip_denoised=True, device=None,
+                 use_cuda_graph=True):
+        diffusion._check_supported()
+        self.d, self.model = diffusion, model
+        self.device = device if device is not None else next(model.parameters()).device
+        self.B = shape[0]
+        self.cfg_scale, self.clip = cfg_scale, clip_denoised
+        self.ctx = diffusion._cfg_inputs(model, self.B, model_kwargs, self.device)
+        length = model_kwargs["length"].reshape(-1).to(device=self.device, dtype=torch.int64)
+        self.length2 = torch.cat([length, length]).contiguous()
+        self.x = torch.zeros(*shape, device=self.device, dtype=torch.float32)
+        self.x0 = torch.zeros_like(self.x)
+        self.noise = torch.zeros_like(self.x)
+        self.t = torch.zeros(self.B, dtype=torch.int64, device=self.device)
+        self.use_graph = use_cuda_graph
+        self.graph = None
+
+    def _run(self):
+        self.d._cfg_step(self.model, self.ctx, self.x, self.t, self.length2, self.noise, self.cfg_scale, self.clip,
+                         self.x, self.x0)
+
+    def _capture(self):
+        pk = self.model._packed or self.model._pack()
+        keep = (self.x.clone(), pk["usage"].clone(), pk["importance"].clone())
+        self._run()                                   # warm-up: allocates workspaces, sets kernel attributes
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._run()
+        self.x.copy_(keep[0])
+        pk["usage"].copy_(keep[1])
+        pk["importance"].copy_(keep[2])
+
+    def step(self, ts, noise=None):
+        """Advance x from timestep ts to ts-1.  noise=None draws torch's normal_ (== randn_like, :1094)."""
+        if self.use_graph and self.graph is None:
+            self._capture()
+        self.t.fill_(int(ts))
+        if noise is None:
+            self.noise.normal_()
+        else:
+            self.noise.copy_(noise)
+        if self.use_graph:
+            self.graph.replay()
+        else:
+            self._run()
+        return self.x
