@@ -430,12 +430,15 @@ def forward(p, cfg, x, timesteps, length, xf_proj, xf_out, nt=None, routing=None
     emb = fused_embedding(p, cfg, timesteps, xf_proj)
     h = _lin(p, "joint_embed", x) + p["sequence_embedding"].unsqueeze(0)[:, :T, :]
     mask = src_mask(T, length)
-    h_low = F.conv1d(h.permute(0, 2, 1), p["downsample.weight"], p["downsample.bias"], stride=2).permute(0, 2, 1)
+    # cuDNN convolutions default to TF32 on CUDA (torch.backends.cudnn.allow_tf32): the oracle is fp32
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        h_low = F.conv1d(h.permute(0, 2, 1), p["downsample.weight"], p["downsample.bias"], stride=2).permute(0, 2, 1)
     mask_low = src_mask(h_low.shape[1], (length / 2).long())
     blks = block_prefixes(cfg)
     for blk in blks[:cfg.num_layers]:
         h_low = decoder_layer(p, blk, h_low, xf_out, emb, mask_low, cfg, nt, routing, counters, tie_order)
-    h_up = F.conv_transpose1d(h_low.permute(0, 2, 1), p["upsample.weight"], p["upsample.bias"], stride=2)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        h_up = F.conv_transpose1d(h_low.permute(0, 2, 1), p["upsample.weight"], p["upsample.bias"], stride=2)
     hc = h_up.permute(0, 2, 1) + h
     for blk in blks[cfg.num_layers:]:
         hc = decoder_layer(p, blk, hc, xf_out, emb, mask, cfg, nt, routing, counters, tie_order)
