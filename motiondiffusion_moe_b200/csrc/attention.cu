@@ -12,6 +12,10 @@ int mdm_fastattn_tc(const void* qkv, const float* P, const float* norm_w, const 
                     const int64_t* length, int length_shift, int B, int H, int T, int hd, int M, void* out,
                     cudaStream_t st);
 
+int mdm_lincross_apply_tc(const void* q, const float* ctx, int B, int T, int H, int hd, void* y, cudaStream_t st);
+int mdm_softmax_cross_tc(const void* q, const void* k, const void* v, const int* nt, int B, int T, int Nt_max, int H,
+                         int hd, float scale, void* o, cudaStream_t st);
+
 namespace {
 
 constexpr int AT = 128;  // threads per CTA == max(hd, M)
@@ -411,6 +415,10 @@ extern "C" MDM_API int mdm_lincross_apply(const void* q, int dt, const float* ct
   if (hd > AT) return MDM_ERR_UNSUPPORTED;
   if (B * H == 0 || T == 0) return MDM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dt == MDM_BF16) {
+    const int r = mdm_lincross_apply_tc(q, ctx, B, T, H, hd, y, st);
+    if (r != MDM_ERR_UNSUPPORTED) return r;
+  }
   if (dt == MDM_F32)
     lincross_apply_kernel<float><<<B * H, AT, 0, st>>>(reinterpret_cast<const float*>(q), ctx, T, H, hd,
                                                         reinterpret_cast<float*>(y));
@@ -429,6 +437,10 @@ extern "C" MDM_API int mdm_softmax_cross(const void* q, const void* k, const voi
   const size_t smem = sizeof(float) * ((size_t)Nt_max * (hd + 1) + (size_t)Nt_max * hd + TC * hd + TC * 96);
   const float scale = (float)(1.0 / sqrt((double)hd));  // python: head_dim ** -0.5, then fp32
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dt == MDM_BF16) {
+    const int r = mdm_softmax_cross_tc(q, k, v, nt, B, T, Nt_max, H, hd, scale, o, st);
+    if (r != MDM_ERR_UNSUPPORTED) return r;
+  }
   if (dt == MDM_F32) {
     if (set_smem(softmax_cross_kernel<float>, smem)) return MDM_ERR_CUDA;
     softmax_cross_kernel<float><<<B * H, AT, smem, st>>>(

@@ -318,6 +318,266 @@ int launch_fastattn(const bf16* qkv, const float* P, const float* nw, const floa
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// LinearTemporalCrossAttention, motion side (fast_attention.py:248,253):
+//   y[t,h,:] = softmax_hd(q[t,h,:]) @ ctx[b,h]        ctx: [hd x hd] fp32 per (sequence, head)
+// One CTA per (b,h): softmax rows -> bf16 smem, ctx -> bf16 smem, one [T x hd x hd] product.
+template <int HD>
+__global__ void __launch_bounds__(256, 2)
+lincross_apply_tc_kernel(const bf16* __restrict__ q, const float* __restrict__ ctx, int H, int T, int Tp,
+                         bf16* __restrict__ y) {
+  constexpr int LDS = HD + 8, EPL = HD / 32, KS = HD / 16, NT = HD / 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem);   // [Tp][LDS] softmax(q)
+  bf16* Cs = Qs + Tp * LDS;                   // [HD][LDS] ctx[d][l]
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int D = H * HD;
+  const float* cg = ctx + ((long)(b * H + h)) * HD * HD;
+  for (int i = tid; i < HD * HD / 4; i += 256) {
+    const float4 c4 = *reinterpret_cast<const float4*>(cg + i * 4);
+    const int d = (i * 4) / HD, l = (i * 4) - d * HD;
+    uint2 pk; pk.x = pack_bf16(c4.x, c4.y); pk.y = pack_bf16(c4.z, c4.w);
+    *reinterpret_cast<uint2*>(Cs + d * LDS + l) = pk;
+  }
+  for (int t0 = warp * 2; t0 < Tp; t0 += 16) {   // two rows per warp iteration (independent chains)
+    float x[2][EPL], mx[2], sm[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const bf16* row = q + ((long)(b * T + min(t0 + rr, T - 1))) * D + h * HD + lane * EPL;
+      if (EPL == 4) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(row);
+        const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+        const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+        x[rr][0] = __low2float(p0); x[rr][1] = __high2float(p0);
+        x[rr][2 % EPL] = __low2float(p1); x[rr][3 % EPL] = __high2float(p1);
+      } else {
+        const uint32_t raw = *reinterpret_cast<const uint32_t*>(row);
+        const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw);
+        x[rr][0] = __low2float(p0); x[rr][1] = __high2float(p0);
+      }
+      mx[rr] = x[rr][0];
+#pragma unroll
+      for (int i = 1; i < EPL; ++i) mx[rr] = fmaxf(mx[rr], x[rr][i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx[0] = fmaxf(mx[0], __shfl_xor_sync(0xffffffffu, mx[0], o));
+      mx[1] = fmaxf(mx[1], __shfl_xor_sync(0xffffffffu, mx[1], o));
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      sm[rr] = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) { x[rr][i] = expf(x[rr][i] - mx[rr]); sm[rr] += x[rr][i]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sm[0] += __shfl_xor_sync(0xffffffffu, sm[0], o);
+      sm[1] += __shfl_xor_sync(0xffffffffu, sm[1], o);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      bf16* dst = Qs + (t0 + rr) * LDS + lane * EPL;
+      const bool live = (t0 + rr) < T;
+      if (EPL == 4) {
+        uint2 pk;
+        pk.x = live ? pack_bf16(x[rr][0] / sm[rr], x[rr][1] / sm[rr]) : 0u;
+        pk.y = live ? pack_bf16(x[rr][2 % EPL] / sm[rr], x[rr][3 % EPL] / sm[rr]) : 0u;
+        *reinterpret_cast<uint2*>(dst) = pk;
+      } else {
+        *reinterpret_cast<uint32_t*>(dst) = live ? pack_bf16(x[rr][0] / sm[rr], x[rr][1] / sm[rr]) : 0u;
+      }
+    }
+  }
+  __syncthreads();
+  const int nstrips = Tp / 16;
+  for (int strip = warp; strip < nstrips; strip += 8) {
+    const int r0 = strip * 16;
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(a, Qs + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t bb[4];
+        ldsm_x4_t(bb, Cs + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8);
+        mma16816(acc[2 * np], a, bb[0], bb[1]);
+        mma16816(acc[2 * np + 1], a, bb[2], bb[3]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = nt * 8 + 2 * tq;
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g) * LDS + col) = pack_bf16(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g + 8) * LDS + col) = pack_bf16(acc[nt][2], acc[nt][3]);
+    }
+    __syncwarp();
+    constexpr int CPR = HD / 8;
+    for (int i = lane; i < 16 * CPR; i += 32) {
+      const int r = i / CPR, c = i - r * CPR;
+      if (r0 + r < T)
+        *reinterpret_cast<uint4*>(y + ((long)(b * T + r0 + r)) * D + h * HD + c * 8) =
+            *reinterpret_cast<const uint4*>(Qs + (r0 + r) * LDS + c * 8);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MemoryEfficientCrossAttentionBlock core (fast_attention.py:313-325):
+//   o[t,h,:] = softmax_n((q[t,h,:] * hd^-0.5) . k[b,n,h,:]) @ v[b,n,h,:],  n < nt[b]  (nt <= 96)
+// One CTA per (b,h); per 16-row strip: S = Q K^T (registers) -> masked softmax -> O = P V.
+template <int HD>
+__global__ void __launch_bounds__(256, 2)
+softmax_cross_tc_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
+                        const int* __restrict__ nt, int H, int T, int Tp, int Nt_max, int NtP, float scale,
+                        bf16* __restrict__ o) {
+  constexpr int LDS = HD + 8, KS = HD / 16, NT = HD / 8, CPR = HD / 8;
+  constexpr int MAXNT = 12;   // 96 keys / 8
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem);   // [Tp][LDS]
+  bf16* Ks = Qs + Tp * LDS;                   // [NtP][LDS]
+  bf16* Vs = Ks + NtP * LDS;                  // [NtP][LDS]
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int D = H * HD;
+  const int n_tok = nt ? min(nt[b], Nt_max) : Nt_max;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < Tp * CPR; i += 256) {
+    const int r = i / CPR, c = i - r * CPR;
+    *reinterpret_cast<uint4*>(Qs + r * LDS + c * 8) =
+        r < T ? *reinterpret_cast<const uint4*>(q + ((long)(b * T + r)) * D + h * HD + c * 8) : zero;
+  }
+  for (int i = tid; i < NtP * CPR; i += 256) {
+    const int r = i / CPR, c = i - r * CPR;
+    const long off = ((long)(b * Nt_max + r)) * D + h * HD + c * 8;
+    *reinterpret_cast<uint4*>(Ks + r * LDS + c * 8) = r < n_tok ? *reinterpret_cast<const uint4*>(k + off) : zero;
+    *reinterpret_cast<uint4*>(Vs + r * LDS + c * 8) = r < n_tok ? *reinterpret_cast<const uint4*>(v + off) : zero;
+  }
+  __syncthreads();
+  const int nstrips = Tp / 16, ntk = NtP / 8;   // key n-tiles (even count: NtP is a multiple of 16)
+  for (int strip = warp; strip < nstrips; strip += 8) {
+    const int r0 = strip * 16;
+    float sc[MAXNT][4];
+#pragma unroll
+    for (int i = 0; i < MAXNT; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(a, Qs + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int np = 0; np < MAXNT / 2; ++np) {
+        if (np * 2 < ntk) {
+          uint32_t bb[4];
+          ldsm_x4(bb, Ks + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
+          mma16816(sc[2 * np], a, bb[0], bb[1]);
+          mma16816(sc[2 * np + 1], a, bb[2], bb[3]);
+        }
+      }
+    }
+    // masked softmax over keys; rows g (values [i][0..1]) and g+8 (values [i][2..3]) live in a quad
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < MAXNT; ++i) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const bool ok = (i * 8 + 2 * tq + j) < n_tok;
+        sc[i][j] = ok ? sc[i][j] * scale : -INFINITY;
+        sc[i][2 + j] = ok ? sc[i][2 + j] * scale : -INFINITY;
+        m0 = fmaxf(m0, sc[i][j]);
+        m1 = fmaxf(m1, sc[i][2 + j]);
+      }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXNT; ++i) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        sc[i][j] = expf(sc[i][j] - m0); s0 += sc[i][j];
+        sc[i][2 + j] = expf(sc[i][2 + j] - m1); s1 += sc[i][2 + j];
+      }
+    }
+    s0 = quad_sum(s0); s1 = quad_sum(s1);
+    const float i0 = 1.f / s0, i1 = 1.f / s1;
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < MAXNT / 2; ++ks) {
+      if (ks * 2 < ntk) {
+        uint32_t a[4];   // C-fragment of S -> A-fragment of P (rows g / g+8, keys 16*ks + ...)
+        a[0] = pack_bf16(sc[2 * ks][0] * i0, sc[2 * ks][1] * i0);
+        a[1] = pack_bf16(sc[2 * ks][2] * i1, sc[2 * ks][3] * i1);
+        a[2] = pack_bf16(sc[2 * ks + 1][0] * i0, sc[2 * ks + 1][1] * i0);
+        a[3] = pack_bf16(sc[2 * ks + 1][2] * i1, sc[2 * ks + 1][3] * i1);
+#pragma unroll
+        for (int np = 0; np < NT / 2; ++np) {
+          uint32_t bb[4];
+          ldsm_x4_t(bb, Vs + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8);
+          mma16816(acc[2 * np], a, bb[0], bb[1]);
+          mma16816(acc[2 * np + 1], a, bb[2], bb[3]);
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int ntile = 0; ntile < NT; ++ntile) {
+      const int col = ntile * 8 + 2 * tq;
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g) * LDS + col) = pack_bf16(acc[ntile][0], acc[ntile][1]);
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g + 8) * LDS + col) = pack_bf16(acc[ntile][2], acc[ntile][3]);
+    }
+    __syncwarp();
+    for (int i = lane; i < 16 * CPR; i += 32) {
+      const int r = i / CPR, c = i - r * CPR;
+      if (r0 + r < T)
+        *reinterpret_cast<uint4*>(o + ((long)(b * T + r0 + r)) * D + h * HD + c * 8) =
+            *reinterpret_cast<const uint4*>(Qs + (r0 + r) * LDS + c * 8);
+    }
+  }
+}
+
+template <typename Kern>
+int ensure_smem(Kern kern, size_t smem, size_t& cur) {
+  if (smem > 227 * 1024) return MDM_ERR_UNSUPPORTED;
+  if (smem > cur && smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return MDM_ERR_CUDA;
+    cur = smem;
+  }
+  return MDM_OK;
+}
+
+template <int HD>
+int launch_lincross(const bf16* q, const float* ctx, int B, int H, int T, bf16* y, cudaStream_t st) {
+  const int Tp = (T + 15) / 16 * 16;
+  const size_t smem = (size_t)(Tp + HD) * (HD + 8) * 2;
+  static size_t cur = 0;
+  const int r = ensure_smem(lincross_apply_tc_kernel<HD>, smem, cur);
+  if (r) return r;
+  lincross_apply_tc_kernel<HD><<<B * H, 256, smem, st>>>(q, ctx, H, T, Tp, y);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+template <int HD>
+int launch_softmax_cross(const bf16* q, const bf16* k, const bf16* v, const int* nt, int B, int H, int T, int Nt_max,
+                         float scale, bf16* o, cudaStream_t st) {
+  const int Tp = (T + 15) / 16 * 16, NtP = (Nt_max + 15) / 16 * 16;
+  if (NtP > 96) return MDM_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(Tp + 2 * NtP) * (HD + 8) * 2;
+  static size_t cur = 0;
+  const int r = ensure_smem(softmax_cross_tc_kernel<HD>, smem, cur);
+  if (r) return r;
+  softmax_cross_tc_kernel<HD><<<B * H, 256, smem, st>>>(q, k, v, nt, H, T, Tp, Nt_max, NtP, scale, o);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
 }  // namespace
 
 // Returns MDM_ERR_UNSUPPORTED when the shape does not fit this kernel (the caller then uses the
@@ -331,5 +591,24 @@ int mdm_fastattn_tc(const void* qkv, const float* P, const float* norm_w, const 
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(o) & 15)) return MDM_ERR_UNSUPPORTED;
   if (hd == 128) return launch_fastattn<128>(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, st);
   if (hd == 64) return launch_fastattn<64>(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, st);
+  return MDM_ERR_UNSUPPORTED;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int mdm_lincross_apply_tc(const void* q, const float* ctx, int B, int T, int H, int hd, void* y, cudaStream_t st) {
+  if (!aligned16(q) || !aligned16(y) || !aligned16(ctx)) return MDM_ERR_UNSUPPORTED;
+  if (hd == 128) return launch_lincross<128>(reinterpret_cast<const bf16*>(q), ctx, B, H, T, reinterpret_cast<bf16*>(y), st);
+  if (hd == 64) return launch_lincross<64>(reinterpret_cast<const bf16*>(q), ctx, B, H, T, reinterpret_cast<bf16*>(y), st);
+  return MDM_ERR_UNSUPPORTED;
+}
+
+int mdm_softmax_cross_tc(const void* q, const void* k, const void* v, const int* nt, int B, int T, int Nt_max, int H,
+                         int hd, float scale, void* o, cudaStream_t st) {
+  if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o)) return MDM_ERR_UNSUPPORTED;
+  const bf16 *qq = reinterpret_cast<const bf16*>(q), *kk = reinterpret_cast<const bf16*>(k),
+             *vv = reinterpret_cast<const bf16*>(v);
+  if (hd == 128) return launch_softmax_cross<128>(qq, kk, vv, nt, B, H, T, Nt_max, scale, reinterpret_cast<bf16*>(o), st);
+  if (hd == 64) return launch_softmax_cross<64>(qq, kk, vv, nt, B, H, T, Nt_max, scale, reinterpret_cast<bf16*>(o), st);
   return MDM_ERR_UNSUPPORTED;
 }
