@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmdm_b200.so")
+# MDM_B200_LIB: developer knob to A/B a differently-built copy of the same library (tools/op_bench.py)
+LIB_PATH = os.environ.get("MDM_B200_LIB") or os.path.join(_HERE, "csrc", "libmdm_b200.so")
 
 MDM_F32, MDM_BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_SILU, ACT_EXPFEAT = 0, 1, 2, 3

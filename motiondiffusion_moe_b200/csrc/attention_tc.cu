@@ -32,14 +32,27 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// exp(clamp(x, -15, 15)) * 0.1 == 2^(clamp(x) * log2(e) + log2(0.1)) on the MUFU ex2 unit (rel. err 2^-22)
+__device__ __forceinline__ float expfeat(float x) {
+  const float c = fminf(fmaxf(x, -15.f), 15.f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(c, 1.4426950408889634f, -3.3219280948873623f)));
+  return e;
+}
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
   return v;
 }
 
-template <int HD>
-__global__ void __launch_bounds__(256, 1)
+template <int HD, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, const float* __restrict__ nw,
                    const float* __restrict__ nb, const int64_t* __restrict__ length, int length_shift, int H,
                    int T, int Tp, bf16* __restrict__ out) {
@@ -63,12 +76,35 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
   const int len = length ? (int)min((long)T, (long)(length[b] >> length_shift)) : T;
   const int nstrips = Tp / 16;
 
-  // ---- S0: P^T as bf16, LN affine
-  for (int i = tid; i < HD * HD; i += 256) {
-    const int n = i / HD, m = i - n * HD;
-    Ps[m * LDS + n] = __float2bfloat16_rn(P[i]);
+  constexpr int NTHR = NW * 32;
+  // ---- S0a: the whole (sequence, head) slab of q, k, v goes to shared memory with one round of
+  // asynchronous 16-byte copies (every load of the CTA is in flight at once); pad rows are zeroed.
+  {
+    constexpr int CPR = HD / 8;
+    const int per = T * CPR;
+    for (int i = tid; i < 3 * per; i += NTHR) {
+      const int w = i / per, rem = i - w * per, t = rem / CPR, c = rem - t * CPR;
+      bf16* dst = (w == 0 ? Qs : (w == 1 ? Ks : Vs)) + t * LDS + c * 8;
+      cp_async16(dst, qkv + ((long)(b * T + t)) * 3 * D + w * D + h * HD + c * 8);
+    }
+    const int padc = (Tp - T) * CPR;
+    for (int i = tid; i < 3 * padc; i += NTHR) {
+      const int w = i / padc, rem = i - w * padc, t = T + rem / CPR, c = rem % CPR;
+      bf16* dst = (w == 0 ? Qs : (w == 1 ? Ks : Vs)) + t * LDS + c * 8;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
-  for (int i = tid; i < HD; i += 256) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }
+  // ---- S0b: P^T as bf16 (lane -> n: conflict-free 2-byte stores, 16-byte L1/L2 reads), LN affine
+  for (int i = tid; i < HD * HD / 4; i += NTHR) {
+    const int n = i % HD, m4 = i / HD;
+    const float4 p4 = __ldg(reinterpret_cast<const float4*>(P + n * HD + 4 * m4));
+    Ps[(4 * m4) * LDS + n] = __float2bfloat16_rn(p4.x);
+    Ps[(4 * m4 + 1) * LDS + n] = __float2bfloat16_rn(p4.y);
+    Ps[(4 * m4 + 2) * LDS + n] = __float2bfloat16_rn(p4.z);
+    Ps[(4 * m4 + 3) * LDS + n] = __float2bfloat16_rn(p4.w);
+  }
+  for (int i = tid; i < HD; i += NTHR) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }
+  cp_async_wait_all();
   __syncthreads();
 
   // ---- S1: per-row LayerNorm (+ L2 norm) of 0.1*q, 0.1*k, 0.1*v.  Two rows x three tensors are
@@ -77,22 +113,22 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
     float wv[EPL], bv[EPL];
 #pragma unroll
     for (int i = 0; i < EPL; ++i) { wv[i] = nw_s[lane * EPL + i]; bv[i] = nb_s[lane * EPL + i]; }
-    for (int t0 = warp * 2; t0 < Tp; t0 += 16) {
+    for (int t0 = warp * 2; t0 < Tp; t0 += 2 * NW) {
       float x[6][EPL];
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int t = t0 + rr;
-        const bf16* row = qkv + ((long)(b * T + min(t, T - 1))) * 3 * D + h * HD + lane * EPL;
+        const bf16* srow[3] = {Qs + t * LDS + lane * EPL, Ks + t * LDS + lane * EPL, Vs + t * LDS + lane * EPL};
 #pragma unroll
         for (int w = 0; w < 3; ++w) {
           if (EPL == 4) {
-            const uint2 raw = *reinterpret_cast<const uint2*>(row + w * D);
+            const uint2 raw = *reinterpret_cast<const uint2*>(srow[w]);
             const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
             const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
             x[rr * 3 + w][0] = __low2float(p0); x[rr * 3 + w][1] = __high2float(p0);
             x[rr * 3 + w][2 % EPL] = __low2float(p1); x[rr * 3 + w][3 % EPL] = __high2float(p1);
           } else {
-            const uint32_t raw = *reinterpret_cast<const uint32_t*>(row + w * D);
+            const uint32_t raw = *reinterpret_cast<const uint32_t*>(srow[w]);
             const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw);
             x[rr * 3 + w][0] = __low2float(p0); x[rr * 3 + w][1] = __high2float(p0);
           }
@@ -166,7 +202,7 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
   __syncthreads();
 
   // ---- S2: feature maps in place: X' = exp(clamp(X . P)) * 0.1 ; key rows t >= len are zeroed
-  for (int job = warp; job < 2 * nstrips; job += 8) {
+  for (int job = warp; job < 2 * nstrips; job += NW) {
     const bool isK = job >= nstrips;
     bf16* X = isK ? Ks : Qs;
     const int r0 = (isK ? job - nstrips : job) * 16;
@@ -192,7 +228,7 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
       const int col = nt * 8 + 2 * tq;
       float f[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) f[i] = expf(fminf(fmaxf(c[nt][i], -15.f), 15.f)) * 0.1f;
+      for (int i = 0; i < 4; ++i) f[i] = expfeat(c[nt][i]);
       *reinterpret_cast<uint32_t*>(X + (r0 + g) * LDS + col) = live0 ? pack_bf16(f[0], f[1]) : 0u;
       *reinterpret_cast<uint32_t*>(X + (r0 + g + 8) * LDS + col) = live1 ? pack_bf16(f[2], f[3]) : 0u;
     }
@@ -200,7 +236,7 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
   __syncthreads();
 
   // ---- S2b: per-frame denominator (same-t product, fast_attention.py:81-82)
-  for (int t = warp; t < Tp; t += 8) {
+  for (int t = warp; t < Tp; t += NW) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < EPL; ++i)
@@ -211,7 +247,7 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
 
   // ---- S3: kv[m][n] = 0.1 * sum_t K'[t][m] V[t][n]
   constexpr int MS = HD / 16;        // 16-row m-strips
-  constexpr int NSPLIT = 8 / MS;     // warps per m-strip
+  constexpr int NSPLIT = NW / MS;    // warps per m-strip
   constexpr int NCOLS = HD / NSPLIT; // columns per warp
   constexpr int NTW = NCOLS / 8;
   {
@@ -242,7 +278,7 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
   __syncthreads();
 
   // ---- S4: out = LN((Q' kv) * 0.1 / den), staged in the strip's own Qs rows, then coalesced store
-  for (int strip = warp; strip < nstrips; strip += 8) {
+  for (int strip = warp; strip < nstrips; strip += NW) {
     const int r0 = strip * 16;
     float acc[NT][4];
 #pragma unroll
@@ -307,14 +343,15 @@ int launch_fastattn(const bf16* qkv, const float* P, const float* nw, const floa
   const int Tp = (T + 15) / 16 * 16;
   const size_t smem = (size_t)(3 * Tp + HD) * (HD + 8) * 2 + sizeof(float) * (Tp + 2 * HD);
   if (smem > 227 * 1024) return MDM_ERR_UNSUPPORTED;
+  constexpr int NW = HD >= 128 ? 16 : 8;   // 16 warps hide the ldmatrix -> mma latency of the 128-wide products
   static size_t attr = 0;
   if (smem > attr) {
-    if (cudaFuncSetAttribute(fastattn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+    if (cudaFuncSetAttribute(fastattn_tc_kernel<HD, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess)
       return MDM_ERR_CUDA;
     attr = smem;
   }
-  fastattn_tc_kernel<HD><<<B * H, 256, smem, st>>>(qkv, P, nw, nb, length, shift, H, T, Tp, out);
+  fastattn_tc_kernel<HD, NW><<<B * H, NW * 32, smem, st>>>(qkv, P, nw, nb, length, shift, H, T, Tp, out);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 

@@ -78,85 +78,112 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&p)[GP], int lane) {
   for (; off > 0; off >>= 1) p[0] += __shfl_xor_sync(0xffffffffu, p[0], off);
 }
 
+// Two tokens per warp iteration: every shared-memory read of a gate / LayerNorm weight vector feeds
+// both tokens (the kernel was bound by shared-memory bandwidth with one), and the softmax / top-2
+// of the TT*NB (token, branch) pairs is evaluated once, each by its own lane, instead of 32 times.
+// The per-(token, expert) arithmetic order is unchanged (bit-identical logits, probabilities, counters).
 template <int VPT, int E, int NB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (VPT <= 16 && NB * E <= 16) ? 2 : 1)
 moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restrict__ ln_w,
                 const float* __restrict__ ln_b, const float* __restrict__ gate_w,
                 const float* __restrict__ gate_b, int* __restrict__ idx, float* __restrict__ vals,
                 float* __restrict__ stats, int* __restrict__ blk_hist, float* __restrict__ blk_imp) {
   constexpr int G = NB * E;
   constexpr int LG = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : (G == 4) ? 2 : 1;
+  constexpr int TT = 2;
   extern __shared__ float sm[];
   float* gw = sm;               // [G][D] gate weights
   float* lw = gw + G * D;       // [NB][D] LayerNorm weight
   float* lb = lw + NB * D;      // [NB][D] LayerNorm bias
   __shared__ int w_all[8][MAX_G], w_top1[8][MAX_G];
   __shared__ float w_imp[8][MAX_G];
-  for (int i = threadIdx.x; i < G * D; i += 256) gw[i] = gate_w[i];
+  for (int i = threadIdx.x; i < G * D / 4; i += 256)
+    reinterpret_cast<float4*>(gw)[i] = __ldg(reinterpret_cast<const float4*>(gate_w) + i);
   for (int i = threadIdx.x; i < NB * D; i += 256) { lw[i] = ln_w[i]; lb[i] = ln_b[i]; }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int cnt_all = 0, cnt_top1 = 0;  // lane g owns group g
   float imp = 0.f;
   const long tok0 = (long)blockIdx.x * TOK_PER_BLK + warp * 16;
-  float nxt[VPT];
-  if (tok0 < N) load_row<VPT, float>(x + tok0 * D, lane, nxt);
-  for (int it = 0; it < 16; ++it) {
+  const int my_t = (lane / NB) % TT, my_br = lane % NB;   // the (token, branch) pair this lane resolves
+  for (int it = 0; it < 16; it += TT) {
     const long tok = tok0 + it;
     if (tok >= N) break;
-    float v[VPT];
+    const bool two = tok + 1 < N;
+    float v[TT][VPT];
+    load_row<VPT, float>(x + tok * D, lane, v[0]);
+    load_row<VPT, float>(x + (two ? tok + 1 : tok) * D, lane, v[1]);
+    float mean[TT], rstd[TT];
 #pragma unroll
-    for (int i = 0; i < VPT; ++i) v[i] = nxt[i];
-    if (it + 1 < 16 && tok + 1 < N) load_row<VPT, float>(x + (tok + 1) * D, lane, nxt);  // prefetch
-    float mean, rstd;
-    row_stats<VPT>(v, D, mean, rstd);
-    if (lane == 0) { stats[tok * 2] = mean; stats[tok * 2 + 1] = rstd; }
-    float part[G];
+    for (int t = 0; t < TT; ++t) row_stats<VPT>(v[t], D, mean[t], rstd[t]);
+    if (lane == 0) {
+      *reinterpret_cast<float2*>(stats + tok * 2) = make_float2(mean[0], rstd[0]);
+      if (two) *reinterpret_cast<float2*>(stats + (tok + 1) * 2) = make_float2(mean[1], rstd[1]);
+    }
+    float part[TT][G];
 #pragma unroll
     for (int br = 0; br < NB; ++br) {
-      float hrow[VPT];
+      float hrow[TT][VPT];
 #pragma unroll
       for (int j = 0; j < VPT / 4; ++j) {
         const float4 w4 = *reinterpret_cast<const float4*>(lw + br * D + (j * 32 + lane) * 4);
         const float4 b4 = *reinterpret_cast<const float4*>(lb + br * D + (j * 32 + lane) * 4);
-        hrow[4 * j] = (v[4 * j] - mean) * rstd * w4.x + b4.x;
-        hrow[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * w4.y + b4.y;
-        hrow[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * w4.z + b4.z;
-        hrow[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * w4.w + b4.w;
+#pragma unroll
+        for (int t = 0; t < TT; ++t) {
+          hrow[t][4 * j] = (v[t][4 * j] - mean[t]) * rstd[t] * w4.x + b4.x;
+          hrow[t][4 * j + 1] = (v[t][4 * j + 1] - mean[t]) * rstd[t] * w4.y + b4.y;
+          hrow[t][4 * j + 2] = (v[t][4 * j + 2] - mean[t]) * rstd[t] * w4.z + b4.z;
+          hrow[t][4 * j + 3] = (v[t][4 * j + 3] - mean[t]) * rstd[t] * w4.w + b4.w;
+        }
       }
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const float* wr = gw + (br * E + e) * D;
-        float a = 0.f;
+        float a[TT];
+#pragma unroll
+        for (int t = 0; t < TT; ++t) a[t] = 0.f;
 #pragma unroll
         for (int j = 0; j < VPT / 4; ++j) {
           const float4 w4 = *reinterpret_cast<const float4*>(wr + (j * 32 + lane) * 4);
-          a = fmaf(hrow[4 * j], w4.x, a);
-          a = fmaf(hrow[4 * j + 1], w4.y, a);
-          a = fmaf(hrow[4 * j + 2], w4.z, a);
-          a = fmaf(hrow[4 * j + 3], w4.w, a);
+#pragma unroll
+          for (int t = 0; t < TT; ++t) {
+            a[t] = fmaf(hrow[t][4 * j], w4.x, a[t]);
+            a[t] = fmaf(hrow[t][4 * j + 1], w4.y, a[t]);
+            a[t] = fmaf(hrow[t][4 * j + 2], w4.z, a[t]);
+            a[t] = fmaf(hrow[t][4 * j + 3], w4.w, a[t]);
+          }
         }
-        part[br * E + e] = a;
+#pragma unroll
+        for (int t = 0; t < TT; ++t) part[t][br * E + e] = a[t];
       }
     }
-    warp_reduce_scatter<G>(part, lane);   // lane (g << (5-LG)) now holds the dot product of group g
 #pragma unroll
-    for (int br = 0; br < NB; ++br) {
-      float logits[E], probs[E];
+    for (int t = 0; t < TT; ++t) warp_reduce_scatter<G>(part[t], lane);  // lane (g << (5-LG)) holds group g
+    float logits[E], probs[E];
 #pragma unroll
-      for (int e = 0; e < E; ++e)
-        logits[e] = __shfl_sync(0xffffffffu, part[0], (br * E + e) << (5 - LG)) + __ldg(gate_b + br * E + e);
-      int i0, i1;
-      float v0, v1;
-      softmax_top2<E>(logits, probs, i0, i1, v0, v1);
-      if (lane == 0) {
-        const long o = (tok * NB + br) * 2;
-        *reinterpret_cast<int2*>(idx + o) = make_int2(i0, i1);
-        *reinterpret_cast<float2*>(vals + o) = make_float2(v0, v1);
+    for (int e = 0; e < E; ++e) {
+      const int src = (my_br * E + e) << (5 - LG);
+      const float d0 = __shfl_sync(0xffffffffu, part[0][0], src);
+      const float d1 = __shfl_sync(0xffffffffu, part[1][0], src);
+      logits[e] = (my_t ? d1 : d0) + __ldg(gate_b + my_br * E + e);
+    }
+    int i0, i1;
+    float v0, v1;
+    softmax_top2<E>(logits, probs, i0, i1, v0, v1);
+    if (lane < TT * NB && (my_t == 0 || two)) {
+      const long o = ((tok + my_t) * NB + my_br) * 2;
+      *reinterpret_cast<int2*>(idx + o) = make_int2(i0, i1);
+      *reinterpret_cast<float2*>(vals + o) = make_float2(v0, v1);
+    }
+    const int mg0 = my_br * E + i0, mg1 = my_br * E + i1;
+#pragma unroll
+    for (int q = 0; q < TT * NB; ++q) {   // token-major, branch-minor: the accumulation order of v1
+      const int g0 = __shfl_sync(0xffffffffu, mg0, q), g1 = __shfl_sync(0xffffffffu, mg1, q);
+      const float a0 = __shfl_sync(0xffffffffu, v0, q), a1 = __shfl_sync(0xffffffffu, v1, q);
+      if (q / NB == 0 || two) {
+        if (lane == g0) { cnt_all++; cnt_top1++; imp += a0; }
+        if (lane == g1) { cnt_all++; imp += a1; }
       }
-      const int g0 = br * E + i0, g1 = br * E + i1;
-      if (lane == g0) { cnt_all++; cnt_top1++; imp += v0; }
-      if (lane == g1) { cnt_all++; imp += v1; }
     }
   }
   w_all[warp][lane] = cnt_all;

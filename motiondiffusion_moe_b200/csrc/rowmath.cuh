@@ -117,9 +117,9 @@ __device__ __forceinline__ void l2norm_row(float (&v)[VPT], int D) {
 #pragma unroll
   for (int i = 0; i < VPT; ++i) q = fmaf(v[i], v[i], q);
   const float denom = fmaxf(sqrtf(warp_sum(q)), 1e-12f);
-  const float s = sqrtf((float)D);
+  const float s = sqrtf((float)D) / denom;   // one IEEE divide per row
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) v[i] = v[i] / denom * s;
+  for (int i = 0; i < VPT; ++i) v[i] = v[i] * s;
 }
 
 // v * (1 + scale) + shift, film = [scale(D) | shift(D)]   (models/stylization.py:27-29)

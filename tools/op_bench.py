@@ -1,0 +1,106 @@
+"""Per-op timing at the config-2 shapes (N = 128 sequences x 196 frames, D 512, F 1024, 16 expert groups),
+each op alone, CUDA events, buffers rotated through > 126 MB so nothing is L2-resident between calls.
+Prints achieved TFLOP/s (GEMMs) or GB/s of algorithmic bytes (row / routing / attention kernels).
+MDM_B200_LIB=<path> selects a library variant (tools/build_variant.sh)."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from motiondiffusion_moe_b200 import ops
+from motiondiffusion_moe_b200._lib import ACT_NONE, ACT_GELU, MDM_BF16
+dev = torch.device("cuda")
+torch.manual_seed(0)
+bf, f32 = torch.bfloat16, torch.float32
+ONLY = os.environ.get("ONLY", "")
+NSEQ = int(os.environ.get("NSEQ", "128"))
+T = int(os.environ.get("T", "196"))
+N, D, H = NSEQ * T, 512, 4
+
+
+def timeit(name, fn, nset, work, unit, iters=30):
+    if ONLY and ONLY not in name:
+        return
+    for i in range(3):
+        fn(i % nset)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for i in range(iters):
+        fn(i % nset)
+    e.record()
+    torch.cuda.synchronize()
+    us = s.elapsed_time(e) / iters * 1e3
+    print("%-44s %8.1f us  %8.1f %s" % (name, us, work / us / (1e6 if unit == "TFLOP/s" else 1e3), unit), flush=True)
+
+
+def gemm_case(name, M, Nn, K, act=ACT_NONE, f32out=False, resid=False, bf16out=True, rowscale=False):
+    nset = 4
+    A = [torch.randn(M, K, device=dev).to(bf) for _ in range(nset)]
+    W = (torch.randn(Nn, K, device=dev) / K ** 0.5).to(bf)
+    b = torch.randn(Nn, device=dev)
+    R = [torch.randn(M, Nn, device=dev) for _ in range(nset)] if resid else None
+    Of = [torch.empty(M, Nn, device=dev) for _ in range(nset)] if f32out else None
+    Ob = [torch.empty(M, Nn, device=dev, dtype=bf) for _ in range(nset)] if bf16out else None
+    rs = torch.rand(M, device=dev) if rowscale else None
+
+    def fn(i):
+        ops.gemm(A[i], W, b, act=act, out_f32=Of[i] if Of else None, out_a=Ob[i] if Ob else None,
+                 resid=R[i] if R else None, alpha=1.0, beta=1.0 if resid else 0.0, rowscale=rs)
+    timeit(name, fn, nset, 2.0 * M * Nn * K, "TFLOP/s")
+
+
+gemm_case("gemm qkv      N x1536x512  bf16", N, 1536, 512)
+gemm_case("gemm p0       N x512 x512  gelu bf16", N, 512, 512, act=ACT_GELU)
+gemm_case("gemm p3       N x512 x512  bf16", N, 512, 512)
+gemm_case("gemm s_out    N x512 x512  f32+resid", N, 512, 512, f32out=True, resid=True, bf16out=False)
+gemm_case("gemm skip     N x512 x512  gelu f32+resid", N, 512, 512, act=ACT_GELU, f32out=True, resid=True, bf16out=False)
+gemm_case("gemm ffn_out  N x512 x512  f32+resid+bf16", N, 512, 512, f32out=True, resid=True, bf16out=True)
+gemm_case("gemm up       4N x1024x512 gelu bf16", 4 * N, 1024, 512, act=ACT_GELU)
+gemm_case("gemm down     4N x512x1024 rowscale bf16", 4 * N, 512, 1024, rowscale=True)
+gemm_case("gemm f1       N x2048x512  gelu bf16", N, 2048, 512, act=ACT_GELU)
+gemm_case("gemm f3       N x512x2048  f32+resid", N, 512, 2048, f32out=True, resid=True, bf16out=False)
+
+# ---- row pipeline
+nset = 4
+xb = [torch.randn(N, D, device=dev).to(bf) for _ in range(nset)]
+xf = [torch.randn(N, D, device=dev) for _ in range(nset)]
+ob = [torch.empty(N, D, device=dev, dtype=bf) for _ in range(nset)]
+ob2 = [torch.empty(N, D, device=dev, dtype=bf) for _ in range(nset)]
+of = [torch.empty(N, D, device=dev) for _ in range(nset)]
+ln = (torch.rand(D, device=dev) + 0.5, torch.randn(D, device=dev))
+ln2 = (torch.rand(D, device=dev) + 0.5, torch.randn(D, device=dev))
+film = torch.randn(NSEQ, 2 * D, device=dev)
+timeit("rowop bf16->bf16 ln+l2+ln+film+silu", lambda i: ops.rowop(xb[i], N, D, MDM_BF16, ln1=ln, l2norm=True, ln2=ln2, film=film,
+       rows_per_seq=T, silu=True, out2_a=ob[i]), nset, N * D * 4, "GB/s")
+timeit("rowop bf16->bf16 ln", lambda i: ops.rowop(xb[i], N, D, MDM_BF16, ln1=ln, out1_a=ob[i]), nset, N * D * 4, "GB/s")
+timeit("rowop f32->f32+bf16+bf16 ln,ln", lambda i: ops.rowop(xf[i], N, D, MDM_BF16, ln1=ln, out1_f32=of[i], ln2=ln2, out2_a=ob[i],
+       out0_a=ob2[i]), nset, N * D * 12, "GB/s")
+timeit("rowop f32->bf16 ln", lambda i: ops.rowop(xf[i], N, D, MDM_BF16, ln1=ln, out1_a=ob[i]), nset, N * D * 6, "GB/s")
+
+# ---- MoE routing
+E, NB = 8, 2
+G = NB * E
+lnw = torch.rand(NB, D, device=dev) + 0.5
+lnb = torch.randn(NB, D, device=dev)
+gw = torch.randn(G, D, device=dev) * 0.05
+gb = torch.zeros(G, device=dev)
+idx = torch.empty(N, NB, 2, dtype=torch.int32, device=dev)
+vals = torch.empty(N, NB, 2, device=dev)
+stats = torch.empty(N, 2, device=dev)
+nblk = (N + 127) // 128
+hist = torch.empty(nblk, 2, G, dtype=torch.int32, device=dev)
+imp = torch.empty(nblk, G, device=dev)
+timeit("moe_gate", lambda i: ops.moe_gate(xf[i], N, D, NB, E, lnw, lnb, gw, gb, idx, vals, stats, hist, imp), nset, N * D * 4, "GB/s")
+
+# ---- FastAttention core
+hd = D // H
+qkv = [(torch.randn(N, 3 * D, device=dev)).to(bf) for _ in range(nset)]
+P = torch.randn(hd, hd, device=dev) * hd ** -0.5
+nw, nb_ = torch.rand(hd, device=dev) + 0.5, torch.randn(hd, device=dev) * 0.1
+length = torch.randint(40, T + 1, (NSEQ,), device=dev, dtype=torch.int64)
+timeit("fastattn", lambda i: ops.fastattn(qkv[i], P, nw, nb_, length, 0, NSEQ, H, T, hd, ob[i]), nset, N * D * 8, "GB/s")
+ctx = torch.randn(NSEQ, H, hd, hd, device=dev)
+timeit("lincross_apply", lambda i: ops.lincross_apply(xb[i], ctx, NSEQ, T, H, hd, ob[i]), nset, N * D * 4, "GB/s")
+Nt = 20
+k2 = torch.randn(NSEQ * Nt, D, device=dev).to(bf)
+v2 = torch.randn(NSEQ * Nt, D, device=dev).to(bf)
+nt = torch.full((NSEQ,), Nt, dtype=torch.int32, device=dev)
+timeit("softmax_cross", lambda i: ops.softmax_cross(xb[i], k2, v2, nt, NSEQ, T, Nt, H, hd, ob[i]), nset, N * D * 4, "GB/s")
