@@ -7,9 +7,7 @@
 // this one kernel family.  Persistent, warp-specialised:
 //   warp 0 lane 0 : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma 128 x BN x 16, fp32 accumulate in TMEM, 2 stages)
-//   warps 4..11   : epilogue       (tcgen05.ld -> bias/act/scale -> (smem transpose) -> residual -> global)
-// Roles are aligned to warpgroups so that setmaxnreg can move registers from warpgroup 0 (40 each)
-// to the two epilogue warpgroups (232 each): the software-pipelined epilogue needs ~190.
+//   warps 2..9    : epilogue       (tcgen05.ld -> bias/act/scale -> (smem transpose) -> residual -> global)
 // Grouped mode (MoE experts, stacked FiLM MLPs): an MTile table maps each 128-row tile to its
 // A rows, C rows and weight rows; the table and its length may be produced on the device.
 #include "common.cuh"
@@ -20,8 +18,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int FIRST_EPI_WARP = 4;  // warpgroup 0 = {TMA, MMA, 2 idle warps}; warpgroups 1, 2 = epilogue
-constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int STAGE_T_BYTES = 32 * 32 * 4;  // per-warp 32x32 fp32 transpose buffer
 
 template <int BN, int STAGES>
@@ -54,7 +51,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // |x| <= 6, tools/fit_gelu.py) so that tanh(x Q(x^2)) == erf(x / sqrt 2): these are NOT the constants of
 // the "tanh GELU" variant.  Max abs deviation from the exact-erf GELU: 5.4e-5 from the fit plus
 // 2^-11 relative from MUFU.TANH, i.e. <= 1/8 of a bf16 rounding step of the result.  8 issue slots
-// and one MUFU op per element, which keeps the epilogue of a K = 512 GEMM under its MMA time.
+// and one MUFU op per element instead of 15 and two (expert up-projection: 169 -> 142 us).
 __device__ __forceinline__ float gelu_tanh_fit(float x) {
   const float s = fminf(x * x, 25.0f);
   float q = fmaf(-3.81889112e-04f, s, 3.72153111e-02f);
@@ -77,29 +74,11 @@ __device__ __forceinline__ float act_fast(float v, int act) {
   return v;
 }
 
-// explicit shared-space 128-bit accesses (the generic-pointer form compiled to LD.E / ST.E)
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&p);
 }
 template <int BN, int STAGES>
-// (warps are allocated in groups of 4, so 10 warps cost 12: 65536 / 384 -> at most 168 registers)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, int num_m_tiles_host, const int* __restrict__ num_m_tiles_dev,
@@ -142,8 +121,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (K + BK - 1) / BK;
 
-  if (warp < FIRST_EPI_WARP) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
@@ -194,26 +171,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  } else if (warp >= 2) {
     // ------------------------------------------------------------ epilogue (8 warps)
-    // warp -> TMEM lane quadrant (warp & 3) x column parity ((warp-2) >> 2): two warps share a
+    // warp -> TMEM lane quadrant (warp & 3) x unit parity ((warp-2) >> 2): two warps share a
     // quadrant and take alternate column units.  Accumulators arrive with lane == row; bias,
     // activation and row scale are applied in that layout, then the 32-row block is transposed
     // through a 4 KB XOR-swizzled shared-memory buffer with 128-bit accesses so that every global
     // access (residual load, fp32 / bf16 store) is a full 128-byte row segment:
     //   read phase: lane -> (row = 4*i + lane/8, 16-byte chunk = lane%8), i = 0..7.
-    // The TMEM load of chunk k+1 is issued before the math of chunk k (two register buffers), and
-    // bias / residual loads are issued before the wait for the TMEM load they are combined with:
-    // with only two epilogue warps per scheduler the epilogue is latency-, not issue-bound (ncu:
-    // 6.9 cycles per issued instruction before this change).
     const int quad = warp & 3;
-    const int cpar = (warp - FIRST_EPI_WARP) >> 2;
-    const uint32_t tr_s = smem_u32(smem + L::TR_OFFSET) + (warp - FIRST_EPI_WARP) * STAGE_T_BYTES;  // 32 rows x 8 x 16 B
+    const int cpar = (warp - 2) >> 2;
+    uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - 2) * 256;  // 32 rows x 8 chunks
     const bool f32_path = (epi.out_f32 != nullptr) || (epi.resid != nullptr);
     const int rsub = lane >> 3, ch = lane & 7;
-    constexpr int NCH = BN / 64;   // 32-column chunks per warp and tile
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -225,6 +195,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         w_row0 = mi.w_row0;
         rows_valid = mi.rows_valid;
       }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       const int r = quad * 32 + lane;
       const bool row_ok = r < rows_valid;
       const long m = (long)c_row0 + r;
@@ -240,23 +212,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bf16* ob_blk = epi.out_bf16 ? reinterpret_cast<bf16*>(epi.out_bf16) + blk_row0 * epi.ld_bf16 : nullptr;
       const float* rs_blk = (epi.resid && epi.resid_mod <= 0) ? epi.resid + blk_row0 * epi.ld_resid : epi.resid;
       const int rmod_base = epi.resid_mod > 0 ? (int)(blk_row0 % epi.resid_mod) : 0;
-      const float* bias_t = epi.bias ? epi.bias + w_row0 : nullptr;
 
-      // bias (optionally preloaded in b4), activation and row scale on one 32-column chunk
-      auto finish_chunk = [&](uint32_t (&raw)[32], int n0, const float4 (&b4)[8], bool have_b4, float (&v)[32]) {
+      auto load_chunk = [&](int c, int n0, float (&v)[32]) {
+        uint32_t raw[32];
+        tmem_ld32(t_addr + c * 32, raw);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (bias_t) {
+        if (epi.bias) {
+          const float* bp = epi.bias + w_row0 + n0;
           if (n0 + 32 <= N) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = have_b4 ? b4[j] : __ldg(reinterpret_cast<const float4*>(bias_t + n0) + j);
-              v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (n0 + j < N) v[j] += __ldg(bias_t + n0 + j);
+              if (n0 + j < N) v[j] += __ldg(bp + j);
           }
         }
         if (epi.act == MDM_ACT_GELU) {
@@ -280,36 +254,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
 
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      uint32_t raw[2][32];
-
       if (f32_path) {
-        // chunk k of this warp = TMEM chunk cpar + 2k; every chunk is one transposition round
-        const bool vec_ok32 = ((epi.ld_f32 & 3) == 0 || !epi.out_f32) && ((epi.ld_resid & 3) == 0 || !epi.resid) &&
-                              ((epi.ld_bf16 & 3) == 0 || !epi.out_bf16);
-        tmem_ld32(t_addr + cpar * 32, raw[0]);
-#pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-          const int c = cpar + 2 * k;
+        const bool vec_ok = ((epi.ld_f32 & 3) == 0 || !epi.out_f32) && ((epi.ld_resid & 3) == 0 || !epi.resid) &&
+                            ((epi.ld_bf16 & 3) == 0 || !epi.out_bf16);
+#pragma unroll 1
+        for (int c = cpar; c < BN / 32; c += 2) {
           const int n0 = nt * BN + c * 32;
+          if (n0 >= N) break;
           const int n = n0 + ch * 4;                        // this lane's 4 columns in the read phase
-          const bool cvec = vec_ok32 && (n + 4 <= N);
-          // residual tile in the read-phase layout (volatile: issued here, ahead of the TMEM wait)
+          const bool cvec = vec_ok && (n + 4 <= N);
+          // residual prefetch (volatile: issued here, ahead of the TMEM load and the math)
           float4 res[8];
-          if (epi.resid && n0 < N) {
+          if (epi.resid) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int row = i * 4 + rsub;
               res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (row < rmax && n < N) {
+              if (row < rmax) {
                 const int rr_ = epi.resid_mod > 0 ? (rmod_base + row) % epi.resid_mod : row;
                 const float* rp = rs_blk + (long)rr_ * epi.ld_resid + n;
                 if (cvec) {
                   asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
                                : "=f"(res[i].x), "=f"(res[i].y), "=f"(res[i].z), "=f"(res[i].w) : "l"(rp));
                 } else {
-                  res[i].x = __ldg(rp);
+                  if (n < N) res[i].x = __ldg(rp);
                   if (n + 1 < N) res[i].y = __ldg(rp + 1);
                   if (n + 2 < N) res[i].z = __ldg(rp + 2);
                   if (n + 3 < N) res[i].w = __ldg(rp + 3);
@@ -317,118 +285,100 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          tmem_ld_wait();
-          if (k + 1 < NCH) tmem_ld32(t_addr + (c + 2) * 32, raw[(k + 1) & 1]);
-          if (n0 < N) {
-            float v[32];
-            const float4 nob[8] = {};
-            finish_chunk(raw[k & 1], n0, nob, false, v);
+          float v[32];
+          load_chunk(c, n0, v);
+          float4* trf = reinterpret_cast<float4*>(tr);
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8)
-              sts128f(tr_s + (uint32_t)(lane * 8 + (c8 ^ (lane & 7))) * 16, v[4 * c8], v[4 * c8 + 1], v[4 * c8 + 2], v[4 * c8 + 3]);
-            __syncwarp();
+          for (int c8 = 0; c8 < 8; ++c8)
+            trf[lane * 8 + (c8 ^ (lane & 7))] = make_float4(v[4 * c8], v[4 * c8 + 1], v[4 * c8 + 2], v[4 * c8 + 3]);
+          __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = i * 4 + rsub;
-              float4 x = lds128f(tr_s + (uint32_t)(row * 8 + (ch ^ (row & 7))) * 16);
-              if (row < rmax && n < N) {
-                bf16* ob = ob_blk ? ob_blk + row * epi.ld_bf16 + n : nullptr;
-                float* of = of_blk ? of_blk + row * epi.ld_f32 + n : nullptr;
-                if (ob && epi.bf16_pre_resid) {
-                  if (cvec) {
-                    uint2 pk; pk.x = pack2(x.x, x.y); pk.y = pack2(x.z, x.w);
-                    *reinterpret_cast<uint2*>(ob) = pk;
-                  } else {
-                    ob[0] = __float2bfloat16_rn(x.x);
-                    if (n + 1 < N) ob[1] = __float2bfloat16_rn(x.y);
-                    if (n + 2 < N) ob[2] = __float2bfloat16_rn(x.z);
-                    if (n + 3 < N) ob[3] = __float2bfloat16_rn(x.w);
-                  }
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + rsub;
+            float4 x = trf[row * 8 + (ch ^ (row & 7))];
+            if (row < rmax && n < N) {
+              bf16* ob = ob_blk ? ob_blk + row * epi.ld_bf16 + n : nullptr;
+              float* of = of_blk ? of_blk + row * epi.ld_f32 + n : nullptr;
+              if (ob && epi.bf16_pre_resid) {
+                if (cvec) {
+                  uint2 pk; pk.x = pack2(x.x, x.y); pk.y = pack2(x.z, x.w);
+                  *reinterpret_cast<uint2*>(ob) = pk;
+                } else {
+                  ob[0] = __float2bfloat16_rn(x.x);
+                  if (n + 1 < N) ob[1] = __float2bfloat16_rn(x.y);
+                  if (n + 2 < N) ob[2] = __float2bfloat16_rn(x.z);
+                  if (n + 3 < N) ob[3] = __float2bfloat16_rn(x.w);
                 }
-                if (epi.resid) {
-                  x.x = fmaf(epi.beta, res[i].x, x.x); x.y = fmaf(epi.beta, res[i].y, x.y);
-                  x.z = fmaf(epi.beta, res[i].z, x.z); x.w = fmaf(epi.beta, res[i].w, x.w);
+              }
+              if (epi.resid) {
+                x.x = fmaf(epi.beta, res[i].x, x.x); x.y = fmaf(epi.beta, res[i].y, x.y);
+                x.z = fmaf(epi.beta, res[i].z, x.z); x.w = fmaf(epi.beta, res[i].w, x.w);
+              }
+              if (of) {
+                if (cvec) {
+                  *reinterpret_cast<float4*>(of) = x;
+                } else {
+                  of[0] = x.x;
+                  if (n + 1 < N) of[1] = x.y;
+                  if (n + 2 < N) of[2] = x.z;
+                  if (n + 3 < N) of[3] = x.w;
                 }
-                if (of) {
-                  if (cvec) {
-                    *reinterpret_cast<float4*>(of) = x;
-                  } else {
-                    of[0] = x.x;
-                    if (n + 1 < N) of[1] = x.y;
-                    if (n + 2 < N) of[2] = x.z;
-                    if (n + 3 < N) of[3] = x.w;
-                  }
-                }
-                if (ob && !epi.bf16_pre_resid) {
-                  if (cvec) {
-                    uint2 pk; pk.x = pack2(x.x, x.y); pk.y = pack2(x.z, x.w);
-                    *reinterpret_cast<uint2*>(ob) = pk;
-                  } else {
-                    ob[0] = __float2bfloat16_rn(x.x);
-                    if (n + 1 < N) ob[1] = __float2bfloat16_rn(x.y);
-                    if (n + 2 < N) ob[2] = __float2bfloat16_rn(x.z);
-                    if (n + 3 < N) ob[3] = __float2bfloat16_rn(x.w);
-                  }
+              }
+              if (ob && !epi.bf16_pre_resid) {
+                if (cvec) {
+                  uint2 pk; pk.x = pack2(x.x, x.y); pk.y = pack2(x.z, x.w);
+                  *reinterpret_cast<uint2*>(ob) = pk;
+                } else {
+                  ob[0] = __float2bfloat16_rn(x.x);
+                  if (n + 1 < N) ob[1] = __float2bfloat16_rn(x.y);
+                  if (n + 2 < N) ob[2] = __float2bfloat16_rn(x.z);
+                  if (n + 3 < N) ob[3] = __float2bfloat16_rn(x.w);
                 }
               }
             }
-            __syncwarp();
           }
+          __syncwarp();
         }
       } else if (ob_blk) {
-        // bf16-only output: chunk k of this warp = half (k & 1) of 64-column unit cpar + 2*(k >> 1);
-        // a unit is staged as bf16 (128 bytes per row) and written after its second half.
+        // bf16-only output: 64-column units (two TMEM chunks), staged as bf16 (128 bytes per row)
         const bool vec_ok = (epi.ld_bf16 & 7) == 0;
-        tmem_ld32(t_addr + (2 * cpar) * 32, raw[0]);
+#pragma unroll 1
+        for (int u = cpar; u < BN / 64; u += 2) {
+          const int n0 = nt * BN + u * 64;
+          if (n0 >= N) break;
 #pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-          const int hh = k & 1;
-          const int c = 2 * (cpar + 2 * (k >> 1)) + hh;
-          const int n0 = nt * BN + c * 32;
-          float4 b4[8];
-          const bool have_b4 = bias_t && (n0 + 32 <= N);
-          if (have_b4) {
+          for (int hh = 0; hh < 2; ++hh) {
+            if (n0 + hh * 32 < N) {
+              float v[32];
+              load_chunk(u * 2 + hh, n0 + hh * 32, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias_t + n0) + j);
-          }
-          tmem_ld_wait();
-          if (k + 1 < NCH) {
-            const int cn = 2 * (cpar + 2 * ((k + 1) >> 1)) + ((k + 1) & 1);
-            tmem_ld32(t_addr + cn * 32, raw[(k + 1) & 1]);
-          }
-          if (n0 < N) {
-            float v[32];
-            finish_chunk(raw[k & 1], n0, b4, have_b4, v);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4)
-              sts128(tr_s + (uint32_t)(lane * 8 + ((hh * 4 + c4) ^ (lane & 7))) * 16,
-                     pack2(v[8 * c4], v[8 * c4 + 1]), pack2(v[8 * c4 + 2], v[8 * c4 + 3]),
-                     pack2(v[8 * c4 + 4], v[8 * c4 + 5]), pack2(v[8 * c4 + 6], v[8 * c4 + 7]));
-          }
-          if (hh == 1) {
-            const int nu = n0 - 32;                 // first column of the unit
-            if (nu < N) {
-              __syncwarp();
-              const int n = nu + ch * 8;            // this lane's 8 columns in the read phase
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int row = i * 4 + rsub;
-                const uint4 w = lds128(tr_s + (uint32_t)(row * 8 + (ch ^ (row & 7))) * 16);
-                if (row < rmax && n < N) {
-                  bf16* ob = ob_blk + row * epi.ld_bf16 + n;
-                  if (vec_ok && n + 8 <= N) {
-                    *reinterpret_cast<uint4*>(ob) = w;
-                  } else {
-                    const bf16* e = reinterpret_cast<const bf16*>(&w);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                      if (n + j < N) ob[j] = e[j];
-                  }
-                }
+              for (int c4 = 0; c4 < 4; ++c4) {
+                uint4 pk;
+                pk.x = pack2(v[8 * c4], v[8 * c4 + 1]); pk.y = pack2(v[8 * c4 + 2], v[8 * c4 + 3]);
+                pk.z = pack2(v[8 * c4 + 4], v[8 * c4 + 5]); pk.w = pack2(v[8 * c4 + 6], v[8 * c4 + 7]);
+                tr[lane * 8 + ((hh * 4 + c4) ^ (lane & 7))] = pk;
               }
-              __syncwarp();
             }
           }
+          __syncwarp();
+          const int n = n0 + ch * 8;   // this lane's 8 columns in the read phase
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + rsub;
+            const uint4 w = tr[row * 8 + (ch ^ (row & 7))];
+            if (row < rmax && n < N) {
+              bf16* ob = ob_blk + row * epi.ld_bf16 + n;
+              if (vec_ok && n + 8 <= N) {
+                *reinterpret_cast<uint4*>(ob) = w;
+              } else {
+                const bf16* e = reinterpret_cast<const bf16*>(&w);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (n + j < N) ob[j] = e[j];
+              }
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
