@@ -35,9 +35,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
 // exp(clamp(x, -15, 15)) * 0.1 == 2^(clamp(x) * log2(e) + log2(0.1)) on the MUFU ex2 unit (rel. err 2^-22)
 __device__ __forceinline__ float expfeat(float x) {
   const float c = fminf(fmaxf(x, -15.f), 15.f);
@@ -57,7 +54,6 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
                    const float* __restrict__ nb, const int64_t* __restrict__ length, int length_shift, int H,
                    int T, int Tp, bf16* __restrict__ out) {
   constexpr int LDS = HD + 8;   // padded row pitch (elements): 16-byte row shift => conflict-free ldmatrix
-  constexpr int EPL = HD / 32;  // elements per lane in the row passes
   constexpr int KS = HD / 16;   // k-steps over hd (== M)
   constexpr int NT = HD / 8;    // 8-wide n-tiles over hd (== M)
   extern __shared__ __align__(16) uint8_t smem[];
@@ -77,16 +73,21 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
   const int nstrips = Tp / 16;
 
   constexpr int NTHR = NW * 32;
-  // ---- S0a: the whole (sequence, head) slab of q, k, v goes to shared memory with one round of
-  // asynchronous 16-byte copies (every load of the CTA is in flight at once); pad rows are zeroed.
+  constexpr int CPR = HD / 8;   // 16-byte chunks per row
+  // ---- S0a: the (sequence, head) slab goes to shared memory as two groups of asynchronous 16-byte
+  // copies: k and v first, q second, so that q is still in flight while k and v are normalised.
   {
-    constexpr int CPR = HD / 8;
     const int per = T * CPR;
-    for (int i = tid; i < 3 * per; i += NTHR) {
+    for (int i = tid; i < 2 * per; i += NTHR) {
       const int w = i / per, rem = i - w * per, t = rem / CPR, c = rem - t * CPR;
-      bf16* dst = (w == 0 ? Qs : (w == 1 ? Ks : Vs)) + t * LDS + c * 8;
-      cp_async16(dst, qkv + ((long)(b * T + t)) * 3 * D + w * D + h * HD + c * 8);
+      cp_async16((w == 0 ? Ks : Vs) + t * LDS + c * 8, qkv + ((long)(b * T + t)) * 3 * D + (w + 1) * D + h * HD + c * 8);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = tid; i < per; i += NTHR) {
+      const int t = i / CPR, c = i - t * CPR;
+      cp_async16(Qs + t * LDS + c * 8, qkv + ((long)(b * T + t)) * 3 * D + h * HD + c * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     const int padc = (Tp - T) * CPR;
     for (int i = tid; i < 3 * padc; i += NTHR) {
       const int w = i / padc, rem = i - w * padc, t = T + rem / CPR, c = rem % CPR;
@@ -104,145 +105,133 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
     Ps[(4 * m4 + 3) * LDS + n] = __float2bfloat16_rn(p4.w);
   }
   for (int i = tid; i < HD; i += NTHR) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }
-  cp_async_wait_all();
+  asm volatile("cp.async.wait_group 1;" ::: "memory");   // k, v have landed
   __syncthreads();
 
-  // ---- S1: per-row LayerNorm (+ L2 norm) of 0.1*q, 0.1*k, 0.1*v.  Two rows x three tensors are
-  // normalised together so that six independent shuffle-reduction chains are in flight per warp.
-  {
-    float wv[EPL], bv[EPL];
+  // ---- S1: per-row LayerNorm (+ L2 norm for q, k) of the 0.1-scaled rows, in place.
+  // Eight lanes per row (EPT = hd/8 elements each, 16-byte accesses), four rows per warp pass: the
+  // three reductions of a row cost 3 shuffle steps instead of 5 and every per-row scalar (mean,
+  // rstd, 1/norm) is computed once per 8 lanes; reciprocals replace the per-element IEEE divides.
+  constexpr int EPT = HD / 8;
+  const int sub = lane & 7, rsub4 = lane >> 3;
+  float wv[EPT], bv[EPT];
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) { wv[i] = nw_s[lane * EPL + i]; bv[i] = nb_s[lane * EPL + i]; }
-    for (int t0 = warp * 2; t0 < Tp; t0 += 2 * NW) {
-      float x[6][EPL];
+  for (int cc = 0; cc < EPT / 8; ++cc)
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int t = t0 + rr;
-        const bf16* srow[3] = {Qs + t * LDS + lane * EPL, Ks + t * LDS + lane * EPL, Vs + t * LDS + lane * EPL};
+    for (int i = 0; i < 8; ++i) {
+      wv[cc * 8 + i] = nw_s[cc * 64 + sub * 8 + i];
+      bv[cc * 8 + i] = nb_s[cc * 64 + sub * 8 + i];
+    }
+  auto ln_rows = [&](bf16* X, bool l2) {
+    for (int t = warp * 4 + rsub4; t < Tp; t += 4 * NW) {
+      float x[EPT];
+      bf16* row = X + t * LDS + sub * 8;
 #pragma unroll
-        for (int w = 0; w < 3; ++w) {
-          if (EPL == 4) {
-            const uint2 raw = *reinterpret_cast<const uint2*>(srow[w]);
-            const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-            const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-            x[rr * 3 + w][0] = __low2float(p0); x[rr * 3 + w][1] = __high2float(p0);
-            x[rr * 3 + w][2 % EPL] = __low2float(p1); x[rr * 3 + w][3 % EPL] = __high2float(p1);
-          } else {
-            const uint32_t raw = *reinterpret_cast<const uint32_t*>(srow[w]);
-            const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw);
-            x[rr * 3 + w][0] = __low2float(p0); x[rr * 3 + w][1] = __high2float(p0);
-          }
+      for (int cc = 0; cc < EPT / 8; ++cc) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(row + cc * 64);
+        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[i]);
+          x[cc * 8 + 2 * i] = __low2float(p2) * 0.1f;
+          x[cc * 8 + 2 * i + 1] = __high2float(p2) * 0.1f;
         }
       }
-      float red[6];
+      float sm = 0.f;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        red[c] = 0.f;
+      for (int i = 0; i < EPT; ++i) sm += x[i];
+      sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+      const float mean = sm / (float)HD;
+      float q = 0.f;
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) { x[c][i] *= 0.1f; red[c] += x[c][i]; }
+      for (int i = 0; i < EPT; ++i) { const float d = x[i] - mean; q = fmaf(d, d, q); }
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      q += __shfl_xor_sync(0xffffffffu, q, 4);
+      const float rstd = rsqrtf(q / (float)HD + 1e-5f);
+      float n2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        x[i] = (x[i] - mean) * rstd * wv[i] + bv[i];
+        n2 = fmaf(x[i], x[i], n2);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) red[c] += __shfl_xor_sync(0xffffffffu, red[c], o);
-      float mean[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        mean[c] = red[c] / (float)HD;
-        red[c] = 0.f;
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) { const float d = x[c][i] - mean[c]; red[c] = fmaf(d, d, red[c]); }
+      float inv = 1.0f;
+      if (l2) {   // F.normalize: x / max(||x||, 1e-12)
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
+        inv = 1.0f / fmaxf(sqrtf(n2), 1e-12f);
       }
+      if (t >= T) inv = 0.f;   // pad rows stay zero
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) red[c] += __shfl_xor_sync(0xffffffffu, red[c], o);
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const float rstd = rsqrtf(red[c] / (float)HD + 1e-5f);
-        red[c] = 0.f;
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-          x[c][i] = (x[c][i] - mean[c]) * rstd * wv[i] + bv[i];
-          red[c] = fmaf(x[c][i], x[c][i], red[c]);
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) red[c] += __shfl_xor_sync(0xffffffffu, red[c], o);
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int t = t0 + rr;
-        bf16* dst[3] = {Qs + t * LDS, Ks + t * LDS, Vs + t * LDS};
-#pragma unroll
-        for (int w = 0; w < 3; ++w) {
-          const int c = rr * 3 + w;
-          if (w < 2) {  // F.normalize for q and k
-            const float denom = fmaxf(sqrtf(red[c]), 1e-12f);
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) x[c][i] = x[c][i] / denom;
-          }
-          if (t >= T) {
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) x[c][i] = 0.f;
-          }
-          if (EPL == 4) {
-            uint2 pk;
-            pk.x = pack_bf16(x[c][0], x[c][1]);
-            pk.y = pack_bf16(x[c][2 % EPL], x[c][3 % EPL]);
-            *reinterpret_cast<uint2*>(dst[w] + lane * EPL) = pk;
-          } else {
-            *reinterpret_cast<uint32_t*>(dst[w] + lane * EPL) = pack_bf16(x[c][0], x[c][1]);
-          }
-        }
+      for (int cc = 0; cc < EPT / 8; ++cc) {
+        uint4 pk;
+        pk.x = pack_bf16(x[cc * 8] * inv, x[cc * 8 + 1] * inv);
+        pk.y = pack_bf16(x[cc * 8 + 2] * inv, x[cc * 8 + 3] * inv);
+        pk.z = pack_bf16(x[cc * 8 + 4] * inv, x[cc * 8 + 5] * inv);
+        pk.w = pack_bf16(x[cc * 8 + 6] * inv, x[cc * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(row + cc * 64) = pk;
       }
     }
-  }
+  };
+  ln_rows(Ks, true);
+  ln_rows(Vs, false);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");   // q has landed
+  __syncthreads();
+  ln_rows(Qs, true);
   __syncthreads();
 
-  // ---- S2: feature maps in place: X' = exp(clamp(X . P)) * 0.1 ; key rows t >= len are zeroed
-  for (int job = warp; job < 2 * nstrips; job += NW) {
-    const bool isK = job >= nstrips;
+  // ---- S2: feature maps in place: X' = exp(clamp(X . P)) * 0.1 ; key rows t >= len are zeroed.
+  // Key strips first; the query strips (second sync-separated round) also produce the per-frame
+  // denominator den[t] = max(sum_m q'[t,m] k'[t,m], 1e-6) (same-t product, fast_attention.py:81-82)
+  // from their accumulator fragments and the k' values already in shared memory.
+  for (int round = 0; round < 2; ++round) {
+    const bool isK = round == 0;
     bf16* X = isK ? Ks : Qs;
-    const int r0 = (isK ? job - nstrips : job) * 16;
-    float c[NT][4];
+    for (int job = warp; job < nstrips; job += NW) {
+      const int r0 = job * 16;
+      float c[NT][4];
 #pragma unroll
-    for (int i = 0; i < NT; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+      for (int i = 0; i < NT; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      uint32_t a[4];
-      ldsm_x4(a, X + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t a[4];
+        ldsm_x4(a, X + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
-      for (int np = 0; np < NT / 2; ++np) {
-        uint32_t bb[4];
-        ldsm_x4(bb, Ps + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
-        mma16816(c[2 * np], a, bb[0], bb[1]);
-        mma16816(c[2 * np + 1], a, bb[2], bb[3]);
+        for (int np = 0; np < NT / 2; ++np) {
+          uint32_t bb[4];
+          ldsm_x4(bb, Ps + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
+          mma16816(c[2 * np], a, bb[0], bb[1]);
+          mma16816(c[2 * np + 1], a, bb[2], bb[3]);
+        }
+      }
+      __syncwarp();  // every A fragment of this strip is in registers: the rows may now be overwritten
+      const bool live0 = !isK || (r0 + g) < len, live1 = !isK || (r0 + g + 8) < len;
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int col = nt * 8 + 2 * tq;
+        const uint32_t p0 = live0 ? pack_bf16(expfeat(c[nt][0]), expfeat(c[nt][1])) : 0u;
+        const uint32_t p1 = live1 ? pack_bf16(expfeat(c[nt][2]), expfeat(c[nt][3])) : 0u;
+        *reinterpret_cast<uint32_t*>(X + (r0 + g) * LDS + col) = p0;
+        *reinterpret_cast<uint32_t*>(X + (r0 + g + 8) * LDS + col) = p1;
+        if (!isK) {   // denominator from the bf16-rounded q', k' (what S3 / S4 consume)
+          const __nv_bfloat162 q0 = *reinterpret_cast<const __nv_bfloat162*>(&p0);
+          const __nv_bfloat162 q1 = *reinterpret_cast<const __nv_bfloat162*>(&p1);
+          const __nv_bfloat162 k0 = *reinterpret_cast<const __nv_bfloat162*>(Ks + (r0 + g) * LDS + col);
+          const __nv_bfloat162 k1 = *reinterpret_cast<const __nv_bfloat162*>(Ks + (r0 + g + 8) * LDS + col);
+          d0 = fmaf(__low2float(q0), __low2float(k0), d0); d0 = fmaf(__high2float(q0), __high2float(k0), d0);
+          d1 = fmaf(__low2float(q1), __low2float(k1), d1); d1 = fmaf(__high2float(q1), __high2float(k1), d1);
+        }
+      }
+      if (!isK) {
+        d0 = quad_sum(d0); d1 = quad_sum(d1);
+        if (tq == 0) { den_s[r0 + g] = fmaxf(d0, 1e-6f); den_s[r0 + g + 8] = fmaxf(d1, 1e-6f); }
       }
     }
-    __syncwarp();  // every A fragment of this strip is in registers: the rows may now be overwritten
-    const bool live0 = !isK || (r0 + g) < len, live1 = !isK || (r0 + g + 8) < len;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const int col = nt * 8 + 2 * tq;
-      float f[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) f[i] = expfeat(c[nt][i]);
-      *reinterpret_cast<uint32_t*>(X + (r0 + g) * LDS + col) = live0 ? pack_bf16(f[0], f[1]) : 0u;
-      *reinterpret_cast<uint32_t*>(X + (r0 + g + 8) * LDS + col) = live1 ? pack_bf16(f[2], f[3]) : 0u;
-    }
-  }
-  __syncthreads();
-
-  // ---- S2b: per-frame denominator (same-t product, fast_attention.py:81-82)
-  for (int t = warp; t < Tp; t += NW) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < EPL; ++i)
-      s = fmaf(__bfloat162float(Qs[t * LDS + lane * EPL + i]), __bfloat162float(Ks[t * LDS + lane * EPL + i]), s);
-    s = warp_sum(s);
-    if (lane == 0) den_s[t] = fmaxf(s, 1e-6f);
+    __syncthreads();
   }
 
   // ---- S3: kv[m][n] = 0.1 * sum_t K'[t][m] V[t][n]
