@@ -353,7 +353,7 @@ template <int HD>
 __global__ void __launch_bounds__(256, 2)
 lincross_apply_tc_kernel(const bf16* __restrict__ q, const float* __restrict__ ctx, int H, int T, int Tp,
                          bf16* __restrict__ y) {
-  constexpr int LDS = HD + 8, EPL = HD / 32, KS = HD / 16, NT = HD / 8;
+  constexpr int LDS = HD + 8, KS = HD / 16, NT = HD / 8;
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* Qs = reinterpret_cast<bf16*>(smem);   // [Tp][LDS] softmax(q)
   bf16* Cs = Qs + Tp * LDS;                   // [HD][LDS] ctx[d][l]
@@ -361,59 +361,68 @@ lincross_apply_tc_kernel(const bf16* __restrict__ q, const float* __restrict__ c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
   const int D = H * HD;
   const float* cg = ctx + ((long)(b * H + h)) * HD * HD;
+  {   // all q rows of this (sequence, head) in flight at once; pad rows zeroed
+    constexpr int CPR = HD / 8;
+    for (int i = tid; i < T * CPR; i += 256) {
+      const int t = i / CPR, c = i - t * CPR;
+      cp_async16(Qs + t * LDS + c * 8, q + ((long)(b * T + t)) * D + h * HD + c * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = tid; i < (Tp - T) * CPR; i += 256) {
+      const int t = T + i / CPR, c = i % CPR;
+      *reinterpret_cast<uint4*>(Qs + t * LDS + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   for (int i = tid; i < HD * HD / 4; i += 256) {
     const float4 c4 = *reinterpret_cast<const float4*>(cg + i * 4);
     const int d = (i * 4) / HD, l = (i * 4) - d * HD;
     uint2 pk; pk.x = pack_bf16(c4.x, c4.y); pk.y = pack_bf16(c4.z, c4.w);
     *reinterpret_cast<uint2*>(Cs + d * LDS + l) = pk;
   }
-  for (int t0 = warp * 2; t0 < Tp; t0 += 16) {   // two rows per warp iteration (independent chains)
-    float x[2][EPL], mx[2], sm[2];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // softmax over the head dimension, in place: 8 lanes per row (16-byte accesses), 4 rows per warp pass
+  {
+    constexpr int EPT = HD / 8;
+    const int sub = lane & 7, r4 = lane >> 3;
+    for (int t = warp * 4 + r4; t < Tp; t += 32) {
+      float x[EPT];
+      bf16* row = Qs + t * LDS + sub * 8;
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const bf16* row = q + ((long)(b * T + min(t0 + rr, T - 1))) * D + h * HD + lane * EPL;
-      if (EPL == 4) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(row);
-        const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-        const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-        x[rr][0] = __low2float(p0); x[rr][1] = __high2float(p0);
-        x[rr][2 % EPL] = __low2float(p1); x[rr][3 % EPL] = __high2float(p1);
-      } else {
-        const uint32_t raw = *reinterpret_cast<const uint32_t*>(row);
-        const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw);
-        x[rr][0] = __low2float(p0); x[rr][1] = __high2float(p0);
+      for (int cc = 0; cc < EPT / 8; ++cc) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(row + cc * 64);
+        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[i]);
+          x[cc * 8 + 2 * i] = __low2float(p2);
+          x[cc * 8 + 2 * i + 1] = __high2float(p2);
+        }
       }
-      mx[rr] = x[rr][0];
+      float mx = x[0];
 #pragma unroll
-      for (int i = 1; i < EPL; ++i) mx[rr] = fmaxf(mx[rr], x[rr][i]);
-    }
+      for (int i = 1; i < EPT; ++i) mx = fmaxf(mx, x[i]);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      float sm = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mx[0] = fmaxf(mx[0], __shfl_xor_sync(0xffffffffu, mx[0], o));
-      mx[1] = fmaxf(mx[1], __shfl_xor_sync(0xffffffffu, mx[1], o));
-    }
+      for (int i = 0; i < EPT; ++i) {
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x[i]) : "f"((x[i] - mx) * 1.4426950408889634f));
+        sm += x[i];
+      }
+      sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+      const float inv = t < T ? 1.0f / sm : 0.f;
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      sm[rr] = 0.f;
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) { x[rr][i] = expf(x[rr][i] - mx[rr]); sm[rr] += x[rr][i]; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sm[0] += __shfl_xor_sync(0xffffffffu, sm[0], o);
-      sm[1] += __shfl_xor_sync(0xffffffffu, sm[1], o);
-    }
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      bf16* dst = Qs + (t0 + rr) * LDS + lane * EPL;
-      const bool live = (t0 + rr) < T;
-      if (EPL == 4) {
-        uint2 pk;
-        pk.x = live ? pack_bf16(x[rr][0] / sm[rr], x[rr][1] / sm[rr]) : 0u;
-        pk.y = live ? pack_bf16(x[rr][2 % EPL] / sm[rr], x[rr][3 % EPL] / sm[rr]) : 0u;
-        *reinterpret_cast<uint2*>(dst) = pk;
-      } else {
-        *reinterpret_cast<uint32_t*>(dst) = live ? pack_bf16(x[rr][0] / sm[rr], x[rr][1] / sm[rr]) : 0u;
+      for (int cc = 0; cc < EPT / 8; ++cc) {
+        uint4 pk;
+        pk.x = pack_bf16(x[cc * 8] * inv, x[cc * 8 + 1] * inv);
+        pk.y = pack_bf16(x[cc * 8 + 2] * inv, x[cc * 8 + 3] * inv);
+        pk.z = pack_bf16(x[cc * 8 + 4] * inv, x[cc * 8 + 5] * inv);
+        pk.w = pack_bf16(x[cc * 8 + 6] * inv, x[cc * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(row + cc * 64) = pk;
       }
     }
   }
