@@ -244,6 +244,7 @@ def main():
     bufs = {k: net._ws[(k, s, dt)] for (k, s, dt) in net._ws if k.startswith("moe_") and (s[0] in (cap, cap // 128, 1))}
     reps = 10
     torch.cuda.synchronize(dev)
+    torch.cuda.nvtx.range_push("expert_ffn")      # ncu --nvtx --nvtx-include "expert_ffn/" captures exactly these
     ev0.record()
     for _ in range(reps):
         ops.gemm(bufs["moe_xp"], Lr["w1"], Lr["b1"], act=ACT_GELU, out_a=bufs["moe_hp"], N=Fd, M=cap,
@@ -252,13 +253,18 @@ def main():
                  tiles=bufs["moe_tdn"], num_tiles=cap // 128, num_tiles_dev=bufs["moe_ntile"], a_rows=cap, w_rows=2 * E * D)
     ev1.record()
     torch.cuda.synchronize(dev)
+    torch.cuda.nvtx.range_pop()
     moe_ms = ev0.elapsed_time(ev1) / reps
     moe_flops = 2 * (4 * N2) * D * Fd * 2            # up + down, 4N routed rows (2 branches x top-2)
     pkv, src = peaks()
     ach = moe_flops / (moe_ms * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (grouped expert FFN up+down of one MoEMultiBranchFFN)",
             "achieved": ach, "peak": pkv["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pkv["bf16_tflops"],
-            "peak_source": src + " burst (kernel timed alone)", "traffic": None,
+            "peak_source": src + " burst (kernel timed alone)",
+            # dram__bytes_read.sum + dram__bytes_write.sum of the two launches (up: 120.6 + 149.9 MB,
+            # down: 224.6 + 71.5 MB) from profiles/expert_ffn_r1b_ncu.txt (ncu --set full of this very loop)
+            "traffic": 566.6e6, "traffic_source": "profiles/expert_ffn_r1b_ncu.txt",
+            "tensor_pipe_active_pct": {"up": 44.4, "down": 67.4, "source": "ncu sm__pipe_tensor_cycles_active"},
             "flops_per_launch_pair": moe_flops, "ms_per_launch_pair": moe_ms}
 
     # ---- max over ranks
