@@ -178,6 +178,59 @@ MDM_API int mdm_cfg_update(const float* x, const float* eps_c, const float* eps_
 MDM_API int mdm_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tables2,
                          int n_steps, int B, long per_sample, float* x_t, void* stream);
 
+/* ---- expert-parallel MoE over NVLink peer memory (BASELINE.json configs[3]) -------------------------
+ * The reference has no expert parallelism (experts are a local nn.ModuleList: models/switch_moe.py:
+ * 19-25, looped at :97-109); these entry points replace that loop when the E experts of every branch are
+ * spread over R ranks of one NVSwitch node (expert e lives on rank e / (E/R)), tokens staying sharded by
+ * sequence.  All pointers in MdmEpPeers are valid on the calling GPU: entry [p] is rank p's buffer,
+ * mapped with CUDA IPC (mdm_ipc_*); entry [me] is the local buffer.
+ *   xp        [cap, D]  expert-sorted LN'ed rows received by rank p     (dt)
+ *   rowscale  [cap]     gate weight / NB of each received row           (fp32)
+ *   yp        [cap, D]  expert outputs of rank p                        (dt)
+ *   cnt       [R, NB*E] rows every rank routes to every group           (int32)
+ *   flags     [R]       barrier epochs                                  (uint32)
+ * Sequence per MoE call:  mdm_moe_gate -> mdm_ep_counts -> barrier -> mdm_ep_scan -> mdm_ep_dispatch ->
+ * barrier -> mdm_gemm_bf16 x2 (local tile tables) -> barrier -> mdm_ep_combine_film. */
+#define MDM_EP_MAX_RANKS 8
+typedef struct MdmEpPeers {
+  void* xp[MDM_EP_MAX_RANKS];
+  float* rowscale[MDM_EP_MAX_RANKS];
+  void* yp[MDM_EP_MAX_RANKS];
+  int* cnt[MDM_EP_MAX_RANKS];
+  unsigned* flags[MDM_EP_MAX_RANKS];
+} MdmEpPeers;
+/* Per-group totals of this rank (from the gate's block histograms) -> row [me] of every peer's cnt table;
+ * per-block bases blk_base [nblk, NB*E]; usage / importance counters (switch_moe.py:72-92), per rank as
+ * in the reference. */
+MDM_API int mdm_ep_counts(const int* blk_hist, const float* blk_imp, long N, int NB, int E, int K, int R,
+                          int me, const MdmEpPeers* peers, int* blk_base, float* usage, float* importance,
+                          void* stream);
+/* From the complete cnt table: dest_base[g] = first row of this rank's rows inside the segment of group g
+ * on its owner (segments ordered by local group, rows by source rank, padded to 128); the tile tables and
+ * tile count of the groups owned by this rank; *overflow = 1 if a segment exceeds cap. */
+MDM_API int mdm_ep_scan(const int* cnt, int NB, int E, int K, int R, int me, int F, int D, int cap,
+                        int* dest_base, void* tiles_up, void* tiles_down, int* num_tiles, int* overflow,
+                        void* stream);
+/* Token dispatch: LN_b(x[token]) -> row of the owning rank's xp (NVLink store), its gate weight / NB ->
+ * rowscale; perm[token, b, k] = owner * cap + row. */
+MDM_API int mdm_ep_dispatch(const float* x, long N, int D, int NB, int E, int K, int R, int me, int cap,
+                            const float* ln_w, const float* ln_b, const int* idx, const float* vals,
+                            const float* stats, const int* blk_base, const int* dest_base,
+                            const MdmEpPeers* peers, int dt, int* perm, void* stream);
+/* Combine: gathers the NB*K expert rows of each token from the owners' yp (NVLink loads), then the same
+ * LN + FiLM + SiLU as mdm_moe_combine_film. */
+MDM_API int mdm_ep_combine_film(const MdmEpPeers* peers, int dt, const int* perm, long N, int D, int NBK,
+                                int cap, const float* ln_w, const float* ln_b, const float* film,
+                                int rows_per_seq, void* out, void* stream);
+/* Flag barrier of the R ranks in stream order (epochs must increase by one per call on every rank);
+ * *err is set to 1 if a peer does not arrive within ~2 s. */
+MDM_API int mdm_ep_barrier(const MdmEpPeers* peers, int R, int me, unsigned epoch, int* err, void* stream);
+/* CUDA IPC: 64-byte handle of the allocation containing ptr (+ byte offset of ptr inside it); open /
+ * close a peer's handle (returns the base of the mapped allocation). */
+MDM_API int mdm_ipc_get_handle(const void* ptr, void* handle64, long* offset);
+MDM_API int mdm_ipc_open_handle(const void* handle64, void** base);
+MDM_API int mdm_ipc_close_handle(void* base);
+
 MDM_API int mdm_num_sms(void);
 MDM_API const char* mdm_version(void);
 

@@ -40,6 +40,15 @@ class RowOp(C.Structure):
     ]
 
 
+EP_MAX_RANKS = 8
+
+
+class EpPeers(C.Structure):
+    _fields_ = [("xp", C.c_void_p * EP_MAX_RANKS), ("rowscale", C.c_void_p * EP_MAX_RANKS),
+                ("yp", C.c_void_p * EP_MAX_RANKS), ("cnt", C.c_void_p * EP_MAX_RANKS),
+                ("flags", C.c_void_p * EP_MAX_RANKS)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_long, C.c_float
 
 _SIGS = {
@@ -60,6 +69,14 @@ _SIGS = {
     "mdm_pad_cast": [_P, _L, _I, _P, _I, _I, _P],
     "mdm_cfg_update": [_P, _P, _P, _P, _P, _P, _I, _F, _I, _I, _L, _P, _P, _P],
     "mdm_q_sample": [_P, _P, _P, _P, _I, _I, _L, _P, _P],
+    "mdm_ep_counts": [_P, _P, _L, _I, _I, _I, _I, _I, C.POINTER(EpPeers), _P, _P, _P, _P],
+    "mdm_ep_scan": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "mdm_ep_dispatch": [_P, _L, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, C.POINTER(EpPeers), _I, _P, _P],
+    "mdm_ep_combine_film": [C.POINTER(EpPeers), _I, _P, _L, _I, _I, _I, _P, _P, _P, _I, _P, _P],
+    "mdm_ep_barrier": [C.POINTER(EpPeers), _I, _I, C.c_uint, _P, _P],
+    "mdm_ipc_get_handle": [_P, _P, C.POINTER(C.c_long)],
+    "mdm_ipc_open_handle": [_P, C.POINTER(C.c_void_p)],
+    "mdm_ipc_close_handle": [_P],
     "mdm_num_sms": [],
 }
 

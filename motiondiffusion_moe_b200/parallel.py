@@ -1,0 +1,72 @@
+"""Data-parallel CFG sampling across the GPUs of one node (BASELINE.json configs[2]).
+
+The reference's only multi-GPU code is a DDP wrapper around training whose gradient all-reduce never
+fires; sampling is single-GPU (trainers/ddpm_trainer.py:145-174).  Sequences are
+independent in every op of the denoiser, so the batch shards by sequence with NO collective inside the
+1000-step loop: each rank owns rows [lo, hi) of the global batch, weights are replicated, the global
+initial / per-step noise is drawn from one seed on every rank and sliced, so that the G-GPU result equals
+the 1-GPU result for the same seed, and one all_gather assembles the samples at the end.
+"""
+from typing import Callable, Optional, Tuple
+
+import torch
+
+
+def shard_range(batch: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced split: the first batch % world ranks get one extra sequence."""
+    base, extra = divmod(batch, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def global_noise(shape, seed: int, step: int, device) -> torch.Tensor:
+    """The [B, T, F] noise of reverse step `step` (step = -1: the initial x_T), identical on every rank.
+    Drawn on the CPU generator so that it does not depend on the device type or the rank's RNG state."""
+    g = torch.Generator(device="cpu").manual_seed((int(seed) * 1000003 + int(step) + 1) & 0x7FFFFFFFFFFFFFFF)
+    return torch.randn(*shape, generator=g).to(device)
+
+
+def slice_kwargs(model_kwargs: dict, lo: int, hi: int) -> dict:
+    out = {}
+    for k, v in model_kwargs.items():
+        if isinstance(v, torch.Tensor) and v.dim() > 0:
+            out[k] = v[lo:hi].contiguous()
+        elif isinstance(v, (list, tuple)):
+            out[k] = list(v[lo:hi])
+        else:
+            out[k] = v
+    return out
+
+
+def sample_dp(make_stepper: Callable, shape, model_kwargs: dict, num_timesteps: int, seed: int = 0,
+              group=None, num_steps: Optional[int] = None, device=None) -> torch.Tensor:
+    """Sharded p_sample_loop_with_cfg.  make_stepper(local_shape, local_kwargs) must return an object with
+    `.x` (the local state tensor) and `.step(t, noise)` (GaussianDiffusion.make_cfg_stepper does).  Returns
+    the full [B, T, F] sample on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = shape[0]
+    lo, hi = shard_range(B, world, rank)
+    st = make_stepper((hi - lo,) + tuple(shape[1:]), slice_kwargs(model_kwargs, lo, hi))
+    dev = device if device is not None else st.x.device
+    st.x.copy_(global_noise(shape, seed, -1, dev)[lo:hi])
+    steps = list(reversed(range(num_timesteps)))
+    if num_steps is not None:
+        steps = steps[:num_steps]
+    for t in steps:
+        st.step(t, global_noise(shape, seed, t, dev)[lo:hi])
+    local = st.x.contiguous()
+    if world == 1:
+        return local.clone()
+    # ragged all_gather: pad every shard to the largest one
+    mx = (B + world - 1) // world
+    pad = torch.zeros((mx,) + tuple(shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:hi - lo] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = []
+    for r in range(world):
+        a, b = shard_range(B, world, r)
+        out.append(parts[r][:b - a])
+    return torch.cat(out)
