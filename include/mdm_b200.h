@@ -54,6 +54,8 @@ typedef struct MdmGemmEpi {
   void* out_bf16; /* secondary output in the operand type: bf16 (mdm_gemm_bf16) / fp32 (mdm_gemm_f32) */
   int ld_bf16;
   int bf16_pre_resid; /* 1: the secondary output omits the residual term */
+  int pair_tiles;     /* grouped GEMM only: 1 = tiles 2i and 2i+1 of the table share w_row0 (segments padded
+                         to 256 rows), which lets the CTA-pair (cta_group::2) kernel take them together */
 } MdmGemmEpi;
 
 /* One 128-row tile of a grouped GEMM: rows [a_row0, a_row0+128) of A times the weight rows starting

@@ -85,8 +85,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Every legitimate wait in these kernels lasts microseconds; a protocol bug must fault (trap ->
+// launch error on the host), never spin forever and take the GPU with it.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins == (1u << 22)) __trap();
   }
 }
 

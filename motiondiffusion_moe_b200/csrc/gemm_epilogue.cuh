@@ -1,0 +1,340 @@
+// Shared pieces of the tcgen05 GEMM kernels (gemm_tc.cu: one CTA per 128-row tile; gemm_tc2.cu: CTA pairs,
+// cta_group::2): tile constants, fast activations and the per-tile epilogue of one epilogue warp.
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int FIRST_EPI_WARP = 4;  // warpgroup 0 = {TMA, MMA, 2 idle warps}; warpgroups 1, 2 = epilogue
+constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
+constexpr int STAGE_T_BYTES = 32 * 32 * 4;  // per-warp 32x32 fp32 transpose buffer
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = TR_OFFSET + NUM_EPI_WARPS * STAGE_T_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024 align slack
+};
+
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) on
+// the MUFU rcp / ex2 units: ~14 issue slots instead of erff's ~50, so that the epilogue of a K=512
+// GEMM stays under its MMA time.  Max abs deviation from the exact erf GELU: 4.5e-7 (bf16 ulp at 1 is 7.8e-3).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+// GELU for bf16-only outputs: x * Phi(x) with Phi(x) = 0.5 + 0.5 tanh(x Q(x^2)), Q fitted (minimax over
+// |x| <= 6, tools/fit_gelu.py) so that tanh(x Q(x^2)) == erf(x / sqrt 2): these are NOT the constants of
+// the "tanh GELU" variant.  Max abs deviation from the exact-erf GELU: 5.4e-5 from the fit plus
+// 2^-11 relative from MUFU.TANH, i.e. <= 1/8 of a bf16 rounding step of the result.  8 issue slots
+// and one MUFU op per element instead of 15 and two (expert up-projection: 169 -> 142 us).
+__device__ __forceinline__ float gelu_tanh_fit(float x) {
+  const float s = fminf(x * x, 25.0f);
+  float q = fmaf(-3.81889112e-04f, s, 3.72153111e-02f);
+  q = fmaf(q, s, 7.97237410e-01f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * q));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
+}
+__device__ __forceinline__ float silu_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-x * 1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+__device__ __forceinline__ float act_fast(float v, int act) {
+  if (act == MDM_ACT_GELU) return gelu_fast(v);
+  if (act == MDM_ACT_SILU) return silu_fast(v);
+  if (act == MDM_ACT_EXPFEAT) return expf(fminf(fmaxf(v, -15.f), 15.f)) * 0.1f;
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+// Epilogue flavours.  Each is its own kernel instantiation so that the hot loop of a launch stays
+// inside the instruction cache: with all variants (and their scalar tail code) in one body the fp32
+// epilogue ran at ~20 cycles per issued instruction, "no instruction" being its largest stall (ncu).
+//   EPI_BF16 : bf16 output only, 16-byte vector stores (N % 8 == 0, aligned)
+//   EPI_F32  : fp32 output and/or residual (+ optional bf16 copy), vector accesses (N % 4 == 0, aligned)
+//   EPI_ANY  : any shape / alignment (scalar tails); used for the few odd shapes (263 features ...)
+enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_ANY = 2 };
+
+// The epilogue of ONE warp for ONE 128 x BN accumulator tile: TMEM lane quadrant `quad` (rows quad*32 ..
+// +31 of the tile), column chunks of parity `cpar`.  t_addr = TMEM address of (lane quad*32, first column
+// of the accumulator buffer); acc_bar / acc_phase: the "accumulator complete" barrier to wait on.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt, int c_row0, int w_row0,
+                                              int rows_valid, uint32_t t_addr, uint64_t* acc_bar,
+                                              uint32_t acc_phase, uint4* tr, int quad, int cpar, int lane) {
+  float4* trf = reinterpret_cast<float4*>(tr);
+  const bool f32_path = EPI == EPI_F32 || (EPI == EPI_ANY && (epi.out_f32 != nullptr || epi.resid != nullptr));
+  const int rsub = lane >> 3, ch = lane & 7;
+  constexpr int NCH = BN / 64;   // 32-column chunks per warp and tile
+  const int r = quad * 32 + lane;
+  const bool row_ok = r < rows_valid;
+  const long m = (long)c_row0 + r;
+  const float rs = (epi.rowscale && row_ok) ? epi.rowscale[m] : 1.0f;
+  const float rm = (epi.rowmask && row_ok) ? epi.rowmask[m] : 1.0f;
+  const float scale = rs * rm * epi.alpha;
+  const bool has_scale = epi.rowscale || epi.rowmask || epi.alpha != 1.0f;   // warp-uniform
+  const int rmax = min(32, rows_valid - quad * 32);   // valid rows of this warp's 32-row block
+    // per-tile base pointers; in-tile offsets stay 32-bit
+  const long blk_row0 = (long)c_row0 + quad * 32;
+  float* of_blk = epi.out_f32 ? epi.out_f32 + blk_row0 * epi.ld_f32 : nullptr;
+  bf16* ob_blk = epi.out_bf16 ? reinterpret_cast<bf16*>(epi.out_bf16) + blk_row0 * epi.ld_bf16 : nullptr;
+  const float* rs_blk = (epi.resid && epi.resid_mod <= 0) ? epi.resid + blk_row0 * epi.ld_resid : epi.resid;
+  const int rmod_base = epi.resid_mod > 0 ? (int)(blk_row0 % epi.resid_mod) : 0;
+
+  // TMEM chunk c (32 columns from n0) -> registers, + bias, activation, row scale
+  auto load_chunk = [&](int c, int n0, float (&v)[32]) {
+    uint32_t raw[32];
+    tmem_ld32(t_addr + c * 32, raw);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+    if (epi.bias) {
+      const float* bp = epi.bias + w_row0 + n0;
+      if (n0 + 32 <= N) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      } else if (EPI != EPI_ANY) {   // N % 4 == 0 here: 4-column granules, static register indices
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (n0 + j + 4 <= N) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < N) v[j] += __ldg(bp + j);
+      }
+    }
+    if (epi.act == MDM_ACT_GELU) {
+      if (f32_path) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fit(v[j]);
+      }
+    } else if (epi.act == MDM_ACT_SILU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
+    } else if (epi.act != MDM_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = act_fast(v[j], epi.act);
+    }
+    if (has_scale) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= scale;
+    }
+  };
+
+  if constexpr (EPI == EPI_F32) {
+    // ---------------- fp32 / residual outputs, vector accesses only
+    // The residual rows of all NCH chunks of this warp (read-phase layout) are requested before
+    // the wait for the accumulator: NCH x 4 KB per warp in flight while the MMAs of the tile run.
+    float4 res[NCH][8];
+    if (epi.resid) {
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int n = nt * BN + (cpar + 2 * k) * 32 + ch * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + rsub;
+          res[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < rmax && n < N) {
+            const int rr_ = epi.resid_mod > 0 ? (rmod_base + row) % epi.resid_mod : row;
+            const float* rp = rs_blk + (long)rr_ * epi.ld_resid + n;
+            asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(res[k][i].x), "=f"(res[k][i].y), "=f"(res[k][i].z), "=f"(res[k][i].w) : "l"(rp));
+          }
+        }
+      }
+    }
+    mbar_wait(acc_bar, acc_phase);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = cpar + 2 * k;
+      const int n0 = nt * BN + c * 32;
+      if (n0 < N) {
+        const int n = n0 + ch * 4;                        // this lane's 4 columns in the read phase
+        float v[32];
+        load_chunk(c, n0, v);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8)
+          trf[lane * 8 + (c8 ^ (lane & 7))] = make_float4(v[4 * c8], v[4 * c8 + 1], v[4 * c8 + 2], v[4 * c8 + 3]);
+        __syncwarp();
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + rsub;
+          x[i] = trf[row * 8 + (ch ^ (row & 7))];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + rsub;
+          if (row < rmax && n < N) {
+            if (ob_blk && epi.bf16_pre_resid) {
+              uint2 pk; pk.x = pack2(x[i].x, x[i].y); pk.y = pack2(x[i].z, x[i].w);
+              *reinterpret_cast<uint2*>(ob_blk + row * epi.ld_bf16 + n) = pk;
+            }
+            if (epi.resid) {
+              x[i].x = fmaf(epi.beta, res[k][i].x, x[i].x); x[i].y = fmaf(epi.beta, res[k][i].y, x[i].y);
+              x[i].z = fmaf(epi.beta, res[k][i].z, x[i].z); x[i].w = fmaf(epi.beta, res[k][i].w, x[i].w);
+            }
+            if (of_blk) *reinterpret_cast<float4*>(of_blk + row * epi.ld_f32 + n) = x[i];
+            if (ob_blk && !epi.bf16_pre_resid) {
+              uint2 pk; pk.x = pack2(x[i].x, x[i].y); pk.y = pack2(x[i].z, x[i].w);
+              *reinterpret_cast<uint2*>(ob_blk + row * epi.ld_bf16 + n) = pk;
+            }
+          }
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_BF16) {
+    // ---------------- bf16-only output: 64-column units (two TMEM chunks) staged as bf16
+    mbar_wait(acc_bar, acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int u = cpar; u < BN / 64; u += 2) {
+      const int n0 = nt * BN + u * 64;
+      if (n0 >= N) break;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        if (n0 + hh * 32 < N) {
+          float v[32];
+          load_chunk(u * 2 + hh, n0 + hh * 32, v);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint4 pk;
+            pk.x = pack2(v[8 * c4], v[8 * c4 + 1]); pk.y = pack2(v[8 * c4 + 2], v[8 * c4 + 3]);
+            pk.z = pack2(v[8 * c4 + 4], v[8 * c4 + 5]); pk.w = pack2(v[8 * c4 + 6], v[8 * c4 + 7]);
+            tr[lane * 8 + ((hh * 4 + c4) ^ (lane & 7))] = pk;
+          }
+        }
+      }
+      __syncwarp();
+      const int n = n0 + ch * 8;   // this lane's 8 columns in the read phase
+      uint4 w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + rsub;
+        w[i] = tr[row * 8 + (ch ^ (row & 7))];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + rsub;
+        if (row < rmax && n < N) *reinterpret_cast<uint4*>(ob_blk + row * epi.ld_bf16 + n) = w[i];
+      }
+    }
+  } else {
+    // ---------------- any shape / alignment (scalar tails), rolled loops
+    mbar_wait(acc_bar, acc_phase);
+    tc_fence_after();
+    if (f32_path) {
+      const bool vec_ok = ((epi.ld_f32 & 3) == 0 || !epi.out_f32) && ((epi.ld_resid & 3) == 0 || !epi.resid) &&
+                          ((epi.ld_bf16 & 3) == 0 || !epi.out_bf16);
+#pragma unroll 1
+      for (int c = cpar; c < BN / 32; c += 2) {
+        const int n0 = nt * BN + c * 32;
+        if (n0 >= N) break;
+        const int n = n0 + ch * 4;
+        const bool cvec = vec_ok && (n + 4 <= N);
+        float v[32];
+        load_chunk(c, n0, v);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8)
+          trf[lane * 8 + (c8 ^ (lane & 7))] = make_float4(v[4 * c8], v[4 * c8 + 1], v[4 * c8 + 2], v[4 * c8 + 3]);
+        __syncwarp();
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + rsub;
+          const float4 x4 = trf[row * 8 + (ch ^ (row & 7))];
+          if (row < rmax && n < N) {
+            float x[4] = {x4.x, x4.y, x4.z, x4.w};
+            const int rr_ = epi.resid_mod > 0 ? (rmod_base + row) % epi.resid_mod : row;
+            const float* rp = epi.resid ? rs_blk + (long)rr_ * epi.ld_resid + n : nullptr;
+            bf16* ob = ob_blk ? ob_blk + row * epi.ld_bf16 + n : nullptr;
+            float* of = of_blk ? of_blk + row * epi.ld_f32 + n : nullptr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (n + j < N) {
+                if (ob && epi.bf16_pre_resid) ob[j] = __float2bfloat16_rn(x[j]);
+                if (rp) x[j] = fmaf(epi.beta, __ldg(rp + j), x[j]);
+                if (of) of[j] = x[j];
+                if (ob && !epi.bf16_pre_resid) ob[j] = __float2bfloat16_rn(x[j]);
+              }
+            }
+            (void)cvec;
+          }
+        }
+        __syncwarp();
+      }
+    } else if (ob_blk) {
+#pragma unroll 1
+      for (int u = cpar; u < BN / 64; u += 2) {
+        const int n0 = nt * BN + u * 64;
+        if (n0 >= N) break;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          if (n0 + hh * 32 < N) {
+            float v[32];
+            load_chunk(u * 2 + hh, n0 + hh * 32, v);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              uint4 pk;
+              pk.x = pack2(v[8 * c4], v[8 * c4 + 1]); pk.y = pack2(v[8 * c4 + 2], v[8 * c4 + 3]);
+              pk.z = pack2(v[8 * c4 + 4], v[8 * c4 + 5]); pk.w = pack2(v[8 * c4 + 6], v[8 * c4 + 7]);
+              tr[lane * 8 + ((hh * 4 + c4) ^ (lane & 7))] = pk;
+            }
+          }
+        }
+        __syncwarp();
+        const int n = n0 + ch * 8;
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + rsub;
+          const uint4 w = tr[row * 8 + (ch ^ (row & 7))];
+          if (row < rmax && n < N) {
+            bf16* ob = ob_blk + row * epi.ld_bf16 + n;
+            const bf16* e = reinterpret_cast<const bf16*>(&w);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (n + j < N) ob[j] = e[j];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+}  // namespace

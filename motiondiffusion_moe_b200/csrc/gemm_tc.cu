@@ -13,82 +13,12 @@
 // warp (128 registers) in flight while the MMAs of the tile are still running.
 // Grouped mode (MoE experts, stacked FiLM MLPs): an MTile table maps each 128-row tile to its
 // A rows, C rows and weight rows; the table and its length may be produced on the device.
-#include "common.cuh"
+
+#include <stdlib.h>
+#include "gemm_epilogue.cuh"
 
 namespace {
 
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int FIRST_EPI_WARP = 4;  // warpgroup 0 = {TMA, MMA, 2 idle warps}; warpgroups 1, 2 = epilogue
-constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
-constexpr int STAGE_T_BYTES = 32 * 32 * 4;  // per-warp 32x32 fp32 transpose buffer
-
-template <int BN, int STAGES>
-struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = TR_OFFSET + NUM_EPI_WARPS * STAGE_T_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024 align slack
-};
-
-// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) on
-// the MUFU rcp / ex2 units: ~14 issue slots instead of erff's ~50, so that the epilogue of a K=512
-// GEMM stays under its MMA time.  Max abs deviation from the exact erf GELU: 4.5e-7 (bf16 ulp at 1 is 7.8e-3).
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-  const float erf_abs = fmaf(-p, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
-}
-// GELU for bf16-only outputs: x * Phi(x) with Phi(x) = 0.5 + 0.5 tanh(x Q(x^2)), Q fitted (minimax over
-// |x| <= 6, tools/fit_gelu.py) so that tanh(x Q(x^2)) == erf(x / sqrt 2): these are NOT the constants of
-// the "tanh GELU" variant.  Max abs deviation from the exact-erf GELU: 5.4e-5 from the fit plus
-// 2^-11 relative from MUFU.TANH, i.e. <= 1/8 of a bf16 rounding step of the result.  8 issue slots
-// and one MUFU op per element instead of 15 and two (expert up-projection: 169 -> 142 us).
-__device__ __forceinline__ float gelu_tanh_fit(float x) {
-  const float s = fminf(x * x, 25.0f);
-  float q = fmaf(-3.81889112e-04f, s, 3.72153111e-02f);
-  q = fmaf(q, s, 7.97237410e-01f);
-  float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * q));
-  const float hx = 0.5f * x;
-  return fmaf(hx, th, hx);
-}
-__device__ __forceinline__ float silu_fast(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-x * 1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return x * r;
-}
-__device__ __forceinline__ float act_fast(float v, int act) {
-  if (act == MDM_ACT_GELU) return gelu_fast(v);
-  if (act == MDM_ACT_SILU) return silu_fast(v);
-  if (act == MDM_ACT_EXPFEAT) return expf(fminf(fmaxf(v, -15.f), 15.f)) * 0.1f;
-  return v;
-}
-
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&p);
-}
-// Epilogue flavours.  Each is its own kernel instantiation so that the hot loop of a launch stays
-// inside the instruction cache: with all variants (and their scalar tail code) in one body the fp32
-// epilogue ran at ~20 cycles per issued instruction, "no instruction" being its largest stall (ncu).
-//   EPI_BF16 : bf16 output only, 16-byte vector stores (N % 8 == 0, aligned)
-//   EPI_F32  : fp32 output and/or residual (+ optional bf16 copy), vector accesses (N % 4 == 0, aligned)
-//   EPI_ANY  : any shape / alignment (scalar tails); used for the few odd shapes (263 features ...)
-enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_ANY = 2 };
 
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -199,10 +129,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;
     const int cpar = (warp - FIRST_EPI_WARP) >> 2;
     uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - FIRST_EPI_WARP) * 256;  // 32 rows x 8 chunks
-    float4* trf = reinterpret_cast<float4*>(tr);
-    const bool f32_path = EPI == EPI_F32 || (EPI == EPI_ANY && (epi.out_f32 != nullptr || epi.resid != nullptr));
-    const int rsub = lane >> 3, ch = lane & 7;
-    constexpr int NCH = BN / 64;   // 32-column chunks per warp and tile
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -214,253 +140,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         w_row0 = mi.w_row0;
         rows_valid = mi.rows_valid;
       }
-      const int r = quad * 32 + lane;
-      const bool row_ok = r < rows_valid;
-      const long m = (long)c_row0 + r;
-      const float rs = (epi.rowscale && row_ok) ? epi.rowscale[m] : 1.0f;
-      const float rm = (epi.rowmask && row_ok) ? epi.rowmask[m] : 1.0f;
-      const float scale = rs * rm * epi.alpha;
-      const bool has_scale = epi.rowscale || epi.rowmask || epi.alpha != 1.0f;   // warp-uniform
-      const int rmax = min(32, rows_valid - quad * 32);   // valid rows of this warp's 32-row block
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-      // per-tile base pointers; in-tile offsets stay 32-bit
-      const long blk_row0 = (long)c_row0 + quad * 32;
-      float* of_blk = epi.out_f32 ? epi.out_f32 + blk_row0 * epi.ld_f32 : nullptr;
-      bf16* ob_blk = epi.out_bf16 ? reinterpret_cast<bf16*>(epi.out_bf16) + blk_row0 * epi.ld_bf16 : nullptr;
-      const float* rs_blk = (epi.resid && epi.resid_mod <= 0) ? epi.resid + blk_row0 * epi.ld_resid : epi.resid;
-      const int rmod_base = epi.resid_mod > 0 ? (int)(blk_row0 % epi.resid_mod) : 0;
-
-      // TMEM chunk c (32 columns from n0) -> registers, + bias, activation, row scale
-      auto load_chunk = [&](int c, int n0, float (&v)[32]) {
-        uint32_t raw[32];
-        tmem_ld32(t_addr + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (epi.bias) {
-          const float* bp = epi.bias + w_row0 + n0;
-          if (n0 + 32 <= N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          } else if (EPI != EPI_ANY) {   // N % 4 == 0 here: 4-column granules, static register indices
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (n0 + j + 4 <= N) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < N) v[j] += __ldg(bp + j);
-          }
-        }
-        if (epi.act == MDM_ACT_GELU) {
-          if (f32_path) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fit(v[j]);
-          }
-        } else if (epi.act == MDM_ACT_SILU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
-        } else if (epi.act != MDM_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = act_fast(v[j], epi.act);
-        }
-        if (has_scale) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= scale;
-        }
-      };
-
-      if constexpr (EPI == EPI_F32) {
-        // ---------------- fp32 / residual outputs, vector accesses only
-        // The residual rows of all NCH chunks of this warp (read-phase layout) are requested before
-        // the wait for the accumulator: NCH x 4 KB per warp in flight while the MMAs of the tile run.
-        float4 res[NCH][8];
-        if (epi.resid) {
-#pragma unroll
-          for (int k = 0; k < NCH; ++k) {
-            const int n = nt * BN + (cpar + 2 * k) * 32 + ch * 4;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = i * 4 + rsub;
-              res[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (row < rmax && n < N) {
-                const int rr_ = epi.resid_mod > 0 ? (rmod_base + row) % epi.resid_mod : row;
-                const float* rp = rs_blk + (long)rr_ * epi.ld_resid + n;
-                asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
-                             : "=f"(res[k][i].x), "=f"(res[k][i].y), "=f"(res[k][i].z), "=f"(res[k][i].w) : "l"(rp));
-              }
-            }
-          }
-        }
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-          const int c = cpar + 2 * k;
-          const int n0 = nt * BN + c * 32;
-          if (n0 < N) {
-            const int n = n0 + ch * 4;                        // this lane's 4 columns in the read phase
-            float v[32];
-            load_chunk(c, n0, v);
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8)
-              trf[lane * 8 + (c8 ^ (lane & 7))] = make_float4(v[4 * c8], v[4 * c8 + 1], v[4 * c8 + 2], v[4 * c8 + 3]);
-            __syncwarp();
-            float4 x[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = i * 4 + rsub;
-              x[i] = trf[row * 8 + (ch ^ (row & 7))];
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = i * 4 + rsub;
-              if (row < rmax && n < N) {
-                if (ob_blk && epi.bf16_pre_resid) {
-                  uint2 pk; pk.x = pack2(x[i].x, x[i].y); pk.y = pack2(x[i].z, x[i].w);
-                  *reinterpret_cast<uint2*>(ob_blk + row * epi.ld_bf16 + n) = pk;
-                }
-                if (epi.resid) {
-                  x[i].x = fmaf(epi.beta, res[k][i].x, x[i].x); x[i].y = fmaf(epi.beta, res[k][i].y, x[i].y);
-                  x[i].z = fmaf(epi.beta, res[k][i].z, x[i].z); x[i].w = fmaf(epi.beta, res[k][i].w, x[i].w);
-                }
-                if (of_blk) *reinterpret_cast<float4*>(of_blk + row * epi.ld_f32 + n) = x[i];
-                if (ob_blk && !epi.bf16_pre_resid) {
-                  uint2 pk; pk.x = pack2(x[i].x, x[i].y); pk.y = pack2(x[i].z, x[i].w);
-                  *reinterpret_cast<uint2*>(ob_blk + row * epi.ld_bf16 + n) = pk;
-                }
-              }
-            }
-          }
-        }
-      } else if constexpr (EPI == EPI_BF16) {
-        // ---------------- bf16-only output: 64-column units (two TMEM chunks) staged as bf16
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-#pragma unroll 1
-        for (int u = cpar; u < BN / 64; u += 2) {
-          const int n0 = nt * BN + u * 64;
-          if (n0 >= N) break;
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            if (n0 + hh * 32 < N) {
-              float v[32];
-              load_chunk(u * 2 + hh, n0 + hh * 32, v);
-#pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) {
-                uint4 pk;
-                pk.x = pack2(v[8 * c4], v[8 * c4 + 1]); pk.y = pack2(v[8 * c4 + 2], v[8 * c4 + 3]);
-                pk.z = pack2(v[8 * c4 + 4], v[8 * c4 + 5]); pk.w = pack2(v[8 * c4 + 6], v[8 * c4 + 7]);
-                tr[lane * 8 + ((hh * 4 + c4) ^ (lane & 7))] = pk;
-              }
-            }
-          }
-          __syncwarp();
-          const int n = n0 + ch * 8;   // this lane's 8 columns in the read phase
-          uint4 w[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = i * 4 + rsub;
-            w[i] = tr[row * 8 + (ch ^ (row & 7))];
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = i * 4 + rsub;
-            if (row < rmax && n < N) *reinterpret_cast<uint4*>(ob_blk + row * epi.ld_bf16 + n) = w[i];
-          }
-        }
-      } else {
-        // ---------------- any shape / alignment (scalar tails), rolled loops
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-        if (f32_path) {
-          const bool vec_ok = ((epi.ld_f32 & 3) == 0 || !epi.out_f32) && ((epi.ld_resid & 3) == 0 || !epi.resid) &&
-                              ((epi.ld_bf16 & 3) == 0 || !epi.out_bf16);
-#pragma unroll 1
-          for (int c = cpar; c < BN / 32; c += 2) {
-            const int n0 = nt * BN + c * 32;
-            if (n0 >= N) break;
-            const int n = n0 + ch * 4;
-            const bool cvec = vec_ok && (n + 4 <= N);
-            float v[32];
-            load_chunk(c, n0, v);
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8)
-              trf[lane * 8 + (c8 ^ (lane & 7))] = make_float4(v[4 * c8], v[4 * c8 + 1], v[4 * c8 + 2], v[4 * c8 + 3]);
-            __syncwarp();
-#pragma unroll 1
-            for (int i = 0; i < 8; ++i) {
-              const int row = i * 4 + rsub;
-              const float4 x4 = trf[row * 8 + (ch ^ (row & 7))];
-              if (row < rmax && n < N) {
-                float x[4] = {x4.x, x4.y, x4.z, x4.w};
-                const int rr_ = epi.resid_mod > 0 ? (rmod_base + row) % epi.resid_mod : row;
-                const float* rp = epi.resid ? rs_blk + (long)rr_ * epi.ld_resid + n : nullptr;
-                bf16* ob = ob_blk ? ob_blk + row * epi.ld_bf16 + n : nullptr;
-                float* of = of_blk ? of_blk + row * epi.ld_f32 + n : nullptr;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  if (n + j < N) {
-                    if (ob && epi.bf16_pre_resid) ob[j] = __float2bfloat16_rn(x[j]);
-                    if (rp) x[j] = fmaf(epi.beta, __ldg(rp + j), x[j]);
-                    if (of) of[j] = x[j];
-                    if (ob && !epi.bf16_pre_resid) ob[j] = __float2bfloat16_rn(x[j]);
-                  }
-                }
-                (void)cvec;
-              }
-            }
-            __syncwarp();
-          }
-        } else if (ob_blk) {
-#pragma unroll 1
-          for (int u = cpar; u < BN / 64; u += 2) {
-            const int n0 = nt * BN + u * 64;
-            if (n0 >= N) break;
-#pragma unroll 1
-            for (int hh = 0; hh < 2; ++hh) {
-              if (n0 + hh * 32 < N) {
-                float v[32];
-                load_chunk(u * 2 + hh, n0 + hh * 32, v);
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                  uint4 pk;
-                  pk.x = pack2(v[8 * c4], v[8 * c4 + 1]); pk.y = pack2(v[8 * c4 + 2], v[8 * c4 + 3]);
-                  pk.z = pack2(v[8 * c4 + 4], v[8 * c4 + 5]); pk.w = pack2(v[8 * c4 + 6], v[8 * c4 + 7]);
-                  tr[lane * 8 + ((hh * 4 + c4) ^ (lane & 7))] = pk;
-                }
-              }
-            }
-            __syncwarp();
-            const int n = n0 + ch * 8;
-#pragma unroll 1
-            for (int i = 0; i < 8; ++i) {
-              const int row = i * 4 + rsub;
-              const uint4 w = tr[row * 8 + (ch ^ (row & 7))];
-              if (row < rmax && n < N) {
-                bf16* ob = ob_blk + row * epi.ld_bf16 + n;
-                const bf16* e = reinterpret_cast<const bf16*>(&w);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (n + j < N) ob[j] = e[j];
-              }
-            }
-            __syncwarp();
-          }
-        }
-      }
+      epilogue_tile<BN, EPI>(epi, N, nt, c_row0, w_row0, rows_valid,
+                             tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN, &tmem_full[acc], acc_phase, tr,
+                             quad, cpar, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -473,6 +155,219 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// =============================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs computes one 256 x 256 tile.  CTA r
+// stages rows [128 r, 128 r + 128) of A and rows [128 r, +128) of the 256 weight rows of the tile, so a
+// k-block costs each SM 32 KB of L2 -> shared-memory traffic instead of 48 KB (the single-CTA kernel
+// is bound by exactly that feed: 67 % tensor-pipe on the K = 1024 expert down-projection).  The leader
+// CTA issues the MMAs for both; accumulator rows 128 r .. live in CTA r's TMEM and are drained by
+// that CTA's own epilogue warps (same epilogue code as above).
+//   full[s]       leader only, 1 arrival (leader's expect_tx of both CTAs' bytes) + TMA bytes of both
+//   empty[s]      one per CTA, signalled by the leader's multicast tcgen05.commit
+//   tmem_full[a]  one per CTA, multicast commit after the last k-block
+//   tmem_empty[a] leader only, 2 x 8 arrivals (the peer's epilogue warps arrive remotely)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // same smem offset in both CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+
+constexpr int BN2 = 256;        // tile width of the pair kernel
+constexpr int HALF_N2 = 128;    // weight rows staged per CTA
+
+template <int STAGES>
+struct SmemLayout2 {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = HALF_N2 * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = TR_OFFSET + NUM_EPI_WARPS * STAGE_T_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <int STAGES, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                int M, int N, int K, int num_m_tiles_host, const int* __restrict__ num_m_tiles_dev,
+                const MTile* __restrict__ mtiles, const GemmEpi epi) {
+  using L = SmemLayout2<STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 2 * NUM_EPI_WARPS);
+    mbar_init(&tmem_empty[1], 2 * NUM_EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_ptr, 2 * BN2);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_m_tiles = num_m_tiles_dev ? *num_m_tiles_dev : num_m_tiles_host;
+  const int num_pairs = (num_m_tiles + 1) >> 1;
+  const int num_n_tiles = (N + BN2 - 1) / BN2;
+  const int num_work = num_pairs * num_n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp < FIRST_EPI_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------ TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const int pm = w / num_n_tiles, nt = w - pm * num_n_tiles;
+        const int mt = 2 * pm + (int)rank;
+        int a_row0 = mt * BM, w_row0 = 0;
+        if (mtiles) {
+          const MTile m0 = mtiles[2 * pm];            // both tiles of a pair share the weight rows
+          w_row0 = m0.w_row0;
+          a_row0 = mt < num_m_tiles ? mtiles[mt].a_row0 : m0.a_row0 + BM;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+          tma_load_2d_2sm(&tmA, fb, sa, kb * BK, a_row0);
+          tma_load_2d_2sm(&tmB, fb, sb, kb * BK, w_row0 + nt * BN2 + (int)rank * HALF_N2);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0 && leader) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN2);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN2;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ------------------------------------------------------------ epilogue (8 warps per CTA, own 128 rows)
+    const int quad = warp & 3;
+    const int cpar = (warp - FIRST_EPI_WARP) >> 2;
+    uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - FIRST_EPI_WARP) * 256;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = cluster_id; w < num_work; w += num_clusters) {
+      const int pm = w / num_n_tiles, nt = w - pm * num_n_tiles;
+      const int mt = 2 * pm + (int)rank;
+      int c_row0 = mt * BM, w_row0 = 0, rows_valid = M - mt * BM;
+      if (mtiles) {
+        w_row0 = mtiles[2 * pm].w_row0;
+        if (mt < num_m_tiles) {
+          const MTile mi = mtiles[mt];
+          c_row0 = mi.c_row0;
+          rows_valid = mi.rows_valid;
+        } else {
+          rows_valid = 0;
+        }
+      }
+      if (mt >= num_m_tiles) rows_valid = 0;
+      epilogue_tile<BN2, EPI>(epi, N, nt, c_row0, w_row0, rows_valid,
+                              tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN2, &tmem_full[acc], acc_phase, tr,
+                              quad, cpar, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BN2);
   }
 }
 
@@ -541,6 +436,26 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, in
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
+template <int STAGES, int EPI>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int num_m_tiles,
+            const int* num_m_tiles_dev, const MTile* mtiles, const GemmEpi& epi, int max_ctas, cudaStream_t stream) {
+  using L = SmemLayout2<STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+        cudaSuccess)
+      return MDM_ERR_CUDA;
+    attr_set = true;
+  }
+  const long work = (long)((num_m_tiles + 1) / 2) * ((N + BN2 - 1) / BN2);
+  long clusters = max_ctas / 2;
+  if (!num_m_tiles_dev && work < clusters) clusters = work;
+  if (clusters < 1) clusters = 1;
+  gemm_tc2_kernel<STAGES, EPI><<<(unsigned)(2 * clusters), NUM_THREADS, L::TOTAL, stream>>>(
+      ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
 }  // namespace
 
 // C-ABI: see include/mdm_b200.h
@@ -563,9 +478,14 @@ extern "C" MDM_API int mdm_gemm_bf16(const void* A, int lda, long a_rows, const 
     const double e128 = (double)t128 / (double)(((t128 + max_ctas - 1) / max_ctas) * max_ctas);
     if (e128 > e256 + 0.12) wide = false;
   }
+  // CTA pairs (cta_group::2, 256 x 256 tiles) for wide GEMMs with at least two row tiles; a grouped
+  // GEMM must declare that its tile table is pair-aligned (tiles 2i, 2i+1 share their weight rows)
+  static const int pair_env = [] { const char* e = getenv("MDM_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  const bool pair = pair_env && wide && (num_m_tiles_dev || num_m_tiles >= 2) && (!mtiles || epi->pair_tiles) &&
+                    max_ctas >= 2;
   CUtensorMap ta, tb;
   if (!make_map(&ta, A, a_rows, K, lda, BM)) return MDM_ERR_CUDA;
-  if (!make_map(&tb, W, w_rows, K, ldw, wide ? 256 : 128)) return MDM_ERR_CUDA;
+  if (!make_map(&tb, W, w_rows, K, ldw, (wide && !pair) ? 256 : 128)) return MDM_ERR_CUDA;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const MTile* mt = reinterpret_cast<const MTile*>(mtiles);
   // epilogue flavour: the vectorised kernels need aligned rows and N % 8 (bf16) / N % 4 (fp32)
@@ -577,6 +497,9 @@ extern "C" MDM_API int mdm_gemm_bf16(const void* A, int lda, long a_rows, const 
       (!epi->resid || ((epi->ld_resid & 3) == 0 && al(epi->resid, 16))) &&
       (!epi->out_bf16 || ((epi->ld_bf16 & 3) == 0 && al(epi->out_bf16, 8))))
     kind = EPI_F32;
+#define MDM_LAUNCH2(E_) launch2<6, E_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st)
+  if (pair) return kind == EPI_BF16 ? MDM_LAUNCH2(EPI_BF16) : kind == EPI_F32 ? MDM_LAUNCH2(EPI_F32) : MDM_LAUNCH2(EPI_ANY);
+#undef MDM_LAUNCH2
 #define MDM_LAUNCH(BN_, ST_, E_) launch<BN_, ST_, E_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st)
   if (wide) return kind == EPI_BF16 ? MDM_LAUNCH(256, 4, EPI_BF16) : kind == EPI_F32 ? MDM_LAUNCH(256, 4, EPI_F32) : MDM_LAUNCH(256, 4, EPI_ANY);
   return kind == EPI_BF16 ? MDM_LAUNCH(128, 6, EPI_BF16) : kind == EPI_F32 ? MDM_LAUNCH(128, 6, EPI_F32) : MDM_LAUNCH(128, 6, EPI_ANY);
