@@ -3,6 +3,13 @@
 #pragma once
 #include "common.cuh"
 
+#ifdef MDM_GEMM_PROFILE
+__device__ unsigned long long g_epi_phase[8];   // cycles summed over (warp 4 lane 0 of every CTA): see tools/gemm_prof.py
+#define EPI_MARK(k) do { if (prof_on) { const long long now_ = clock64(); atomicAdd(&g_epi_phase[k], (unsigned long long)(now_ - tprev_)); tprev_ = now_; } } while (0)
+#else
+#define EPI_MARK(k) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int BM = 128;
@@ -81,10 +88,17 @@ enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_ANY = 2 };
 // The epilogue of ONE warp for ONE 128 x BN accumulator tile: TMEM lane quadrant `quad` (rows quad*32 ..
 // +31 of the tile), column chunks of parity `cpar`.  t_addr = TMEM address of (lane quad*32, first column
 // of the accumulator buffer); acc_bar / acc_phase: the "accumulator complete" barrier to wait on.
-template <int BN, int EPI>
+// ACT >= 0: the activation is a compile-time constant (one instantiation per activation keeps the hot
+// loop small: with every activation inlined a 32-column chunk was 826 SASS instructions of which ~100
+// execute, and four unrolled chunks overflowed the instruction cache); ACT < 0: epi.act at run time.
+template <int BN, int EPI, int ACT>
 __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt, int c_row0, int w_row0,
                                               int rows_valid, uint32_t t_addr, uint64_t* acc_bar,
                                               uint32_t acc_phase, uint4* tr, int quad, int cpar, int lane) {
+#ifdef MDM_GEMM_PROFILE
+  const bool prof_on = (threadIdx.x == FIRST_EPI_WARP * 32);
+  long long tprev_ = clock64();
+#endif
   float4* trf = reinterpret_cast<float4*>(tr);
   const bool f32_path = EPI == EPI_F32 || (EPI == EPI_ANY && (epi.out_f32 != nullptr || epi.resid != nullptr));
   const int rsub = lane >> 3, ch = lane & 7;
@@ -104,36 +118,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
   const float* rs_blk = (epi.resid && epi.resid_mod <= 0) ? epi.resid + blk_row0 * epi.ld_resid : epi.resid;
   const int rmod_base = epi.resid_mod > 0 ? (int)(blk_row0 % epi.resid_mod) : 0;
 
-  // TMEM chunk c (32 columns from n0) -> registers, + bias, activation, row scale
-  auto load_chunk = [&](int c, int n0, float (&v)[32]) {
-    uint32_t raw[32];
-    tmem_ld32(t_addr + c * 32, raw);
-    tmem_ld_wait();
+  // Bias of the NCH chunks of this warp, one column per lane, requested before the accumulator wait and
+  // broadcast with shuffles when a chunk is finished.  (The chunks' bias used to be re-read with 8
+  // LDG.128 right after every TMEM load; with 227 KB of the SM configured as shared memory there is
+  // practically no L1, so those were L2 round trips on the critical path: ~900 cycles per chunk.)
+  // chunk k of this warp -> TMEM chunk index: fp32 path cpar + 2k ; bf16 path 2 (cpar + 2 (k / 2)) + k % 2
+  auto chunk_of = [&](int k) { return f32_path ? cpar + 2 * k : 2 * (cpar + 2 * (k >> 1)) + (k & 1); };
+  float bias_r[NCH];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int n = nt * BN + chunk_of(k) * 32 + lane;
+    bias_r[k] = (epi.bias && n < N) ? __ldg(epi.bias + w_row0 + n) : 0.f;
+  }
+
+  // bias (lane-distributed register bk), activation and row scale on the 32 accumulator columns in raw
+  auto finish_chunk = [&](const uint32_t (&raw)[32], float bk, float (&v)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
     if (epi.bias) {
-      const float* bp = epi.bias + w_row0 + n0;
-      if (n0 + 32 <= N) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
-          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-        }
-      } else if (EPI != EPI_ANY) {   // N % 4 == 0 here: 4-column granules, static register indices
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (n0 + j + 4 <= N) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < N) v[j] += __ldg(bp + j);
-      }
+      for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bk, j);
     }
-    if (epi.act == MDM_ACT_GELU) {
+    const int act = ACT >= 0 ? ACT : epi.act;
+    if (act == MDM_ACT_GELU) {
       if (f32_path) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
@@ -141,17 +148,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fit(v[j]);
       }
-    } else if (epi.act == MDM_ACT_SILU) {
+    } else if (act == MDM_ACT_SILU) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
-    } else if (epi.act != MDM_ACT_NONE) {
+    } else if (act != MDM_ACT_NONE) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = act_fast(v[j], epi.act);
+      for (int j = 0; j < 32; ++j) v[j] = act_fast(v[j], act);
     }
     if (has_scale) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= scale;
     }
+  };
+  // TMEM chunk c -> registers, then finish_chunk (one chunk at a time)
+  auto load_chunk = [&](int c, float bk, float (&v)[32]) {
+    uint32_t raw[32];
+    EPI_MARK(7);
+    tmem_ld32(t_addr + c * 32, raw);
+    tmem_ld_wait();
+    EPI_MARK(0);
+    finish_chunk(raw, bk, v);
   };
 
   if constexpr (EPI == EPI_F32) {
@@ -176,8 +192,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
         }
       }
     }
+    EPI_MARK(4);
     mbar_wait(acc_bar, acc_phase);
     tc_fence_after();
+    EPI_MARK(5);
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int c = cpar + 2 * k;
@@ -185,10 +203,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
       if (n0 < N) {
         const int n = n0 + ch * 4;                        // this lane's 4 columns in the read phase
         float v[32];
-        load_chunk(c, n0, v);
+        load_chunk(c, bias_r[k], v);
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8)
           trf[lane * 8 + (c8 ^ (lane & 7))] = make_float4(v[4 * c8], v[4 * c8 + 1], v[4 * c8 + 2], v[4 * c8 + 3]);
+        EPI_MARK(1);
         __syncwarp();
         float4 x[8];
 #pragma unroll
@@ -197,6 +216,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
           x[i] = trf[row * 8 + (ch ^ (row & 7))];
         }
         __syncwarp();
+        EPI_MARK(2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = i * 4 + rsub;
@@ -216,21 +236,32 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
             }
           }
         }
+        EPI_MARK(3);
       }
     }
   } else if constexpr (EPI == EPI_BF16) {
     // ---------------- bf16-only output: 64-column units (two TMEM chunks) staged as bf16
+    EPI_MARK(4);
     mbar_wait(acc_bar, acc_phase);
     tc_fence_after();
-#pragma unroll 1
-    for (int u = cpar; u < BN / 64; u += 2) {
+    EPI_MARK(5);
+#pragma unroll
+    for (int uu = 0; uu < NCH / 2; ++uu) {
+      const int u = cpar + 2 * uu;
       const int n0 = nt * BN + u * 64;
       if (n0 >= N) break;
+      // both 32-column halves of the unit are requested from TMEM before either is processed
+      uint32_t raw[2][32];
+      EPI_MARK(7);
+      tmem_ld32(t_addr + (u * 2) * 32, raw[0]);
+      tmem_ld32(t_addr + (u * 2 + 1) * 32, raw[1]);
+      tmem_ld_wait();
+      EPI_MARK(0);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         if (n0 + hh * 32 < N) {
           float v[32];
-          load_chunk(u * 2 + hh, n0 + hh * 32, v);
+          finish_chunk(raw[hh], bias_r[2 * uu + hh], v);
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             uint4 pk;
@@ -240,6 +271,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
           }
         }
       }
+      EPI_MARK(1);
       __syncwarp();
       const int n = n0 + ch * 8;   // this lane's 8 columns in the read phase
       uint4 w[8];
@@ -249,16 +281,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
         w[i] = tr[row * 8 + (ch ^ (row & 7))];
       }
       __syncwarp();
+      EPI_MARK(2);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = i * 4 + rsub;
         if (row < rmax && n < N) *reinterpret_cast<uint4*>(ob_blk + row * epi.ld_bf16 + n) = w[i];
       }
+      EPI_MARK(3);
     }
   } else {
     // ---------------- any shape / alignment (scalar tails), rolled loops
+    EPI_MARK(4);
     mbar_wait(acc_bar, acc_phase);
     tc_fence_after();
+    EPI_MARK(5);
     if (f32_path) {
       const bool vec_ok = ((epi.ld_f32 & 3) == 0 || !epi.out_f32) && ((epi.ld_resid & 3) == 0 || !epi.resid) &&
                           ((epi.ld_bf16 & 3) == 0 || !epi.out_bf16);
@@ -269,7 +305,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
         const int n = n0 + ch * 4;
         const bool cvec = vec_ok && (n + 4 <= N);
         float v[32];
-        load_chunk(c, n0, v);
+        load_chunk(c, (epi.bias && n0 + lane < N) ? __ldg(epi.bias + w_row0 + n0 + lane) : 0.f, v);
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8)
           trf[lane * 8 + (c8 ^ (lane & 7))] = make_float4(v[4 * c8], v[4 * c8 + 1], v[4 * c8 + 2], v[4 * c8 + 3]);
@@ -307,7 +343,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
         for (int hh = 0; hh < 2; ++hh) {
           if (n0 + hh * 32 < N) {
             float v[32];
-            load_chunk(u * 2 + hh, n0 + hh * 32, v);
+            const int nb = n0 + hh * 32 + lane;
+            load_chunk(u * 2 + hh, (epi.bias && nb < N) ? __ldg(epi.bias + w_row0 + nb) : 0.f, v);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               uint4 pk;

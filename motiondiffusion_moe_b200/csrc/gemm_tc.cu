@@ -17,10 +17,28 @@
 #include <stdlib.h>
 #include "gemm_epilogue.cuh"
 
+#ifdef MDM_GEMM_PROFILE
+// bring-up instrumentation: per CTA {epilogue wait cycles, epilogue work cycles, MMA-thread cycles waiting
+// for a free accumulator, MMA-thread cycles waiting for operands, total cycles, tiles}
+__device__ unsigned long long g_gemm_prof[148 * 8];
+extern "C" MDM_API int mdm_debug_read_gemm_prof(unsigned long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, g_gemm_prof, sizeof(unsigned long long) * n) == cudaSuccess ? 0 : 2;
+}
+extern "C" MDM_API int mdm_debug_read_epi_phase(unsigned long long* host, int reset) {
+  unsigned long long z[8] = {0};
+  if (cudaMemcpyFromSymbol(host, g_epi_phase, sizeof(z)) != cudaSuccess) return 2;
+  if (reset && cudaMemcpyToSymbol(g_epi_phase, z, sizeof(z)) != cudaSuccess) return 2;
+  return 0;
+}
+#define PROF_T() clock64()
+#else
+#define PROF_T() 0ll
+#endif
+
 namespace {
 
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, int num_m_tiles_host, const int* __restrict__ num_m_tiles_dev,
@@ -95,12 +113,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_acc = 0, w_op = 0;
+      const long long t_begin = PROF_T();
+      (void)t_begin;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        long long c0 = PROF_T();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        w_acc += PROF_T() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          c0 = PROF_T();
           mbar_wait(&full_bar[stage], phase);
+          w_op += PROF_T() - c0;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t adesc = make_sw128_kmajor_desc(sa);
@@ -116,6 +141,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+#ifdef MDM_GEMM_PROFILE
+      g_gemm_prof[blockIdx.x * 8 + 2] = w_acc;
+      g_gemm_prof[blockIdx.x * 8 + 3] = w_op;
+      g_gemm_prof[blockIdx.x * 8 + 4] = PROF_T() - t_begin;
+#endif
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
@@ -131,6 +161,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - FIRST_EPI_WARP) * 256;  // 32 rows x 8 chunks
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long e_wait = 0, e_work = 0;
+    int e_tiles = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mt = t / num_n_tiles, nt = t - mt * num_n_tiles;
       int c_row0 = mt * BM, w_row0 = 0, rows_valid = M - mt * BM;
@@ -140,14 +172,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         w_row0 = mi.w_row0;
         rows_valid = mi.rows_valid;
       }
-      epilogue_tile<BN, EPI>(epi, N, nt, c_row0, w_row0, rows_valid,
+      const long long c0 = PROF_T();
+      mbar_wait(&tmem_full[acc], acc_phase);     // (the epilogue waits again: returns at once)
+      const long long c1 = PROF_T();
+      e_wait += c1 - c0;
+      ++e_tiles;
+      epilogue_tile<BN, EPI, ACT>(epi, N, nt, c_row0, w_row0, rows_valid,
                              tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN, &tmem_full[acc], acc_phase, tr,
                              quad, cpar, lane);
       tc_fence_before();
       __syncwarp();
+      e_work += PROF_T() - c1;
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+#ifdef MDM_GEMM_PROFILE
+    if (warp == FIRST_EPI_WARP && lane == 0) {
+      g_gemm_prof[blockIdx.x * 8 + 0] = e_wait;
+      g_gemm_prof[blockIdx.x * 8 + 1] = e_work;
+      g_gemm_prof[blockIdx.x * 8 + 5] = e_tiles;
+    }
+#endif
   }
 
   tc_fence_before();
@@ -231,7 +276,7 @@ struct SmemLayout2 {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
-template <int STAGES, int EPI>
+template <int STAGES, int EPI, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 int M, int N, int K, int num_m_tiles_host, const int* __restrict__ num_m_tiles_dev,
@@ -310,12 +355,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_acc = 0, w_op = 0;
+      const long long t_begin = PROF_T();
+      (void)t_begin;
       for (int w = cluster_id; w < num_work; w += num_clusters) {
+        long long c0 = PROF_T();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        w_acc += PROF_T() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN2;
         for (int kb = 0; kb < num_kb; ++kb) {
+          c0 = PROF_T();
           mbar_wait(&full_bar[stage], phase);
+          w_op += PROF_T() - c0;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t adesc = make_sw128_kmajor_desc(sa);
@@ -329,6 +381,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         umma_commit_2sm(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+#ifdef MDM_GEMM_PROFILE
+      g_gemm_prof[blockIdx.x * 8 + 2] = w_acc;
+      g_gemm_prof[blockIdx.x * 8 + 3] = w_op;
+      g_gemm_prof[blockIdx.x * 8 + 4] = PROF_T() - t_begin;
+#endif
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
@@ -338,6 +395,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - FIRST_EPI_WARP) * 256;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long e_wait = 0, e_work = 0;
+    int e_tiles = 0;
     for (int w = cluster_id; w < num_work; w += num_clusters) {
       const int pm = w / num_n_tiles, nt = w - pm * num_n_tiles;
       const int mt = 2 * pm + (int)rank;
@@ -353,14 +412,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
       if (mt >= num_m_tiles) rows_valid = 0;
-      epilogue_tile<BN2, EPI>(epi, N, nt, c_row0, w_row0, rows_valid,
+      const long long c0 = PROF_T();
+      mbar_wait(&tmem_full[acc], acc_phase);
+      const long long c1 = PROF_T();
+      e_wait += c1 - c0;
+      ++e_tiles;
+      epilogue_tile<BN2, EPI, ACT>(epi, N, nt, c_row0, w_row0, rows_valid,
                               tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN2, &tmem_full[acc], acc_phase, tr,
                               quad, cpar, lane);
       tc_fence_before();
       __syncwarp();
+      e_work += PROF_T() - c1;
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+#ifdef MDM_GEMM_PROFILE
+    if (warp == FIRST_EPI_WARP && lane == 0) {
+      g_gemm_prof[blockIdx.x * 8 + 0] = e_wait;
+      g_gemm_prof[blockIdx.x * 8 + 1] = e_work;
+      g_gemm_prof[blockIdx.x * 8 + 5] = e_tiles;
+    }
+#endif
   }
 
   tc_fence_before();
@@ -414,14 +486,14 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int ACT>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int num_m_tiles,
            const int* num_m_tiles_dev, const MTile* mtiles, const GemmEpi& epi, int max_ctas,
            cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              L::TOTAL) != cudaSuccess)
       return MDM_ERR_CUDA;
     attr_set = true;
@@ -431,18 +503,18 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, in
   int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
   if (num_m_tiles_dev) grid = max_ctas;
   if (grid < 1) grid = 1;
-  gemm_tc_kernel<BN, STAGES, EPI><<<grid, NUM_THREADS, L::TOTAL, stream>>>(
+  gemm_tc_kernel<BN, STAGES, EPI, ACT><<<grid, NUM_THREADS, L::TOTAL, stream>>>(
       ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
-template <int STAGES, int EPI>
+template <int STAGES, int EPI, int ACT>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int num_m_tiles,
             const int* num_m_tiles_dev, const MTile* mtiles, const GemmEpi& epi, int max_ctas, cudaStream_t stream) {
   using L = SmemLayout2<STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+    if (cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
         cudaSuccess)
       return MDM_ERR_CUDA;
     attr_set = true;
@@ -451,7 +523,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, i
   long clusters = max_ctas / 2;
   if (!num_m_tiles_dev && work < clusters) clusters = work;
   if (clusters < 1) clusters = 1;
-  gemm_tc2_kernel<STAGES, EPI><<<(unsigned)(2 * clusters), NUM_THREADS, L::TOTAL, stream>>>(
+  gemm_tc2_kernel<STAGES, EPI, ACT><<<(unsigned)(2 * clusters), NUM_THREADS, L::TOTAL, stream>>>(
       ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
@@ -480,9 +552,12 @@ extern "C" MDM_API int mdm_gemm_bf16(const void* A, int lda, long a_rows, const 
   }
   // CTA pairs (cta_group::2, 256 x 256 tiles) for wide GEMMs with at least two row tiles; a grouped
   // GEMM must declare that its tile table is pair-aligned (tiles 2i, 2i+1 share their weight rows)
-  static const int pair_env = [] { const char* e = getenv("MDM_GEMM_PAIR"); return e ? atoi(e) : 1; }();
-  const bool pair = pair_env && wide && (num_m_tiles_dev || num_m_tiles >= 2) && (!mtiles || epi->pair_tiles) &&
-                    max_ctas >= 2;
+  // Measured on B200 (tools/op_bench.py, tools/gemm_prof.py): K = 512 GEMMs are bound by their
+  // epilogue, where the pair kernel is ~8 % slower; from K = 1024 up (operand-feed bound) it wins
+  // (N x 512 x 2048: 56.8 -> 53.8 us).  MDM_GEMM_PAIR=0/1 forces it off / on for A/B runs.
+  static const int pair_env = [] { const char* e = getenv("MDM_GEMM_PAIR"); return e ? atoi(e) : -1; }();
+  const bool pair_fit = wide && (num_m_tiles_dev || num_m_tiles >= 2) && (!mtiles || epi->pair_tiles) && max_ctas >= 2;
+  const bool pair = pair_fit && (pair_env == 1 || (pair_env < 0 && K >= 1024));
   CUtensorMap ta, tb;
   if (!make_map(&ta, A, a_rows, K, lda, BM)) return MDM_ERR_CUDA;
   if (!make_map(&tb, W, w_rows, K, ldw, (wide && !pair) ? 256 : 128)) return MDM_ERR_CUDA;
@@ -497,11 +572,20 @@ extern "C" MDM_API int mdm_gemm_bf16(const void* A, int lda, long a_rows, const 
       (!epi->resid || ((epi->ld_resid & 3) == 0 && al(epi->resid, 16))) &&
       (!epi->out_bf16 || ((epi->ld_bf16 & 3) == 0 && al(epi->out_bf16, 8))))
     kind = EPI_F32;
-#define MDM_LAUNCH2(E_) launch2<6, E_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st)
-  if (pair) return kind == EPI_BF16 ? MDM_LAUNCH2(EPI_BF16) : kind == EPI_F32 ? MDM_LAUNCH2(EPI_F32) : MDM_LAUNCH2(EPI_ANY);
-#undef MDM_LAUNCH2
-#define MDM_LAUNCH(BN_, ST_, E_) launch<BN_, ST_, E_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st)
-  if (wide) return kind == EPI_BF16 ? MDM_LAUNCH(256, 4, EPI_BF16) : kind == EPI_F32 ? MDM_LAUNCH(256, 4, EPI_F32) : MDM_LAUNCH(256, 4, EPI_ANY);
-  return kind == EPI_BF16 ? MDM_LAUNCH(128, 6, EPI_BF16) : kind == EPI_F32 ? MDM_LAUNCH(128, 6, EPI_F32) : MDM_LAUNCH(128, 6, EPI_ANY);
-#undef MDM_LAUNCH
+  // one instantiation per (epilogue flavour, activation): bf16 {none, gelu, silu}, fp32 {none, gelu};
+  // anything else goes through the any-shape kernel with the activation decided at run time
+  const int act = epi->act;
+#define MDM_GO(E_, A_)                                                                                            \
+  do {                                                                                                            \
+    if (pair) return launch2<6, E_, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);   \
+    if (wide) return launch<256, 4, E_, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st); \
+    return launch<128, 6, E_, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);          \
+  } while (0)
+  if (kind == EPI_BF16 && act == MDM_ACT_NONE) MDM_GO(EPI_BF16, MDM_ACT_NONE);
+  if (kind == EPI_BF16 && act == MDM_ACT_GELU) MDM_GO(EPI_BF16, MDM_ACT_GELU);
+  if (kind == EPI_BF16 && act == MDM_ACT_SILU) MDM_GO(EPI_BF16, MDM_ACT_SILU);
+  if (kind == EPI_F32 && act == MDM_ACT_NONE) MDM_GO(EPI_F32, MDM_ACT_NONE);
+  if (kind == EPI_F32 && act == MDM_ACT_GELU) MDM_GO(EPI_F32, MDM_ACT_GELU);
+  MDM_GO(EPI_ANY, -1);
+#undef MDM_GO
 }
