@@ -15,10 +15,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int FIRST_EPI_WARP = 4;  // warpgroup 0 = {TMA, MMA, 2 idle warps}; warpgroups 1, 2 = epilogue
-constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
-constexpr int STAGE_T_BYTES = 32 * 32 * 4;  // per-warp 32x32 fp32 transpose buffer
+constexpr int FIRST_EPI_WARP = 4;  // warpgroup 0 = {TMA, MMA, 2 idle warps}; the following warpgroups = epilogue
+constexpr int TR_BYTES = 32 * 1024;  // transpose buffers of all epilogue warps: 8 x 4 KB or 16 x 2 KB
+// Epilogue flavours (each its own kernel instantiation, see below).  EPI_BF16W is EPI_BF16 with 16
+// epilogue warps (four per TMEM lane quadrant, one 64-column unit each, 104 registers): the 8-warp
+// epilogue is latency-bound at two warps per scheduler (ncu: 6.9 cycles per issued instruction).
+enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_ANY = 2, EPI_BF16W = 3 };
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == EPI_BF16W ? 16 : 8; }
+__host__ __device__ constexpr int num_threads(int epi) { return (FIRST_EPI_WARP + epi_warps(epi)) * 32; }
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -26,7 +30,7 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = TR_OFFSET + NUM_EPI_WARPS * STAGE_T_BYTES;
+  static constexpr int BAR_OFFSET = TR_OFFSET + TR_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024 align slack
 };
 
@@ -83,7 +87,6 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 //   EPI_BF16 : bf16 output only, 16-byte vector stores (N % 8 == 0, aligned)
 //   EPI_F32  : fp32 output and/or residual (+ optional bf16 copy), vector accesses (N % 4 == 0, aligned)
 //   EPI_ANY  : any shape / alignment (scalar tails); used for the few odd shapes (263 features ...)
-enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_ANY = 2 };
 
 // The epilogue of ONE warp for ONE 128 x BN accumulator tile: TMEM lane quadrant `quad` (rows quad*32 ..
 // +31 of the tile), column chunks of parity `cpar`.  t_addr = TMEM address of (lane quad*32, first column
@@ -102,7 +105,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
   float4* trf = reinterpret_cast<float4*>(tr);
   const bool f32_path = EPI == EPI_F32 || (EPI == EPI_ANY && (epi.out_f32 != nullptr || epi.resid != nullptr));
   const int rsub = lane >> 3, ch = lane & 7;
-  constexpr int NCH = BN / 64;   // 32-column chunks per warp and tile
+  constexpr int NCH = EPI == EPI_BF16W ? 2 : BN / 64;   // 32-column chunks per warp and tile
   const int r = quad * 32 + lane;
   const bool row_ok = r < rows_valid;
   const long m = (long)c_row0 + r;
@@ -123,7 +126,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
   // LDG.128 right after every TMEM load; with 227 KB of the SM configured as shared memory there is
   // practically no L1, so those were L2 round trips on the critical path: ~900 cycles per chunk.)
   // chunk k of this warp -> TMEM chunk index: fp32 path cpar + 2k ; bf16 path 2 (cpar + 2 (k / 2)) + k % 2
-  auto chunk_of = [&](int k) { return f32_path ? cpar + 2 * k : 2 * (cpar + 2 * (k >> 1)) + (k & 1); };
+  auto chunk_of = [&](int k) {
+    return EPI == EPI_BF16W ? 2 * cpar + k : (f32_path ? cpar + 2 * k : 2 * (cpar + 2 * (k >> 1)) + (k & 1));
+  };
   float bias_r[NCH];
 #pragma unroll
   for (int k = 0; k < NCH; ++k) {
@@ -237,6 +242,56 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
           }
         }
         EPI_MARK(3);
+      }
+    }
+  } else if constexpr (EPI == EPI_BF16W) {
+    // ---------------- bf16-only output, 16 warps: this warp owns the 64-column unit `cpar` (0..3) of its
+    // lane quadrant; each 32-column half goes through a 2 KB buffer (32 rows x 64 bytes, 16-byte slots
+    // XOR-swizzled by (row >> 1) & 3: conflict-free writes by row and reads by 2 rows x 4 slots).
+    EPI_MARK(4);
+    mbar_wait(acc_bar, acc_phase);
+    tc_fence_after();
+    EPI_MARK(5);
+    const int n0 = nt * BN + cpar * 64;
+    if (n0 < N) {
+      uint32_t raw[2][32];
+      EPI_MARK(7);
+      tmem_ld32(t_addr + (cpar * 2) * 32, raw[0]);
+      tmem_ld32(t_addr + (cpar * 2 + 1) * 32, raw[1]);
+      tmem_ld_wait();
+      EPI_MARK(0);
+      const int r4 = lane >> 2, c4r = lane & 3;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int nh = n0 + hh * 32;
+        if (nh < N) {
+          float v[32];
+          finish_chunk(raw[hh], bias_r[hh], v);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint4 pk;
+            pk.x = pack2(v[8 * c4], v[8 * c4 + 1]); pk.y = pack2(v[8 * c4 + 2], v[8 * c4 + 3]);
+            pk.z = pack2(v[8 * c4 + 4], v[8 * c4 + 5]); pk.w = pack2(v[8 * c4 + 6], v[8 * c4 + 7]);
+            tr[lane * 4 + (c4 ^ ((lane >> 1) & 3))] = pk;
+          }
+          EPI_MARK(1);
+          __syncwarp();
+          uint4 w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + r4;
+            w[i] = tr[row * 4 + (c4r ^ ((row >> 1) & 3))];
+          }
+          __syncwarp();
+          EPI_MARK(2);
+          const int n = nh + c4r * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + r4;
+            if (row < rmax && n < N) *reinterpret_cast<uint4*>(ob_blk + row * epi.ld_bf16 + n) = w[i];
+          }
+          EPI_MARK(3);
+        }
       }
     }
   } else if constexpr (EPI == EPI_BF16) {

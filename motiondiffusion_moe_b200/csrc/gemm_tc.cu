@@ -39,7 +39,7 @@ namespace {
 
 
 template <int BN, int STAGES, int EPI, int ACT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, int num_m_tiles_host, const int* __restrict__ num_m_tiles_dev,
                const MTile* __restrict__ mtiles, const GemmEpi epi) {
@@ -67,8 +67,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], NUM_EPI_WARPS);
-    mbar_init(&tmem_empty[1], NUM_EPI_WARPS);
+    mbar_init(&tmem_empty[0], epi_warps(EPI));
+    mbar_init(&tmem_empty[1], epi_warps(EPI));
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);
@@ -148,7 +148,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    if constexpr (EPI == EPI_BF16W) {
+      // 640 threads x 96 registers are allocated at launch; warpgroup 0 returns 128 x 56, i.e. +14 per
+      // epilogue thread: 104 is the largest multiple of 8 that can be granted (112 would block forever)
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    }
     // ------------------------------------------------------------ epilogue (8 warps)
     // warp -> TMEM lane quadrant (warp & 3) x column parity: two warps share a quadrant and take
     // alternate column units.  Accumulators arrive with lane == row; bias, activation and row scale
@@ -158,7 +164,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     //   read phase: lane -> (row = 4*i + lane/8, 16-byte chunk = lane%8), i = 0..7.
     const int quad = warp & 3;
     const int cpar = (warp - FIRST_EPI_WARP) >> 2;
-    uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - FIRST_EPI_WARP) * 256;  // 32 rows x 8 chunks
+    uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - FIRST_EPI_WARP) * (EPI == EPI_BF16W ? 128 : 256);
     int acc = 0;
     uint32_t acc_phase = 0;
     long long e_wait = 0, e_work = 0;
@@ -272,12 +278,12 @@ struct SmemLayout2 {
   static constexpr int B_BYTES = HALF_N2 * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = TR_OFFSET + NUM_EPI_WARPS * STAGE_T_BYTES;
+  static constexpr int BAR_OFFSET = TR_OFFSET + TR_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
 template <int STAGES, int EPI, int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(num_threads(EPI), 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 int M, int N, int K, int num_m_tiles_host, const int* __restrict__ num_m_tiles_dev,
                 const MTile* __restrict__ mtiles, const GemmEpi epi) {
@@ -305,8 +311,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 2 * NUM_EPI_WARPS);
-    mbar_init(&tmem_empty[1], 2 * NUM_EPI_WARPS);
+    mbar_init(&tmem_empty[0], 2 * epi_warps(EPI));
+    mbar_init(&tmem_empty[1], 2 * epi_warps(EPI));
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_ptr, 2 * BN2);
@@ -388,11 +394,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #endif
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    if constexpr (EPI == EPI_BF16W) {
+      // 640 threads x 96 registers are allocated at launch; warpgroup 0 returns 128 x 56, i.e. +14 per
+      // epilogue thread: 104 is the largest multiple of 8 that can be granted (112 would block forever)
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    }
     // ------------------------------------------------------------ epilogue (8 warps per CTA, own 128 rows)
     const int quad = warp & 3;
     const int cpar = (warp - FIRST_EPI_WARP) >> 2;
-    uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - FIRST_EPI_WARP) * 256;
+    uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - FIRST_EPI_WARP) * (EPI == EPI_BF16W ? 128 : 256);
     int acc = 0;
     uint32_t acc_phase = 0;
     long long e_wait = 0, e_work = 0;
@@ -503,7 +515,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, in
   int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
   if (num_m_tiles_dev) grid = max_ctas;
   if (grid < 1) grid = 1;
-  gemm_tc_kernel<BN, STAGES, EPI, ACT><<<grid, NUM_THREADS, L::TOTAL, stream>>>(
+  gemm_tc_kernel<BN, STAGES, EPI, ACT><<<grid, num_threads(EPI), L::TOTAL, stream>>>(
       ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
@@ -523,7 +535,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, i
   long clusters = max_ctas / 2;
   if (!num_m_tiles_dev && work < clusters) clusters = work;
   if (clusters < 1) clusters = 1;
-  gemm_tc2_kernel<STAGES, EPI, ACT><<<(unsigned)(2 * clusters), NUM_THREADS, L::TOTAL, stream>>>(
+  gemm_tc2_kernel<STAGES, EPI, ACT><<<(unsigned)(2 * clusters), num_threads(EPI), L::TOTAL, stream>>>(
       ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
@@ -581,6 +593,18 @@ extern "C" MDM_API int mdm_gemm_bf16(const void* A, int lda, long a_rows, const 
     if (wide) return launch<256, 4, E_, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st); \
     return launch<128, 6, E_, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);          \
   } while (0)
+  static const int epiw_env = [] { const char* e = getenv("MDM_GEMM_EPIW"); return e ? atoi(e) : 1; }();
+  if (kind == EPI_BF16 && epiw_env && (wide || pair)) {   // 256-wide tiles: 16 epilogue warps
+#define MDM_GOW(A_)                                                                                                  \
+  do {                                                                                                               \
+    if (pair) return launch2<6, EPI_BF16W, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st); \
+    return launch<256, 4, EPI_BF16W, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);      \
+  } while (0)
+    if (act == MDM_ACT_NONE) MDM_GOW(MDM_ACT_NONE);
+    if (act == MDM_ACT_GELU) MDM_GOW(MDM_ACT_GELU);
+    if (act == MDM_ACT_SILU) MDM_GOW(MDM_ACT_SILU);
+#undef MDM_GOW
+  }
   if (kind == EPI_BF16 && act == MDM_ACT_NONE) MDM_GO(EPI_BF16, MDM_ACT_NONE);
   if (kind == EPI_BF16 && act == MDM_ACT_GELU) MDM_GO(EPI_BF16, MDM_ACT_GELU);
   if (kind == EPI_BF16 && act == MDM_ACT_SILU) MDM_GO(EPI_BF16, MDM_ACT_SILU);
