@@ -13,6 +13,21 @@
 // which is why they live here rather than in the tcgen05 GEMM.
 #include "common.cuh"
 
+#ifdef MDM_ATTN_PROFILE
+__device__ unsigned long long g_fa_phase[16];   // cycles per phase summed over CTAs (thread 0)
+extern "C" MDM_API int mdm_debug_read_fa_phase(unsigned long long* host, int reset) {
+  unsigned long long z[16] = {0};
+  if (cudaMemcpyFromSymbol(host, g_fa_phase, sizeof(z)) != cudaSuccess) return 2;
+  if (reset && cudaMemcpyToSymbol(g_fa_phase, z, sizeof(z)) != cudaSuccess) return 2;
+  return 0;
+}
+#define FA_MARK(k) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_fa_phase[k], (unsigned long long)(n_ - fa_t_)); fa_t_ = n_; } } while (0)
+#define FA_INIT() long long fa_t_ = clock64()
+#else
+#define FA_MARK(k) do { } while (0)
+#define FA_INIT() do { } while (0)
+#endif
+
 namespace {
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
@@ -73,6 +88,7 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
   const int nstrips = Tp / 16;
 
   constexpr int NTHR = NW * 32;
+  FA_INIT();
   constexpr int CPR = HD / 8;   // 16-byte chunks per row
   // ---- S0a: the (sequence, head) slab goes to shared memory as two groups of asynchronous 16-byte
   // copies: k and v first, q second, so that q is still in flight while k and v are normalised.
@@ -107,6 +123,7 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
   for (int i = tid; i < HD; i += NTHR) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }
   asm volatile("cp.async.wait_group 1;" ::: "memory");   // k, v have landed
   __syncthreads();
+  FA_MARK(0);
 
   // ---- S1: per-row LayerNorm (+ L2 norm for q, k) of the 0.1-scaled rows, in place.
   // Eight lanes per row (EPT = hd/8 elements each, 16-byte accesses), four rows per warp pass: the
@@ -180,8 +197,10 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
   ln_rows(Vs, false);
   asm volatile("cp.async.wait_group 0;" ::: "memory");   // q has landed
   __syncthreads();
+  FA_MARK(1);
   ln_rows(Qs, true);
   __syncthreads();
+  FA_MARK(2);
 
   // ---- S2: feature maps in place: X' = exp(clamp(X . P)) * 0.1 ; key rows t >= len are zeroed.
   // Key strips first; the query strips (second sync-separated round) also produce the per-frame
@@ -232,6 +251,7 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
       }
     }
     __syncthreads();
+  FA_MARK(3);
   }
 
   // ---- S3: kv[m][n] = 0.1 * sum_t K'[t][m] V[t][n]
@@ -265,6 +285,7 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
     }
   }
   __syncthreads();
+  FA_MARK(4);
 
   // ---- S4: out = LN((Q' kv) * 0.1 / den), staged in the strip's own Qs rows, then coalesced store
   for (int strip = warp; strip < nstrips; strip += NW) {
@@ -324,6 +345,7 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
             *reinterpret_cast<const uint4*>(Qs + (r0 + r) * LDS + c * 8);
     }
   }
+  FA_MARK(7);
 }
 
 template <int HD>
