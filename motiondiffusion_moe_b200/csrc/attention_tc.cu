@@ -11,6 +11,7 @@
 // The three matrix products use mma.sync.m16n8k16 (bf16 in, fp32 accumulate) fed by ldmatrix from
 // padded (conflict-free) shared-memory tiles.  They are small per-(b,h) products (<= 208x128x128),
 // which is why they live here rather than in the tcgen05 GEMM.
+#include <stdlib.h>
 #include "common.cuh"
 
 #ifdef MDM_ATTN_PROFILE
@@ -348,6 +349,331 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
   FA_MARK(7);
 }
 
+// ---------------------------------------------------------------------------------------------
+// FastAttention, streamed variant for hd = 128: two CTAs per SM instead of one.
+// The one-CTA-per-(sequence, head) kernel above keeps q, k, v and P^T resident (206 KB) and runs its
+// phases back to back with the memory system idle during the math.  Here only Q' (all frames) and P^T
+// stay resident (91 KB); k and v stream through a double-buffered 16-frame window:
+//   per window: LayerNorm/L2 of the 32 rows -> K'^T = exp(P^T K^T) as the TRANSPOSED product, so that warp
+//   w holds K'^T[16 w .. 16 w + 15][t] in accumulator fragments, which are exactly the A fragments of
+//   kv[16 w .., :] += K'^T V (no shared-memory round trip of K'), and the per-frame denominator
+//   sum_m q'[t,m] k'[t,m] is taken from the same fragments.
+// kv (128 x 128 fp32) lives in registers across the windows (64 per thread), then replaces P^T in
+// shared memory for out = LN(Q' kv * 0.1 / den).  109 KB of shared memory, 256 threads, <= 128 registers.
+__global__ void __launch_bounds__(256, 2)
+fastattn_stream_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, const float* __restrict__ nw,
+                       const float* __restrict__ nb, const int64_t* __restrict__ length, int length_shift, int H,
+                       int T, int Tp, bf16* __restrict__ out) {
+  constexpr int HD = 128, LDS = HD + 8, KS = HD / 16, NT = HD / 8, CPR = HD / 8, NW = 8, CR = 16, EPT = HD / 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem);                  // [Tp][LDS]  q -> q'
+  bf16* Ps = Qs + Tp * LDS;                                  // [HD][LDS]  P^T, later kv
+  bf16* KV = Ps + HD * LDS;                                  // [2][2 * CR][LDS]  window: 16 k rows, 16 v rows
+  float* den_part = reinterpret_cast<float*>(KV + 2 * 2 * CR * LDS);   // [2][NW][CR]
+  float* den_s = den_part + 2 * NW * CR;                     // [Tp]
+  float* nw_s = den_s + Tp;
+  float* nb_s = nw_s + HD;
+
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int D = H * HD;
+  const int len = length ? (int)min((long)T, (long)(length[b] >> length_shift)) : T;
+  const int nstrips = Tp / 16, NC = Tp / CR;
+  FA_INIT();
+
+  auto load_window = [&](int c) {          // frames [16 c, 16 c + 16) of k and v -> buffer c & 1
+    bf16* dst0 = KV + (c & 1) * 2 * CR * LDS;
+    for (int i = tid; i < 2 * CR * CPR; i += 256) {
+      const int w = i / (CR * CPR), rem = i - w * CR * CPR, r = rem / CPR, cc = rem - r * CPR;
+      const int t = c * CR + r;
+      bf16* dst = dst0 + (w * CR + r) * LDS + cc * 8;
+      if (t < T) cp_async16(dst, qkv + ((long)(b * T + t)) * 3 * D + (w + 1) * D + h * HD + cc * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // ---- S0: q (all frames) and the first two k/v windows in flight; P^T as bf16; LN affine
+  for (int i = tid; i < T * CPR; i += 256) {
+    const int t = i / CPR, c = i - t * CPR;
+    cp_async16(Qs + t * LDS + c * 8, qkv + ((long)(b * T + t)) * 3 * D + h * HD + c * 8);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < (Tp - T) * CPR; i += 256) {
+    const int t = T + i / CPR, c = i % CPR;
+    *reinterpret_cast<uint4*>(Qs + t * LDS + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  load_window(0);
+  if (NC > 1) load_window(1); else asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < HD * HD / 4; i += 256) {
+    const int n = i % HD, m4 = i / HD;
+    const float4 p4 = __ldg(reinterpret_cast<const float4*>(P + n * HD + 4 * m4));
+    Ps[(4 * m4) * LDS + n] = __float2bfloat16_rn(p4.x);
+    Ps[(4 * m4 + 1) * LDS + n] = __float2bfloat16_rn(p4.y);
+    Ps[(4 * m4 + 2) * LDS + n] = __float2bfloat16_rn(p4.z);
+    Ps[(4 * m4 + 3) * LDS + n] = __float2bfloat16_rn(p4.w);
+  }
+  for (int i = tid; i < HD; i += 256) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }
+  asm volatile("cp.async.wait_group 2;" ::: "memory");   // q has landed (the two windows may still fly)
+  __syncthreads();
+  FA_MARK(0);
+
+  // ---- row LayerNorm (+ L2) of the 0.1-scaled rows, in place: 8 lanes per row, 4 rows per warp pass
+  const int sub = lane & 7, rsub4 = lane >> 3;
+  float wv[EPT], bv[EPT];
+#pragma unroll
+  for (int cc = 0; cc < EPT / 8; ++cc)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      wv[cc * 8 + i] = nw_s[cc * 64 + sub * 8 + i];
+      bv[cc * 8 + i] = nb_s[cc * 64 + sub * 8 + i];
+    }
+  auto ln_row = [&](bf16* row, bool l2, bool valid) {
+    float x[EPT];
+#pragma unroll
+    for (int cc = 0; cc < EPT / 8; ++cc) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(row + cc * 64);
+      const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[i]);
+        x[cc * 8 + 2 * i] = __low2float(p2) * 0.1f;
+        x[cc * 8 + 2 * i + 1] = __high2float(p2) * 0.1f;
+      }
+    }
+    float sm = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) sm += x[i];
+    sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+    sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+    sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+    const float mean = sm / (float)HD;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) { const float d = x[i] - mean; q = fmaf(d, d, q); }
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 4);
+    const float rstd = rsqrtf(q / (float)HD + 1e-5f);
+    float n2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      x[i] = (x[i] - mean) * rstd * wv[i] + bv[i];
+      n2 = fmaf(x[i], x[i], n2);
+    }
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
+    float inv = l2 ? 1.0f / fmaxf(sqrtf(n2), 1e-12f) : 1.0f;
+    if (!valid) inv = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < EPT / 8; ++cc) {
+      uint4 pk;
+      pk.x = pack_bf16(x[cc * 8] * inv, x[cc * 8 + 1] * inv);
+      pk.y = pack_bf16(x[cc * 8 + 2] * inv, x[cc * 8 + 3] * inv);
+      pk.z = pack_bf16(x[cc * 8 + 4] * inv, x[cc * 8 + 5] * inv);
+      pk.w = pack_bf16(x[cc * 8 + 6] * inv, x[cc * 8 + 7] * inv);
+      *reinterpret_cast<uint4*>(row + cc * 64) = pk;
+    }
+  };
+  for (int t = warp * 4 + rsub4; t < Tp; t += 4 * NW) ln_row(Qs + t * LDS + sub * 8, true, t < T);
+  __syncthreads();
+  FA_MARK(1);
+
+  // ---- query feature map in place: Q' = exp(clamp(Q . P)) * 0.1
+  for (int job = warp; job < nstrips; job += NW) {
+    const int r0 = job * 16;
+    float c[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(a, Qs + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t bb[4];
+        ldsm_x4(bb, Ps + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
+        mma16816(c[2 * np], a, bb[0], bb[1]);
+        mma16816(c[2 * np + 1], a, bb[2], bb[3]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = nt * 8 + 2 * tq;
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g) * LDS + col) = pack_bf16(expfeat(c[nt][0]), expfeat(c[nt][1]));
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g + 8) * LDS + col) = pack_bf16(expfeat(c[nt][2]), expfeat(c[nt][3]));
+    }
+  }
+  __syncthreads();
+  FA_MARK(2);
+
+  // ---- stream the k / v windows: kv[16 warp .. +15][:] accumulates in registers
+  const int m0 = warp * 16;
+  float acc[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int c = 0; c < NC; ++c) {
+    bf16* Kc = KV + (c & 1) * 2 * CR * LDS;
+    bf16* Vc = Kc + CR * LDS;
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // window c has landed (c + 1 may still fly)
+    __syncthreads();
+    {
+      const int r = warp * 4 + rsub4;                        // rows 0..15: k, 16..31: v (warp-uniform kind)
+      ln_row(Kc + r * LDS + sub * 8, r < CR, c * CR + (r & (CR - 1)) < T);
+    }
+    if (c > 0 && tid < CR) {                                 // denominator of the previous window
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += den_part[(((c - 1) & 1) * NW + w) * CR + tid];
+      den_s[(c - 1) * CR + tid] = fmaxf(s, 1e-6f);
+    }
+    __syncthreads();
+    // K'^T[m0.., t] = exp(clamp(P^T[m0.., :] . K[t, :])) * 0.1, masked for t >= len
+    float kc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) kc[i][0] = kc[i][1] = kc[i][2] = kc[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t a[4], bb[4];
+      ldsm_x4(a, Ps + (m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
+      ldsm_x4(bb, Kc + ((lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
+      mma16816(kc[0], a, bb[0], bb[1]);
+      mma16816(kc[1], a, bb[2], bb[3]);
+    }
+    uint32_t ka[4];
+    float dp[4];                                             // denominators of frames nt*8 + 2 tq + {0,1}
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int tl = nt * 8 + 2 * tq, t0 = c * CR + tl;
+      const float f00 = t0 < len ? expfeat(kc[nt][0]) : 0.f, f01 = t0 + 1 < len ? expfeat(kc[nt][1]) : 0.f;
+      const float f10 = t0 < len ? expfeat(kc[nt][2]) : 0.f, f11 = t0 + 1 < len ? expfeat(kc[nt][3]) : 0.f;
+      const uint32_t lo = pack_bf16(f00, f01), hi = pack_bf16(f10, f11);   // rows m0+g / m0+g+8
+      ka[nt * 2] = lo;
+      ka[nt * 2 + 1] = hi;
+      const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&lo);
+      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&hi);
+      const bf16* q0 = Qs + t0 * LDS + m0 + g;                // q'[t0][m0+g], q'[t0][m0+g+8], next frame +LDS
+      dp[nt * 2] = __low2float(l2) * __bfloat162float(q0[0]) + __low2float(h2) * __bfloat162float(q0[8]);
+      dp[nt * 2 + 1] = __high2float(l2) * __bfloat162float(q0[LDS]) + __high2float(h2) * __bfloat162float(q0[LDS + 8]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                            // sum over the 8 row groups g (lanes 4 apart)
+      dp[i] += __shfl_xor_sync(0xffffffffu, dp[i], 4);
+      dp[i] += __shfl_xor_sync(0xffffffffu, dp[i], 8);
+      dp[i] += __shfl_xor_sync(0xffffffffu, dp[i], 16);
+    }
+    if (g == 0) {
+      float* dst = den_part + ((c & 1) * NW + warp) * CR;
+      dst[2 * tq] = dp[0]; dst[2 * tq + 1] = dp[1]; dst[8 + 2 * tq] = dp[2]; dst[8 + 2 * tq + 1] = dp[3];
+    }
+    // kv[m0.., :] += K'^T[m0.., t] . V[t, :]   (accumulator fragments reused as A fragments)
+    const uint32_t afr[4] = {ka[0], ka[1], ka[2], ka[3]};
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t bb[4];
+      ldsm_x4_t(bb, Vc + ((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8);
+      mma16816(acc[2 * np], afr, bb[0], bb[1]);
+      mma16816(acc[2 * np + 1], afr, bb[2], bb[3]);
+    }
+    __syncthreads();                                         // every warp is done with window buffer c & 1
+    if (c + 2 < NC) load_window(c + 2); else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  FA_MARK(3);
+  // P^T is dead: kv (x 0.1) takes its place; last window's denominators
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int col = nt * 8 + 2 * tq;
+    *reinterpret_cast<uint32_t*>(Ps + (m0 + g) * LDS + col) = pack_bf16(acc[nt][0] * 0.1f, acc[nt][1] * 0.1f);
+    *reinterpret_cast<uint32_t*>(Ps + (m0 + g + 8) * LDS + col) = pack_bf16(acc[nt][2] * 0.1f, acc[nt][3] * 0.1f);
+  }
+  if (tid < CR) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += den_part[(((NC - 1) & 1) * NW + w) * CR + tid];
+    den_s[(NC - 1) * CR + tid] = fmaxf(s, 1e-6f);
+  }
+  __syncthreads();
+  FA_MARK(4);
+
+  // ---- out = LN((Q' kv) * 0.1 / den), staged in the strip's own Qs rows, then coalesced store
+  for (int strip = warp; strip < nstrips; strip += NW) {
+    const int r0 = strip * 16;
+    float o[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(a, Qs + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t bb[4];
+        ldsm_x4_t(bb, Ps + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8);
+        mma16816(o[2 * np], a, bb[0], bb[1]);
+        mma16816(o[2 * np + 1], a, bb[2], bb[3]);
+      }
+    }
+    const float d0 = den_s[r0 + g], d1 = den_s[r0 + g + 8];
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      o[nt][0] = (o[nt][0] * 0.1f) / d0; o[nt][1] = (o[nt][1] * 0.1f) / d0;
+      o[nt][2] = (o[nt][2] * 0.1f) / d1; o[nt][3] = (o[nt][3] * 0.1f) / d1;
+      s0 += o[nt][0] + o[nt][1];
+      s1 += o[nt][2] + o[nt][3];
+    }
+    const float mean0 = quad_sum(s0) / (float)HD, mean1 = quad_sum(s1) / (float)HD;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float d;
+      d = o[nt][0] - mean0; q0 = fmaf(d, d, q0);
+      d = o[nt][1] - mean0; q0 = fmaf(d, d, q0);
+      d = o[nt][2] - mean1; q1 = fmaf(d, d, q1);
+      d = o[nt][3] - mean1; q1 = fmaf(d, d, q1);
+    }
+    const float rstd0 = rsqrtf(quad_sum(q0) / (float)HD + 1e-5f);
+    const float rstd1 = rsqrtf(quad_sum(q1) / (float)HD + 1e-5f);
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = nt * 8 + 2 * tq;
+      const float w0 = nw_s[col], w1 = nw_s[col + 1], b0 = nb_s[col], b1 = nb_s[col + 1];
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g) * LDS + col) =
+          pack_bf16((o[nt][0] - mean0) * rstd0 * w0 + b0, (o[nt][1] - mean0) * rstd0 * w1 + b1);
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g + 8) * LDS + col) =
+          pack_bf16((o[nt][2] - mean1) * rstd1 * w0 + b0, (o[nt][3] - mean1) * rstd1 * w1 + b1);
+    }
+    __syncwarp();
+    for (int i = lane; i < 16 * CPR; i += 32) {
+      const int r = i / CPR, c = i - r * CPR;
+      if (r0 + r < T)
+        *reinterpret_cast<uint4*>(out + ((long)(b * T + r0 + r)) * D + h * HD + c * 8) =
+            *reinterpret_cast<const uint4*>(Qs + (r0 + r) * LDS + c * 8);
+    }
+  }
+  FA_MARK(7);
+}
+
+int launch_fastattn_stream(const bf16* qkv, const float* P, const float* nw, const float* nb, const int64_t* length,
+                           int shift, int B, int H, int T, bf16* out, cudaStream_t st) {
+  constexpr int HD = 128, LDS = HD + 8;
+  const int Tp = (T + 15) / 16 * 16;
+  const size_t smem = (size_t)(Tp + HD + 4 * 16) * LDS * 2 + sizeof(float) * (2 * 8 * 16 + Tp + 2 * HD);
+  if (smem > 113 * 1024) return MDM_ERR_UNSUPPORTED;      // two CTAs per SM or not at all
+  static size_t attr = 0;
+  if (smem > attr) {
+    if (cudaFuncSetAttribute(fastattn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return MDM_ERR_CUDA;
+    attr = smem;
+  }
+  fastattn_stream_kernel<<<B * H, 256, smem, st>>>(qkv, P, nw, nb, length, shift, H, T, Tp, out);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
 template <int HD>
 int launch_fastattn(const bf16* qkv, const float* P, const float* nw, const float* nb, const int64_t* length,
                     int shift, int B, int H, int T, bf16* out, cudaStream_t st) {
@@ -646,7 +972,14 @@ int mdm_fastattn_tc(const void* qkv, const float* P, const float* norm_w, const 
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
   bf16* o = reinterpret_cast<bf16*>(out);
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(o) & 15)) return MDM_ERR_UNSUPPORTED;
-  if (hd == 128) return launch_fastattn<128>(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, st);
+  if (hd == 128) {
+    static const int stream_env = [] { const char* e = getenv("MDM_FA_STREAM"); return e ? atoi(e) : 1; }();
+    if (stream_env) {
+      const int r = launch_fastattn_stream(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, st);
+      if (r != MDM_ERR_UNSUPPORTED) return r;
+    }
+    return launch_fastattn<128>(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, st);
+  }
   if (hd == 64) return launch_fastattn<64>(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, st);
   return MDM_ERR_UNSUPPORTED;
 }

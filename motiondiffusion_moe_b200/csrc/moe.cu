@@ -200,46 +200,75 @@ moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restr
   }
 }
 
-__global__ void __launch_bounds__(32)
+// One warp per expert group: lane l owns a contiguous run of blocks (two passes: run totals, warp
+// exclusive scan, per-block bases), then warp 0 does the segment scan over the groups.  (The first
+// version walked the 196 blocks of every group with a single lane: 15-20 us per call.)
+__global__ void __launch_bounds__(1024)
 moe_scan_kernel(const int* __restrict__ blk_hist, const float* __restrict__ blk_imp, int nblk, int G, int E,
                 int F, int D, int* __restrict__ blk_base, int* __restrict__ seg_offsets,
                 MTile* __restrict__ tiles_up, MTile* __restrict__ tiles_down, int* __restrict__ num_tiles,
                 float* __restrict__ usage, float* __restrict__ importance) {
-  const int g = threadIdx.x;
-  int total = 0, top1 = 0;
-  float imp = 0.f;
+  __shared__ int total_s[MAX_G];
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g < G) {
-    for (int b = 0; b < nblk; ++b) {
-      blk_base[(long)b * G + g] = total;
-      total += blk_hist[((long)b * 2) * G + g];
+    const int per = (nblk + 31) / 32, b0 = lane * per, b1 = min(nblk, b0 + per);
+    int tot = 0, top1 = 0;
+    float imp = 0.f;
+    for (int b = b0; b < b1; ++b) {
+      tot += blk_hist[((long)b * 2) * G + g];
       top1 += blk_hist[((long)b * 2 + 1) * G + g];
       imp += blk_imp[(long)b * G + g];
     }
-    if (usage) usage[g] += (float)top1;
-    if (importance) importance[g] += imp;
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    int run = incl - tot;
+    for (int b = b0; b < b1; ++b) {
+      blk_base[(long)b * G + g] = run;
+      run += blk_hist[((long)b * 2) * G + g];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) top1 += __shfl_xor_sync(0xffffffffu, top1, o);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    // importance: per-lane runs in block order, then the 32 run sums in lane order (a fixed order:
+    // the counter is deterministic from launch to launch)
+    float imp_tot = 0.f;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) imp_tot += __shfl_sync(0xffffffffu, imp, l);
+    if (lane == 0) {
+      total_s[g] = total;
+      if (usage) usage[g] += (float)top1;
+      if (importance) importance[g] += imp_tot;
+    }
   }
-  const int padded = g < G ? ((total + 127) / 128) * 128 : 0;
-  // exclusive scan of padded sizes across the warp
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int gg = threadIdx.x;
+  const int total = gg < G ? total_s[gg] : 0;
+  const int padded = ((total + 127) / 128) * 128;
   int incl = padded;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (g >= o) incl += n;
+    if (gg >= o) incl += n;
   }
   const int off = incl - padded;
-  if (g < G) {
-    seg_offsets[g] = off;
+  if (gg < G) {
+    seg_offsets[gg] = off;
     const int ntile = padded / 128, tile0 = off / 128;
     for (int i = 0; i < ntile; ++i) {
       const int rows = min(128, total - i * 128);
-      MTile u; u.a_row0 = off + i * 128; u.c_row0 = u.a_row0; u.w_row0 = g * F; u.rows_valid = rows;
-      MTile d = u; d.w_row0 = g * D;
+      MTile u; u.a_row0 = off + i * 128; u.c_row0 = u.a_row0; u.w_row0 = gg * F; u.rows_valid = rows;
+      MTile d = u; d.w_row0 = gg * D;
       tiles_up[tile0 + i] = u;
       tiles_down[tile0 + i] = d;
     }
   }
   const int all = __shfl_sync(0xffffffffu, incl, 31);
-  if (g == 0) { seg_offsets[G] = all; *num_tiles = all / 128; }
+  if (gg == 0) { seg_offsets[G] = all; *num_tiles = all / 128; }
 }
 
 template <int VPT, typename TO>
@@ -418,7 +447,7 @@ extern "C" MDM_API int mdm_moe_scan(const int* blk_hist, const float* blk_imp, c
     return MDM_ERR_ARG;
   if (K != 2 || NB * E > MAX_G) return MDM_ERR_UNSUPPORTED;
   const int nblk = (int)((N + TOK_PER_BLK - 1) / TOK_PER_BLK);
-  moe_scan_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  moe_scan_kernel<<<1, 32 * (NB * E), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       blk_hist, blk_imp, nblk, NB * E, E, F, D, blk_base, seg_offsets, reinterpret_cast<MTile*>(tiles_up),
       reinterpret_cast<MTile*>(tiles_down), num_tiles, usage, importance);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;

@@ -37,7 +37,7 @@ def test_emulated_ranks_match_local_moe_bit_exact(dtype, R, E, n_seq, T):
         assert torch.equal(inst[r].idx, idx) and torch.equal(inst[r].vals, vals)      # routing bit-exact
         assert torch.equal(outs[r], res)                                               # output bit-exact
         assert torch.equal(inst[r].usage, 2 * usage)                                   # two calls accumulated
-        assert torch.allclose(inst[r].importance, 2 * importance, rtol=1e-6)
+        assert torch.allclose(inst[r].importance, 2 * importance, rtol=1e-5)   # different (fixed) summation orders
     # every owner received exactly the rows routed to its experts
     total_rows = sum(int(i.cnt[i.me].sum()) for i in inst)
     assert total_rows == R * n_seq * T * 4

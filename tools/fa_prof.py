@@ -23,7 +23,7 @@ for T in (196, 98):
     torch.cuda.synchronize()
     lib.mdm_debug_read_fa_phase(ph, 1)
     n = NSEQ * H
-    names = ["S0 load k,v + P^T", "S1 LN k,v (+wait q)", "S1 LN q", "S2 features (+den)", "S3 kv", "", "", "S4 apply + LN + store"]
+    names = (["S0 load q + P^T", "LN q", "S2 q features", "k/v window loop", "kv -> smem", "", "", "S4 apply + LN + store"] if os.environ.get("MDM_FA_STREAM", "1") != "0" else ["S0 load k,v + P^T", "S1 LN k,v (+wait q)", "S1 LN q", "S2 features (+den)", "S3 kv", "", "", "S4 apply + LN + store"])
     tot = sum(ph[i] for i in range(8))
     print("T=%d: cycles per CTA %.0f" % (T, tot / n))
     for i, nm in enumerate(names):
