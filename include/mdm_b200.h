@@ -224,9 +224,10 @@ MDM_API int mdm_ep_dispatch(const float* x, long N, int D, int NB, int E, int K,
 MDM_API int mdm_ep_combine_film(const MdmEpPeers* peers, int dt, const int* perm, long N, int D, int NBK,
                                 int cap, const float* ln_w, const float* ln_b, const float* film,
                                 int rows_per_seq, void* out, void* stream);
-/* Flag barrier of the R ranks in stream order (epochs must increase by one per call on every rank);
- * *err is set to 1 if a peer does not arrive within ~2 s. */
-MDM_API int mdm_ep_barrier(const MdmEpPeers* peers, int R, int me, unsigned epoch, int* err, void* stream);
+/* Flag barrier of the R ranks in stream order.  *epoch_ctr (device memory, start at 0, private to this
+ * rank) is incremented by the kernel, so the call can be captured in a CUDA graph and replayed; every rank
+ * must execute the same number of barriers.  *err is set to 1 if a peer does not arrive within ~2 s. */
+MDM_API int mdm_ep_barrier(const MdmEpPeers* peers, int R, int me, unsigned* epoch_ctr, int* err, void* stream);
 /* CUDA IPC: 64-byte handle of the allocation containing ptr (+ byte offset of ptr inside it); open /
  * close a peer's handle (returns the base of the mapped allocation). */
 MDM_API int mdm_ipc_get_handle(const void* ptr, void* handle64, long* offset);

@@ -73,7 +73,7 @@ _SIGS = {
     "mdm_ep_scan": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "mdm_ep_dispatch": [_P, _L, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, C.POINTER(EpPeers), _I, _P, _P],
     "mdm_ep_combine_film": [C.POINTER(EpPeers), _I, _P, _L, _I, _I, _I, _P, _P, _P, _I, _P, _P],
-    "mdm_ep_barrier": [C.POINTER(EpPeers), _I, _I, C.c_uint, _P, _P],
+    "mdm_ep_barrier": [C.POINTER(EpPeers), _I, _I, _P, _P, _P],
     "mdm_ipc_get_handle": [_P, _P, C.POINTER(C.c_long)],
     "mdm_ipc_open_handle": [_P, C.POINTER(C.c_void_p)],
     "mdm_ipc_close_handle": [_P],

@@ -192,11 +192,16 @@ ep_combine_film_kernel(MdmEpPeers peers, const int* __restrict__ perm, long N, i
 
 // Flag barrier across the R ranks of one node.  Thread p publishes `epoch` into slot [me] of rank p's
 // flag array (release, system scope) and then waits until rank p has published >= epoch into this
-// rank's slot [p].  Epochs only grow, so no reset is needed.  The spin is bounded (~2 s): on expiry the
+// rank's slot [p].  Epochs only grow (a device-side counter per rank), so no reset is needed.  The spin is bounded (~2 s): on expiry the
 // error word is set and the kernel returns, so a dead peer cannot hang the GPU.
 __global__ void __launch_bounds__(32)
-ep_barrier_kernel(MdmEpPeers peers, int R, int me, unsigned epoch, int* __restrict__ err) {
+ep_barrier_kernel(MdmEpPeers peers, int R, int me, unsigned* __restrict__ epoch_ctr, int* __restrict__ err) {
   const int p = threadIdx.x;
+  // the epoch lives in device memory and advances by one per barrier, so that a captured CUDA graph
+  // (fixed kernel arguments) can be replayed: every rank executes the same sequence of barriers
+  unsigned epoch = 0;
+  if (p == 0) epoch = ++(*epoch_ctr);
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
   __threadfence_system();
   if (p < R) {
     unsigned* remote = peers.flags[p] + me;
@@ -298,9 +303,10 @@ extern "C" MDM_API int mdm_ep_combine_film(const MdmEpPeers* peers, int dt, cons
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
-extern "C" MDM_API int mdm_ep_barrier(const MdmEpPeers* peers, int R, int me, unsigned epoch, int* err, void* stream) {
-  if (!peers || !err || R < 1 || R > MDM_EP_MAX_RANKS || me < 0 || me >= R) return MDM_ERR_ARG;
-  ep_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*peers, R, me, epoch, err);
+extern "C" MDM_API int mdm_ep_barrier(const MdmEpPeers* peers, int R, int me, unsigned* epoch_ctr, int* err,
+                                      void* stream) {
+  if (!peers || !err || !epoch_ctr || R < 1 || R > MDM_EP_MAX_RANKS || me < 0 || me >= R) return MDM_ERR_ARG;
+  ep_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*peers, R, me, epoch_ctr, err);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 

@@ -86,23 +86,32 @@ class ExpertParallelFFN:
         self.perm = z(N, NB * 2, dtype=i32)
         self.usage = z(self.GT)
         self.importance = z(self.GT)
-        self.epoch = 0
+        self.epoch_ctr = z(1, dtype=i32)      # device-side barrier epoch (graph-replay safe)
         self.peers = None
         self._opened = []
         self.group = None
 
     # ------------------------------------------------------------------ construction
-    def set_weights(self, ln_w, ln_b, gate_w, gate_b, w1, b1, w2, b2):
+    def shard_weights(self, ln_w, ln_b, gate_w, gate_b, w1, b1, w2, b2):
         """Full (all-expert) tensors in the single-GPU packed layout (MotionTransformer._pack): w1 [GT*F, D],
-        b1 [GT*F], w2 [GT*D, F], b2 [GT*D], group g = branch * E + expert.  Only the owned experts are kept."""
+        b1 [GT*F], w2 [GT*D, F], b2 [GT*D], group g = branch * E + expert.  Returns the dict of tensors this
+        rank needs: gate / LayerNorm of every expert (routing is local), FFN weights of the owned experts only."""
         D, F, E, EPR = self.D, self.F, self.E, self.EPR
         own = [g for g in range(self.GT) if owner_of(g % E, E, self.R) == self.me]
         own.sort(key=lambda g: (g // E) * EPR + (g % E) % EPR)
         sel = lambda t, width: torch.cat([t[g * width:(g + 1) * width] for g in own]).contiguous()
-        self.ln_w, self.ln_b = ln_w.float().contiguous(), ln_b.float().contiguous()
-        self.gate_w, self.gate_b = gate_w.float().contiguous(), gate_b.float().contiguous()
-        self.w1, self.b1 = sel(w1, F).to(self.dtype), sel(b1, F).float()
-        self.w2, self.b2 = sel(w2, D).to(self.dtype), sel(b2, D).float()
+        return dict(ln_w=ln_w.float().contiguous(), ln_b=ln_b.float().contiguous(),
+                    gate_w=gate_w.float().contiguous(), gate_b=gate_b.float().contiguous(),
+                    w1=sel(w1, F).to(self.dtype), b1=sel(b1, F).float(),
+                    w2=sel(w2, D).to(self.dtype), b2=sel(b2, D).float())
+
+    def use_weights(self, wd):
+        """Select the (already sharded) weights of the MoE layer the next calls belong to."""
+        for k, t in wd.items():
+            setattr(self, k, t)
+
+    def set_weights(self, ln_w, ln_b, gate_w, gate_b, w1, b1, w2, b2):
+        self.use_weights(self.shard_weights(ln_w, ln_b, gate_w, gate_b, w1, b1, w2, b2))
 
     def _fill_peers(self, ptrs):
         """ptrs[p] = dict(xp=, rowscale=, yp=, cnt=, flags=) of device addresses valid on this GPU."""
@@ -164,16 +173,19 @@ class ExpertParallelFFN:
         self._opened = []
 
     # ------------------------------------------------------------------ phases of one MoE call
-    def phase_gate(self, x):
-        """x [N, D] fp32 (the residual stream before the MoE FFN)."""
-        ops._c(x)
+    def phase_gate(self, x, usage=None, importance=None):
+        """x [N, D] fp32 (the residual stream before the MoE FFN); usage / importance: the [NB*E] counter
+        rows of this layer (default: the instance's own)."""
+        ops._c(x, usage, importance)
+        usage = self.usage if usage is None else usage
+        importance = self.importance if importance is None else importance
         N, D, NB, E = self.N, self.D, self.NB, self.E
         ops.moe_gate(x, N, D, NB, E, self.ln_w, self.ln_b, self.gate_w, self.gate_b, self.idx, self.vals, self.stats,
                      self.hist, self.imp)
         lib = _lib.load()
         _lib.check(lib.mdm_ep_counts(self.hist.data_ptr(), self.imp.data_ptr(), N, NB, E, 2, self.R, self.me,
-                                     C.byref(self.peers), self.blk_base.data_ptr(), self.usage.data_ptr(),
-                                     self.importance.data_ptr(), ops._stream()), "mdm_ep_counts")
+                                     C.byref(self.peers), self.blk_base.data_ptr(), usage.data_ptr(),
+                                     importance.data_ptr(), ops._stream()), "mdm_ep_counts")
         self._x = x
 
     def phase_dispatch(self):
@@ -208,14 +220,13 @@ class ExpertParallelFFN:
                    "mdm_ep_combine_film")
 
     def barrier(self):
-        self.epoch += 1
-        _lib.check(_lib.load().mdm_ep_barrier(C.byref(self.peers), self.R, self.me, self.epoch, self.err.data_ptr(),
-                                              ops._stream()), "mdm_ep_barrier")
+        _lib.check(_lib.load().mdm_ep_barrier(C.byref(self.peers), self.R, self.me, self.epoch_ctr.data_ptr(),
+                                              self.err.data_ptr(), ops._stream()), "mdm_ep_barrier")
 
-    def forward(self, x, s_norm_w, s_norm_b, film, rows_per_seq, out):
+    def forward(self, x, s_norm_w, s_norm_b, film, rows_per_seq, out, usage=None, importance=None):
         """One MoEMultiBranchFFN call up to (not including) its output Linear, in stream order; every rank
-        must call it the same number of times (the barriers count epochs)."""
-        self.phase_gate(x)
+        must call it the same number of times (the barriers count epochs).  CUDA-graph capturable."""
+        self.phase_gate(x, usage, importance)
         self.barrier()
         self.phase_dispatch()
         self.barrier()

@@ -83,6 +83,9 @@ class MotionTransformer(nn.Module):
         self._packed = None
         self._ws = {}
         self._film_tiles = {}
+        self._ep_group = None      # expert parallelism: off (see enable_expert_parallel)
+        self._ep_on = False
+        self._ep_inst = {}
         self._build_tree()
         self.reset_parameters()
 
@@ -318,6 +321,36 @@ class MotionTransformer(nn.Module):
         self._ws = {}
         self._film_tiles = {}
         return r
+
+    # ------------------------------------------------------------------ expert parallelism
+    def enable_expert_parallel(self, group=None):
+        """Shard the experts of every MoEMultiBranchFFN over the ranks of `group` (default: the default
+        torch.distributed group; one process per GPU on one NVSwitch node): expert e of both branches lives
+        on rank e // (E // world).  Tokens stay on the rank that owns their sequence; the dispatch / combine
+        kernels move rows over NVLink peer memory (expert_parallel.py, csrc/ep.cu).  Every rank must call
+        forward() the same number of times with the same shapes.  The result is bit-identical to the
+        single-GPU path.  (The reference has no expert parallelism: models/switch_moe.py:97-109.)"""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise MdmError("enable_expert_parallel needs an initialised torch.distributed process group")
+        world = dist.get_world_size(group)
+        if self.moe_num_experts % world:
+            raise MdmError("moe_num_experts=%d is not divisible by the %d ranks" % (self.moe_num_experts, world))
+        self._ep_group, self._ep_on = group, True
+        self._ep_inst = {}
+        if self._packed is not None:
+            for L in self._packed["layers"]:
+                L.pop("ep_w", None)
+
+    def _ep_for(self, n_tokens):
+        from .expert_parallel import ExpertParallelFFN
+        ep = self._ep_inst.get(n_tokens)
+        if ep is None:    # collective (IPC handle exchange): first use happens in the same order on every rank
+            ep = ExpertParallelFFN.create_distributed(self.latent_dim, self.ff_size, self.moe_num_experts, 2, n_tokens,
+                                                      self._adt(), self._t("sequence_embedding").device,
+                                                      group=self._ep_group)
+            self._ep_inst[n_tokens] = ep
+        return ep
 
     def repack(self):
         """Call after modifying parameters in place (the packed kernel layouts are cached)."""
@@ -593,6 +626,17 @@ class MotionTransformer(nn.Module):
         ops.rowop(a2, N, D, adti, ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T, silu=True, out2_a=a1)
         self._lin(a1, L["ca_out"], out_f32=x2, resid=x1, alpha=1.0, beta=1.0)
         # ---- MoEMultiBranchFFN (multi_branch.py:52-61, switch_moe.py:44-111)
+        if self._ep_on:
+            ep = self._ep_for(N)
+            if "ep_w" not in L:
+                L["ep_w"] = ep.shard_weights(L["moe_ln_w"], L["moe_ln_b"], L["gate_w"], L["gate_b"], L["w1"], L["b1"],
+                                             L["w2"], L["b2"])
+            ep.use_weights(L["ep_w"])
+            ep.forward(x2, L["ffn_s_norm"][0], L["ffn_s_norm"][1], film[3], T, a1, usage=pk["usage"][li],
+                       importance=pk["importance"][li])
+            if self.record_routing:
+                self.last_routing.append((ep.idx.clone(), ep.vals.clone()))
+            return self._layer_tail(li, L, x, x2, None, a1, a2, xa, x1, ctx, Bn, T, N)
         NB, NBK, G = 2, 4, 2 * E
         cap = NBK * N + G * 128
         nblk = (N + 127) // 128
@@ -627,6 +671,13 @@ class MotionTransformer(nn.Module):
         self._lin(hp, (L["w2"], L["b2"]), out_a=yp, N=D, rowscale=rscale, a_rows=cap, w_rows=G * D,
                   **dict(kw, tiles=t_dn))
         ops.moe_combine_film(yp, perm, N, D, NBK, L["ffn_s_norm"][0], L["ffn_s_norm"][1], film[3], T, a1)
+        return self._layer_tail(li, L, x, x2, None, a1, a2, xa, x1, ctx, Bn, T, N)
+
+    def _layer_tail(self, li, L, x, x2, _unused, a1, a2, xa, x1, ctx, Bn, T, N):
+        """ffn.proj_out Linear + MemoryEfficientCrossAttentionBlock (fast_attention.py:301-330)."""
+        adt, D, H = self._adt(), self.latent_dim, self.num_heads
+        adti = MDM_BF16 if adt == torch.bfloat16 else MDM_F32
+        x3 = self._buf("x3", (N, D), torch.float32)
         if adt == torch.bfloat16:
             self._lin(a1, L["ffn_out"], out_f32=x3, out_a=xa, resid=x2, alpha=1.0, beta=1.0)
             x3a = xa
