@@ -133,6 +133,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--expert-parallel", action="store_true",
+                    help="N > 1 only: shard the experts over the ranks (NVLink dispatch/combine) instead of replicating them")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -176,6 +178,8 @@ def main():
     randomize_zero_init(net)
     state_cpu, extras_cpu = net.state_dict(), net.extras_state()
     net.to(dev)
+    if args.expert_parallel and world > 1:
+        net.enable_expert_parallel()
     B = B_PER_GPU
     x0, length, xf_c, xf_u = synth_inputs(B, 1000 + rank, dev)     # each rank denoises its own batch
     text_stub = {"c": (xf_c.mean(1), xf_c), "u": (xf_u.mean(1), xf_u)}
@@ -240,22 +244,33 @@ def main():
     from motiondiffusion_moe_b200._lib import ACT_GELU
     pk, Lr = net._packed, net._packed["layers"][-1]
     N2, D, Fd, E = 2 * B * T, CFG["latent_dim"], CFG["ff_size"], CFG["moe_num_experts"]
-    cap = 4 * N2 + 2 * E * 128
-    bufs = {k: net._ws[(k, s, dt)] for (k, s, dt) in net._ws if k.startswith("moe_") and (s[0] in (cap, cap // 128, 1))}
     reps = 10
+    ep_mode = args.expert_parallel and world > 1
+    if ep_mode:          # the expert GEMMs of this rank on the rows it received in the last step
+        ep = net._ep_for(N2)
+        ep.use_weights(Lr["ep_w"])
+        run_ffn = ep.phase_experts
+        moe_rows = int(ep.ntile.item()) * 128
+    else:
+        cap = 4 * N2 + 2 * E * 128
+        bufs = {k: net._ws[(k, s, dt)] for (k, s, dt) in net._ws if k.startswith("moe_") and (s[0] in (cap, cap // 128, 1))}
+
+        def run_ffn():
+            ops.gemm(bufs["moe_xp"], Lr["w1"], Lr["b1"], act=ACT_GELU, out_a=bufs["moe_hp"], N=Fd, M=cap,
+                     tiles=bufs["moe_tup"], num_tiles=cap // 128, num_tiles_dev=bufs["moe_ntile"], a_rows=cap, w_rows=2 * E * Fd)
+            ops.gemm(bufs["moe_hp"], Lr["w2"], Lr["b2"], out_a=bufs["moe_yp"], N=D, M=cap, rowscale=bufs["moe_rscale"],
+                     tiles=bufs["moe_tdn"], num_tiles=cap // 128, num_tiles_dev=bufs["moe_ntile"], a_rows=cap, w_rows=2 * E * D)
+        moe_rows = 4 * N2                               # 2 branches x top-2 routed rows per token
     torch.cuda.synchronize(dev)
     torch.cuda.nvtx.range_push("expert_ffn")      # ncu --nvtx --nvtx-include "expert_ffn/" captures exactly these
     ev0.record()
     for _ in range(reps):
-        ops.gemm(bufs["moe_xp"], Lr["w1"], Lr["b1"], act=ACT_GELU, out_a=bufs["moe_hp"], N=Fd, M=cap,
-                 tiles=bufs["moe_tup"], num_tiles=cap // 128, num_tiles_dev=bufs["moe_ntile"], a_rows=cap, w_rows=2 * E * Fd)
-        ops.gemm(bufs["moe_hp"], Lr["w2"], Lr["b2"], out_a=bufs["moe_yp"], N=D, M=cap, rowscale=bufs["moe_rscale"],
-                 tiles=bufs["moe_tdn"], num_tiles=cap // 128, num_tiles_dev=bufs["moe_ntile"], a_rows=cap, w_rows=2 * E * D)
+        run_ffn()
     ev1.record()
     torch.cuda.synchronize(dev)
     torch.cuda.nvtx.range_pop()
     moe_ms = ev0.elapsed_time(ev1) / reps
-    moe_flops = 2 * (4 * N2) * D * Fd * 2            # up + down, 4N routed rows (2 branches x top-2)
+    moe_flops = 2 * moe_rows * D * Fd * 2            # up + down
     pkv, src = peaks()
     ach = moe_flops / (moe_ms * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (grouped expert FFN up+down of one MoEMultiBranchFFN)",
@@ -281,7 +296,10 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": world * B, "frames": T, "cfg_scale": CFG_SCALE,
-                   "parallelism": "dp%d (independent batches, no collective in the loop)" % world,
+                   "parallelism": ("dp%d x ep%d (batch sharded by sequence, experts sharded over the ranks: NVLink peer-memory "
+                                   "dispatch/combine + flag barriers inside the step graph)" % (world, world))
+                   if (args.expert_parallel and world > 1) else
+                   "dp%d (independent batches, no collective in the loop)" % world,
                    "l2_policy": "per-step working set (1.06 GB bf16 weights + >2 GB activations) exceeds the 126 MB L2",
                    "timed_region": "CUDA-graph replay of the CFG step; inputs resident in HBM"},
         "model_tflops_per_gpu": step_flops / (ms / args.steps * 1e-3) / 1e12,
