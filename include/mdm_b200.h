@@ -176,6 +176,13 @@ MDM_API int mdm_pad_cast(const float* x, long rows, int F, void* out, int ld_out
 MDM_API int mdm_cfg_update(const float* x, const float* eps_c, const float* eps_u, const float* noise,
                            const int64_t* t, const float* tables, int n_steps, float cfg_scale,
                            int clip, int B, long per_sample, float* x_prev, float* x0, void* stream);
+/* p_mean_variance after the model call (EPSILON mean, :538-552 with :554-558 and :462-475) and, when
+ * `sample` is non-NULL, the p_sample update (:606-613): x0 = c_recip*x - c_recipm1*eps (clamped to [-1,1]
+ * if clip); mean = coef1*x0 + coef2*x; sample = mean + (t != 0)*exp(0.5*logvar)*noise.  Same tables as
+ * mdm_cfg_update; mean / x0 / sample may each be NULL. */
+MDM_API int mdm_p_mean_variance(const float* x, const float* eps, const float* noise, const int64_t* t,
+                                const float* tables, int n_steps, int clip, int B, long per_sample,
+                                float* mean, float* x0, float* sample, void* stream);
 /* q_sample, :449-460: x_t = sqrt_ac[t]*x0 + sqrt_1mac[t]*noise.  tables2: [2, n_steps]. */
 MDM_API int mdm_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tables2,
                          int n_steps, int B, long per_sample, float* x_t, void* stream);

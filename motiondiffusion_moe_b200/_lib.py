@@ -69,6 +69,7 @@ _SIGS = {
     "mdm_pad_cast": [_P, _L, _I, _P, _I, _I, _P],
     "mdm_cfg_update": [_P, _P, _P, _P, _P, _P, _I, _F, _I, _I, _L, _P, _P, _P],
     "mdm_q_sample": [_P, _P, _P, _P, _I, _I, _L, _P, _P],
+    "mdm_p_mean_variance": [_P, _P, _P, _P, _P, _I, _I, _I, _L, _P, _P, _P, _P],
     "mdm_ep_counts": [_P, _P, _L, _I, _I, _I, _I, _I, C.POINTER(EpPeers), _P, _P, _P, _P],
     "mdm_ep_scan": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "mdm_ep_dispatch": [_P, _L, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, C.POINTER(EpPeers), _I, _P, _P],

@@ -66,6 +66,27 @@ __global__ void cfg_update_kernel(const float* __restrict__ x, const float* __re
   if (x0_out) x0_out[i] = guided;
 }
 
+// p_mean_variance after the model call + (optionally) the p_sample update, torch-eager op order
+__global__ void p_mean_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                              const float* __restrict__ noise, const int64_t* __restrict__ t,
+                              const float* __restrict__ tables, int n_steps, int clip, long per_sample, long total,
+                              float* __restrict__ mean_out, float* __restrict__ x0_out, float* __restrict__ sample) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t ts = t[i / per_sample];
+  const float xv = x[i];
+  float x0 = __fsub_rn(__fmul_rn(tables[ts], xv), __fmul_rn(tables[n_steps + ts], eps[i]));
+  if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+  const float mean = __fadd_rn(__fmul_rn(tables[2 * n_steps + ts], x0), __fmul_rn(tables[3 * n_steps + ts], xv));
+  if (mean_out) mean_out[i] = mean;
+  if (x0_out) x0_out[i] = x0;
+  if (sample) {
+    const float nz = ts != 0 ? 1.f : 0.f;
+    const float sd = expf(__fmul_rn(0.5f, tables[4 * n_steps + ts]));
+    sample[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, sd), noise[i]));
+  }
+}
+
 __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                 const int64_t* __restrict__ t, const float* __restrict__ tables, int n_steps,
                                 long per_sample, long total, float* __restrict__ x_t) {
@@ -126,5 +147,16 @@ extern "C" MDM_API int mdm_q_sample(const float* x0, const float* noise, const i
   if (total == 0) return MDM_OK;
   q_sample_kernel<<<blocks(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x0, noise, t, tables2, n_steps,
                                                                                      per_sample, total, x_t);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_p_mean_variance(const float* x, const float* eps, const float* noise, const int64_t* t,
+                                           const float* tables, int n_steps, int clip, int B, long per_sample,
+                                           float* mean, float* x0, float* sample, void* stream) {
+  if (!x || !eps || !t || !tables || (sample && !noise)) return MDM_ERR_ARG;
+  const long total = (long)B * per_sample;
+  if (total == 0) return MDM_OK;
+  p_mean_kernel<<<blocks(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, eps, noise, t, tables, n_steps, clip,
+                                                                                   per_sample, total, mean, x0, sample);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }

@@ -114,6 +114,72 @@ class GaussianDiffusion:
                      self.num_timesteps, out)
         return out
 
+    # ------------------------------------------------------------------ p(x_{t-1} | x_t)
+    def _extract(self, arr, t, shape):
+        """_extract_into_tensor, :329-341 (gather, .float(), broadcast); plumbing on small tables."""
+        res = torch.from_numpy(arr).to(device=t.device)[t].float()
+        while res.dim() < len(shape):
+            res = res[..., None]
+        return res.expand(shape)
+
+    def _p_mean_variance(self, model, x, t, clip_denoised, denoised_fn, model_kwargs, noise=None):
+        self._check_supported()
+        if denoised_fn is not None:
+            raise NotImplementedError("denoised_fn is not supported by the fused update")
+        if model_kwargs is None:
+            model_kwargs = {}
+        B = x.shape[0]
+        assert t.shape == (B,)
+        x = x.float().contiguous()
+        t = t.to(torch.int64).contiguous()
+        eps = model(x, t, **model_kwargs)                               # :493
+        assert eps.shape == x.shape
+        step, _ = self._tables(x.device)
+        mean, x0 = torch.empty_like(x), torch.empty_like(x)
+        sample = torch.empty_like(x) if noise is not None else None
+        ops.p_mean_variance(x, eps.contiguous(), t, step, self.num_timesteps, clip_denoised, mean=mean, x0=x0,
+                            noise=None if noise is None else noise.float().contiguous(), sample=sample)
+        out = {"mean": mean, "variance": self._extract(self.posterior_variance, t, x.shape),
+               "log_variance": self._extract(self.posterior_log_variance_clipped, t, x.shape), "pred_xstart": x0}
+        if sample is not None:
+            out["sample"] = sample
+        return out
+
+    def p_mean_variance(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None):
+        """:481-552 for the trainer's configuration (EPSILON mean, FIXED_SMALL variance): one model forward,
+        then x0 and the posterior mean in one kernel (mdm_p_mean_variance).  Returns the reference's dict."""
+        return self._p_mean_variance(model, x, t, clip_denoised, denoised_fn, model_kwargs)
+
+    def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                 noise_fn=None, noise=None):
+        """:582-614.  The reference's default noise_fn=th.randn_like is called as noise_fn(shape, device=...,
+        dtype=...) and raises TypeError; here noise_fn=None means torch.randn_like(x), a
+        shape-style callable (e.g. torch.randn) is called the way the reference calls it, and `noise`
+        (keyword-only extra) injects a tensor."""
+        if cond_fn is not None:
+            raise NotImplementedError("cond_fn (classifier guidance) is not used by the reference trainer")
+        if noise is None:
+            noise = torch.randn_like(x, dtype=torch.float32) if noise_fn is None else \
+                noise_fn(x.shape, device=x.device, dtype=torch.float32)
+        out = self._p_mean_variance(model, x, t, clip_denoised, denoised_fn, model_kwargs, noise=noise)
+        return {"sample": out["sample"], "pred_xstart": out["pred_xstart"]}
+
+    def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                      model_kwargs=None, device=None, progress=False, noise_fn=None):
+        """:616-697 (plain ancestral sampling, one forward per step, no guidance)."""
+        if device is None:
+            device = next(model.parameters()).device
+        img = torch.randn(*shape, device=device) if noise is None else noise.to(device).float()
+        steps = list(reversed(range(self.num_timesteps)))
+        if progress:
+            from tqdm.auto import tqdm
+            steps = tqdm(steps)
+        for i in steps:
+            t = torch.full((shape[0],), i, dtype=torch.int64, device=device)
+            img = self.p_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
+                                model_kwargs=model_kwargs, noise_fn=noise_fn)["sample"]
+        return img
+
     # ------------------------------------------------------------------ CFG sampling
     def _cfg_inputs(self, model, B, model_kwargs, device):
         """Conditional + unconditional text batched as 2B sequences with per-sequence token counts.

@@ -194,6 +194,14 @@ def cfg_update(x, eps_c, eps_u, noise, t, tables, n_steps, cfg_scale, clip, x_pr
                                           _stream()), "mdm_cfg_update")
 
 
+def p_mean_variance(x, eps, t, tables, n_steps, clip, mean=None, x0=None, noise=None, sample=None):
+    _c(x, eps, t, tables, mean, x0, noise, sample)
+    B = x.shape[0]
+    _lib.check(_lib.load().mdm_p_mean_variance(x.data_ptr(), eps.data_ptr(), _ptr(noise), t.data_ptr(), tables.data_ptr(),
+                                               n_steps, 1 if clip else 0, B, x.numel() // B, _ptr(mean), _ptr(x0),
+                                               _ptr(sample), _stream()), "mdm_p_mean_variance")
+
+
 def q_sample(x0, noise, t, tables2, n_steps, x_t):
     _c(x0, noise, t, tables2, x_t)
     B = x0.shape[0]

@@ -506,6 +506,22 @@ def cfg_update(tab, x, t, eps_c, eps_u, noise, cfg_scale=7.5, clip_denoised=Fals
     return mean + nz * torch.exp(0.5 * logvar) * noise, guided
 
 
+def p_mean_variance_update(tab, x, t, eps, clip_denoised=True, noise=None):
+    """p_mean_variance after the model call (EPSILON / FIXED_SMALL: gaussian_diffusion.py:510-521,538-552,
+    554-558, 462-475) and, with `noise`, the p_sample update (:606-613).  Returns a dict like the reference."""
+    x0 = _extract(tab["sqrt_recip_alphas_cumprod"], t, x.shape) * x - \
+        _extract(tab["sqrt_recipm1_alphas_cumprod"], t, x.shape) * eps
+    if clip_denoised:
+        x0 = x0.clamp(-1, 1)
+    mean = _extract(tab["posterior_mean_coef1"], t, x.shape) * x0 + _extract(tab["posterior_mean_coef2"], t, x.shape) * x
+    out = {"mean": mean, "variance": _extract(tab["posterior_variance"], t, x.shape),
+           "log_variance": _extract(tab["posterior_log_variance_clipped"], t, x.shape), "pred_xstart": x0}
+    if noise is not None:
+        nz = (t != 0).float().view(-1, *([1] * (x.dim() - 1)))
+        out["sample"] = mean + nz * torch.exp(0.5 * out["log_variance"]) * noise
+    return out
+
+
 def cfg_step(p, cfg, tab, x, t, length, cond, uncond, noise, cfg_scale=7.5, clip_denoised=False,
              p_uncond=None):
     """One p_sample_with_cfg step: cond / uncond are (xf_proj, xf_out) pairs.  p_uncond: parameters of

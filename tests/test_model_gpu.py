@@ -218,6 +218,36 @@ def test_full_1000_step_sample_matches_oracle_loop():
     assert err16 < 0.25
 
 
+def test_p_mean_variance_and_p_sample_match_oracle():
+    """p_mean_variance / p_sample (gaussian_diffusion.py:481-552, 582-614): the post-forward arithmetic is
+    bit-identical to the torch-eager op sequence given the same eps; end to end within the fp32 tolerance."""
+    case = "small_b4"
+    cfg_name, B, T = cases.CASES[case]
+    cfg, p, net = build(case, "fp32")
+    x, _, length, xf_proj, xf_out = cases.make_inputs(cfg, B, T, seed=4, device=DEV)
+    t = torch.tensor([0, 1, 500, 999][:B], device=DEV)
+    noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(2)).to(DEV)
+    kw = {"length": length, "xf_proj": xf_proj, "xf_out": xf_out}
+    d = mdm.GaussianDiffusion(betas=mdm.get_named_beta_schedule("linear", 1000))
+    tab = mo.diffusion_tables(1000)
+    for clip in (True, False):
+        out = d.p_mean_variance(net, x, t, clip_denoised=clip, model_kwargs=kw)
+        eps = net(x, t, **kw)
+        ref = mo.p_mean_variance_update(tab, x, t, eps, clip)
+        for k in ("mean", "variance", "log_variance", "pred_xstart"):
+            assert torch.equal(out[k], ref[k]), k                       # same eps => bit-identical update
+        smp = d.p_sample(net, x, t, clip_denoised=clip, model_kwargs=kw, noise=noise)
+        assert torch.equal(smp["sample"], mo.p_mean_variance_update(tab, x, t, eps, clip, noise)["sample"])
+    with torch.no_grad():
+        eps_o = mo.forward(p, cfg, x, t, length, xf_proj, xf_out)
+    full = mo.p_mean_variance_update(tab, x, t, eps_o, False, noise)
+    got = d.p_sample(net, x, t, clip_denoised=False, model_kwargs=kw, noise=noise)
+    assert rel(got["sample"], full["sample"]) < 1e-5
+    # the reference's default noise_fn path raises TypeError (H5); ours samples
+    assert torch.isfinite(d.p_sample(net, x, t, model_kwargs=kw)["sample"]).all()
+    assert torch.isfinite(d.p_sample(net, x, t, model_kwargs=kw, noise_fn=torch.randn)["sample"]).all()
+
+
 def test_state_dict_roundtrip_and_errors():
     cfg, p, net = build("tiny_b3", "fp32")
     sd = net.state_dict()
