@@ -1,16 +1,11 @@
 """Per-kernel GPU time of one default-config forward (2B=128 sequences, bf16) via torch.profiler."""
 import os, sys, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import motiondiffusion_moe_b200 as m
-from oracle import cases, motion_oracle as mo
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _model import build
 from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda")
-cfg = mo.CONFIGS["default"]
-p = mo.make_params(cfg, 0)
-net = m.MotionTransformer(precision="bf16", **cfg)
-net.load_state_dict({k: p[k] for k in net.state_dict()}); net.load_extras(p); net.cuda()
 B = int(os.environ.get("B", "64"))
-x, t, length, xf_proj, xf_out = cases.make_inputs(cfg, 2 * B, 196, seed=5, device=dev)
+net, x, t, length, xf_proj, xf_out = build(dev, 2 * B)
 ctx = net.prepare_text(xf_proj, xf_out)
 for _ in range(2): net(x, t, length, text_ctx=ctx)
 torch.cuda.synchronize()
