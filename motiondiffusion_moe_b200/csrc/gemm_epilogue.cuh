@@ -20,19 +20,35 @@ constexpr int TR_BYTES = 32 * 1024;  // transpose buffers of all epilogue warps:
 // Epilogue flavours (each its own kernel instantiation, see below).  EPI_BF16W is EPI_BF16 with 16
 // epilogue warps (four per TMEM lane quadrant, one 64-column unit each, 104 registers): the 8-warp
 // epilogue is latency-bound at two warps per scheduler (ncu: 6.9 cycles per issued instruction).
-enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_ANY = 2, EPI_BF16W = 3 };
+// EPI_F32T is EPI_F32 with the residual tile arriving by TMA (prefetched one chunk ahead into a
+// 128B-swizzled staging tile), the sum written back row-per-lane into the same tile and leaving through a
+// TMA store: no LSU residual loads (32 x LDG.128 per thread and tile), no transposing pass, no STG.
+enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_ANY = 2, EPI_BF16W = 3, EPI_F32T = 4 };
 __host__ __device__ constexpr int epi_warps(int epi) { return epi == EPI_BF16W ? 16 : 8; }
 __host__ __device__ constexpr int num_threads(int epi) { return (FIRST_EPI_WARP + epi_warps(epi)) * 32; }
+// shared memory of the epilogue staging tiles: 8 x 4 KB / 16 x 2 KB, or for EPI_F32T per warp two 4 KB fp32
+// tiles (residual in / sum out, double-buffered) + one 2 KB bf16 tile (secondary output)
+__host__ __device__ constexpr int tr_bytes(int epi) { return epi == EPI_F32T ? 8 * (8192 + 2048) : TR_BYTES; }
 
-template <int BN, int STAGES>
+struct EpiTma {
+  const CUtensorMap* tmC;   // bf16 output (EPI_BF16W; secondary output of EPI_F32T)
+  const CUtensorMap* tmR;   // fp32 residual (EPI_F32T)
+  const CUtensorMap* tmF;   // fp32 output (EPI_F32T)
+  uint64_t* rbar;           // EPI_F32T: the two residual-arrival barriers of this warp
+  uint32_t* rphase;         // EPI_F32T: their parity bits (bit 0 / 1), kept across tiles
+};
+
+template <int BN, int STAGES, int EPI>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = TR_OFFSET + TR_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024 align slack
+  static constexpr int BAR_OFFSET = TR_OFFSET + tr_bytes(EPI);
+  // barriers: full/empty ring, 2 + 2 accumulator barriers, TMEM pointer, 16 residual barriers; +1024 align slack
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 16 * 8 + 1024;
 };
+
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) on
 // the MUFU rcp / ex2 units: ~14 issue slots instead of erff's ~50, so that the epilogue of a K=512
@@ -95,15 +111,16 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 // loop small: with every activation inlined a 32-column chunk was 826 SASS instructions of which ~100
 // execute, and four unrolled chunks overflowed the instruction cache); ACT < 0: epi.act at run time.
 template <int BN, int EPI, int ACT>
-__device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt, int c_row0, int w_row0,
-                                              int rows_valid, uint32_t t_addr, uint64_t* acc_bar,
+__device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, const EpiTma& tm, int N, int nt, int c_row0,
+                                              int w_row0, int rows_valid, uint32_t t_addr, uint64_t* acc_bar,
                                               uint32_t acc_phase, uint4* tr, int quad, int cpar, int lane) {
+  const CUtensorMap* tmC = tm.tmC;
 #ifdef MDM_GEMM_PROFILE
   const bool prof_on = (threadIdx.x == FIRST_EPI_WARP * 32);
   long long tprev_ = clock64();
 #endif
   float4* trf = reinterpret_cast<float4*>(tr);
-  const bool f32_path = EPI == EPI_F32 || (EPI == EPI_ANY && (epi.out_f32 != nullptr || epi.resid != nullptr));
+  const bool f32_path = EPI == EPI_F32 || EPI == EPI_F32T || (EPI == EPI_ANY && (epi.out_f32 != nullptr || epi.resid != nullptr));
   const int rsub = lane >> 3, ch = lane & 7;
   constexpr int NCH = EPI == EPI_BF16W ? 2 : BN / 64;   // 32-column chunks per warp and tile
   const int r = quad * 32 + lane;
@@ -146,7 +163,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
     }
     const int act = ACT >= 0 ? ACT : epi.act;
     if (act == MDM_ACT_GELU) {
-      if (f32_path) {
+      if (f32_path && EPI != EPI_F32T) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
       } else {
@@ -244,10 +261,91 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
         EPI_MARK(3);
       }
     }
+  } else if constexpr (EPI == EPI_F32T) {
+    // ---------------- fp32 output + fp32 residual (+ optional bf16 copy), all global traffic by TMA.
+    // tr: this warp's two 4 KB fp32 tiles (32 rows x 128 B, SWIZZLE_128B); the 2 KB bf16 tiles of all warps
+    // follow the 8 x 8 KB fp32 area.  Chunk k uses tile k & 1: residual in, (acc + beta * residual) out.
+    // The residuals of chunks 0 and 1 are requested before the accumulator wait, chunk k + 2 as soon as
+    // the store of chunk k has finished reading its tile.
+    float4* ftile = reinterpret_cast<float4*>(tr);
+    const int widx = quad + 4 * cpar;
+    uint4* btile = tr + (8 * 8192 - widx * 8192) / 16 + widx * (2048 / 16);
+    const int row0 = c_row0 + quad * 32;
+    (void)ob_blk; (void)of_blk; (void)rs_blk; (void)rmod_base; (void)rmax; (void)trf; (void)rsub; (void)ch;
+    const bool want_b = epi.out_bf16 != nullptr;
+    auto col_of = [&](int k) { return nt * BN + (cpar + 2 * k) * 32; };
+    auto issue_res = [&](int k) {       // lane 0: residual chunk k -> tile k & 1
+      mbar_expect_tx(&tm.rbar[k & 1], 4096);
+      tma_load_2d(tm.tmR, &tm.rbar[k & 1], ftile + (k & 1) * 256, col_of(k), row0);
+    };
+    if (lane == 0 && col_of(0) < N) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores of the previous tile have left
+      issue_res(0);
+      if (NCH > 1 && col_of(1) < N) issue_res(1);
+    }
+    EPI_MARK(4);
+    mbar_wait(acc_bar, acc_phase);
+    tc_fence_after();
+    EPI_MARK(5);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = cpar + 2 * k;
+      const int n0 = col_of(k);
+      if (n0 < N) {
+        float v[32];
+        load_chunk(c, bias_r[k], v);
+        mbar_wait(&tm.rbar[k & 1], (*tm.rphase >> (k & 1)) & 1u);          // residual chunk k has landed
+        *tm.rphase ^= 1u << (k & 1);
+        EPI_MARK(2);
+        float4* t4 = ftile + (k & 1) * 256 + lane * 8;
+        if (want_b) {     // the previous bf16 store of this warp must have finished reading its tile
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int slot = j ^ (lane & 7);
+          const float4 r4 = t4[slot];
+          const float4 x = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          float4 y;
+          y.x = fmaf(epi.beta, r4.x, x.x); y.y = fmaf(epi.beta, r4.y, x.y);
+          y.z = fmaf(epi.beta, r4.z, x.z); y.w = fmaf(epi.beta, r4.w, x.w);
+          t4[slot] = y;
+          if (want_b) {     // bf16 copy with or without the residual term, SWIZZLE_64B tile (8-byte pieces)
+            const float4 s4 = epi.bf16_pre_resid ? x : y;
+            uint2 pk; pk.x = pack2(s4.x, s4.y); pk.y = pack2(s4.z, s4.w);
+            const int c16 = (j >> 1) ^ ((lane >> 1) & 3);
+            reinterpret_cast<uint2*>(btile + lane * 4 + c16)[j & 1] = pk;
+          }
+        }
+        EPI_MARK(1);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                       ::"l"(reinterpret_cast<uint64_t>(tm.tmF)), "r"(n0), "r"(row0), "r"(smem_u32(ftile + (k & 1) * 256))
+                       : "memory");
+          if (want_b)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                         ::"l"(reinterpret_cast<uint64_t>(tmC)), "r"(n0), "r"(row0), "r"(smem_u32(btile))
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (k + 2 < NCH && col_of(k + 2) < N) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // tile k & 1 is free again
+            issue_res(k + 2);
+          }
+        }
+        EPI_MARK(3);
+      }
+    }
   } else if constexpr (EPI == EPI_BF16W) {
-    // ---------------- bf16-only output, 16 warps: this warp owns the 64-column unit `cpar` (0..3) of its
-    // lane quadrant; each 32-column half goes through a 2 KB buffer (32 rows x 64 bytes, 16-byte slots
-    // XOR-swizzled by (row >> 1) & 3: conflict-free writes by row and reads by 2 rows x 4 slots).
+    // ---------------- bf16-only output, 16 warps, TMA store: this warp owns the 64-column unit `cpar`
+    // (0..3) of its lane quadrant.  Each 32-column half is written row-per-lane into a 2 KB staging tile
+    // in the SWIZZLE_64B layout (16-byte slot ^ ((row >> 1) & 3): conflict-free) and leaves through one
+    // cp.async.bulk.tensor store: no transposing read phase, and no LSU global stores, which measurably
+    // slowed down the shared-memory traffic of the whole SM (tools/gemm_prof.py: qkv tile period 6 980
+    // -> 5 044 cycles with the STG.128s removed).  Rows / columns outside the output are clipped by the
+    // tensor map; rows >= rows_valid of a grouped tile fall into the segment's own padding.
     EPI_MARK(4);
     mbar_wait(acc_bar, acc_phase);
     tc_fence_after();
@@ -260,13 +358,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
       tmem_ld32(t_addr + (cpar * 2 + 1) * 32, raw[1]);
       tmem_ld_wait();
       EPI_MARK(0);
-      const int r4 = lane >> 2, c4r = lane & 3;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int nh = n0 + hh * 32;
         if (nh < N) {
           float v[32];
           finish_chunk(raw[hh], bias_r[hh], v);
+          // the previous store of this warp must have finished READING the staging tile
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             uint4 pk;
@@ -275,20 +375,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& epi, int N, int nt,
             tr[lane * 4 + (c4 ^ ((lane >> 1) & 3))] = pk;
           }
           EPI_MARK(1);
+          fence_proxy_async();          // generic-proxy writes -> visible to the TMA (async proxy)
           __syncwarp();
-          uint4 w[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = i * 8 + r4;
-            w[i] = tr[row * 4 + (c4r ^ ((row >> 1) & 3))];
-          }
-          __syncwarp();
-          EPI_MARK(2);
-          const int n = nh + c4r * 8;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = i * 8 + r4;
-            if (row < rmax && n < N) *reinterpret_cast<uint4*>(ob_blk + row * epi.ld_bf16 + n) = w[i];
+          if (lane == 0) {
+            asm volatile(
+                "cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                ::"l"(reinterpret_cast<uint64_t>(tmC)), "r"(nh), "r"(c_row0 + quad * 32), "r"(smem_u32(tr))
+                : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           EPI_MARK(3);
         }

@@ -37,13 +37,16 @@ extern "C" MDM_API int mdm_debug_read_epi_phase(unsigned long long* host, int re
 
 namespace {
 
+// rows of a grouped GEMM's output buffer (TMA-store bound): the caller passes the buffer height as M
+inline long a_rows_out(const GemmEpi*, int M) { return M; }
 
 template <int BN, int STAGES, int EPI, int ACT>
 __global__ void __launch_bounds__(num_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               int M, int N, int K, int num_m_tiles_host, const int* __restrict__ num_m_tiles_dev,
-               const MTile* __restrict__ mtiles, const GemmEpi epi) {
-  using L = SmemLayout<BN, STAGES>;
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmF, int M, int N, int K, int num_m_tiles_host,
+               const int* __restrict__ num_m_tiles_dev, const MTile* __restrict__ mtiles, const GemmEpi epi) {
+  using L = SmemLayout<BN, STAGES, EPI>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by offset (not by an integer round trip), so that the compiler still knows
   // these are shared-memory addresses and emits LDS/STS instead of generic LD/ST in the epilogue
@@ -53,6 +56,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 4);   // EPI_F32T: two residual barriers per epilogue warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -69,6 +73,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], epi_warps(EPI));
     mbar_init(&tmem_empty[1], epi_warps(EPI));
+    if (EPI == EPI_F32T) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) mbar_init(&res_bar[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 2 * BN);
@@ -164,7 +172,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     //   read phase: lane -> (row = 4*i + lane/8, 16-byte chunk = lane%8), i = 0..7.
     const int quad = warp & 3;
     const int cpar = (warp - FIRST_EPI_WARP) >> 2;
-    uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - FIRST_EPI_WARP) * (EPI == EPI_BF16W ? 128 : 256);
+    uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) +
+                (warp - FIRST_EPI_WARP) * (EPI == EPI_BF16W ? 128 : (EPI == EPI_F32T ? 512 : 256));
+    uint32_t rphase = 0;
+    const EpiTma tm{&tmC, &tmR, &tmF, res_bar + 2 * (warp - FIRST_EPI_WARP), &rphase};
     int acc = 0;
     uint32_t acc_phase = 0;
     long long e_wait = 0, e_work = 0;
@@ -183,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long c1 = PROF_T();
       e_wait += c1 - c0;
       ++e_tiles;
-      epilogue_tile<BN, EPI, ACT>(epi, N, nt, c_row0, w_row0, rows_valid,
+      epilogue_tile<BN, EPI, ACT>(epi, tm, N, nt, c_row0, w_row0, rows_valid,
                              tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN, &tmem_full[acc], acc_phase, tr,
                              quad, cpar, lane);
       tc_fence_before();
@@ -201,6 +212,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
   }
 
+  if ((EPI == EPI_BF16W || EPI == EPI_F32T) && warp >= FIRST_EPI_WARP && lane == 0)
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // TMA stores of this warp have left shared memory
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -272,22 +285,23 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // same smem 
 constexpr int BN2 = 256;        // tile width of the pair kernel
 constexpr int HALF_N2 = 128;    // weight rows staged per CTA
 
-template <int STAGES>
+template <int STAGES, int EPI>
 struct SmemLayout2 {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = HALF_N2 * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = TR_OFFSET + TR_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr int BAR_OFFSET = TR_OFFSET + tr_bytes(EPI);
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 16 * 8 + 1024;
 };
 
 template <int STAGES, int EPI, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(num_threads(EPI), 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                int M, int N, int K, int num_m_tiles_host, const int* __restrict__ num_m_tiles_dev,
-                const MTile* __restrict__ mtiles, const GemmEpi epi) {
-  using L = SmemLayout2<STAGES>;
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                const __grid_constant__ CUtensorMap tmF, int M, int N, int K, int num_m_tiles_host,
+                const int* __restrict__ num_m_tiles_dev, const MTile* __restrict__ mtiles, const GemmEpi epi) {
+  using L = SmemLayout2<STAGES, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -295,6 +309,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 4);   // EPI_F32T: two residual barriers per epilogue warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -313,6 +328,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 2 * epi_warps(EPI));
     mbar_init(&tmem_empty[1], 2 * epi_warps(EPI));
+    if (EPI == EPI_F32T) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) mbar_init(&res_bar[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_ptr, 2 * BN2);
@@ -404,7 +423,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ------------------------------------------------------------ epilogue (8 warps per CTA, own 128 rows)
     const int quad = warp & 3;
     const int cpar = (warp - FIRST_EPI_WARP) >> 2;
-    uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) + (warp - FIRST_EPI_WARP) * (EPI == EPI_BF16W ? 128 : 256);
+    uint4* tr = reinterpret_cast<uint4*>(smem + L::TR_OFFSET) +
+                (warp - FIRST_EPI_WARP) * (EPI == EPI_BF16W ? 128 : (EPI == EPI_F32T ? 512 : 256));
+    uint32_t rphase = 0;
+    const EpiTma tm{&tmC, &tmR, &tmF, res_bar + 2 * (warp - FIRST_EPI_WARP), &rphase};
     int acc = 0;
     uint32_t acc_phase = 0;
     long long e_wait = 0, e_work = 0;
@@ -429,7 +451,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const long long c1 = PROF_T();
       e_wait += c1 - c0;
       ++e_tiles;
-      epilogue_tile<BN2, EPI, ACT>(epi, N, nt, c_row0, w_row0, rows_valid,
+      epilogue_tile<BN2, EPI, ACT>(epi, tm, N, nt, c_row0, w_row0, rows_valid,
                               tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN2, &tmem_full[acc], acc_phase, tr,
                               quad, cpar, lane);
       tc_fence_before();
@@ -447,6 +469,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #endif
   }
 
+  if ((EPI == EPI_BF16W || EPI == EPI_F32T) && warp >= FIRST_EPI_WARP && lane == 0)
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) {
@@ -488,6 +512,36 @@ bool make_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld, 
   return r == CUDA_SUCCESS;
 }
 
+// Output tensor [rows, cols] bf16 with leading dimension ld; box = 32 rows x 32 columns (64-byte rows,
+// SWIZZLE_64B): the staging tile of one epilogue warp.
+bool make_out_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// fp32 tensor [rows, cols] with leading dimension ld; box = 32 rows x 32 columns (128-byte rows, SWIZZLE_128B):
+// one residual / output staging tile of an epilogue warp (EPI_F32T).
+bool make_f32_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int g_num_sms = 0;
 int num_sms() {
   if (!g_num_sms) {
@@ -499,10 +553,12 @@ int num_sms() {
 }
 
 template <int BN, int STAGES, int EPI, int ACT>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int num_m_tiles,
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+           const CUtensorMap& tf, int M, int N, int K, int num_m_tiles,
            const int* num_m_tiles_dev, const MTile* mtiles, const GemmEpi& epi, int max_ctas,
            cudaStream_t stream) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, EPI>;
+  static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -516,14 +572,16 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, in
   if (num_m_tiles_dev) grid = max_ctas;
   if (grid < 1) grid = 1;
   gemm_tc_kernel<BN, STAGES, EPI, ACT><<<grid, num_threads(EPI), L::TOTAL, stream>>>(
-      ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
+      ta, tb, tc, tr, tf, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
 template <int STAGES, int EPI, int ACT>
-int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int num_m_tiles,
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+            const CUtensorMap& tf, int M, int N, int K, int num_m_tiles,
             const int* num_m_tiles_dev, const MTile* mtiles, const GemmEpi& epi, int max_ctas, cudaStream_t stream) {
-  using L = SmemLayout2<STAGES>;
+  using L = SmemLayout2<STAGES, EPI>;
+  static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
@@ -536,7 +594,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, i
   if (!num_m_tiles_dev && work < clusters) clusters = work;
   if (clusters < 1) clusters = 1;
   gemm_tc2_kernel<STAGES, EPI, ACT><<<(unsigned)(2 * clusters), num_threads(EPI), L::TOTAL, stream>>>(
-      ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
+      ta, tb, tc, tr, tf, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -589,21 +647,52 @@ extern "C" MDM_API int mdm_gemm_bf16(const void* A, int lda, long a_rows, const 
   const int act = epi->act;
 #define MDM_GO(E_, A_)                                                                                            \
   do {                                                                                                            \
-    if (pair) return launch2<6, E_, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);   \
-    if (wide) return launch<256, 4, E_, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st); \
-    return launch<128, 6, E_, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);          \
+    if (pair) return launch2<6, E_, A_>(ta, tb, tc, tc, tc, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);   \
+    if (wide) return launch<256, 4, E_, A_>(ta, tb, tc, tc, tc, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st); \
+    return launch<128, 6, E_, A_>(ta, tb, tc, tc, tc, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);          \
   } while (0)
   static const int epiw_env = [] { const char* e = getenv("MDM_GEMM_EPIW"); return e ? atoi(e) : 1; }();
-  if (kind == EPI_BF16 && epiw_env && (wide || pair)) {   // 256-wide tiles: 16 epilogue warps
+  CUtensorMap tc = ta;    // only the TMA-store flavour reads it
+  // rows of the output the kernel may write: the logical M (plain GEMM) or the whole buffer (grouped)
+  const long c_rows = mtiles ? a_rows_out(epi, M) : M;
+  const bool tma_out = kind == EPI_BF16 && epiw_env && (wide || pair) && (epi->ld_bf16 & 7) == 0 &&
+                       make_out_map(&tc, epi->out_bf16, c_rows, N, epi->ld_bf16);
+  if (tma_out) {   // 256-wide tiles: 16 epilogue warps, TMA stores
 #define MDM_GOW(A_)                                                                                                  \
   do {                                                                                                               \
-    if (pair) return launch2<6, EPI_BF16W, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st); \
-    return launch<256, 4, EPI_BF16W, A_>(ta, tb, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);      \
+    if (pair) return launch2<6, EPI_BF16W, A_>(ta, tb, tc, tc, tc, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st); \
+    return launch<256, 4, EPI_BF16W, A_>(ta, tb, tc, tc, tc, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);      \
   } while (0)
     if (act == MDM_ACT_NONE) MDM_GOW(MDM_ACT_NONE);
     if (act == MDM_ACT_GELU) MDM_GOW(MDM_ACT_GELU);
     if (act == MDM_ACT_SILU) MDM_GOW(MDM_ACT_SILU);
 #undef MDM_GOW
+  }
+  // fp32 output + fp32 residual of a plain (not grouped) GEMM: residual in / sum out by TMA (B200, N x 512 x 512:
+  // 35.7 -> 26.5 us, with GELU 44.3 -> 30.3 us, with a bf16 copy 39.3 -> 31.6 us; these GEMMs move 128 MB for
+  // 13 GFLOP, i.e. they are HBM-bound).  Not for the CTA-pair kernel: K >= 1024 is operand-feed bound and the
+  // staging tiles cost it two pipeline stages (53.4 -> 54.5 us).
+  // MDM_GEMM_F32T: 0 = off, 1 = on with the usual tile-width choice (default), 2 = always 128-wide tiles.
+  static const int f32t_env = [] { const char* e = getenv("MDM_GEMM_F32T"); return e ? atoi(e) : 1; }();
+  if (kind == EPI_F32 && f32t_env && !pair && !mtiles && epi->out_f32 && epi->resid && epi->resid_mod <= 0 &&
+      (!epi->out_bf16 || ((epi->ld_bf16 & 7) == 0 && al(epi->out_bf16, 16))) &&
+      (act == MDM_ACT_NONE || act == MDM_ACT_GELU)) {
+    CUtensorMap tr, tf;
+    bool ok = make_f32_map(&tr, epi->resid, M, N, epi->ld_resid) && make_f32_map(&tf, epi->out_f32, M, N, epi->ld_f32);
+    if (ok && epi->out_bf16) ok = make_out_map(&tc, epi->out_bf16, M, N, epi->ld_bf16);
+    if (ok) {
+      const bool wide_t = wide && f32t_env != 2;
+      if (wide_t != wide)     // the weight box follows the tile width
+        if (!make_map(&tb, W, w_rows, K, ldw, wide_t ? 256 : 128)) return MDM_ERR_CUDA;
+#define MDM_GOT(A_)                                                                                                   \
+  do {                                                                                                                \
+    if (wide_t) return launch<256, 3, EPI_F32T, A_>(ta, tb, tc, tr, tf, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st); \
+    return launch<128, 4, EPI_F32T, A_>(ta, tb, tc, tr, tf, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st); \
+  } while (0)
+      if (act == MDM_ACT_NONE) MDM_GOT(MDM_ACT_NONE);
+      MDM_GOT(MDM_ACT_GELU);
+#undef MDM_GOT
+    }
   }
   if (kind == EPI_BF16 && act == MDM_ACT_NONE) MDM_GO(EPI_BF16, MDM_ACT_NONE);
   if (kind == EPI_BF16 && act == MDM_ACT_GELU) MDM_GO(EPI_BF16, MDM_ACT_GELU);

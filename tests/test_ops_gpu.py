@@ -62,6 +62,36 @@ def test_gemm_epilogue(dtype, act):
     assert rel(oa, pre) < (1e-5 if dtype == torch.float32 else 4e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(25, 512, 512), (1000, 512, 2048), (333, 128, 512), (777, 264, 576),
+                                   (4100, 1024, 1024), (130, 36, 64)])
+@pytest.mark.parametrize("act", [ACT_NONE, ACT_GELU])
+@pytest.mark.parametrize("secondary", ["none", "pre", "post"])
+def test_gemm_f32_residual_tma_epilogue(M, N, K, act, secondary):
+    """fp32 output + fp32 residual (the residual-stream GEMMs: s_out / skip / ca_out / ffn_out / sd_o / sd_f3):
+    residual in and sum out by TMA, ragged M / N clipped by the tensor maps, optional bf16 copy before or after
+    the residual, output aliasing the residual."""
+    A = randn(M, K, seed=1).to(torch.bfloat16)
+    W = randn(N, K, seed=2, scale=K ** -0.5).to(torch.bfloat16)
+    b, R = randn(N, seed=3), randn(M, N, seed=4)
+    guard = torch.full((M + 64, N), 3.0, device=DEV)        # rows >= M must stay untouched
+    o32 = guard[:M]
+    oa = torch.full((M + 64, N), 5.0, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, W, b, act=act, alpha=0.1, beta=0.7, resid=R, out_f32=o32,
+             out_a=None if secondary == "none" else oa[:M], a_pre_resid=secondary == "pre")
+    v = A.float() @ W.float().t() + b
+    pre = 0.1 * (F.gelu(v) if act == ACT_GELU else v)
+    assert rel(o32, pre + 0.7 * R) < 1e-4
+    assert torch.all(guard[M:] == 3.0)
+    if secondary != "none":
+        assert rel(oa[:M], pre if secondary == "pre" else pre + 0.7 * R) < 4e-3
+        assert torch.all(oa[M:] == 5.0)
+    # in place (output == residual buffer) gives the same bits as out of place
+    Rc, o2 = R.clone(), torch.empty(M, N, device=DEV)
+    ops.gemm(A, W, b, act=act, alpha=0.1, beta=0.7, resid=R, out_f32=o2)
+    ops.gemm(A, W, b, act=act, alpha=0.1, beta=0.7, resid=Rc, out_f32=Rc)
+    assert torch.equal(Rc, o2)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_gemm_positional_residual_and_secondary(dtype):
     T, B, N, K = 12, 5, 256, 72
