@@ -379,7 +379,9 @@ fastattn_stream_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P
   const int g = lane >> 2, tq = lane & 3;
   const int D = H * HD;
   const int len = length ? (int)min((long)T, (long)(length[b] >> length_shift)) : T;
-  const int nstrips = Tp / 16, NC = Tp / CR;
+  // Key frames t >= len are masked (k' = 0 exactly): windows that lie entirely beyond len add exact zeros to kv
+  // and to the denominators, so they are neither loaded nor computed (den = max(0, 1e-6) for their frames).
+  const int nstrips = Tp / 16, NC = min(Tp / CR, (len + CR - 1) / CR);
   FA_INIT();
 
   auto load_window = [&](int c) {          // frames [16 c, 16 c + 16) of k and v -> buffer c & 1
@@ -404,8 +406,9 @@ fastattn_stream_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P
     const int t = T + i / CPR, c = i % CPR;
     *reinterpret_cast<uint4*>(Qs + t * LDS + c * 8) = make_uint4(0u, 0u, 0u, 0u);
   }
-  load_window(0);
+  if (NC > 0) load_window(0); else asm volatile("cp.async.commit_group;" ::: "memory");
   if (NC > 1) load_window(1); else asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < Tp - NC * CR; i += 256) den_s[NC * CR + i] = 1e-6f;
   for (int i = tid; i < HD * HD / 4; i += 256) {
     const int n = i % HD, m4 = i / HD;
     const float4 p4 = __ldg(reinterpret_cast<const float4*>(P + n * HD + 4 * m4));
@@ -589,7 +592,7 @@ fastattn_stream_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P
     *reinterpret_cast<uint32_t*>(Ps + (m0 + g) * LDS + col) = pack_bf16(acc[nt][0] * 0.1f, acc[nt][1] * 0.1f);
     *reinterpret_cast<uint32_t*>(Ps + (m0 + g + 8) * LDS + col) = pack_bf16(acc[nt][2] * 0.1f, acc[nt][3] * 0.1f);
   }
-  if (tid < CR) {
+  if (tid < CR && NC > 0) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < NW; ++w) s += den_part[(((NC - 1) & 1) * NW + w) * CR + tid];

@@ -189,6 +189,24 @@ def test_fastattn(dtype, B, H, T, hd):
     assert rel(out, ref) < TOL[dtype]
 
 
+def test_fastattn_fully_masked_windows():
+    """Key windows that lie entirely beyond `length` are skipped by the streamed kernel: same result as the
+    oracle, which multiplies them by a zero mask (fast_attention.py:60-61), including length 0."""
+    B, H, T, hd = 6, 4, 196, 128
+    D = H * hd
+    P, nw, nb = _attn_params(hd, 1)
+    qkv = randn(B * T, 3 * D, seed=5, scale=2.0).bfloat16()
+    length = torch.tensor([0, 1, 16, 17, 100, 196], device=DEV)
+    out = torch.empty(B * T, D, device=DEV, dtype=torch.bfloat16)
+    ops.fastattn(qkv, P, nw, nb, length, 0, B, H, T, hd, out)
+    q, k, v = (t.view(B, T, H, hd).permute(0, 2, 1, 3) * 0.1 for t in qkv.float().view(B, T, 3, D).unbind(2))
+    p = {"fa.projection_matrix": P, "fa.norm.weight": nw, "fa.norm.bias": nb}
+    ref = mo.fast_attention(p, "fa", q, k, v, mo.src_mask(T, length)).permute(0, 2, 1, 3).reshape(B, T, D)
+    o = out.view(B, T, D)
+    for i in range(B):
+        assert rel(o[i], ref[i]) < TOL[torch.bfloat16], (i, rel(o[i], ref[i]))
+
+
 def test_fastattn_length_shift():
     B, H, T, hd = 2, 4, 98, 128
     P, nw, nb = _attn_params(hd, 1)
