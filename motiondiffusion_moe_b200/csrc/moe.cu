@@ -82,8 +82,13 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&p)[GP], int lane) {
 // both tokens (the kernel was bound by shared-memory bandwidth with one), and the softmax / top-2
 // of the TT*NB (token, branch) pairs is evaluated once, each by its own lane, instead of 32 times.
 // The per-(token, expert) arithmetic order is unchanged (bit-identical logits, probabilities, counters).
-template <int VPT, int E, int NB>
-__global__ void __launch_bounds__(256, (VPT <= 16 && NB * E <= 16) ? 2 : 1)
+// The 128-token block is the histogram granule of the C-ABI.  Two shapes (B200, D = 512, 16 groups):
+//   GATE_WARPS = 16 (8 tokens per warp, one block per SM, the rows of the next token pair requested before the
+//     current pair is evaluated) when there are fewer blocks than SMs: the parallelism has to come from
+//     inside the block (N = 12 544: 32.5 -> 25.6 us);
+//   GATE_WARPS = 8 (16 tokens per warp, two blocks per SM) otherwise (N = 25 088: 37 us; 16 warps: 49 us).
+template <int VPT, int E, int NB, int GATE_WARPS>
+__global__ void __launch_bounds__(GATE_WARPS * 32, (GATE_WARPS == 8 && VPT <= 16 && NB * E <= 16) ? 2 : 1)
 moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restrict__ ln_w,
                 const float* __restrict__ ln_b, const float* __restrict__ gate_w,
                 const float* __restrict__ gate_b, int* __restrict__ idx, float* __restrict__ vals,
@@ -95,24 +100,38 @@ moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restr
   float* gw = sm;               // [G][D] gate weights
   float* lw = gw + G * D;       // [NB][D] LayerNorm weight
   float* lb = lw + NB * D;      // [NB][D] LayerNorm bias
-  __shared__ int w_all[8][MAX_G], w_top1[8][MAX_G];
-  __shared__ float w_imp[8][MAX_G];
-  for (int i = threadIdx.x; i < G * D / 4; i += 256)
-    reinterpret_cast<float4*>(gw)[i] = __ldg(reinterpret_cast<const float4*>(gate_w) + i);
-  for (int i = threadIdx.x; i < NB * D; i += 256) { lw[i] = ln_w[i]; lb[i] = ln_b[i]; }
-  __syncthreads();
+  constexpr int TPW = TOK_PER_BLK / GATE_WARPS;   // tokens per warp
+  constexpr bool PREFETCH = GATE_WARPS == 16;     // (the 8-warp shape has no registers to spare)
+  __shared__ int w_all[GATE_WARPS][MAX_G], w_top1[GATE_WARPS][MAX_G];
+  __shared__ float w_imp[GATE_WARPS][MAX_G];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long tok0 = (long)blockIdx.x * TOK_PER_BLK + warp * TPW;
+  float nxt[TT][VPT];                              // rows of the next token pair, in flight
+  auto fetch = [&](long tok) {
+    if (tok < N) {
+      load_row<VPT, float>(x + tok * D, lane, nxt[0]);
+      load_row<VPT, float>(x + (tok + 1 < N ? tok + 1 : tok) * D, lane, nxt[1]);
+    }
+  };
+  if (PREFETCH) fetch(tok0);
+  for (int i = threadIdx.x; i < G * D / 4; i += GATE_WARPS * 32)
+    reinterpret_cast<float4*>(gw)[i] = __ldg(reinterpret_cast<const float4*>(gate_w) + i);
+  for (int i = threadIdx.x; i < NB * D; i += GATE_WARPS * 32) { lw[i] = ln_w[i]; lb[i] = ln_b[i]; }
+  __syncthreads();
   int cnt_all = 0, cnt_top1 = 0;  // lane g owns group g
   float imp = 0.f;
-  const long tok0 = (long)blockIdx.x * TOK_PER_BLK + warp * 16;
   const int my_t = (lane / NB) % TT, my_br = lane % NB;   // the (token, branch) pair this lane resolves
-  for (int it = 0; it < 16; it += TT) {
+  for (int it = 0; it < TPW; it += TT) {
     const long tok = tok0 + it;
     if (tok >= N) break;
     const bool two = tok + 1 < N;
     float v[TT][VPT];
-    load_row<VPT, float>(x + tok * D, lane, v[0]);
-    load_row<VPT, float>(x + (two ? tok + 1 : tok) * D, lane, v[1]);
+    if (!PREFETCH) fetch(tok);
+#pragma unroll
+    for (int t = 0; t < TT; ++t)
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) v[t][i] = nxt[t][i];
+    if (PREFETCH && it + TT < TPW) fetch(tok + TT);
     float mean[TT], rstd[TT];
 #pragma unroll
     for (int t = 0; t < TT; ++t) row_stats<VPT>(v[t], D, mean[t], rstd[t]);
@@ -193,7 +212,7 @@ moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restr
   if (threadIdx.x < G) {
     int a = 0, t1 = 0;
     float im = 0.f;
-    for (int w = 0; w < 8; ++w) { a += w_all[w][threadIdx.x]; t1 += w_top1[w][threadIdx.x]; im += w_imp[w][threadIdx.x]; }
+    for (int w = 0; w < GATE_WARPS; ++w) { a += w_all[w][threadIdx.x]; t1 += w_top1[w][threadIdx.x]; im += w_imp[w][threadIdx.x]; }
     blk_hist[((long)blockIdx.x * 2) * G + threadIdx.x] = a;
     blk_hist[((long)blockIdx.x * 2 + 1) * G + threadIdx.x] = t1;
     blk_imp[(long)blockIdx.x * G + threadIdx.x] = im;
@@ -271,8 +290,9 @@ moe_scan_kernel(const int* __restrict__ blk_hist, const float* __restrict__ blk_
   if (gg == 0) { seg_offsets[G] = all; *num_tiles = all / 128; }
 }
 
+constexpr int PERM_WARPS = 16;
 template <int VPT, typename TO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PERM_WARPS * 32)
 moe_permute_kernel(const float* __restrict__ x, long N, int D, int NB, int E, const float* __restrict__ ln_w,
                    const float* __restrict__ ln_b, const int* __restrict__ idx, const float* __restrict__ vals,
                    const float* __restrict__ stats, const int* __restrict__ blk_base,
@@ -285,12 +305,13 @@ moe_permute_kernel(const float* __restrict__ x, long N, int D, int NB, int E, co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npairs = TOK_PER_BLK * NBK;           // <= 512
   const int nseg = npairs / 32;                   // <= 16
-  for (int i = threadIdx.x; i < 16 * MAX_G; i += 256) (&seg_cnt[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < 16 * MAX_G; i += PERM_WARPS * 32) (&seg_cnt[0][0])[i] = 0;
   __syncthreads();
   const long tok_blk0 = (long)blockIdx.x * TOK_PER_BLK;
-  int my_g[2], my_rank[2];
-  for (int r = 0; r < 2; ++r) {
-    const int seg = warp * 2 + r;
+  constexpr int SPW = 16 / PERM_WARPS;            // 32-pair segments per warp
+  int my_g[SPW], my_rank[SPW];
+  for (int r = 0; r < SPW; ++r) {
+    const int seg = warp * SPW + r;
     my_g[r] = -1; my_rank[r] = 0;
     if (seg < nseg) {
       const int p = seg * 32 + lane;
@@ -305,8 +326,8 @@ moe_permute_kernel(const float* __restrict__ x, long N, int D, int NB, int E, co
     }
   }
   __syncthreads();
-  for (int r = 0; r < 2; ++r) {
-    const int seg = warp * 2 + r;
+  for (int r = 0; r < SPW; ++r) {
+    const int seg = warp * SPW + r;
     if (seg < nseg && my_g[r] >= 0) {
       const int g = my_g[r];
       int base = 0;
@@ -321,20 +342,31 @@ moe_permute_kernel(const float* __restrict__ x, long N, int D, int NB, int E, co
     }
   }
   __syncthreads();
-  for (int it = 0; it < 16; ++it) {
-    const int tl = warp * 16 + it;
-    const long tok = tok_blk0 + tl;
-    if (tok >= N) break;
-    float v[VPT];
-    load_row<VPT, float>(x + tok * D, lane, v);
-    const float mean = stats[tok * 2], rstd = stats[tok * 2 + 1];
-    for (int br = 0; br < NB; ++br) {
-      float hrow[VPT];
+  constexpr int TPW = TOK_PER_BLK / PERM_WARPS, UNR = 4;   // tokens per warp; rows in flight per warp
+#pragma unroll 1
+  for (int it = 0; it < TPW; it += UNR) {
+    float v[UNR][VPT];
+    float2 ms[UNR];
 #pragma unroll
-      for (int i = 0; i < VPT; ++i) hrow[i] = v[i];
-      affine_row<VPT>(hrow, mean, rstd, ln_w + br * D, ln_b + br * D, lane);
-      store_row<VPT, TO>(xp + (long)pos_s[tl * NBK + br * 2] * D, lane, hrow);
-      store_row<VPT, TO>(xp + (long)pos_s[tl * NBK + br * 2 + 1] * D, lane, hrow);
+    for (int u = 0; u < UNR; ++u) {
+      const long tok = tok_blk0 + warp * TPW + it + u;
+      if (tok < N) {
+        load_row<VPT, float>(x + tok * D, lane, v[u]);
+        ms[u] = *reinterpret_cast<const float2*>(stats + tok * 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int tl = warp * TPW + it + u;
+      if (tok_blk0 + tl >= N) break;
+      for (int br = 0; br < NB; ++br) {
+        float hrow[VPT];
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) hrow[i] = v[u][i];
+        affine_row<VPT>(hrow, ms[u].x, ms[u].y, ln_w + br * D, ln_b + br * D, lane);
+        store_row<VPT, TO>(xp + (long)pos_s[tl * NBK + br * 2] * D, lane, hrow);
+        store_row<VPT, TO>(xp + (long)pos_s[tl * NBK + br * 2 + 1] * D, lane, hrow);
+      }
     }
   }
 }
@@ -401,11 +433,19 @@ int launch_gate(const float* x, long N, int D, const float* ln_w, const float* l
   const int nblk = (int)((N + TOK_PER_BLK - 1) / TOK_PER_BLK);
   const size_t smem = sizeof(float) * ((size_t)NB * E * D + 2 * (size_t)NB * D);
   if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-          cudaSuccess)
+      (cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+           cudaSuccess ||
+       cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+           cudaSuccess))
     return MDM_ERR_CUDA;
-  moe_gate_kernel<VPT, E, NB><<<nblk, 256, smem, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
-                                                         blk_hist, blk_imp);
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  if (nblk <= sms)
+    moe_gate_kernel<VPT, E, NB, 16><<<nblk, 512, smem, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
+                                                             blk_hist, blk_imp);
+  else
+    moe_gate_kernel<VPT, E, NB, 8><<<nblk, 256, smem, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
+                                                            blk_hist, blk_imp);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -464,10 +504,10 @@ extern "C" MDM_API int mdm_moe_permute(const float* x, long N, int D, int NB, in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VPT_SWITCH(D, {
     if (dt == MDM_F32)
-      moe_permute_kernel<V, float><<<nblk, 256, 0, st>>>(x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
+      moe_permute_kernel<V, float><<<nblk, PERM_WARPS * 32, 0, st>>>(x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
                                                           seg_offsets, reinterpret_cast<float*>(xp), perm, rowscale);
     else
-      moe_permute_kernel<V, bf16><<<nblk, 256, 0, st>>>(x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
+      moe_permute_kernel<V, bf16><<<nblk, PERM_WARPS * 32, 0, st>>>(x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
                                                          seg_offsets, reinterpret_cast<bf16*>(xp), perm, rowscale);
   });
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
