@@ -187,6 +187,29 @@ MDM_API int mdm_p_mean_variance(const float* x, const float* eps, const float* n
 MDM_API int mdm_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tables2,
                          int n_steps, int B, long per_sample, float* x_t, void* stream);
 
+/* DDIM update (ddim_sample, :699-742) after the model call(s): x0 = c_recip*x - c_recipm1*eps_c (clamped if
+ * clip); with eps_u != NULL the two x0 are combined as p_sample_with_cfg does (:1074-1079);
+ *   eps = (c_recip*x - x0) / c_recipm1                                                  (:567-571)
+ *   sigma = eta * sqrt((1 - ab_prev) / (1 - ab)) * sqrt(1 - ab / ab_prev)               (:729-733)
+ *   x_prev = x0*sqrt(ab_prev) + sqrt(1 - ab_prev - sigma^2)*eps + (t != 0)*sigma*noise  (:736-741)
+ * tables4: [4, n_steps] fp32 rows = sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, alphas_cumprod,
+ * alphas_cumprod_prev.  t_prev == NULL: ab_prev = alphas_cumprod_prev[t] (the reference's full-length loop);
+ * otherwise ab_prev = alphas_cumprod[t_prev[b]] (1 when t_prev[b] < 0): strided schedules.  noise may be NULL
+ * when eta == 0; eps_u and x0 may be NULL.  Arithmetic in torch-eager order (bit-identical to the reference). */
+MDM_API int mdm_ddim_update(const float* x, const float* eps_c, const float* eps_u, const float* noise,
+                            const int64_t* t, const int64_t* t_prev, const float* tables4, int n_steps,
+                            float cfg_scale, float eta, int clip, int B, long per_sample, float* x_prev,
+                            float* x0, void* stream);
+
+/* The step after the sampler in the reference's pipeline: de-normalise the generated features
+ * (tools/visualization.py:91: motion * std + mean; mean / std [F] fp32, both NULL = already de-normalised) and
+ * recover the joint positions (utils/motion_process.py:362-417 recover_root_rot_pos + recover_from_ric with
+ * utils/quaternion.py qinv / qrot).  x [B, T, F] fp32 (F >= 4 + 3*(joints-1): 263 for HumanML3D / 22 joints,
+ * 251 for KIT / 21 joints) -> out [B, T, joints, 3] fp32.  One block per sequence, the two cumulative sums over
+ * the frames as block scans. */
+MDM_API int mdm_recover_from_ric(const float* x, const float* mean, const float* stdv, int B, int T, int F,
+                                 int joints, float* out, void* stream);
+
 /* ---- expert-parallel MoE over NVLink peer memory (BASELINE.json configs[3]) -------------------------
  * The reference has no expert parallelism (experts are a local nn.ModuleList: models/switch_moe.py:
  * 19-25, looped at :97-109); these entry points replace that loop when the E experts of every branch are

@@ -96,6 +96,139 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
   x_t[i] = __fadd_rn(__fmul_rn(tables[ts], x0[i]), __fmul_rn(tables[n_steps + ts], noise[i]));
 }
 
+// DDIM update (ddim_sample, gaussian_diffusion.py:721-742) after the model call(s), torch-eager op order.
+// (sqrt.rn / div.rn like torch's CUDA kernels: bit-identical to the reference run on a GPU; torch's CPU sqrt is off by
+// one ulp for 0.6 % of inputs, so a CPU run of the reference agrees to 1e-6 only.)
+// eps_u != NULL: classifier-free guidance on pred_xstart exactly as p_sample_with_cfg combines it (:1074-1079).
+// t_prev == NULL: alpha_bar_prev = alphas_cumprod_prev[t] (the reference's 1000-step loop); otherwise the
+// previous timestep of a strided schedule (alpha_bar_prev = alphas_cumprod[t_prev], 1 for t_prev < 0).
+// tables: [4][n_steps] = sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, alphas_cumprod, alphas_cumprod_prev.
+__global__ void ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_c,
+                                   const float* __restrict__ eps_u, const float* __restrict__ noise,
+                                   const int64_t* __restrict__ t, const int64_t* __restrict__ t_prev,
+                                   const float* __restrict__ tables, int n_steps, float s, float eta, int clip,
+                                   long per_sample, long total, float* __restrict__ x_prev, float* __restrict__ x0_out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = (int)(i / per_sample);
+  const int64_t ts = t[b];
+  const float c_recip = tables[ts], c_recipm1 = tables[n_steps + ts];
+  const float ab = tables[2 * n_steps + ts];
+  float ab_prev = tables[3 * n_steps + ts];
+  if (t_prev) { const int64_t tp = t_prev[b]; ab_prev = tp < 0 ? 1.0f : tables[2 * n_steps + tp]; }
+  const float xv = x[i];
+  float x0 = __fsub_rn(__fmul_rn(c_recip, xv), __fmul_rn(c_recipm1, eps_c[i]));       // :554-558
+  if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+  if (eps_u) {
+    float x0u = __fsub_rn(__fmul_rn(c_recip, xv), __fmul_rn(c_recipm1, eps_u[i]));
+    if (clip) x0u = fminf(fmaxf(x0u, -1.f), 1.f);
+    x0 = __fadd_rn(x0u, __fmul_rn(s, __fsub_rn(x0, x0u)));                             // :1074-1079
+  }
+  const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(c_recip, xv), x0), c_recipm1);        // :567-571
+  const float sigma = __fmul_rn(__fmul_rn(eta, __fsqrt_rn(__fdiv_rn(__fsub_rn(1.f, ab_prev), __fsub_rn(1.f, ab)))),
+                                __fsqrt_rn(__fsub_rn(1.f, __fdiv_rn(ab, ab_prev))));    // :729-733
+  const float mean = __fadd_rn(__fmul_rn(x0, __fsqrt_rn(ab_prev)),
+                               __fmul_rn(__fsqrt_rn(__fsub_rn(__fsub_rn(1.f, ab_prev), __fmul_rn(sigma, sigma))), eps));
+  const float nz = ts != 0 ? 1.f : 0.f;
+  const float nv = noise ? noise[i] : 0.f;
+  x_prev[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, sigma), nv));                     // :740-741
+  if (x0_out) x0_out[i] = x0;
+}
+
+// Inclusive scan of v over the block's threads (one value per thread), result of thread i = sum_{j <= i} v_j.
+// `carry` is added to every result; the block total (incl. carry) is returned to every thread.  warp_tot: [32].
+__device__ __forceinline__ float block_scan_incl(float v, float carry, float* warp_tot, float& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
+  }
+  __syncthreads();                      // warp_tot may still be read by the previous call
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  float base = carry;
+  for (int w = 0; w < warp; ++w) base += warp_tot[w];
+  float tot = carry;
+  for (int w = 0; w < nw; ++w) tot += warp_tot[w];
+  total = tot;
+  return v + base;
+}
+
+// Generated features -> joint positions, the step after the sampler in the reference's pipeline
+// (tools/visualization.py:91 `motion * std + mean`, utils/motion_process.py:362-417 recover_root_rot_pos +
+// recover_from_ric, utils/quaternion.py:16-20,54-73 qinv / qrot).  One block per sequence:
+//   ang[t]  = sum_{s < t} rot_vel[s]                          (root yaw, cumulative)
+//   rpos[t] = sum_{s <= t} qrot(qinv(q[s]), (vx[s-1], 0, vz[s-1]))   (root trajectory; y = data[..., 3])
+//   joint j >= 1: qrot(qinv(q[t]), ric[t, j-1]) + (rpos.x, 0, rpos.z);  joint 0 = rpos
+// with q[t] = (cos ang, 0, sin ang, 0).  x: [B, T, F] normalised features; mean / std: [F] or NULL.
+__global__ void recover_ric_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                   const float* __restrict__ stdv, int T, int F, int J, float* __restrict__ out) {
+  extern __shared__ float sh[];
+  float* ang = sh;            // [T]
+  float* px = ang + T;        // [T]
+  float* pz = px + T;         // [T]
+  __shared__ float warp_tot[32];
+  const int b = blockIdx.x;
+  const float* xb = x + (long)b * T * F;
+  auto feat = [&](int t, int f) {
+    const float v = xb[(long)t * F + f];
+    return mean ? __fadd_rn(__fmul_rn(v, stdv[f]), mean[f]) : v;
+  };
+  // pass 1: root yaw (exclusive prefix sum of the rotation velocity)
+  float carry = 0.f;
+  for (int t0 = 0; t0 < T; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    const float v = (t >= 1 && t < T) ? feat(t - 1, 0) : 0.f;
+    float tot;
+    const float inc = block_scan_incl(v, carry, warp_tot, tot);
+    if (t < T) ang[t] = inc;
+    carry = tot;
+  }
+  __syncthreads();
+  // pass 2: root trajectory (inclusive prefix sums of the rotated planar velocity)
+  float cx = 0.f, cz = 0.f;
+  for (int t0 = 0; t0 < T; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    float rx = 0.f, rz = 0.f;
+    if (t >= 1 && t < T) {
+      // qrot(qinv(q), v), v = (vx, 0, vz), q = (c, 0, s, 0): qvec = (0, -s, 0)
+      const float c = cosf(ang[t]), s = sinf(ang[t]);
+      const float vx = feat(t - 1, 1), vz = feat(t - 1, 2);
+      const float qy = -s;
+      const float uvx = qy * vz, uvz = -(qy * vx);           // cross(qvec, v)   (y component is 0)
+      const float uuvx = qy * uvz, uuvz = -(qy * uvx);       // cross(qvec, uv)
+      rx = vx + 2.f * (c * uvx + uuvx);
+      rz = vz + 2.f * (c * uvz + uuvz);
+    }
+    float tx, tz;
+    const float ix = block_scan_incl(rx, cx, warp_tot, tx);
+    const float iz = block_scan_incl(rz, cz, warp_tot, tz);
+    if (t < T) { px[t] = ix; pz[t] = iz; }
+    cx = tx; cz = tz;
+  }
+  __syncthreads();
+  // pass 3: joints
+  float* ob = out + (long)b * T * J * 3;
+  for (int i = threadIdx.x; i < T * J; i += blockDim.x) {
+    const int t = i / J, j = i - t * J;
+    float ox, oy, oz;
+    if (j == 0) {
+      ox = px[t]; oy = feat(t, 3); oz = pz[t];
+    } else {
+      const float c = cosf(ang[t]), s = sinf(ang[t]);
+      const float vx = feat(t, 4 + (j - 1) * 3), vy = feat(t, 5 + (j - 1) * 3), vz = feat(t, 6 + (j - 1) * 3);
+      const float qy = -s;
+      const float uvx = qy * vz, uvz = -(qy * vx);
+      const float uuvx = qy * uvz, uuvz = -(qy * uvx);
+      ox = vx + 2.f * (c * uvx + uuvx) + px[t];
+      oy = vy;
+      oz = vz + 2.f * (c * uvz + uuvz) + pz[t];
+    }
+    ob[(long)i * 3] = ox; ob[(long)i * 3 + 1] = oy; ob[(long)i * 3 + 2] = oz;
+  }
+}
+
 inline unsigned blocks(long n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
@@ -158,5 +291,28 @@ extern "C" MDM_API int mdm_p_mean_variance(const float* x, const float* eps, con
   if (total == 0) return MDM_OK;
   p_mean_kernel<<<blocks(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, eps, noise, t, tables, n_steps, clip,
                                                                                    per_sample, total, mean, x0, sample);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_ddim_update(const float* x, const float* eps_c, const float* eps_u, const float* noise,
+                                       const int64_t* t, const int64_t* t_prev, const float* tables4, int n_steps,
+                                       float cfg_scale, float eta, int clip, int B, long per_sample, float* x_prev,
+                                       float* x0, void* stream) {
+  if (!x || !eps_c || !t || !tables4 || !x_prev || (eta != 0.f && !noise)) return MDM_ERR_ARG;
+  const long total = (long)B * per_sample;
+  if (total == 0) return MDM_OK;
+  ddim_update_kernel<<<blocks(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, eps_c, eps_u, noise, t, t_prev, tables4, n_steps, cfg_scale, eta, clip, per_sample, total, x_prev, x0);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_recover_from_ric(const float* x, const float* mean, const float* stdv, int B, int T, int F,
+                                            int joints, float* out, void* stream) {
+  if (!x || !out || (mean == nullptr) != (stdv == nullptr) || joints < 1 || F < 4 + (joints - 1) * 3 || T < 1)
+    return MDM_ERR_ARG;
+  if (B == 0) return MDM_OK;
+  const size_t smem = sizeof(float) * 3 * (size_t)T;
+  if (smem > 48 * 1024) return MDM_ERR_UNSUPPORTED;
+  recover_ric_kernel<<<B, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, mean, stdv, T, F, joints, out);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }

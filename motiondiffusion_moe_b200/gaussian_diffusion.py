@@ -95,6 +95,15 @@ class GaussianDiffusion:
                                      torch.from_numpy(q).to(device).contiguous())
         return self._dev_tables[key]
 
+    def _ddim_tables(self, device):
+        """[4, T] fp32: sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, alphas_cumprod, alphas_cumprod_prev."""
+        key = "ddim:" + str(device)
+        if key not in self._dev_tables:
+            tab = np.stack([self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod, self.alphas_cumprod,
+                            self.alphas_cumprod_prev]).astype(np.float32)
+            self._dev_tables[key] = torch.from_numpy(tab).to(device).contiguous()
+        return self._dev_tables[key]
+
     def _check_supported(self):
         if self.model_mean_type != ModelMeanType.EPSILON or self.model_var_type != ModelVarType.FIXED_SMALL:
             raise NotImplementedError("the CUDA sampler implements the trainer's configuration only: "
@@ -257,6 +266,115 @@ class GaussianDiffusion:
             st.step(ts, None if step_noise is None else step_noise(ts))
         return st.x.clone()
 
+    # ------------------------------------------------------------------ DDIM
+    def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                    eta=0.0, *, noise=None):
+        """:699-742: one model forward, then pred_xstart / eps / sigma / sample in one kernel (mdm_ddim_update,
+        torch-eager arithmetic order).  Like the reference, a randn_like(x) is drawn even when eta == 0 (same RNG
+        consumption); `noise` (keyword-only extra) injects the tensor instead."""
+        self._check_supported()
+        if denoised_fn is not None or cond_fn is not None:
+            raise NotImplementedError("denoised_fn / cond_fn are not used by the reference's samplers")
+        if model_kwargs is None:
+            model_kwargs = {}
+        B = x.shape[0]
+        assert t.shape == (B,)
+        x = x.float().contiguous()
+        t = t.to(torch.int64).contiguous()
+        eps = model(x, t, **model_kwargs)                               # p_mean_variance, :493
+        assert eps.shape == x.shape
+        if noise is None:
+            noise = torch.randn_like(x)                                 # :735
+        sample, x0 = torch.empty_like(x), torch.empty_like(x)
+        ops.ddim_update(x, eps.contiguous(), t, self._ddim_tables(x.device), self.num_timesteps, float(eta),
+                        clip_denoised, sample, noise=noise.float().contiguous(), x0=x0)
+        return {"sample": sample, "pred_xstart": x0}
+
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
+                                     cond_fn=None, model_kwargs=None, device=None, progress=False, eta=0.0):
+        """:777-815 (all num_timesteps steps, t = T-1 .. 0)."""
+        if device is None:
+            device = next(model.parameters()).device
+        img = torch.randn(*shape, device=device) if noise is None else noise.to(device).float()
+        indices = list(range(self.num_timesteps))[::-1]
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        for i in indices:
+            t = torch.full((shape[0],), i, dtype=torch.int64, device=device)
+            out = self.ddim_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                   cond_fn=cond_fn, model_kwargs=model_kwargs, eta=eta)
+            yield out
+            img = out["sample"]
+
+    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                         model_kwargs=None, device=None, progress=False, eta=0.0):
+        """:744-775."""
+        final = None
+        for sample in self.ddim_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised,
+                                                        denoised_fn=denoised_fn, cond_fn=cond_fn,
+                                                        model_kwargs=model_kwargs, device=device, progress=progress,
+                                                        eta=eta):
+            final = sample
+        return final["sample"]
+
+    def ddim_timesteps(self, num_inference_steps):
+        """Strided schedule for DDIM with fewer steps: `num_inference_steps` timesteps spread uniformly over
+        [0, T), returned in sampling order (descending) together with each one's predecessor (-1 after the last)."""
+        S = int(num_inference_steps)
+        if not 1 <= S <= self.num_timesteps:
+            raise ValueError("num_inference_steps must be in [1, %d]" % self.num_timesteps)
+        ts = sorted(set(int(round(i * self.num_timesteps / S)) for i in range(S)))
+        order = ts[::-1]
+        return order, order[1:] + [-1]
+
+    def _cfg_ddim_step(self, model, ctx, x, t, t_prev, length2, noise, cfg_scale, eta, clip, x_out, x0_out):
+        B = x.shape[0]
+        eps = model(torch.cat([x, x]), torch.cat([t, t]), length2, text_ctx=ctx)
+        ops.ddim_update(x, eps[:B], t, self._ddim_tables(x.device), self.num_timesteps, float(eta), clip, x_out,
+                        eps_u=eps[B:], cfg_scale=cfg_scale, noise=noise, t_prev=t_prev, x0=x0_out)
+
+    def ddim_sample_with_cfg(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None,
+                             cfg_scale=7.5, eta=0.0, *, t_prev=None, noise=None, text_ctx=None):
+        """The DDIM update (:721-742) on the classifier-free-guided pred_xstart of p_sample_with_cfg (:1065-1079):
+        cond + uncond as one batched forward.  t_prev [B] (optional): previous timestep of a strided schedule."""
+        self._check_supported()
+        if denoised_fn is not None:
+            raise NotImplementedError("denoised_fn is not supported by the fused update")
+        B = x.shape[0]
+        x = x.float().contiguous()
+        t = t.to(torch.int64).contiguous()
+        ctx = text_ctx if text_ctx is not None else self._cfg_inputs(model, B, model_kwargs, x.device)
+        length = model_kwargs["length"].reshape(-1).to(torch.int64)
+        if noise is None and eta != 0.0:
+            noise = torch.randn_like(x)
+        sample, x0 = torch.empty_like(x), torch.empty_like(x)
+        self._cfg_ddim_step(model, ctx, x, t, None if t_prev is None else t_prev.to(torch.int64).contiguous(),
+                            torch.cat([length, length]).contiguous(),
+                            None if noise is None else noise.float().contiguous(), cfg_scale, eta, clip_denoised,
+                            sample, x0)
+        return {"sample": sample, "pred_xstart": x0}
+
+    def ddim_sample_loop_with_cfg(self, model, shape, noise=None, clip_denoised=True, model_kwargs=None, device=None,
+                                  progress=False, cfg_scale=7.5, eta=0.0, num_inference_steps=50, *,
+                                  use_cuda_graph=True):
+        """CFG sampling in `num_inference_steps` DDIM steps (strided schedule, `ddim_timesteps`) on the same
+        CUDA-graph step runner as p_sample_loop_with_cfg: 1000 / num_inference_steps times fewer forwards."""
+        self._check_supported()
+        if device is None:
+            device = next(model.parameters()).device
+        st = CFGStepper(self, model, shape, model_kwargs, cfg_scale, clip_denoised, device, use_cuda_graph,
+                        sampler="ddim", eta=eta)
+        st.x.copy_(torch.randn(*shape, device=device) if noise is None else noise.to(device).float())
+        order, prev = self.ddim_timesteps(num_inference_steps)
+        steps = list(zip(order, prev))
+        if progress:
+            from tqdm.auto import tqdm
+            steps = tqdm(steps, desc="DDIM sampling")
+        for ts, tp in steps:
+            st.step(ts, ts_prev=tp)
+        return st.x.clone()
+
     # ------------------------------------------------------------------ training losses (forward value)
     def training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
         """:923-992, MSE branch, forward values only: {"mse","target","pred","moe_loss"}.
@@ -285,8 +403,11 @@ class CFGStepper:
     eager warm-up step on scratch data, so lazily created workspaces exist) and replayed afterwards."""
 
     def __init__(self, diffusion, model, shape, model_kwargs, cfg_scale=7.5, clip_denoised=True, device=None,
-                 use_cuda_graph=True):
+                 use_cuda_graph=True, sampler="ddpm", eta=0.0):
         diffusion._check_supported()
+        if sampler not in ("ddpm", "ddim"):
+            raise ValueError(sampler)
+        self.sampler, self.eta = sampler, float(eta)
         self.d, self.model = diffusion, model
         self.device = device if device is not None else next(model.parameters()).device
         self.B = shape[0]
@@ -298,10 +419,15 @@ class CFGStepper:
         self.x0 = torch.zeros_like(self.x)
         self.noise = torch.zeros_like(self.x)
         self.t = torch.zeros(self.B, dtype=torch.int64, device=self.device)
+        self.t_prev = torch.zeros(self.B, dtype=torch.int64, device=self.device)
         self.use_graph = use_cuda_graph
         self.graph = None
 
     def _run(self):
+        if self.sampler == "ddim":
+            self.d._cfg_ddim_step(self.model, self.ctx, self.x, self.t, self.t_prev, self.length2, self.noise,
+                                  self.cfg_scale, self.eta, self.clip, self.x, self.x0)
+            return
         self.d._cfg_step(self.model, self.ctx, self.x, self.t, self.length2, self.noise, self.cfg_scale, self.clip,
                          self.x, self.x0)
 
@@ -317,15 +443,17 @@ class CFGStepper:
         pk["usage"].copy_(keep[1])
         pk["importance"].copy_(keep[2])
 
-    def step(self, ts, noise=None):
-        """Advance x from timestep ts to ts-1.  noise=None draws torch's normal_ (== randn_like, :1094)."""
+    def step(self, ts, noise=None, ts_prev=None):
+        """Advance x from timestep ts to ts-1 (DDIM: to ts_prev, default ts-1).  noise=None draws torch's
+        normal_ (== randn_like, :1094); a DDIM step with eta == 0 uses no noise."""
         if self.use_graph and self.graph is None:
             self._capture()
         self.t.fill_(int(ts))
-        if noise is None:
-            self.noise.normal_()
-        else:
+        self.t_prev.fill_(int(ts) - 1 if ts_prev is None else int(ts_prev))
+        if noise is not None:
             self.noise.copy_(noise)
+        elif self.sampler == "ddpm" or self.eta != 0.0:
+            self.noise.normal_()
         if self.use_graph:
             self.graph.replay()
         else:

@@ -202,6 +202,23 @@ def p_mean_variance(x, eps, t, tables, n_steps, clip, mean=None, x0=None, noise=
                                                _ptr(sample), _stream()), "mdm_p_mean_variance")
 
 
+def ddim_update(x, eps_c, t, tables4, n_steps, eta, clip, x_prev, *, eps_u=None, cfg_scale=1.0, noise=None,
+                t_prev=None, x0=None):
+    _c(x, eps_c, eps_u, noise, t, t_prev, tables4, x_prev, x0)
+    B = x.shape[0]
+    _lib.check(_lib.load().mdm_ddim_update(x.data_ptr(), eps_c.data_ptr(), _ptr(eps_u), _ptr(noise), t.data_ptr(),
+                                           _ptr(t_prev), tables4.data_ptr(), n_steps, cfg_scale, eta, 1 if clip else 0,
+                                           B, x.numel() // B, x_prev.data_ptr(), _ptr(x0), _stream()),
+               "mdm_ddim_update")
+
+
+def recover_from_ric(x, joints, out, mean=None, std=None):
+    _c(x, out, mean, std)
+    B, T, F = x.shape
+    _lib.check(_lib.load().mdm_recover_from_ric(x.data_ptr(), _ptr(mean), _ptr(std), B, T, F, joints, out.data_ptr(),
+                                                _stream()), "mdm_recover_from_ric")
+
+
 def q_sample(x0, noise, t, tables2, n_steps, x_t):
     _c(x0, noise, t, tables2, x_t)
     B = x0.shape[0]

@@ -465,6 +465,7 @@ def diffusion_tables(num_steps=1000):
     post_var = betas * (1.0 - ac_prev) / (1.0 - ac)
     return {
         "betas": betas,
+        "alphas_cumprod": ac,
         "sqrt_alphas_cumprod": np.sqrt(ac),
         "sqrt_one_minus_alphas_cumprod": np.sqrt(1.0 - ac),
         "sqrt_recip_alphas_cumprod": np.sqrt(1.0 / ac),
@@ -522,6 +523,25 @@ def p_mean_variance_update(tab, x, t, eps, clip_denoised=True, noise=None):
     return out
 
 
+def ddim_update(tab, x, t, x0, eta, noise, t_prev=None):
+    """ddim_sample after p_mean_variance, models/gaussian_diffusion.py:724-742, given pred_xstart `x0`.
+    t_prev (extension for strided schedules): alpha_bar_prev = alphas_cumprod[t_prev] (1 where t_prev < 0)
+    instead of the reference's alphas_cumprod_prev[t]."""
+    eps = (_extract(tab["sqrt_recip_alphas_cumprod"], t, x.shape) * x - x0) / \
+        _extract(tab["sqrt_recipm1_alphas_cumprod"], t, x.shape)                          # :567-571
+    ac = 1.0 / tab["sqrt_recip_alphas_cumprod"] ** 2 if "alphas_cumprod" not in tab else tab["alphas_cumprod"]
+    alpha_bar = _extract(ac, t, x.shape)
+    if t_prev is None:
+        alpha_bar_prev = _extract(np.append(1.0, ac[:-1]), t, x.shape)
+    else:
+        alpha_bar_prev = _extract(np.append(ac, 1.0), torch.where(t_prev < 0, torch.full_like(t_prev, len(ac)), t_prev),
+                                  x.shape)
+    sigma = eta * torch.sqrt((1 - alpha_bar_prev) / (1 - alpha_bar)) * torch.sqrt(1 - alpha_bar / alpha_bar_prev)
+    mean_pred = x0 * torch.sqrt(alpha_bar_prev) + torch.sqrt(1 - alpha_bar_prev - sigma ** 2) * eps
+    nz = (t != 0).float().view(-1, *([1] * (x.dim() - 1)))
+    return mean_pred + nz * sigma * noise
+
+
 def cfg_step(p, cfg, tab, x, t, length, cond, uncond, noise, cfg_scale=7.5, clip_denoised=False,
              p_uncond=None):
     """One p_sample_with_cfg step: cond / uncond are (xf_proj, xf_out) pairs.  p_uncond: parameters of
@@ -537,3 +557,49 @@ def stub_text(text, dim, device="cpu"):
     g = torch.Generator().manual_seed(1234 if text[0] else 4321)
     tok = torch.randn(len(text), 8 + (12 if text[0] else 2), dim, generator=g).to(device)
     return tok.mean(1), tok
+
+
+# ----------------------------------------------------------------------------------------------
+# Post-processing after the sampler (tools/visualization.py:72-91, utils/motion_process.py, utils/quaternion.py)
+# ----------------------------------------------------------------------------------------------
+def _qinv(q):
+    """utils/quaternion.py:16-20."""
+    mask = torch.ones_like(q)
+    mask[..., 1:] = -mask[..., 1:]
+    return q * mask
+
+
+def _qrot(q, v):
+    """utils/quaternion.py:54-73."""
+    shape = list(v.shape)
+    q = q.contiguous().view(-1, 4)
+    v = v.contiguous().view(-1, 3)
+    qvec = q[:, 1:]
+    uv = torch.cross(qvec, v, dim=1)
+    uuv = torch.cross(qvec, uv, dim=1)
+    return (v + 2 * (q[:, :1] * uv + uuv)).view(shape)
+
+
+def recover_from_ric(data, joints_num, mean=None, std=None):
+    """`motion * std + mean` (tools/visualization.py:91) then recover_root_rot_pos + recover_from_ric
+    (utils/motion_process.py:362-380, 401-417).  data [..., T, F] -> [..., T, joints_num, 3]."""
+    if mean is not None:
+        data = data * std + mean
+    rot_vel = data[..., 0]
+    r_rot_ang = torch.zeros_like(rot_vel)
+    r_rot_ang[..., 1:] = rot_vel[..., :-1]
+    r_rot_ang = torch.cumsum(r_rot_ang, dim=-1)
+    r_rot_quat = torch.zeros(data.shape[:-1] + (4,), device=data.device)
+    r_rot_quat[..., 0] = torch.cos(r_rot_ang)
+    r_rot_quat[..., 2] = torch.sin(r_rot_ang)
+    r_pos = torch.zeros(data.shape[:-1] + (3,), device=data.device)
+    r_pos[..., 1:, [0, 2]] = data[..., :-1, 1:3]
+    r_pos = _qrot(_qinv(r_rot_quat), r_pos)
+    r_pos = torch.cumsum(r_pos, dim=-2)
+    r_pos[..., 1] = data[..., 3]
+    positions = data[..., 4:(joints_num - 1) * 3 + 4]
+    positions = positions.reshape(positions.shape[:-1] + (-1, 3))
+    positions = _qrot(_qinv(r_rot_quat[..., None, :]).expand(positions.shape[:-1] + (4,)), positions)
+    positions[..., 0] += r_pos[..., 0:1]
+    positions[..., 2] += r_pos[..., 2:3]
+    return torch.cat([r_pos.unsqueeze(-2), positions], dim=-2)

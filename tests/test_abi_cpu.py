@@ -89,3 +89,32 @@ def test_diffusion_tables_match_oracle():
                                model_mean_type=mdm.ModelMeanType.START_X)
     with pytest.raises(NotImplementedError):
         d2._check_supported()
+
+
+def test_reference_checkpoint_roundtrip(tmp_path):
+    """DDPMTrainer.save / load layout (trainers/ddpm_trainer.py:260-289): {"encoder", "opt_encoder", "ep",
+    "total_it"}; DDP "module." prefixes and DeBERTa "text_encoder.*" entries of a real checkpoint are tolerated
+    (the reference loads with strict=False)."""
+    import torch
+    import motiondiffusion_moe_b200 as mdm
+    from oracle import cases
+    cfg, p = cases.case_params("tiny_b3")
+    a = mdm.MotionTransformer(precision="fp32", **cfg)
+    a.load_state_dict({k: p[k] for k in a.state_dict()})
+    path = str(tmp_path / "ckpt_e003.tar")
+    mdm.save_reference_checkpoint(a, path, ep=3, total_it=1234)
+    raw = torch.load(path, weights_only=False)
+    assert set(raw) == {"opt_encoder", "ep", "total_it", "encoder"}
+    raw["encoder"] = {"module." + k: v for k, v in raw["encoder"].items()}
+    raw["encoder"]["module.text_encoder.model.embeddings.word_embeddings.weight"] = torch.zeros(4, 4)
+    torch.save(raw, path)
+    b = mdm.MotionTransformer(precision="fp32", **cfg)
+    ep, it, missing, unexpected = mdm.load_reference_checkpoint(b, path)
+    assert (ep, it) == (3, 1234) and not missing and not unexpected
+    sa, sb = a.state_dict(), b.state_dict()
+    assert set(sa) == set(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    import pytest
+    with pytest.raises(KeyError):
+        mdm.load_reference_checkpoint(b, {"model": {}})
+    with pytest.raises(mdm.MdmError):
+        mdm.recover_from_ric(torch.zeros(1, 4, 263), 22)       # CPU tensor: no CPU path

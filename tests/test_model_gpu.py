@@ -248,6 +248,44 @@ def test_p_mean_variance_and_p_sample_match_oracle():
     assert torch.isfinite(d.p_sample(net, x, t, model_kwargs=kw, noise_fn=torch.randn)["sample"]).all()
 
 
+def test_ddim_sampling_matches_oracle_and_graph_equals_eager():
+    """ddim_sample (gaussian_diffusion.py:699-742): post-forward arithmetic bit-identical given the same eps;
+    ddim_sample_loop_with_cfg: strided schedule, CUDA-graph replay == eager, == a step-by-step composition of
+    ddim_sample_with_cfg, and the final step lands on pred_xstart (alpha_bar_prev = 1, eta = 0)."""
+    case = "tiny_b3"
+    cfg_name, B, T = cases.CASES[case]
+    cfg, p, net = build(case, "fp32")
+    net.encode_text = lambda text, device: mo.stub_text(text, cfg.text_latent_dim, device)
+    x, _, length, xf_proj, xf_out = cases.make_inputs(cfg, B, T, seed=4, device=DEV)
+    d = mdm.GaussianDiffusion(betas=mdm.get_named_beta_schedule("linear", 1000))
+    tab = mo.diffusion_tables(1000)
+    kw = {"length": length, "xf_proj": xf_proj, "xf_out": xf_out}
+    t = torch.tensor([0, 500, 999][:B], device=DEV)
+    noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(2)).to(DEV)
+    eps = net(x, t, **kw)
+    for eta in (0.0, 0.7):
+        out = d.ddim_sample(net, x, t, clip_denoised=False, model_kwargs=kw, eta=eta, noise=noise)
+        x0 = mo.p_mean_variance_update(tab, x, t, eps, False)["pred_xstart"]
+        assert torch.equal(out["pred_xstart"], x0)
+        assert torch.equal(out["sample"], mo.ddim_update(tab, x, t, x0, eta, noise))
+    order, prev = d.ddim_timesteps(8)
+    assert order[0] > order[-1] == 0 and prev[-1] == -1 and prev[:-1] == order[1:] and len(order) == 8
+    kwc = dict(kw, text=["a person walks"] * B)
+    shape = (B, T, cfg.input_feats)
+    runs = [d.ddim_sample_loop_with_cfg(net, shape, noise=x, clip_denoised=False, model_kwargs=kwc, cfg_scale=7.5,
+                                        eta=0.0, num_inference_steps=8, use_cuda_graph=gph) for gph in (False, True)]
+    assert torch.equal(runs[0], runs[1])
+    cur, last = x, None
+    for ts, tp in zip(order, prev):
+        last = d.ddim_sample_with_cfg(net, cur, torch.full((B,), ts, device=DEV), clip_denoised=False,
+                                      model_kwargs=kwc, cfg_scale=7.5, eta=0.0,
+                                      t_prev=torch.full((B,), tp, device=DEV))
+        cur = last["sample"]
+    assert torch.equal(cur, runs[0])
+    assert rel(cur, last["pred_xstart"]) < 1e-6
+    assert torch.isfinite(cur).all()
+
+
 def test_state_dict_roundtrip_and_errors():
     cfg, p, net = build("tiny_b3", "fp32")
     sd = net.state_dict()

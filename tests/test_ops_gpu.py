@@ -404,6 +404,56 @@ def test_cfg_update_bit_exact(clip):
     assert np.allclose(d.posterior_log_variance_clipped, tab["posterior_log_variance_clipped"])
 
 
+@pytest.mark.parametrize("eta", [0.0, 0.5, 1.0])
+@pytest.mark.parametrize("clip", [False, True])
+def test_ddim_update_bit_exact(eta, clip):
+    """mdm_ddim_update against the reference's own ddim_sample outputs (tests/golden/ddim_step.npz) and against
+    the oracle for the guided / strided variants: bit for bit."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ddim_step.npz"))
+    x, eps, t, noise = (torch.from_numpy(g[k]).to(DEV) for k in ("x", "eps", "t", "noise"))
+    tab = mo.diffusion_tables(1000)
+    tab4 = torch.from_numpy(np.stack([tab["sqrt_recip_alphas_cumprod"], tab["sqrt_recipm1_alphas_cumprod"],
+                                      tab["alphas_cumprod"], np.append(1.0, tab["alphas_cumprod"][:-1])])
+                            .astype(np.float32)).to(DEV)
+    out, x0 = torch.empty_like(x), torch.empty_like(x)
+    ops.ddim_update(x, eps, t, tab4, 1000, eta, clip, out, noise=noise, x0=x0)
+    assert torch.equal(x0.cpu(), torch.from_numpy(g["x0_eta%g_clip%d" % (eta, int(clip))]))
+    # The golden was produced by the reference on the CPU, where torch.sqrt(float32) is NOT correctly rounded
+    # (0.6 % of inputs are off by one ulp against IEEE sqrt); the kernel uses sqrt.rn like torch's CUDA sqrt.
+    # So: 1e-6 against the CPU golden, bit-identical against the same op sequence evaluated by torch on the GPU.
+    assert rel(out.cpu(), torch.from_numpy(g["sample_eta%g_clip%d" % (eta, int(clip))])) < 1e-6
+    assert torch.equal(out, mo.ddim_update(tab, x, t, x0, eta, noise))
+    # classifier-free guidance on pred_xstart + strided predecessor
+    eps_u = randn(*x.shape, seed=8)
+    t_prev = torch.tensor([-1, -1, 3, 250, 700, 980], device=DEV)
+    ops.ddim_update(x, eps, t, tab4, 1000, eta, clip, out, eps_u=eps_u, cfg_scale=7.5, noise=noise, t_prev=t_prev, x0=x0)
+    _, guided = mo.cfg_update(tab, x, t, eps, eps_u, noise, 7.5, clip)
+    ref = mo.ddim_update(tab, x, t, guided, eta, noise, t_prev=t_prev)
+    assert torch.equal(x0, guided)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("tag,J", [("t2m", 22), ("kit", 21)])
+def test_recover_from_ric_matches_reference_golden(tag, J):
+    """mdm_recover_from_ric (de-normalise + recover_root_rot_pos + recover_from_ric in one kernel) against the
+    reference's own outputs; the cumulative sums run in a different order than torch.cumsum, hence 1e-5."""
+    import os
+    import numpy as np
+    import motiondiffusion_moe_b200 as mdm
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ric.npz"))
+    x, mean, std = (torch.from_numpy(g[tag + k]).to(DEV) for k in ("_x", "_mean", "_std"))
+    ref = torch.from_numpy(g[tag + "_joints"]).to(DEV)
+    got = mdm.recover_from_ric(x, J, mean, std)
+    assert got.shape == ref.shape
+    assert rel(got, ref) < 1e-5 and (got - ref).abs().max() < 1e-3
+    raw = x * std + mean
+    assert torch.equal(mdm.recover_from_ric(raw, J), got)              # already de-normalised input
+    long = torch.randn(2, 700, 263, generator=gen(3)).to(DEV) * 0.1    # more frames than threads in a block
+    assert rel(mdm.recover_from_ric(long, 22), mo.recover_from_ric(long, 22)) < 1e-5
+
+
 def test_q_sample_bit_exact():
     from motiondiffusion_moe_b200 import GaussianDiffusion, get_named_beta_schedule
     d = GaussianDiffusion(betas=get_named_beta_schedule("linear", 1000))
