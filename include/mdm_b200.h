@@ -109,6 +109,13 @@ MDM_API int mdm_rowop(const MdmRowOp* op, long rows, int D, int out_dt, void* st
 MDM_API int mdm_fastattn(const void* qkv, int dt, const float* P, const float* norm_w,
                          const float* norm_b, const int64_t* length, int length_shift, int B, int H,
                          int T, int hd, int M, void* out, void* stream);
+/* Same, with a scheduling hint: seq_order [B] int32 = a permutation of the sequences by DESCENDING length (or
+ * NULL).  The result does not depend on it; CTAs of long sequences (more unmasked key windows) are started
+ * first, which shortens the tail of the 2-wave grid.  `length` is fixed over a sampling loop, so the host
+ * sorts once per loop (CFGStepper), not per step. */
+MDM_API int mdm_fastattn_ordered(const void* qkv, int dt, const float* P, const float* norm_w,
+                                 const float* norm_b, const int64_t* length, int length_shift, int B, int H,
+                                 int T, int hd, int M, void* out, const int* seq_order, void* stream);
 
 /* ---- LinearTemporalCrossAttention, models/fast_attention.py:242-253 --------------------------- */
 /* Text side (step-invariant): ctx[b,h,d,l] = sum_n softmax_n(k[b,n,h,d]) * v[b,n,h,l], n < nt[b].

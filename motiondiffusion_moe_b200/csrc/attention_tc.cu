@@ -363,7 +363,7 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
 __global__ void __launch_bounds__(256, 2)
 fastattn_stream_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, const float* __restrict__ nw,
                        const float* __restrict__ nb, const int64_t* __restrict__ length, int length_shift, int H,
-                       int T, int Tp, bf16* __restrict__ out) {
+                       int T, int Tp, bf16* __restrict__ out, const int* __restrict__ seq_order) {
   constexpr int HD = 128, LDS = HD + 8, KS = HD / 16, NT = HD / 8, CPR = HD / 8, NW = 8, CR = 16, EPT = HD / 8;
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* Qs = reinterpret_cast<bf16*>(smem);                  // [Tp][LDS]  q -> q'
@@ -374,7 +374,9 @@ fastattn_stream_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P
   float* nw_s = den_s + Tp;
   float* nb_s = nw_s + HD;
 
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  // seq_order (optional): sequences by descending length.  The work of a CTA grows with its sequence's length
+  // (masked key windows are skipped) and 512 CTAs run on 296 slots, so starting the long ones first shortens the tail.
+  const int b = seq_order ? seq_order[blockIdx.x / H] : blockIdx.x / H, h = blockIdx.x % H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
   const int D = H * HD;
@@ -662,7 +664,7 @@ fastattn_stream_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P
 }
 
 int launch_fastattn_stream(const bf16* qkv, const float* P, const float* nw, const float* nb, const int64_t* length,
-                           int shift, int B, int H, int T, bf16* out, cudaStream_t st) {
+                           int shift, int B, int H, int T, bf16* out, const int* seq_order, cudaStream_t st) {
   constexpr int HD = 128, LDS = HD + 8;
   const int Tp = (T + 15) / 16 * 16;
   const size_t smem = (size_t)(Tp + HD + 4 * 16) * LDS * 2 + sizeof(float) * (2 * 8 * 16 + Tp + 2 * HD);
@@ -673,7 +675,7 @@ int launch_fastattn_stream(const bf16* qkv, const float* P, const float* nw, con
       return MDM_ERR_CUDA;
     attr = smem;
   }
-  fastattn_stream_kernel<<<B * H, 256, smem, st>>>(qkv, P, nw, nb, length, shift, H, T, Tp, out);
+  fastattn_stream_kernel<<<B * H, 256, smem, st>>>(qkv, P, nw, nb, length, shift, H, T, Tp, out, seq_order);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -970,7 +972,7 @@ int launch_softmax_cross(const bf16* q, const bf16* k, const bf16* v, const int*
 // generic fp32-compute kernel of attention.cu).
 int mdm_fastattn_tc(const void* qkv, const float* P, const float* norm_w, const float* norm_b,
                     const int64_t* length, int length_shift, int B, int H, int T, int hd, int M, void* out,
-                    cudaStream_t st) {
+                    const int* seq_order, cudaStream_t st) {
   if (M != hd) return MDM_ERR_UNSUPPORTED;
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
   bf16* o = reinterpret_cast<bf16*>(out);
@@ -978,7 +980,7 @@ int mdm_fastattn_tc(const void* qkv, const float* P, const float* norm_w, const 
   if (hd == 128) {
     static const int stream_env = [] { const char* e = getenv("MDM_FA_STREAM"); return e ? atoi(e) : 1; }();
     if (stream_env) {
-      const int r = launch_fastattn_stream(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, st);
+      const int r = launch_fastattn_stream(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order, st);
       if (r != MDM_ERR_UNSUPPORTED) return r;
     }
     return launch_fastattn<128>(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, st);

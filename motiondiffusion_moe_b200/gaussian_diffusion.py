@@ -415,6 +415,8 @@ class CFGStepper:
         self.ctx = diffusion._cfg_inputs(model, self.B, model_kwargs, self.device)
         length = model_kwargs["length"].reshape(-1).to(device=self.device, dtype=torch.int64)
         self.length2 = torch.cat([length, length]).contiguous()
+        # `length` is fixed over the loop: sort once, FastAttention starts the longest sequences first
+        self.ctx.seq_order = torch.argsort(self.length2, descending=True, stable=True).to(torch.int32).contiguous()
         self.x = torch.zeros(*shape, device=self.device, dtype=torch.float32)
         self.x0 = torch.zeros_like(self.x)
         self.noise = torch.zeros_like(self.x)

@@ -48,6 +48,7 @@ class TextContext:
         self.k2 = []
         self.v2 = []
         self.xf_proj = None
+        self.seq_order = None     # optional int32 [B]: sequences by descending length (FastAttention launch order)
 
 
 class MotionTransformer(nn.Module):
@@ -578,7 +579,7 @@ class MotionTransformer(nn.Module):
             out_f32, out_a = out_a, None
         ops.gemm(A, wb[0], wb[1], act=act, out_a=out_a, out_f32=out_f32, **kw)
 
-    def _performer(self, Pk, resid, hh, film, out, Bn, T, length, shift):
+    def _performer(self, Pk, resid, hh, film, out, Bn, T, length, shift, order=None):
         """PerformerSelfAttention.forward (fast_attention.py:137-179) after its pre_norm."""
         adt, D, H = self._adt(), self.latent_dim, self.num_heads
         N = Bn * T
@@ -586,7 +587,8 @@ class MotionTransformer(nn.Module):
         a1 = self._buf("a1", (N, D), adt)
         a2 = self._buf("a2", (N, D), adt)
         self._lin(hh, (Pk["qkv_w"], Pk["qkv_b"]), out_a=qkv)
-        ops.fastattn(qkv, Pk["P"], Pk["fa_norm"][0], Pk["fa_norm"][1], length, shift, Bn, H, T, D // H, a1)
+        ops.fastattn(qkv, Pk["P"], Pk["fa_norm"][0], Pk["fa_norm"][1], length, shift, Bn, H, T, D // H, a1,
+                     seq_order=order)
         self._lin(a1, Pk["p0"], out_a=a2, act=ACT_GELU)
         self._lin(a2, Pk["p3"], out_a=a1)
         ops.rowop(a1, N, D, ops._dt(a2), ln1=Pk["post"], l2norm=True, ln2=Pk["s_norm"], film=film,
@@ -614,9 +616,9 @@ class MotionTransformer(nn.Module):
         xa = self._buf("xa", (N, D), adt)
         # ---- DualSelfAttentionBlock (fast_attention.py:208-226)
         ops.rowop(x, N, D, adti, ln1=L["dsa_pre"], out1_f32=h, ln2=L["perf"][0]["pre"], out2_a=a0, out0_a=xa)
-        self._performer(L["perf"][0], h, a0, film[0], loc, Bn, T, length, shift)
+        self._performer(L["perf"][0], h, a0, film[0], loc, Bn, T, length, shift, ctx.seq_order)
         ops.rowop(loc, N, D, adti, ln1=L["perf"][1]["pre"], out1_a=a0)
-        self._performer(L["perf"][1], loc, a0, film[1], glb, Bn, T, length, shift)
+        self._performer(L["perf"][1], loc, a0, film[1], glb, Bn, T, length, shift, ctx.seq_order)
         pre = h  # h is dead from here on
         self._lin(xa, L["skip"], out_f32=pre, act=ACT_GELU, resid=glb, alpha=1.0, beta=0.1)
         ops.rowop(pre, N, D, adti, ln1=L["dsa_post"], out1_f32=x1, ln2=L["ca_norm"], out2_a=a0)

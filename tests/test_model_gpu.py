@@ -284,6 +284,7 @@ def test_ddim_sampling_matches_oracle_and_graph_equals_eager():
     assert torch.equal(cur, runs[0])
     assert rel(cur, last["pred_xstart"]) < 1e-6
     assert torch.isfinite(cur).all()
+    del net.encode_text          # the model is cached across tests: drop the stub again
 
 
 def test_state_dict_roundtrip_and_errors():

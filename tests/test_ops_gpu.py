@@ -205,6 +205,11 @@ def test_fastattn_fully_masked_windows():
     o = out.view(B, T, D)
     for i in range(B):
         assert rel(o[i], ref[i]) < TOL[torch.bfloat16], (i, rel(o[i], ref[i]))
+    # the launch-order hint (longest sequences first) must not change a single bit
+    out2 = torch.empty_like(out)
+    order = torch.argsort(length, descending=True).to(torch.int32)
+    ops.fastattn(qkv, P, nw, nb, length, 0, B, H, T, hd, out2, seq_order=order)
+    assert torch.equal(out, out2)
 
 
 def test_fastattn_length_shift():
