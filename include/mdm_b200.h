@@ -109,13 +109,16 @@ MDM_API int mdm_rowop(const MdmRowOp* op, long rows, int D, int out_dt, void* st
 MDM_API int mdm_fastattn(const void* qkv, int dt, const float* P, const float* norm_w,
                          const float* norm_b, const int64_t* length, int length_shift, int B, int H,
                          int T, int hd, int M, void* out, void* stream);
-/* Same, with a scheduling hint: seq_order [B] int32 = a permutation of the sequences by DESCENDING length (or
- * NULL).  The result does not depend on it; CTAs of long sequences (more unmasked key windows) are started
- * first, which shortens the tail of the 2-wave grid.  `length` is fixed over a sampling loop, so the host
- * sorts once per loop (CFGStepper), not per step. */
+/* Same, with two optional hints that do not change the result:
+ *   seq_order [B] int32: a permutation of the sequences by DESCENDING length.  CTAs of long sequences (more
+ *     unmasked key windows) are started first, which shortens the tail of the 2-wave grid.  `length` is fixed over
+ *     a sampling loop, so the host sorts once per loop (CFGStepper), not per step.
+ *   Pt_bf16 [M, hd] bf16: the projection matrix already transposed and rounded (== what the bf16 kernel builds from
+ *     P in every CTA); packed once per model. */
 MDM_API int mdm_fastattn_ordered(const void* qkv, int dt, const float* P, const float* norm_w,
                                  const float* norm_b, const int64_t* length, int length_shift, int B, int H,
-                                 int T, int hd, int M, void* out, const int* seq_order, void* stream);
+                                 int T, int hd, int M, void* out, const int* seq_order, const void* Pt_bf16,
+                                 void* stream);
 
 /* ---- LinearTemporalCrossAttention, models/fast_attention.py:242-253 --------------------------- */
 /* Text side (step-invariant): ctx[b,h,d,l] = sum_n softmax_n(k[b,n,h,d]) * v[b,n,h,l], n < nt[b].

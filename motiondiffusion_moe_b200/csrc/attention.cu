@@ -10,7 +10,7 @@
 // tensor-core (mma.sync) kernel for the bf16 path, attention_tc.cu
 int mdm_fastattn_tc(const void* qkv, const float* P, const float* norm_w, const float* norm_b,
                     const int64_t* length, int length_shift, int B, int H, int T, int hd, int M, void* out,
-                    const int* seq_order, cudaStream_t st);
+                    const int* seq_order, const void* Pt_bf16, cudaStream_t st);
 
 int mdm_lincross_apply_tc(const void* q, const float* ctx, int B, int T, int H, int hd, void* y, cudaStream_t st);
 int mdm_softmax_cross_tc(const void* q, const void* k, const void* v, const int* nt, int B, int T, int Nt_max, int H,
@@ -364,24 +364,25 @@ int set_smem(K kernel, size_t bytes) {
 extern "C" MDM_API int mdm_fastattn_ordered(const void* qkv, int dt, const float* P, const float* norm_w,
                                             const float* norm_b, const int64_t* length, int length_shift, int B,
                                             int H, int T, int hd, int M, void* out, const int* seq_order,
-                                            void* stream);
+                                            const void* Pt_bf16, void* stream);
 extern "C" MDM_API int mdm_fastattn(const void* qkv, int dt, const float* P, const float* norm_w,
                                     const float* norm_b, const int64_t* length, int length_shift, int B,
                                     int H, int T, int hd, int M, void* out, void* stream) {
-  return mdm_fastattn_ordered(qkv, dt, P, norm_w, norm_b, length, length_shift, B, H, T, hd, M, out, nullptr, stream);
+  return mdm_fastattn_ordered(qkv, dt, P, norm_w, norm_b, length, length_shift, B, H, T, hd, M, out, nullptr, nullptr,
+                              stream);
 }
 
 extern "C" MDM_API int mdm_fastattn_ordered(const void* qkv, int dt, const float* P, const float* norm_w,
                                             const float* norm_b, const int64_t* length, int length_shift, int B,
                                             int H, int T, int hd, int M, void* out, const int* seq_order,
-                                            void* stream) {
+                                            const void* Pt_bf16, void* stream) {
   if (!qkv || !P || !norm_w || !norm_b || !out) return MDM_ERR_ARG;
   if (hd > AT || M > AT || (hd & 3) || (M & 3)) return MDM_ERR_UNSUPPORTED;
   if (B * H == 0 || T == 0) return MDM_OK;
   const size_t smem = sizeof(float) * ((size_t)hd * M + 3 * TC * hd + 2 * M * TC + TC * 4);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dt == MDM_BF16) {
-    const int r = mdm_fastattn_tc(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, M, out, seq_order, st);
+    const int r = mdm_fastattn_tc(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, M, out, seq_order, Pt_bf16, st);
     if (r != MDM_ERR_UNSUPPORTED) return r;  // otherwise: shape outside the tensor-core kernel
   }
   if (dt == MDM_F32) {

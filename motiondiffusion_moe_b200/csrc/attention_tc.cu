@@ -363,7 +363,8 @@ fastattn_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, co
 __global__ void __launch_bounds__(256, 2)
 fastattn_stream_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P, const float* __restrict__ nw,
                        const float* __restrict__ nb, const int64_t* __restrict__ length, int length_shift, int H,
-                       int T, int Tp, bf16* __restrict__ out, const int* __restrict__ seq_order) {
+                       int T, int Tp, bf16* __restrict__ out, const int* __restrict__ seq_order,
+                       const bf16* __restrict__ Pt) {
   constexpr int HD = 128, LDS = HD + 8, KS = HD / 16, NT = HD / 8, CPR = HD / 8, NW = 8, CR = 16, EPT = HD / 8;
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* Qs = reinterpret_cast<bf16*>(smem);                  // [Tp][LDS]  q -> q'
@@ -411,13 +412,20 @@ fastattn_stream_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P
   if (NC > 0) load_window(0); else asm volatile("cp.async.commit_group;" ::: "memory");
   if (NC > 1) load_window(1); else asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = tid; i < Tp - NC * CR; i += 256) den_s[NC * CR + i] = 1e-6f;
-  for (int i = tid; i < HD * HD / 4; i += 256) {
-    const int n = i % HD, m4 = i / HD;
-    const float4 p4 = __ldg(reinterpret_cast<const float4*>(P + n * HD + 4 * m4));
-    Ps[(4 * m4) * LDS + n] = __float2bfloat16_rn(p4.x);
-    Ps[(4 * m4 + 1) * LDS + n] = __float2bfloat16_rn(p4.y);
-    Ps[(4 * m4 + 2) * LDS + n] = __float2bfloat16_rn(p4.z);
-    Ps[(4 * m4 + 3) * LDS + n] = __float2bfloat16_rn(p4.w);
+  if (Pt) {     // P^T already transposed and rounded to bf16 by the host (once per model): plain 16-byte copies
+    for (int i = tid; i < HD * CPR; i += 256) {
+      const int m = i / CPR, c = i - m * CPR;
+      *reinterpret_cast<uint4*>(Ps + m * LDS + c * 8) = __ldg(reinterpret_cast<const uint4*>(Pt + m * HD + c * 8));
+    }
+  } else {
+    for (int i = tid; i < HD * HD / 4; i += 256) {
+      const int n = i % HD, m4 = i / HD;
+      const float4 p4 = __ldg(reinterpret_cast<const float4*>(P + n * HD + 4 * m4));
+      Ps[(4 * m4) * LDS + n] = __float2bfloat16_rn(p4.x);
+      Ps[(4 * m4 + 1) * LDS + n] = __float2bfloat16_rn(p4.y);
+      Ps[(4 * m4 + 2) * LDS + n] = __float2bfloat16_rn(p4.z);
+      Ps[(4 * m4 + 3) * LDS + n] = __float2bfloat16_rn(p4.w);
+    }
   }
   for (int i = tid; i < HD; i += 256) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }
   asm volatile("cp.async.wait_group 2;" ::: "memory");   // q has landed (the two windows may still fly)
@@ -664,7 +672,8 @@ fastattn_stream_kernel(const bf16* __restrict__ qkv, const float* __restrict__ P
 }
 
 int launch_fastattn_stream(const bf16* qkv, const float* P, const float* nw, const float* nb, const int64_t* length,
-                           int shift, int B, int H, int T, bf16* out, const int* seq_order, cudaStream_t st) {
+                           int shift, int B, int H, int T, bf16* out, const int* seq_order, const bf16* Pt,
+                           cudaStream_t st) {
   constexpr int HD = 128, LDS = HD + 8;
   const int Tp = (T + 15) / 16 * 16;
   const size_t smem = (size_t)(Tp + HD + 4 * 16) * LDS * 2 + sizeof(float) * (2 * 8 * 16 + Tp + 2 * HD);
@@ -675,7 +684,7 @@ int launch_fastattn_stream(const bf16* qkv, const float* P, const float* nw, con
       return MDM_ERR_CUDA;
     attr = smem;
   }
-  fastattn_stream_kernel<<<B * H, 256, smem, st>>>(qkv, P, nw, nb, length, shift, H, T, Tp, out, seq_order);
+  fastattn_stream_kernel<<<B * H, 256, smem, st>>>(qkv, P, nw, nb, length, shift, H, T, Tp, out, seq_order, Pt);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -972,7 +981,7 @@ int launch_softmax_cross(const bf16* q, const bf16* k, const bf16* v, const int*
 // generic fp32-compute kernel of attention.cu).
 int mdm_fastattn_tc(const void* qkv, const float* P, const float* norm_w, const float* norm_b,
                     const int64_t* length, int length_shift, int B, int H, int T, int hd, int M, void* out,
-                    const int* seq_order, cudaStream_t st) {
+                    const int* seq_order, const void* Pt_bf16, cudaStream_t st) {
   if (M != hd) return MDM_ERR_UNSUPPORTED;
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
   bf16* o = reinterpret_cast<bf16*>(out);
@@ -980,7 +989,8 @@ int mdm_fastattn_tc(const void* qkv, const float* P, const float* norm_w, const 
   if (hd == 128) {
     static const int stream_env = [] { const char* e = getenv("MDM_FA_STREAM"); return e ? atoi(e) : 1; }();
     if (stream_env) {
-      const int r = launch_fastattn_stream(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order, st);
+      const int r = launch_fastattn_stream(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order,
+                                           reinterpret_cast<const bf16*>(Pt_bf16), st);
       if (r != MDM_ERR_UNSUPPORTED) return r;
     }
     return launch_fastattn<128>(q, P, norm_w, norm_b, length, length_shift, B, H, T, o, st);

@@ -97,11 +97,13 @@ def rowop(x, rows, D, out_dt, *, ln1=None, l2norm=False, out1_f32=None, out1_a=N
     _lib.check(_lib.load().mdm_rowop(C.byref(op), rows, D, out_dt, _stream()), "mdm_rowop")
 
 
-def fastattn(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out, seq_order=None):
-    _c(qkv, P, norm_w, norm_b, length, out, seq_order)
+def fastattn(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out, seq_order=None, Pt=None):
+    _c(qkv, P, norm_w, norm_b, length, out, seq_order, Pt)
+    if Pt is not None and (Pt.dtype != torch.bfloat16 or tuple(Pt.shape) != (P.shape[1], P.shape[0])):
+        raise _lib.MdmError("Pt must be P^T in bf16")
     _lib.check(_lib.load().mdm_fastattn_ordered(qkv.data_ptr(), _dt(qkv), P.data_ptr(), norm_w.data_ptr(),
                                                 norm_b.data_ptr(), _ptr(length), length_shift, B, H, T, hd,
-                                                P.shape[1], out.data_ptr(), _ptr(seq_order), _stream()),
+                                                P.shape[1], out.data_ptr(), _ptr(seq_order), _ptr(Pt), _stream()),
                "mdm_fastattn")
 
 

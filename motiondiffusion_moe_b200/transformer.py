@@ -462,6 +462,8 @@ class MotionTransformer(nn.Module):
                       "qkv_b": torch.cat([g(p + ".query.bias"), g(p + ".key.bias"),
                                           g(p + ".value.bias")]).float().contiguous(),
                       "P": g(p + ".fast_attention.projection_matrix").float().contiguous(),
+                      "Pt": (g(p + ".fast_attention.projection_matrix").float().t().contiguous().to(torch.bfloat16)
+                             if wdt == torch.bfloat16 else None),
                       "fa_norm": LN(p + ".fast_attention.norm"),
                       "p0": (W(p + ".proj_out.0"), Bf(p + ".proj_out.0")),
                       "p3": (W(p + ".proj_out.3"), Bf(p + ".proj_out.3")),
@@ -588,7 +590,7 @@ class MotionTransformer(nn.Module):
         a2 = self._buf("a2", (N, D), adt)
         self._lin(hh, (Pk["qkv_w"], Pk["qkv_b"]), out_a=qkv)
         ops.fastattn(qkv, Pk["P"], Pk["fa_norm"][0], Pk["fa_norm"][1], length, shift, Bn, H, T, D // H, a1,
-                     seq_order=order)
+                     seq_order=order, Pt=Pk["Pt"])
         self._lin(a1, Pk["p0"], out_a=a2, act=ACT_GELU)
         self._lin(a2, Pk["p3"], out_a=a1)
         ops.rowop(a1, N, D, ops._dt(a2), ln1=Pk["post"], l2norm=True, ln2=Pk["s_norm"], film=film,

@@ -210,6 +210,10 @@ def test_fastattn_fully_masked_windows():
     order = torch.argsort(length, descending=True).to(torch.int32)
     ops.fastattn(qkv, P, nw, nb, length, 0, B, H, T, hd, out2, seq_order=order)
     assert torch.equal(out, out2)
+    # nor does the pre-transposed bf16 projection matrix (what every CTA otherwise builds from P)
+    out2.zero_()
+    ops.fastattn(qkv, P, nw, nb, length, 0, B, H, T, hd, out2, Pt=P.t().contiguous().to(torch.bfloat16))
+    assert torch.equal(out, out2)
 
 
 def test_fastattn_length_shift():
