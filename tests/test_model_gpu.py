@@ -287,6 +287,52 @@ def test_ddim_sampling_matches_oracle_and_graph_equals_eager():
     del net.encode_text          # the model is cached across tests: drop the stub again
 
 
+VARIANTS = {
+    # KIT-ML shaped: 251 features (21 joints), short clips, the longest text the tokenizer allows (8 + 77 tokens)
+    "kit_T60_nt85": (dict(input_feats=251, num_frames=196, latent_dim=256, ff_size=512, num_layers=1, num_heads=4,
+                          text_latent_dim=256, moe_num_experts=4), 5, 60, 85),
+    # 8 heads of 64 (the 64-wide tensor-core attention kernels), 2 experts, odd batch
+    "heads8_hd64": (dict(input_feats=263, num_frames=196, latent_dim=512, ff_size=1024, num_layers=1, num_heads=8,
+                         text_latent_dim=128, moe_num_experts=2), 3, 196, 20),
+    # 16 experts, T not a multiple of 16, short text
+    "e16_T50": (dict(input_feats=263, num_frames=60, latent_dim=512, ff_size=512, num_layers=1, num_heads=4,
+                     text_latent_dim=256, moe_num_experts=16), 2, 50, 9),
+}
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
+def test_shape_variants_match_oracle(name, precision, tol):
+    """Shapes besides the three golden cases (KIT features, other head sizes / expert counts / text lengths, ragged
+    T): forward against the oracle on the same device, routing identical in fp32."""
+    kw, B, T, Nt = VARIANTS[name]
+    cfg = mo.Config(**kw)
+    p = mo.make_params(cfg, 3)
+    p.update(mo.draw_ephemerals(cfg, 5))
+    net = mdm.MotionTransformer(precision=precision, **cfg)
+    net.load_state_dict({k: p[k] for k in net.state_dict()})
+    net.load_extras(p)
+    net.to(DEV)
+    pd = {k: v.to(DEV) for k, v in p.items()}
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, T, cfg.input_feats, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+    length = torch.randint(2, T + 1, (B,), generator=g).to(DEV)
+    xf_out = torch.nn.functional.gelu(torch.randn(B, Nt, cfg.text_latent_dim, generator=g)).to(DEV)
+    routing = []
+    with torch.no_grad():
+        ref = mo.forward(pd, cfg, x, t, length, xf_out.mean(1), xf_out, routing=routing)
+    net.record_routing = True
+    y = net(x, t, length, None, xf_out.mean(1), xf_out)
+    assert y.shape == ref.shape and torch.isfinite(y).all()
+    assert rel(y, ref) < tol, rel(y, ref)
+    if precision == "fp32":
+        assert len(routing) == 2 * len(net.last_routing)                          # oracle: one entry per MoE branch
+        for i, (idx, _) in enumerate(net.last_routing):                           # idx [N_i, NB, 2]
+            for br in range(2):
+                assert torch.equal(idx[:, br].long().cpu(), routing[2 * i + br][1].long().cpu()), (i, br)
+
+
 def test_state_dict_roundtrip_and_errors():
     cfg, p, net = build("tiny_b3", "fp32")
     sd = net.state_dict()
