@@ -461,3 +461,49 @@ class CFGStepper:
         else:
             self._run()
         return self.x
+
+    # ------------------------------------------------------------------ host-buffer interface (pipelined copies)
+    def step_host(self, x_host, ts, out_host, noise=None, ts_prev=None):
+        """One step on HOST data: x_host (pinned, [B,T,F] fp32) -> device, step(ts), result -> out_host (pinned).
+        The copies run on two side streams through double-buffered device staging tensors, so the upload of the next
+        call and the download of the previous result overlap the compute of the current step (PCIe and the SMs work
+        concurrently; a call returns as soon as its work is enqueued).  Call flush() before reading out_host."""
+        if not (x_host.is_pinned() and out_host.is_pinned()):
+            raise ValueError("step_host needs pinned host tensors (the copies are asynchronous)")
+        if not hasattr(self, "_hp"):
+            mk = lambda: [torch.empty_like(self.x) for _ in range(2)]
+            ev = lambda: [torch.cuda.Event() for _ in range(2)]
+            self._hp = {"xin": mk(), "xout": mk(), "s_in": torch.cuda.Stream(self.device), "s_out": torch.cuda.Stream(self.device),
+                        "in_ready": ev(), "in_free": ev(), "out_ready": ev(), "out_free": ev(), "i": 0}
+            if self.use_graph and self.graph is None:
+                self._capture()
+        hp = self._hp
+        k = hp["i"] & 1
+        first = hp["i"] < 2
+        hp["i"] += 1
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(hp["s_in"]):
+            if not first:
+                hp["s_in"].wait_event(hp["in_free"][k])          # the step two calls ago has consumed xin[k]
+            hp["xin"][k].copy_(x_host, non_blocking=True)
+            hp["in_ready"][k].record(hp["s_in"])
+        main.wait_event(hp["in_ready"][k])
+        self.x.copy_(hp["xin"][k])
+        hp["in_free"][k].record(main)
+        self.step(ts, noise=noise, ts_prev=ts_prev)
+        if not first:
+            main.wait_event(hp["out_free"][k])                    # the download two calls ago has left xout[k]
+        hp["xout"][k].copy_(self.x)
+        hp["out_ready"][k].record(main)
+        with torch.cuda.stream(hp["s_out"]):
+            hp["s_out"].wait_event(hp["out_ready"][k])
+            out_host.copy_(hp["xout"][k], non_blocking=True)
+            hp["out_free"][k].record(hp["s_out"])
+
+    def flush(self):
+        """Make the current stream wait for every download issued by step_host()."""
+        hp = getattr(self, "_hp", None)
+        if hp is not None:
+            main = torch.cuda.current_stream(self.device)
+            for k in range(min(2, hp["i"])):
+                main.wait_event(hp["out_free"][k])

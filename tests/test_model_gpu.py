@@ -179,6 +179,37 @@ def test_sampling_loop_graph_equals_eager_and_is_deterministic():
     assert torch.isfinite(runs[0]).all()
 
 
+def test_step_host_pipelined_copies_equal_device_steps():
+    """CFGStepper.step_host (upload / step / download with the copies on side streams, double-buffered) returns
+    exactly what step() computes from the same inputs, call after call."""
+    case = "tiny_b3"
+    cfg_name, B, T = cases.CASES[case]
+    cfg, p, net = build(case, "bf16")
+    net.encode_text = lambda text, device: mo.stub_text(text, cfg.text_latent_dim, device)
+    _, _, length, xf_proj, xf_out = cases.make_inputs(cfg, B, T, seed=3, device=DEV)
+    d = mdm.GaussianDiffusion(betas=mdm.get_named_beta_schedule("linear", 1000))
+    kw = {"text": ["a person walks"] * B, "length": length, "xf_proj": xf_proj, "xf_out": xf_out}
+    shape = (B, T, cfg.input_feats)
+    st = d.make_cfg_stepper(net, shape, kw, cfg_scale=7.5, clip_denoised=False, device=DEV)
+    gen = torch.Generator().manual_seed(4)
+    xs = [torch.randn(shape, generator=gen).pin_memory() for _ in range(5)]
+    ns = [torch.randn(shape, generator=gen).to(DEV) for _ in range(5)]
+    want = []
+    for i in range(5):
+        st.x.copy_(xs[i].to(DEV))
+        want.append(st.step(900 - i, noise=ns[i]).clone())
+    outs = [torch.empty(shape).pin_memory() for _ in range(5)]
+    for i in range(5):
+        st.step_host(xs[i], 900 - i, outs[i], noise=ns[i])
+    st.flush()
+    torch.cuda.synchronize()
+    for i in range(5):
+        assert torch.equal(outs[i], want[i].cpu()), i
+    with pytest.raises(ValueError):
+        st.step_host(torch.zeros(shape), 5, outs[0])            # not pinned
+    del net.encode_text
+
+
 def test_full_1000_step_sample_matches_oracle_loop():
     """north_star: 'the final 1000-step sample within a stated tolerance'.  All 1000 reverse steps of
     p_sample_loop_with_cfg (CUDA-graph replay) against the oracle's loop (two forwards + update per
