@@ -281,10 +281,10 @@ def main():
     roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (grouped expert FFN up+down of one MoEMultiBranchFFN)",
             "achieved": ach, "peak": pkv["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pkv["bf16_tflops"],
             "peak_source": src + " burst (kernel timed alone)",
-            # dram__bytes_read.sum + dram__bytes_write.sum of the two launches (up: 120.7 + 157.0 MB,
-            # down: 224.9 + 75.6 MB) from profiles/expert_ffn_r1e_ncu.txt (ncu --set full of this very loop)
-            "traffic": 578.2e6, "traffic_source": "profiles/expert_ffn_r1e_ncu.txt",
-            "tensor_pipe_active_pct": {"up": 56.6, "down": 64.5, "source": "ncu sm__pipe_tensor_cycles_active"},
+            # dram__bytes_read.sum + dram__bytes_write.sum of the two launches (up: 120.7 + 156.7 MB,
+            # down: 224.9 + 75.5 MB) from profiles/expert_ffn_r1f_ncu.txt (ncu --set full of this very loop)
+            "traffic": 577.8e6, "traffic_source": "profiles/expert_ffn_r1f_ncu.txt",
+            "tensor_pipe_active_pct": {"up": 58.9, "down": 65.0, "source": "ncu sm__pipe_tensor_cycles_active"},
             "flops_per_launch_pair": moe_flops, "ms_per_launch_pair": moe_ms}
 
     # ---- max over ranks
