@@ -5,12 +5,18 @@
 //   mdm_softmax_cross   MemoryEfficientCrossAttentionBlock :313-325
 // fp32-compute version: one CTA per (sequence, head), the [M x hd] state lives in registers
 // (one column per thread).  Activations are read/written as fp32 or bf16.
+#include <stdlib.h>
 #include "common.cuh"
 
 // tensor-core (mma.sync) kernel for the bf16 path, attention_tc.cu
 int mdm_fastattn_tc(const void* qkv, const float* P, const float* norm_w, const float* norm_b,
                     const int64_t* length, int length_shift, int B, int H, int T, int hd, int M, void* out,
                     const int* seq_order, const void* Pt_bf16, cudaStream_t st);
+
+// tcgen05 kernel (attention_umma.cu): hd == M == 128, T <= 256, needs the pre-transposed bf16 projection matrix
+int mdm_fastattn_umma(const void* qkv, const void* Pt_bf16, const float* norm_w, const float* norm_b,
+                      const int64_t* length, int length_shift, int B, int H, int T, int hd, int M, void* out,
+                      const int* seq_order, cudaStream_t st);
 
 int mdm_lincross_apply_tc(const void* q, const float* ctx, int B, int T, int H, int hd, void* y, cudaStream_t st);
 int mdm_softmax_cross_tc(const void* q, const void* k, const void* v, const int* nt, int B, int T, int Nt_max, int H,
@@ -382,6 +388,12 @@ extern "C" MDM_API int mdm_fastattn_ordered(const void* qkv, int dt, const float
   const size_t smem = sizeof(float) * ((size_t)hd * M + 3 * TC * hd + 2 * M * TC + TC * 4);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dt == MDM_BF16) {
+    // MDM_FA_UMMA=0 keeps the mma.sync kernels (A/B runs)
+    static const int umma_env = [] { const char* e = getenv("MDM_FA_UMMA"); return e ? atoi(e) : 1; }();
+    if (umma_env && Pt_bf16) {
+      const int r = mdm_fastattn_umma(qkv, Pt_bf16, norm_w, norm_b, length, length_shift, B, H, T, hd, M, out, seq_order, st);
+      if (r != MDM_ERR_UNSUPPORTED) return r;
+    }
     const int r = mdm_fastattn_tc(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, M, out, seq_order, Pt_bf16, st);
     if (r != MDM_ERR_UNSUPPORTED) return r;  // otherwise: shape outside the tensor-core kernel
   }

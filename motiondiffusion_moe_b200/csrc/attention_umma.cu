@@ -1,0 +1,558 @@
+// FastAttention.forward (reference: models/fast_attention.py:29-92) on the 5th-generation tensor cores:
+// one CTA per (sequence, head), hd = M = 128, T <= 256.  The four products of the op run as tcgen05.mma
+// with fp32 accumulators in TMEM; every operand is built in shared memory in the canonical K-major,
+// 128B-swizzled layout by the CUDA cores (LayerNorm / L2 norm / feature maps are row-wise passes whose
+// output IS the next operand), so nothing but q, k, v (in) and the result (out) touches global memory.
+//
+//   P0  q, k rows: 0.1 x -> LayerNorm(hd) -> L2 norm -> bf16         -> Qs [t][d], Ks [t][d]   (A / B operands)
+//       v rows:    0.1 x -> LayerNorm(hd) -> bf16, TRANSPOSED          -> VT [l][t]            (B operand of kv)
+//       P^T bf16 (packed once per model)                               -> Pt [m][d]
+//   P1  K'^T = Pt . Ks^T   [m][t]  (M 128, N TP, K 128)    Q'' = Qs . Pt^T  [t][m]  (TP/128 tiles of M 128, N 128)
+//   P2  K'^T epilogue: exp(clamp(.)) * 0.1, key mask (t >= len -> 0), bf16 -> KT [m][t] over Ks (A operand of kv)
+//   P3  kv = KT . VT^T     [m][l]  (K = frames, only the 64-frame chunks below len)
+//       Q' epilogue (overlaps the kv MMAs): feature map -> bf16 -> Qs in place (A operand of the apply product);
+//       den[t] = max(sum_m q'[t][m] k'[t][m], 1e-6)            (fast_attention.py:83-86)
+//   P4  kv epilogue: x 0.1 -> bf16, transposed -> kvT [l][m] over Pt (B operand of the apply product)
+//   P5  out = Q' . kvT^T   [t][l]
+//   P6  out epilogue: x 0.1 / den -> LayerNorm(hd) (lane == row: the row statistics need no shuffles) -> bf16 -> global
+//
+// bf16 rounding points are those of the mma.sync kernels in attention_tc.cu (normalised q / k / v, q', k', kv).
+// TMEM: K'^T in columns [0, TP), later kv in [0, 128); Q'' / out tiles in [256, 256 + TP).
+#include <stdlib.h>
+#include "common.cuh"
+
+#ifdef MDM_ATTN_PROFILE
+__device__ unsigned long long g_fau_phase[16];   // cycles per phase summed over CTAs (thread 0): tools/fa_prof.py
+extern "C" MDM_API int mdm_debug_read_fau_phase(unsigned long long* host, int reset) {
+  unsigned long long z[16] = {0};
+  if (cudaMemcpyFromSymbol(host, g_fau_phase, sizeof(z)) != cudaSuccess) return 2;
+  if (reset && cudaMemcpyToSymbol(g_fau_phase, z, sizeof(z)) != cudaSuccess) return 2;
+  return 0;
+}
+#define FAU_MARK(k) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_fau_phase[k], (unsigned long long)(n_ - fau_t_)); fau_t_ = n_; } } while (0)
+#define FAU_INIT() long long fau_t_ = clock64()
+#else
+#define FAU_MARK(k) do { } while (0)
+#define FAU_INIT() do { } while (0)
+#endif
+
+namespace {
+
+constexpr int HD = 128;
+constexpr int NTHR = 256;
+
+__device__ __forceinline__ uint32_t pack2u(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float expfeat_u(float x) {
+  const float c = fminf(fmaxf(x, -15.f), 15.f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(c, 1.4426950408889634f, -3.3219280948873623f)));
+  return e;
+}
+// byte offset of element (row r, column c) in a K-major SWIZZLE_128B tile whose rows are 64 bf16 (128 B)
+__device__ __forceinline__ uint32_t sw_off(int r, int c) {
+  return (uint32_t)(r * 128 + ((((c >> 3) ^ r) & 7) << 4) + ((c & 7) << 1));
+}
+
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {      // packed bf16 pair -> two fp32 (exact)
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ float group8_sum(float v, unsigned gmask) {
+  v += __shfl_xor_sync(gmask, v, 1);
+  v += __shfl_xor_sync(gmask, v, 2);
+  v += __shfl_xor_sync(gmask, v, 4);
+  return v;
+}
+// The slice of one row owned by a thread (16 elements as 8 packed pairs; 8 threads per row): 0.1 x -> LayerNorm(128)
+// with the affine pairs w2 / b2 -> optional L2 normalisation of the whole row.  FFMA2 / FMUL2 / FADD2 throughout.
+template <bool L2>
+__device__ __forceinline__ void norm_slice(float2 (&x)[8], const float2 (&w2)[8], const float2 (&b2)[8], unsigned gmask) {
+  const float2 tenth = make_float2(0.1f, 0.1f);
+  float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { x[i] = mul2(x[i], tenth); s2 = add2(s2, x[i]); }
+  const float mean = group8_sum(s2.x + s2.y, gmask) / (float)HD;
+  const float2 nm = make_float2(-mean, -mean);
+  float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { x[i] = add2(x[i], nm); q2 = fma2(x[i], x[i], q2); }
+  const float rstd = rsqrtf(group8_sum(q2.x + q2.y, gmask) / (float)HD + 1e-5f);
+  const float2 r2 = make_float2(rstd, rstd);
+  float2 n2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    x[i] = fma2(x[i], mul2(w2[i], r2), b2[i]);
+    if (L2) n2 = fma2(x[i], x[i], n2);
+  }
+  if (L2) {
+    const float inv = 1.0f / fmaxf(sqrtf(group8_sum(n2.x + n2.y, gmask)), 1e-12f);
+    const float2 i2 = make_float2(inv, inv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = mul2(x[i], i2);
+  }
+}
+
+// norm_slice<true> on two rows at once (independent dependency chains interleaved by hand)
+__device__ __forceinline__ void norm_slice2(float2 (&x)[8], float2 (&y)[8], const float2 (&w2)[8], const float2 (&b2)[8],
+                                            unsigned gmask) {
+  const float2 tenth = make_float2(0.1f, 0.1f);
+  float2 sx = make_float2(0.f, 0.f), sy = sx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    x[i] = mul2(x[i], tenth); y[i] = mul2(y[i], tenth);
+    sx = add2(sx, x[i]); sy = add2(sy, y[i]);
+  }
+  float ax = sx.x + sx.y, ay = sy.x + sy.y;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const float tx = __shfl_xor_sync(gmask, ax, o), ty = __shfl_xor_sync(gmask, ay, o);
+    ax += tx; ay += ty;
+  }
+  const float2 nmx = make_float2(-ax / (float)HD, -ax / (float)HD), nmy = make_float2(-ay / (float)HD, -ay / (float)HD);
+  float2 qx = make_float2(0.f, 0.f), qy = qx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    x[i] = add2(x[i], nmx); y[i] = add2(y[i], nmy);
+    qx = fma2(x[i], x[i], qx); qy = fma2(y[i], y[i], qy);
+  }
+  ax = qx.x + qx.y; ay = qy.x + qy.y;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const float tx = __shfl_xor_sync(gmask, ax, o), ty = __shfl_xor_sync(gmask, ay, o);
+    ax += tx; ay += ty;
+  }
+  const float rx = rsqrtf(ax / (float)HD + 1e-5f), ry = rsqrtf(ay / (float)HD + 1e-5f);
+  const float2 rx2 = make_float2(rx, rx), ry2 = make_float2(ry, ry);
+  float2 nx = make_float2(0.f, 0.f), ny = nx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    x[i] = fma2(x[i], mul2(w2[i], rx2), b2[i]); y[i] = fma2(y[i], mul2(w2[i], ry2), b2[i]);
+    nx = fma2(x[i], x[i], nx); ny = fma2(y[i], y[i], ny);
+  }
+  ax = nx.x + nx.y; ay = ny.x + ny.y;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const float tx = __shfl_xor_sync(gmask, ax, o), ty = __shfl_xor_sync(gmask, ay, o);
+    ax += tx; ay += ty;
+  }
+  const float ix = 1.0f / fmaxf(sqrtf(ax), 1e-12f), iy = 1.0f / fmaxf(sqrtf(ay), 1e-12f);
+  const float2 ix2 = make_float2(ix, ix), iy2 = make_float2(iy, iy);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { x[i] = mul2(x[i], ix2); y[i] = mul2(y[i], iy2); }
+}
+
+template <int TP>   // padded frames: 128 or 256
+struct Smem {
+  static constexpr int QS = 0;                        // 2 K-halves x [TP rows x 128 B]
+  static constexpr int KS = QS + 2 * TP * 128;        // 2 K-halves x [TP rows x 128 B]; later KT: TP/64 chunks x [128 x 128 B]
+  static constexpr int PT = KS + 2 * TP * 128;        // 2 K-halves x [128 rows x 128 B]; later kvT
+  static constexpr int VT = PT + 2 * 128 * 128;       // TP/64 chunks x [128 rows x 128 B]
+  static constexpr int NW = VT + (TP / 64) * 128 * 128;   // float[128] x 2
+  static constexpr int BAR = NW + 2 * HD * 4;         // 4 mbarriers + tmem pointer
+  static constexpr int TOTAL = BAR + 64 + 1024;       // + alignment slack
+};
+
+template <int TP>
+__global__ void __launch_bounds__(NTHR, 1)
+fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg, const float* __restrict__ nw,
+                     const float* __restrict__ nb, const int64_t* __restrict__ length, int length_shift, int H, int T,
+                     bf16* __restrict__ out, const int* __restrict__ seq_order) {
+  using L = Smem<TP>;
+  constexpr int MT = TP / 128;        // 128-row tiles of the query side
+  constexpr int KC = TP / 64;         // 64-frame chunks (K of the kv product)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* Qs = smem + L::QS;
+  uint8_t* Ks = smem + L::KS;
+  uint8_t* Pt = smem + L::PT;
+  uint8_t* VT = smem + L::VT;
+  float* nw_s = reinterpret_cast<float*>(smem + L::NW);
+  float* nb_s = nw_s + HD;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);     // kt, q, kv, out
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int b = seq_order ? seq_order[blockIdx.x / H] : blockIdx.x / H, h = blockIdx.x % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = H * HD;
+  const int len = length ? (int)min((long)T, (long)(length[b] >> length_shift)) : T;
+  const int kc_used = min(KC, (len + 63) / 64);      // frame chunks that contain unmasked keys
+
+  FAU_INIT();
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+
+  // ------------------------------------------------------------------ P0: operands
+  // Every global load of the CTA is issued before anything waits: v by register prefetch (it is consumed first and
+  // leaves transposed), raw q / k by cp.async straight into their final swizzled slots, where the SAME thread
+  // normalises them in place afterwards (so a per-thread cp.async.wait_group is all the ordering needed).
+  const int sub = tid & 7, rr = tid >> 3;            // 8 lanes per row, 32 rows per pass
+  const unsigned gmask = 0xffu << (lane & 24);       // the 8 lanes of this row (rows of a warp may diverge)
+  const bf16* base = qkv + (long)b * T * 3 * D + h * HD;
+  constexpr int NP = TP / 32;
+  uint32_t vraw[NP][8];                              // v: thread owns the column pairs {2 sub + 16 j, + 1}
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int t = rr + 32 * p;
+    if (t < len) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(base + (long)t * 3 * D + 2 * D) + sub;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vraw[p][j] = __ldg(src + 8 * j);
+    }
+  }
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    uint8_t* dst = (which == 0 ? Qs : Ks) + (sub >> 2) * (TP * 128);
+    const int rows_live = which == 0 ? T : len;      // key rows >= len are masked: no need to load them
+#pragma unroll 1
+    for (int t = rr; t < TP; t += 32) {
+      uint8_t* d0 = dst + sw_off(t, (sub & 3) * 16);
+      uint8_t* d1 = dst + sw_off(t, (sub & 3) * 16 + 8);
+      if (t < rows_live) {
+        const bf16* src = base + (long)t * 3 * D + which * D + sub * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d0)), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d1)), "l"(src + 8) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(d0) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(d1) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+  for (int i = tid; i < HD * 16; i += NTHR) {        // Pt [m][d]: 16-byte chunks, needed by the MMAs only
+    const int m = i >> 4, c = i & 15;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                 ::"r"(smem_u32(Pt + (c >> 3) * (128 * 128) + sw_off(m, (c & 7) * 8))), "l"(Ptg + m * HD + c * 8) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < HD; i += NTHR) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }   // read again after the barrier below
+  FAU_MARK(0);
+  // v: LayerNorm, transposed 2-byte stores (the pair ownership costs a 2-way bank conflict, the loads are 4 bytes)
+  {
+    float2 w2[8], b2[8];                               // straight from global: no barrier before this pass
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      w2[j] = __ldg(reinterpret_cast<const float2*>(nw + 2 * sub + 16 * j));
+      b2[j] = __ldg(reinterpret_cast<const float2*>(nb + 2 * sub + 16 * j));
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int t = rr + 32 * p;
+      uint8_t* dcol = VT + (t >> 6) * (128 * 128);
+      if (t >= len) {                                  // masked keys: their value rows only need to be finite
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          *reinterpret_cast<uint16_t*>(dcol + sw_off(2 * sub + 16 * (j >> 1) + (j & 1), t & 63)) = 0;
+        continue;
+      }
+      float2 x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = bf2_to_f2(vraw[p][j]);
+      norm_slice<false>(x, w2, b2, gmask);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t pk = pack2u(x[j].x, x[j].y);
+        *reinterpret_cast<uint16_t*>(dcol + sw_off(2 * sub + 16 * j, t & 63)) = (uint16_t)(pk & 0xffffu);
+        *reinterpret_cast<uint16_t*>(dcol + sw_off(2 * sub + 16 * j + 1, t & 63)) = (uint16_t)(pk >> 16);
+      }
+    }
+  }
+  FAU_MARK(1);
+  // q and k in place: thread owns columns [16 sub, 16 sub + 16) of its rows (the chunks it requested itself);
+  // two rows per iteration so that the shuffle / rsqrt latencies of one row hide behind the other's arithmetic
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  {
+    float2 w2[8], b2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      w2[i] = __ldg(reinterpret_cast<const float2*>(nw + sub * 16 + 2 * i));
+      b2[i] = __ldg(reinterpret_cast<const float2*>(nb + sub * 16 + 2 * i));
+    }
+    auto load8 = [&](uint8_t* dst, int t, float2 (&x)[8]) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(dst + sw_off(t, (sub & 3) * 16));
+      const uint4 r1 = *reinterpret_cast<const uint4*>(dst + sw_off(t, (sub & 3) * 16 + 8));
+      x[0] = bf2_to_f2(r0.x); x[1] = bf2_to_f2(r0.y); x[2] = bf2_to_f2(r0.z); x[3] = bf2_to_f2(r0.w);
+      x[4] = bf2_to_f2(r1.x); x[5] = bf2_to_f2(r1.y); x[6] = bf2_to_f2(r1.z); x[7] = bf2_to_f2(r1.w);
+    };
+    auto store8 = [&](uint8_t* dst, int t, const float2 (&x)[8]) {
+      *reinterpret_cast<uint4*>(dst + sw_off(t, (sub & 3) * 16)) =
+          make_uint4(pack2u(x[0].x, x[0].y), pack2u(x[1].x, x[1].y), pack2u(x[2].x, x[2].y), pack2u(x[3].x, x[3].y));
+      *reinterpret_cast<uint4*>(dst + sw_off(t, (sub & 3) * 16 + 8)) =
+          make_uint4(pack2u(x[4].x, x[4].y), pack2u(x[5].x, x[5].y), pack2u(x[6].x, x[6].y), pack2u(x[7].x, x[7].y));
+    };
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      uint8_t* dst = (which == 0 ? Qs : Ks) + (sub >> 2) * (TP * 128);
+      const int rows_live = which == 0 ? T : len;
+#pragma unroll 1
+      for (int t = rr; t < rows_live; t += 64) {
+        const bool two = t + 32 < rows_live;           // uniform over the 8 lanes of a row
+        float2 xa[8], xb[8];
+        load8(dst, t, xa);
+        load8(dst, two ? t + 32 : t, xb);
+        norm_slice2(xa, xb, w2, b2, gmask);
+        store8(dst, t, xa);
+        if (two) store8(dst, t + 32, xb);
+      }
+    }
+  }
+  FAU_MARK(2);
+  fence_proxy_async();                 // generic-proxy writes of the operands -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t qs_a = smem_u32(Qs), ks_a = smem_u32(Ks), pt_a = smem_u32(Pt), vt_a = smem_u32(VT);
+
+  // ------------------------------------------------------------------ P1: K'^T and Q'' products
+  if (tid == 0) {
+    constexpr uint32_t id_kt = make_idesc_bf16(128, TP);
+    constexpr uint32_t id_q = make_idesc_bf16(128, 128);
+#pragma unroll
+    for (int kc = 0; kc < 2; ++kc) {
+      const uint64_t ad = make_sw128_kmajor_desc(pt_a + kc * (128 * 128));
+      const uint64_t bd = make_sw128_kmajor_desc(ks_a + kc * (TP * 128));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, id_kt, (kc | k) != 0);
+    }
+    umma_commit(&bars[0]);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        const uint64_t ad = make_sw128_kmajor_desc(qs_a + kc * (TP * 128) + mt * (128 * 128));
+        const uint64_t bd = make_sw128_kmajor_desc(pt_a + kc * (128 * 128));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256 + mt * 128, ad + 2 * k, bd + 2 * k, id_q, (kc | k) != 0);
+      }
+    }
+    umma_commit(&bars[1]);
+  }
+  const int quad = warp & 3, hi = warp >> 2;          // TMEM lane quadrant, second role index
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+
+  // ------------------------------------------------------------------ P2: K'^T epilogue -> KT (over Ks)
+  {
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const int m = quad * 32 + lane;
+    constexpr int CH = TP / 64;                        // 32-column chunks per warp: columns [hi * TP/2, +TP/2)
+#pragma unroll 1
+    for (int c = 0; c < CH; ++c) {
+      const int t0 = hi * (TP / 2) + c * 32;
+      uint8_t* dst = Ks + (t0 >> 6) * (128 * 128);
+      if (t0 >= len) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(dst + sw_off(m, (t0 & 63) + 8 * j)) = make_uint4(0u, 0u, 0u, 0u);
+        continue;
+      }
+      uint32_t raw[32];
+      tmem_ld32(t_lane + t0, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = (t0 + 8 * j + e) < len ? expfeat_u(__uint_as_float(raw[8 * j + e])) : 0.f;
+        uint4 pk;
+        pk.x = pack2u(f[0], f[1]); pk.y = pack2u(f[2], f[3]); pk.z = pack2u(f[4], f[5]); pk.w = pack2u(f[6], f[7]);
+        *reinterpret_cast<uint4*>(dst + sw_off(m, (t0 & 63) + 8 * j)) = pk;
+      }
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  FAU_MARK(3);
+  // ------------------------------------------------------------------ P3: kv product; Q' epilogue + denominators
+  if (tid == 0) {
+    constexpr uint32_t id_kv = make_idesc_bf16(128, 128);
+    for (int kc = 0; kc < kc_used; ++kc) {
+      const uint64_t ad = make_sw128_kmajor_desc(ks_a + kc * (128 * 128));
+      const uint64_t bd = make_sw128_kmajor_desc(vt_a + kc * (128 * 128));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, id_kv, (kc | k) != 0);
+    }
+    umma_commit(&bars[2]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  float den_r = 1.f;                                   // denominator of this thread's frame (same thread in P6)
+  if (hi < MT) {
+    const int t = hi * 128 + quad * 32 + lane;
+    float den = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(t_lane + 256 + hi * 128 + c * 32, raw);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) pk[e] = pack2u(expfeat_u(__uint_as_float(raw[2 * e])), expfeat_u(__uint_as_float(raw[2 * e + 1])));
+      if (t < len) {                                   // k'[t][:] == 0 for masked frames: den stays 0 -> 1e-6
+        const uint8_t* kt = Ks + (t >> 6) * (128 * 128);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&pk[e]);
+          const int m = c * 32 + 2 * e;
+          const float k0 = __bfloat162float(*reinterpret_cast<const bf16*>(kt + sw_off(m, t & 63)));
+          const float k1 = __bfloat162float(*reinterpret_cast<const bf16*>(kt + sw_off(m + 1, t & 63)));
+          den = fmaf(__low2float(q2), k0, den);
+          den = fmaf(__high2float(q2), k1, den);
+        }
+      }
+      uint8_t* dst = Qs + (c >> 1) * (TP * 128);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(dst + sw_off(t, (c & 1) * 32 + 8 * j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+    den_r = fmaxf(den, 1e-6f);
+  }
+
+  FAU_MARK(4);
+  // ------------------------------------------------------------------ P4: kv epilogue -> kvT (over Pt)
+  {
+    mbar_wait(&bars[2], 0);
+    tc_fence_after();
+    const int m = quad * 32 + lane;
+    uint8_t* dst = Pt + (m >> 6) * (128 * 128);
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int l0 = hi * 64 + c * 32;
+      uint32_t raw[32];
+      if (kc_used > 0) {
+        tmem_ld32(t_lane + l0, raw);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) raw[e] = 0u;     // no unmasked key: no MMA was issued, kv == 0
+      }
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        *reinterpret_cast<bf16*>(dst + sw_off(l0 + e, m & 63)) = __float2bfloat16_rn(__uint_as_float(raw[e]) * 0.1f);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  FAU_MARK(5);
+  // ------------------------------------------------------------------ P5: out = Q' . kv
+  if (tid == 0) {
+    constexpr uint32_t id_o = make_idesc_bf16(128, 128);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        const uint64_t ad = make_sw128_kmajor_desc(qs_a + kc * (TP * 128) + mt * (128 * 128));
+        const uint64_t bd = make_sw128_kmajor_desc(pt_a + kc * (128 * 128));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256 + mt * 128, ad + 2 * k, bd + 2 * k, id_o, (kc | k) != 0);
+      }
+    }
+    umma_commit(&bars[3]);
+  }
+
+  // ------------------------------------------------------------------ P6: out epilogue
+  // x 0.1 / den -> LayerNorm over the thread's own row -> bf16 row in a staging area (KT and kvT are dead: their
+  // regions are contiguous; 272-byte pitch keeps the row-per-lane 16-byte stores conflict-free) -> coalesced stores.
+  mbar_wait(&bars[3], 0);
+  tc_fence_after();
+  constexpr int PITCH = 272;
+  static_assert(256 * PITCH <= L::VT - L::KS || TP == 128, "staging area");
+  uint8_t* stage = Ks;
+  if (hi < MT) {
+    const int t = hi * 128 + quad * 32 + lane;
+    const float sc = 0.1f / den_r;
+    const float2 sc2 = make_float2(sc, sc);
+    float2 o[HD / 2];
+    float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(t_lane + 256 + hi * 128 + c * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        o[c * 16 + e] = mul2(make_float2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1])), sc2);
+        s2 = add2(s2, o[c * 16 + e]);
+      }
+    }
+    const float mean = (s2.x + s2.y) / (float)HD;
+    const float2 nm = make_float2(-mean, -mean);
+    float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < HD / 2; ++i) { o[i] = add2(o[i], nm); q2 = fma2(o[i], o[i], q2); }
+    const float rstd = rsqrtf((q2.x + q2.y) / (float)HD + 1e-5f);
+    const float2 r2 = make_float2(rstd, rstd);
+    if (t < T) {
+      uint4* dst = reinterpret_cast<uint4*>(stage + t * PITCH);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 w = make_float2(nw_s[8 * j + 2 * e], nw_s[8 * j + 2 * e + 1]);
+          const float2 bb = make_float2(nb_s[8 * j + 2 * e], nb_s[8 * j + 2 * e + 1]);
+          const float2 y = fma2(o[4 * j + e], mul2(w, r2), bb);
+          pk[e] = pack2u(y.x, y.y);
+        }
+        dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < T * 16; i += NTHR) {
+    const int r = i >> 4, c = i & 15;
+    *reinterpret_cast<uint4*>(out + ((long)(b * T + r)) * D + h * HD + c * 8) =
+        *reinterpret_cast<const uint4*>(stage + r * PITCH + c * 16);
+  }
+  FAU_MARK(6);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int TP>
+int launch(const bf16* qkv, const bf16* Pt, const float* nw, const float* nb, const int64_t* length, int shift, int B,
+           int H, int T, bf16* out, const int* seq_order, cudaStream_t st) {
+  using L = Smem<TP>;
+  static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(fastattn_umma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+      return MDM_ERR_CUDA;
+    attr = true;
+  }
+  fastattn_umma_kernel<TP><<<B * H, NTHR, L::TOTAL, st>>>(qkv, Pt, nw, nb, length, shift, H, T, out, seq_order);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+}  // namespace
+
+// hd == M == 128, bf16, T <= 256, with the pre-transposed bf16 projection matrix; MDM_ERR_UNSUPPORTED otherwise
+// (the caller falls back to the mma.sync kernels of attention_tc.cu).
+int mdm_fastattn_umma(const void* qkv, const void* Pt_bf16, const float* norm_w, const float* norm_b,
+                      const int64_t* length, int length_shift, int B, int H, int T, int hd, int M, void* out,
+                      const int* seq_order, cudaStream_t st) {
+  if (hd != HD || M != HD || T > 256 || !Pt_bf16) return MDM_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(Pt_bf16) & 15))
+    return MDM_ERR_UNSUPPORTED;
+  const bf16* q = reinterpret_cast<const bf16*>(qkv);
+  const bf16* p = reinterpret_cast<const bf16*>(Pt_bf16);
+  bf16* o = reinterpret_cast<bf16*>(out);
+  if (T <= 128) return launch<128>(q, p, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order, st);
+  return launch<256>(q, p, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order, st);
+}

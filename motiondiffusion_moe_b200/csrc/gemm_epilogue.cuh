@@ -80,29 +80,6 @@ __device__ __forceinline__ float gelu_tanh_fit(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, th, hx);
 }
-// Packed fp32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100): one issue slot per two elements.  The bf16 epilogues
-// are issue-bound (ncu: 15.6 k warp instructions per 128 x 256 GELU tile against 4 k MMA cycles).
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};"
-      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd;}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};"
-      "mul.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd;}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};"
-      "add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd;}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
 // gelu_tanh_fit on two elements: the same operations in the same order (bit-identical results)
 __device__ __forceinline__ float2 gelu_tanh_fit2(float2 x) {
   float2 s = mul2(x, x);

@@ -187,6 +187,12 @@ def test_fastattn(dtype, B, H, T, hd):
     p = {"fa.projection_matrix": P, "fa.norm.weight": nw, "fa.norm.bias": nb}
     ref = mo.fast_attention(p, "fa", q, k, v, mo.src_mask(T, length)).permute(0, 2, 1, 3).reshape(B * T, D)
     assert rel(out, ref) < TOL[dtype]
+    if dtype == torch.bfloat16 and hd == 128:
+        # with the packed bf16 P^T the tcgen05 kernel (attention_umma.cu) runs instead of the mma.sync one
+        out2 = torch.full_like(out, float("nan"))
+        ops.fastattn(qkv, P, nw, nb, length, 0, B, H, T, hd, out2, Pt=P.t().contiguous().to(torch.bfloat16))
+        assert rel(out2, ref) < TOL[dtype]
+        assert rel(out2, out) < 1e-2
 
 
 def test_fastattn_fully_masked_windows():
@@ -210,10 +216,17 @@ def test_fastattn_fully_masked_windows():
     order = torch.argsort(length, descending=True).to(torch.int32)
     ops.fastattn(qkv, P, nw, nb, length, 0, B, H, T, hd, out2, seq_order=order)
     assert torch.equal(out, out2)
-    # nor does the pre-transposed bf16 projection matrix (what every CTA otherwise builds from P)
-    out2.zero_()
-    ops.fastattn(qkv, P, nw, nb, length, 0, B, H, T, hd, out2, Pt=P.t().contiguous().to(torch.bfloat16))
-    assert torch.equal(out, out2)
+    # tcgen05 kernel (selected by the packed bf16 P^T): same masking semantics, every sequence within tolerance,
+    # and independent of the launch order too
+    Pt = P.t().contiguous().to(torch.bfloat16)
+    out3 = torch.full_like(out, float("nan"))
+    ops.fastattn(qkv, P, nw, nb, length, 0, B, H, T, hd, out3, Pt=Pt)
+    o3 = out3.view(B, T, D)
+    for i in range(B):
+        assert rel(o3[i], ref[i]) < TOL[torch.bfloat16], (i, rel(o3[i], ref[i]))
+    out4 = torch.empty_like(out)
+    ops.fastattn(qkv, P, nw, nb, length, 0, B, H, T, hd, out4, seq_order=order, Pt=Pt)
+    assert torch.equal(out3, out4)
 
 
 def test_fastattn_length_shift():

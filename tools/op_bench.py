@@ -105,7 +105,11 @@ qkv = [(torch.randn(N, 3 * D, device=dev)).to(bf) for _ in range(nset)]
 P = torch.randn(hd, hd, device=dev) * hd ** -0.5
 nw, nb_ = torch.rand(hd, device=dev) + 0.5, torch.randn(hd, device=dev) * 0.1
 length = torch.randint(40, T + 1, (NSEQ,), device=dev, dtype=torch.int64)
-timeit("fastattn", lambda i: ops.fastattn(qkv[i], P, nw, nb_, length, 0, NSEQ, H, T, hd, ob[i]), nset, N * D * 8, "GB/s")
+Pt = P.t().contiguous().to(bf)
+order = torch.argsort(length, descending=True).to(torch.int32)
+timeit("fastattn tcgen05 (Pt, longest first)", lambda i: ops.fastattn(qkv[i], P, nw, nb_, length, 0, NSEQ, H, T, hd, ob[i], seq_order=order, Pt=Pt), nset, N * D * 8, "GB/s")
+timeit("fastattn tcgen05 (Pt)", lambda i: ops.fastattn(qkv[i], P, nw, nb_, length, 0, NSEQ, H, T, hd, ob[i], Pt=Pt), nset, N * D * 8, "GB/s")
+timeit("fastattn mma.sync", lambda i: ops.fastattn(qkv[i], P, nw, nb_, length, 0, NSEQ, H, T, hd, ob[i], seq_order=order), nset, N * D * 8, "GB/s")
 ctx = torch.randn(NSEQ, H, hd, hd, device=dev)
 timeit("lincross_apply", lambda i: ops.lincross_apply(xb[i], ctx, NSEQ, T, H, hd, ob[i]), nset, N * D * 4, "GB/s")
 Nt = 20
