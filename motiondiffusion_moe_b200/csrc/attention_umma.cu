@@ -148,20 +148,24 @@ struct Smem {
   static constexpr int QS = 0;                        // 2 K-halves x [TP rows x 128 B]
   static constexpr int KS = QS + 2 * TP * 128;        // 2 K-halves x [TP rows x 128 B]; later KT: TP/64 chunks x [128 x 128 B]
   static constexpr int PT = KS + 2 * TP * 128;        // 2 K-halves x [128 rows x 128 B]; later kvT
-  static constexpr int VT = PT + 2 * 128 * 128;       // TP/64 chunks x [128 rows x 128 B]
+  // V^T: TP/64 chunks x [128 rows x 128 B].  For TP = 128 it shares the 32 KB of Pt (v waits in registers until both
+  // P products are done, then kvT takes the place of V^T once the kv product is done): 97 KB -> two CTAs per SM.
+  static constexpr int VT = TP == 128 ? PT : PT + 2 * 128 * 128;
   static constexpr int NW = VT + (TP / 64) * 128 * 128;   // float[128] x 2
   static constexpr int BAR = NW + 2 * HD * 4;         // 4 mbarriers + tmem pointer
   static constexpr int TOTAL = BAR + 64 + 1024;       // + alignment slack
 };
 
 template <int TP>
-__global__ void __launch_bounds__(NTHR, 1)
+__global__ void __launch_bounds__(NTHR, TP == 128 ? 2 : 1)
 fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg, const float* __restrict__ nw,
                      const float* __restrict__ nb, const int64_t* __restrict__ length, int length_shift, int H, int T,
                      bf16* __restrict__ out, const int* __restrict__ seq_order) {
   using L = Smem<TP>;
   constexpr int MT = TP / 128;        // 128-row tiles of the query side
   constexpr int KC = TP / 64;         // 64-frame chunks (K of the kv product)
+  constexpr int QCOL = TP;            // TMEM: K'^T / kv in columns [0, TP), Q'' / out tiles from QCOL on
+  constexpr int NCOLS = 2 * TP;       // 256 columns per CTA at TP = 128 (two CTAs per SM), 512 at TP = 256
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* Qs = smem + L::QS;
@@ -185,7 +189,7 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  if (warp == 0) tmem_alloc(tmem_ptr, NCOLS);
 
   // ------------------------------------------------------------------ P0: operands
   // Every global load of the CTA is issued before anything waits: v by register prefetch (it is consumed first and
@@ -232,7 +236,7 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   for (int i = tid; i < HD; i += NTHR) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }   // read again after the barrier below
   FAU_MARK(0);
   // v: LayerNorm, transposed 2-byte stores (the pair ownership costs a 2-way bank conflict, the loads are 4 bytes)
-  {
+  auto v_pass = [&]() {
     float2 w2[8], b2[8];                               // straight from global: no barrier before this pass
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -260,7 +264,8 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
         *reinterpret_cast<uint16_t*>(dcol + sw_off(2 * sub + 16 * j + 1, t & 63)) = (uint16_t)(pk >> 16);
       }
     }
-  }
+  };
+  if (TP != 128) v_pass();
   FAU_MARK(1);
   // q and k in place: thread owns columns [16 sub, 16 sub + 16) of its rows (the chunks it requested itself);
   // two rows per iteration so that the shuffle / rsqrt latencies of one row hide behind the other's arithmetic
@@ -327,7 +332,7 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
         const uint64_t ad = make_sw128_kmajor_desc(qs_a + kc * (TP * 128) + mt * (128 * 128));
         const uint64_t bd = make_sw128_kmajor_desc(pt_a + kc * (128 * 128));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256 + mt * 128, ad + 2 * k, bd + 2 * k, id_q, (kc | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + QCOL + mt * 128, ad + 2 * k, bd + 2 * k, id_q, (kc | k) != 0);
       }
     }
     umma_commit(&bars[1]);
@@ -365,6 +370,11 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
       }
     }
   }
+  if (TP == 128) {            // V^T shares Pt's memory: both P products must have retired before it is written
+    mbar_wait(&bars[1], 0);
+    tc_fence_after();
+    v_pass();
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -391,7 +401,7 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t raw[32];
-      tmem_ld32(t_lane + 256 + hi * 128 + c * 32, raw);
+      tmem_ld32(t_lane + QCOL + hi * 128 + c * 32, raw);
       tmem_ld_wait();
       uint32_t pk[16];
 #pragma unroll
@@ -455,7 +465,7 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
         const uint64_t ad = make_sw128_kmajor_desc(qs_a + kc * (TP * 128) + mt * (128 * 128));
         const uint64_t bd = make_sw128_kmajor_desc(pt_a + kc * (128 * 128));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256 + mt * 128, ad + 2 * k, bd + 2 * k, id_o, (kc | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + QCOL + mt * 128, ad + 2 * k, bd + 2 * k, id_o, (kc | k) != 0);
       }
     }
     umma_commit(&bars[3]);
@@ -467,45 +477,59 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   mbar_wait(&bars[3], 0);
   tc_fence_after();
   constexpr int PITCH = 272;
-  static_assert(256 * PITCH <= L::VT - L::KS || TP == 128, "staging area");
+  static_assert((TP == 128 ? 128 : 256) * PITCH <= L::NW - L::KS - (TP == 128 ? 0 : (TP / 64) * 128 * 128), "staging area");
   uint8_t* stage = Ks;
   if (hi < MT) {
+    // three passes over the thread's TMEM row (mean, variance, normalise) instead of 128 live registers
     const int t = hi * 128 + quad * 32 + lane;
     const float sc = 0.1f / den_r;
     const float2 sc2 = make_float2(sc, sc);
-    float2 o[HD / 2];
+    const uint32_t t_row = t_lane + QCOL + hi * 128;
     float2 s2 = make_float2(0.f, 0.f);
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t raw[32];
-      tmem_ld32(t_lane + 256 + hi * 128 + c * 32, raw);
+      tmem_ld32(t_row + c * 32, raw);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        o[c * 16 + e] = mul2(make_float2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1])), sc2);
-        s2 = add2(s2, o[c * 16 + e]);
-      }
+      for (int e = 0; e < 16; ++e)
+        s2 = fma2(make_float2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1])), sc2, s2);
     }
     const float mean = (s2.x + s2.y) / (float)HD;
     const float2 nm = make_float2(-mean, -mean);
     float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(t_row + c * 32, raw);
+      tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < HD / 2; ++i) { o[i] = add2(o[i], nm); q2 = fma2(o[i], o[i], q2); }
+      for (int e = 0; e < 16; ++e) {
+        const float2 d = fma2(make_float2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1])), sc2, nm);
+        q2 = fma2(d, d, q2);
+      }
+    }
     const float rstd = rsqrtf((q2.x + q2.y) / (float)HD + 1e-5f);
     const float2 r2 = make_float2(rstd, rstd);
-    if (t < T) {
-      uint4* dst = reinterpret_cast<uint4*>(stage + t * PITCH);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(t_row + c * 32, raw);
+      tmem_ld_wait();
+      if (t < T) {
+        uint4* dst = reinterpret_cast<uint4*>(stage + t * PITCH + c * 64);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        uint32_t pk[4];
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 w = make_float2(nw_s[8 * j + 2 * e], nw_s[8 * j + 2 * e + 1]);
-          const float2 bb = make_float2(nb_s[8 * j + 2 * e], nb_s[8 * j + 2 * e + 1]);
-          const float2 y = fma2(o[4 * j + e], mul2(w, r2), bb);
-          pk[e] = pack2u(y.x, y.y);
+          for (int e = 0; e < 4; ++e) {
+            const int col = c * 32 + 8 * j + 2 * e;
+            const float2 d = fma2(make_float2(__uint_as_float(raw[8 * j + 2 * e]), __uint_as_float(raw[8 * j + 2 * e + 1])), sc2, nm);
+            const float2 y = fma2(d, mul2(make_float2(nw_s[col], nw_s[col + 1]), r2), make_float2(nb_s[col], nb_s[col + 1]));
+            pk[e] = pack2u(y.x, y.y);
+          }
+          dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
   }
@@ -520,7 +544,7 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, NCOLS);
   }
 }
 
