@@ -128,6 +128,12 @@ MDM_API int mdm_lincross_ctx(const void* k, const void* v, int dt, const int* nt
 /* Motion side: y[t,h,:] = softmax_hd(q[t,h,:]) @ ctx[b,h]. */
 MDM_API int mdm_lincross_apply(const void* q, int dt, const float* ctx, int B, int T, int H, int hd,
                                void* y, void* stream);
+/* Same, with ctxT_bf16 [B, H, hd(l), hd(d)] = ctx transposed and rounded to bf16 (mdm_transpose_cast_bf16, packed once
+ * per sampling loop: ctx is step-invariant): selects the tcgen05 kernel (hd = 128, T <= 256, bf16). */
+MDM_API int mdm_lincross_apply_ex(const void* q, int dt, const float* ctx, const void* ctxT_bf16, int B, int T, int H,
+                                  int hd, void* y, void* stream);
+/* dst[n][c][r] (bf16) = src[n][r][c] (fp32). */
+MDM_API int mdm_transpose_cast_bf16(const float* src, long n, int R, int C, void* dst, void* stream);
 
 /* ---- MemoryEfficientCrossAttentionBlock core, models/fast_attention.py:305-325 ----------------
  * o[t,h,:] = softmax_n(q[t,h,:]·k[b,n,h,:] * hd^-0.5) @ v[b,n,h,:], n < nt[b] (Nt_max <= 96). */

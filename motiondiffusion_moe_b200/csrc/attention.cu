@@ -18,6 +18,7 @@ int mdm_fastattn_umma(const void* qkv, const void* Pt_bf16, const float* norm_w,
                       const int64_t* length, int length_shift, int B, int H, int T, int hd, int M, void* out,
                       const int* seq_order, cudaStream_t st);
 
+int mdm_lincross_apply_umma(const void* q, const void* ctxT_bf16, int B, int T, int H, int hd, void* y, cudaStream_t st);
 int mdm_lincross_apply_tc(const void* q, const float* ctx, int B, int T, int H, int hd, void* y, cudaStream_t st);
 int mdm_softmax_cross_tc(const void* q, const void* k, const void* v, const int* nt, int B, int T, int Nt_max, int H,
                          int hd, float scale, void* o, cudaStream_t st);
@@ -433,12 +434,26 @@ extern "C" MDM_API int mdm_lincross_ctx(const void* k, const void* v, int dt, co
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
+extern "C" MDM_API int mdm_lincross_apply_ex(const void* q, int dt, const float* ctx, const void* ctxT_bf16, int B, int T,
+                                             int H, int hd, void* y, void* stream);
 extern "C" MDM_API int mdm_lincross_apply(const void* q, int dt, const float* ctx, int B, int T, int H,
                                           int hd, void* y, void* stream) {
+  return mdm_lincross_apply_ex(q, dt, ctx, nullptr, B, T, H, hd, y, stream);
+}
+
+extern "C" MDM_API int mdm_lincross_apply_ex(const void* q, int dt, const float* ctx, const void* ctxT_bf16, int B, int T,
+                                             int H, int hd, void* y, void* stream) {
   if (!q || !ctx || !y) return MDM_ERR_ARG;
   if (hd > AT) return MDM_ERR_UNSUPPORTED;
   if (B * H == 0 || T == 0) return MDM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dt == MDM_BF16 && ctxT_bf16) {
+    static const int umma_env = [] { const char* e = getenv("MDM_LC_UMMA"); return e ? atoi(e) : 1; }();
+    if (umma_env) {
+      const int r = mdm_lincross_apply_umma(q, ctxT_bf16, B, T, H, hd, y, st);
+      if (r != MDM_ERR_UNSUPPORTED) return r;
+    }
+  }
   if (dt == MDM_BF16) {
     const int r = mdm_lincross_apply_tc(q, ctx, B, T, H, hd, y, st);
     if (r != MDM_ERR_UNSUPPORTED) return r;

@@ -563,6 +563,191 @@ int launch(const bf16* qkv, const bf16* Pt, const float* nw, const float* nb, co
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------------
+// LinearTemporalCrossAttention, motion side (fast_attention.py:248,253) on tcgen05:
+//   y[t,h,:] = softmax_hd(q[t,h,:]) @ ctx[b,h]
+// One CTA per (sequence, head), 97 KB of shared memory and 256 TMEM columns (two CTAs per SM): raw q rows arrive by
+// cp.async in their swizzled A-operand slots and are soft-maxed in place by the thread that requested them; the
+// step-invariant state ctx^T [l][d] (bf16, packed once per sampling loop) is the B operand; the result leaves
+// through a staging area as coalesced stores.
+template <int TP>
+struct SmemLC {
+  static constexpr int QS = 0;                        // 2 K-halves x [TP rows x 128 B]; later the output staging
+  static constexpr int CT = QS + 2 * TP * 128;        // 2 K-halves x [128 rows x 128 B]
+  static constexpr int STG = CT + 2 * 128 * 128;      // staging tail (rows beyond what fits over QS): none needed, see PITCH
+  static constexpr int BAR = STG;
+  static constexpr int TOTAL = BAR + 64 + 1024;
+};
+
+template <int TP>
+__global__ void __launch_bounds__(NTHR, 2)
+lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, int H, int T, bf16* __restrict__ y) {
+  using L = SmemLC<TP>;
+  constexpr int MT = TP / 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* Qs = smem + L::QS;
+  uint8_t* Ct = smem + L::CT;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::BAR);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = H * HD;
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(tmem_ptr, TP);
+  const int sub = tid & 7, rr = tid >> 3;
+  const unsigned gmask = 0xffu << (lane & 24);
+  const bf16* base = q + (long)b * T * D + h * HD;
+  uint8_t* dstq = Qs + (sub >> 2) * (TP * 128);
+#pragma unroll 1
+  for (int t = rr; t < TP; t += 32) {
+    uint8_t* d0 = dstq + sw_off(t, (sub & 3) * 16);
+    uint8_t* d1 = dstq + sw_off(t, (sub & 3) * 16 + 8);
+    if (t < T) {
+      const bf16* src = base + (long)t * D + sub * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d0)), "l"(src) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d1)), "l"(src + 8) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(d0) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(d1) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  const bf16* cg = ctxT + ((long)(b * H + h)) * HD * HD;
+  for (int i = tid; i < HD * 16; i += NTHR) {        // ctx^T [l][d]: 16-byte chunks
+    const int l = i >> 4, c = i & 15;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                 ::"r"(smem_u32(Ct + (c >> 3) * (128 * 128) + sw_off(l, (c & 7) * 8))), "l"(cg + l * HD + c * 8) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // softmax over the head dimension, in place; two rows per iteration
+  {
+    auto load8 = [&](int t, float2 (&x)[8]) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(dstq + sw_off(t, (sub & 3) * 16));
+      const uint4 r1 = *reinterpret_cast<const uint4*>(dstq + sw_off(t, (sub & 3) * 16 + 8));
+      x[0] = bf2_to_f2(r0.x); x[1] = bf2_to_f2(r0.y); x[2] = bf2_to_f2(r0.z); x[3] = bf2_to_f2(r0.w);
+      x[4] = bf2_to_f2(r1.x); x[5] = bf2_to_f2(r1.y); x[6] = bf2_to_f2(r1.z); x[7] = bf2_to_f2(r1.w);
+    };
+    auto store8 = [&](int t, const float2 (&x)[8]) {
+      *reinterpret_cast<uint4*>(dstq + sw_off(t, (sub & 3) * 16)) =
+          make_uint4(pack2u(x[0].x, x[0].y), pack2u(x[1].x, x[1].y), pack2u(x[2].x, x[2].y), pack2u(x[3].x, x[3].y));
+      *reinterpret_cast<uint4*>(dstq + sw_off(t, (sub & 3) * 16 + 8)) =
+          make_uint4(pack2u(x[4].x, x[4].y), pack2u(x[5].x, x[5].y), pack2u(x[6].x, x[6].y), pack2u(x[7].x, x[7].y));
+    };
+    const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+#pragma unroll 1
+    for (int t = rr; t < T; t += 64) {
+      const bool two = t + 32 < T;
+      float2 xa[8], xb[8];
+      load8(t, xa);
+      load8(two ? t + 32 : t, xb);
+      float ma = fmaxf(xa[0].x, xa[0].y), mb = fmaxf(xb[0].x, xb[0].y);
+#pragma unroll
+      for (int i = 1; i < 8; ++i) { ma = fmaxf(ma, fmaxf(xa[i].x, xa[i].y)); mb = fmaxf(mb, fmaxf(xb[i].x, xb[i].y)); }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        ma = fmaxf(ma, __shfl_xor_sync(gmask, ma, o));
+        mb = fmaxf(mb, __shfl_xor_sync(gmask, mb, o));
+      }
+      const float2 na = make_float2(-ma * 1.4426950408889634f, -ma * 1.4426950408889634f);
+      const float2 nb2 = make_float2(-mb * 1.4426950408889634f, -mb * 1.4426950408889634f);
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 ea = fma2(xa[i], l2e, na), eb = fma2(xb[i], l2e, nb2);
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(xa[i].x) : "f"(ea.x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(xa[i].y) : "f"(ea.y));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(xb[i].x) : "f"(eb.x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(xb[i].y) : "f"(eb.y));
+        sa += xa[i].x + xa[i].y;
+        sb += xb[i].x + xb[i].y;
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        sa += __shfl_xor_sync(gmask, sa, o);
+        sb += __shfl_xor_sync(gmask, sb, o);
+      }
+      const float ia = 1.0f / sa, ib = 1.0f / sb;
+      const float2 ia2 = make_float2(ia, ia), ib2 = make_float2(ib, ib);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { xa[i] = mul2(xa[i], ia2); xb[i] = mul2(xb[i], ib2); }
+      store8(t, xa);
+      if (two) store8(t + 32, xb);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (tid == 0) {
+    constexpr uint32_t id = make_idesc_bf16(128, 128);
+    const uint32_t qs_a = smem_u32(Qs), ct_a = smem_u32(Ct);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        const uint64_t ad = make_sw128_kmajor_desc(qs_a + kc * (TP * 128) + mt * (128 * 128));
+        const uint64_t bd = make_sw128_kmajor_desc(ct_a + kc * (128 * 128));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + mt * 128, ad + 2 * k, bd + 2 * k, id, (kc | k) != 0);
+      }
+    }
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  // epilogue: each warp drains 32 rows x 64 columns; staging over Qs (the product has retired), 272-byte pitch
+  constexpr int PITCH = 272;
+  static_assert(TP * PITCH <= L::STG - L::QS, "staging area");
+  {
+    const int quad = warp & 3, hi = warp >> 2;
+    constexpr int CH = MT == 2 ? 4 : 2;                // 32-column chunks per warp
+    const int mt = MT == 2 ? hi : 0, c0 = MT == 2 ? 0 : hi * 2;
+    const int t = mt * 128 + quad * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + mt * 128;
+#pragma unroll 1
+    for (int c = c0; c < c0 + CH; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(t_row + c * 32, raw);
+      tmem_ld_wait();
+      if (t < T) {
+        uint4* dst = reinterpret_cast<uint4*>(Qs + t * PITCH + c * 64);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_uint4(pack2u(__uint_as_float(raw[8 * j]), __uint_as_float(raw[8 * j + 1])),
+                              pack2u(__uint_as_float(raw[8 * j + 2]), __uint_as_float(raw[8 * j + 3])),
+                              pack2u(__uint_as_float(raw[8 * j + 4]), __uint_as_float(raw[8 * j + 5])),
+                              pack2u(__uint_as_float(raw[8 * j + 6]), __uint_as_float(raw[8 * j + 7])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  for (int i = tid; i < T * 16; i += NTHR) {
+    const int r = i >> 4, c = i & 15;
+    *reinterpret_cast<uint4*>(y + ((long)(b * T + r)) * D + h * HD + c * 8) =
+        *reinterpret_cast<const uint4*>(Qs + r * PITCH + c * 16);
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TP);
+  }
+}
+
+template <int TP>
+int launch_lc(const bf16* q, const bf16* ctxT, int B, int H, int T, bf16* y, cudaStream_t st) {
+  using L = SmemLC<TP>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(lincross_umma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+      return MDM_ERR_CUDA;
+    attr = true;
+  }
+  lincross_umma_kernel<TP><<<B * H, NTHR, L::TOTAL, st>>>(q, ctxT, H, T, y);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
 }  // namespace
 
 // hd == M == 128, bf16, T <= 256, with the pre-transposed bf16 projection matrix; MDM_ERR_UNSUPPORTED otherwise
@@ -579,4 +764,17 @@ int mdm_fastattn_umma(const void* qkv, const void* Pt_bf16, const float* norm_w,
   bf16* o = reinterpret_cast<bf16*>(out);
   if (T <= 128) return launch<128>(q, p, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order, st);
   return launch<256>(q, p, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order, st);
+}
+
+// hd == 128, bf16, T <= 256, with ctx^T in bf16 ([B, H, l, d]); MDM_ERR_UNSUPPORTED otherwise.
+int mdm_lincross_apply_umma(const void* q, const void* ctxT_bf16, int B, int T, int H, int hd, void* y, cudaStream_t st) {
+  if (hd != HD || T > 256 || !ctxT_bf16) return MDM_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
+      (reinterpret_cast<uintptr_t>(ctxT_bf16) & 15))
+    return MDM_ERR_UNSUPPORTED;
+  const bf16* qq = reinterpret_cast<const bf16*>(q);
+  const bf16* cc = reinterpret_cast<const bf16*>(ctxT_bf16);
+  bf16* yy = reinterpret_cast<bf16*>(y);
+  if (T <= 128) return launch_lc<128>(qq, cc, B, H, T, yy, st);
+  return launch_lc<256>(qq, cc, B, H, T, yy, st);
 }

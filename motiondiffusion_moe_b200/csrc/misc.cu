@@ -229,6 +229,15 @@ __global__ void recover_ric_kernel(const float* __restrict__ x, const float* __r
   }
 }
 
+// dst[n][c][r] (bf16) = src[n][r][c] (fp32): packs step-invariant fp32 state as a K-major bf16 tensor-core operand
+__global__ void transpose_cast_kernel(const float* __restrict__ src, int R, int Cc, long total, bf16* __restrict__ dst) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long n = i / ((long)R * Cc);
+  const int rem = (int)(i - n * R * Cc), c = rem / R, r = rem - c * R;
+  dst[i] = __float2bfloat16_rn(src[(n * R + r) * Cc + c]);
+}
+
 inline unsigned blocks(long n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
@@ -314,5 +323,14 @@ extern "C" MDM_API int mdm_recover_from_ric(const float* x, const float* mean, c
   const size_t smem = sizeof(float) * 3 * (size_t)T;
   if (smem > 48 * 1024) return MDM_ERR_UNSUPPORTED;
   recover_ric_kernel<<<B, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, mean, stdv, T, F, joints, out);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_transpose_cast_bf16(const float* src, long n, int R, int Cc, void* dst, void* stream) {
+  if (!src || !dst || R <= 0 || Cc <= 0) return MDM_ERR_ARG;
+  const long total = n * R * Cc;
+  if (total == 0) return MDM_OK;
+  transpose_cast_kernel<<<blocks(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, R, Cc, total,
+                                                                                         reinterpret_cast<bf16*>(dst));
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }

@@ -113,10 +113,18 @@ def lincross_ctx(k, v, nt, B, Nt_max, H, hd, ctx):
                                             ctx.data_ptr(), _stream()), "mdm_lincross_ctx")
 
 
-def lincross_apply(q, ctx, B, T, H, hd, y):
-    _c(q, ctx, y)
-    _lib.check(_lib.load().mdm_lincross_apply(q.data_ptr(), _dt(q), ctx.data_ptr(), B, T, H, hd, y.data_ptr(),
-                                              _stream()), "mdm_lincross_apply")
+def lincross_apply(q, ctx, B, T, H, hd, y, ctxT=None):
+    _c(q, ctx, y, ctxT)
+    _lib.check(_lib.load().mdm_lincross_apply_ex(q.data_ptr(), _dt(q), ctx.data_ptr(), _ptr(ctxT), B, T, H, hd,
+                                                 y.data_ptr(), _stream()), "mdm_lincross_apply")
+
+
+def transpose_cast_bf16(src, dst):
+    """dst[n][c][r] (bf16) = src[n][r][c] (fp32); src [..., R, C] contiguous."""
+    _c(src, dst)
+    R, Cc = src.shape[-2], src.shape[-1]
+    _lib.check(_lib.load().mdm_transpose_cast_bf16(src.data_ptr(), src.numel() // (R * Cc), R, Cc, dst.data_ptr(),
+                                                   _stream()), "mdm_transpose_cast_bf16")
 
 
 def softmax_cross(q, k, v, nt, B, T, Nt_max, H, hd, o):

@@ -45,6 +45,7 @@ class TextContext:
         self.nt = None
         self.nt_max = 0
         self.lin_ctx = []
+        self.lin_ctxT = []        # bf16 [B, H, l, d] copies of lin_ctx (B operand of the tcgen05 apply kernel) or None
         self.k2 = []
         self.v2 = []
         self.xf_proj = None
@@ -570,6 +571,11 @@ class MotionTransformer(nn.Module):
             self._lin(xa, L["sd_k"], out_a=k2)
             self._lin(xa, L["sd_v"], out_a=v2)
             ctx.lin_ctx.append(c)
+            cT = None
+            if adt == torch.bfloat16:
+                cT = torch.empty(B, H, hd, hd, dtype=torch.bfloat16, device=dev)
+                ops.transpose_cast_bf16(c, cT)
+            ctx.lin_ctxT.append(cT)
             ctx.k2.append(k2)
             ctx.v2.append(v2)
         return ctx
@@ -626,7 +632,7 @@ class MotionTransformer(nn.Module):
         ops.rowop(pre, N, D, adti, ln1=L["dsa_post"], out1_f32=x1, ln2=L["ca_norm"], out2_a=a0)
         # ---- GatedCrossAttention (fast_attention.py:242-272)
         self._lin(a0, L["ca_q"], out_a=a1)
-        ops.lincross_apply(a1, ctx.lin_ctx[li], Bn, T, H, D // H, a2)
+        ops.lincross_apply(a1, ctx.lin_ctx[li], Bn, T, H, D // H, a2, ctxT=ctx.lin_ctxT[li])
         ops.rowop(a2, N, D, adti, ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T, silu=True, out2_a=a1)
         self._lin(a1, L["ca_out"], out_f32=x2, resid=x1, alpha=1.0, beta=1.0)
         # ---- MoEMultiBranchFFN (multi_branch.py:52-61, switch_moe.py:44-111)

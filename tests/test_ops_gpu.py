@@ -261,6 +261,19 @@ def test_linear_cross_attention(dtype, B, H, T, hd, Nt):
     qs = F.softmax(q.float().view(B, T, H, hd), dim=-1)
     ref = torch.einsum("bnhd,bhdl->bnhl", qs, att).reshape(B * T, D)
     assert rel(y, ref) < TOL[dtype]
+    if dtype == torch.bfloat16 and hd == 128:
+        # with ctx^T packed as bf16 the tcgen05 kernel (attention_umma.cu) runs; also at the half resolution
+        ctxT = torch.empty(B, H, hd, hd, device=DEV, dtype=torch.bfloat16)
+        ops.transpose_cast_bf16(ctx, ctxT)
+        assert torch.equal(ctxT, ctx.transpose(-1, -2).contiguous().to(torch.bfloat16))
+        y2 = torch.full_like(y, float("nan"))
+        ops.lincross_apply(q, ctx, B, T, H, hd, y2, ctxT=ctxT)
+        assert rel(y2, ref) < TOL[dtype]
+        Th = T // 2
+        qh = q.view(B, T, D)[:, :Th].contiguous().view(B * Th, D)
+        yh = torch.full((B * Th, D), float("nan"), device=DEV, dtype=dtype)
+        ops.lincross_apply(qh, ctx, B, Th, H, hd, yh, ctxT=ctxT)
+        assert rel(yh, ref.view(B, T, D)[:, :Th].reshape(B * Th, D)) < TOL[dtype]
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

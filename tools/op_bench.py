@@ -111,7 +111,10 @@ timeit("fastattn tcgen05 (Pt, longest first)", lambda i: ops.fastattn(qkv[i], P,
 timeit("fastattn tcgen05 (Pt)", lambda i: ops.fastattn(qkv[i], P, nw, nb_, length, 0, NSEQ, H, T, hd, ob[i], Pt=Pt), nset, N * D * 8, "GB/s")
 timeit("fastattn mma.sync", lambda i: ops.fastattn(qkv[i], P, nw, nb_, length, 0, NSEQ, H, T, hd, ob[i], seq_order=order), nset, N * D * 8, "GB/s")
 ctx = torch.randn(NSEQ, H, hd, hd, device=dev)
-timeit("lincross_apply", lambda i: ops.lincross_apply(xb[i], ctx, NSEQ, T, H, hd, ob[i]), nset, N * D * 4, "GB/s")
+ctxT = torch.empty(NSEQ, H, hd, hd, device=dev, dtype=bf)
+ops.transpose_cast_bf16(ctx, ctxT)
+timeit("lincross_apply tcgen05", lambda i: ops.lincross_apply(xb[i], ctx, NSEQ, T, H, hd, ob[i], ctxT=ctxT), nset, N * D * 4, "GB/s")
+timeit("lincross_apply mma.sync", lambda i: ops.lincross_apply(xb[i], ctx, NSEQ, T, H, hd, ob[i]), nset, N * D * 4, "GB/s")
 Nt = 20
 k2 = torch.randn(NSEQ * Nt, D, device=dev).to(bf)
 v2 = torch.randn(NSEQ * Nt, D, device=dev).to(bf)
