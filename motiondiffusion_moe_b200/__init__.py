@@ -5,7 +5,8 @@ from .transformer import MotionTransformer, TextContext  # noqa: F401
 from .gaussian_diffusion import (GaussianDiffusion, CFGStepper, get_named_beta_schedule, ModelMeanType,  # noqa: F401
                                  ModelVarType, LossType)
 
+from .trainer import DDPMTrainer  # noqa: F401
 from .postprocess import load_reference_checkpoint, save_reference_checkpoint, recover_from_ric  # noqa: F401
 
-__all__ = ["load_reference_checkpoint", "save_reference_checkpoint", "recover_from_ric", "MotionTransformer", "TextContext", "GaussianDiffusion", "CFGStepper", "get_named_beta_schedule", "ModelMeanType",
+__all__ = ["DDPMTrainer", "load_reference_checkpoint", "save_reference_checkpoint", "recover_from_ric", "MotionTransformer", "TextContext", "GaussianDiffusion", "CFGStepper", "get_named_beta_schedule", "ModelMeanType",
            "ModelVarType", "LossType", "MdmError", "load_library"]

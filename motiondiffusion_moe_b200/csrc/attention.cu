@@ -20,6 +20,8 @@ int mdm_fastattn_umma(const void* qkv, const void* Pt_bf16, const float* norm_w,
 
 int mdm_lincross_apply_umma(const void* q, const void* ctxT_bf16, int B, int T, int H, int hd, void* y, cudaStream_t st);
 int mdm_lincross_apply_tc(const void* q, const float* ctx, int B, int T, int H, int hd, void* y, cudaStream_t st);
+int mdm_softmax_cross_umma(const void* q, const void* k, const void* v, const int* nt, int B, int T, int Nt_max, int H,
+                           int hd, float scale, void* o, cudaStream_t st);
 int mdm_softmax_cross_tc(const void* q, const void* k, const void* v, const int* nt, int B, int T, int Nt_max, int H,
                          int hd, float scale, void* o, cudaStream_t st);
 
@@ -477,6 +479,11 @@ extern "C" MDM_API int mdm_softmax_cross(const void* q, const void* k, const voi
   const float scale = (float)(1.0 / sqrt((double)hd));  // python: head_dim ** -0.5, then fp32
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dt == MDM_BF16) {
+    static const int umma_env = [] { const char* e = getenv("MDM_SC_UMMA"); return e ? atoi(e) : 1; }();
+    if (umma_env) {
+      const int r = mdm_softmax_cross_umma(q, k, v, nt, B, T, Nt_max, H, hd, scale, o, st);
+      if (r != MDM_ERR_UNSUPPORTED) return r;
+    }
     const int r = mdm_softmax_cross_tc(q, k, v, nt, B, T, Nt_max, H, hd, scale, o, st);
     if (r != MDM_ERR_UNSUPPORTED) return r;
   }

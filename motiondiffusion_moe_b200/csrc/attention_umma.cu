@@ -748,6 +748,236 @@ int launch_lc(const bf16* q, const bf16* ctxT, int B, int H, int T, bf16* y, cud
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------------
+// MemoryEfficientCrossAttentionBlock core (fast_attention.py:313-325) on tcgen05:
+//   o[t,h,:] = softmax_n((q[t,h,:] * hd^-0.5) . k[b,n,h,:]) @ v[b,n,h,:],  n < nt[b] <= 96
+// One CTA per (sequence, head), 97 KB of shared memory, TP TMEM columns (two CTAs per SM).  S = Q K^T with raw q / k
+// rows brought by cp.async straight into operand layout (K = head dim); the softmax over the keys is lane-local in
+// TMEM (lane == frame) and its bf16 result P overwrites Q as the A operand of O = P V (K = keys, only the NK/16
+// k-steps that hold keys); v waits in registers and is stored transposed over K once S has retired.
+template <int TP>
+__global__ void __launch_bounds__(NTHR, 2)
+softmax_cross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
+                          const int* __restrict__ nt, int H, int T, int Nt_max, int NK, float scale,
+                          bf16* __restrict__ o) {
+  using L = SmemLC<TP>;                  // Qs (later P, later staging) + a 32 KB operand region (K, later V^T)
+  constexpr int MT = TP / 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* Qs = smem + L::QS;
+  uint8_t* Kv = smem + L::CT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = H * HD;
+  const int n_tok = nt ? min(nt[b], Nt_max) : Nt_max;
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(tmem_ptr, TP);
+  const int sub = tid & 7, rr = tid >> 3;
+  // v rows -> registers (pairs {2 sub + 16 j, +1} of row n = rr + 32 p)
+  uint32_t vraw[3][8];
+  const bf16* vb = v + (long)b * Nt_max * D + h * HD;
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    const int n = rr + 32 * p;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      vraw[p][j] = n < n_tok ? __ldg(reinterpret_cast<const uint32_t*>(vb + (long)n * D) + sub + 8 * j) : 0u;
+  }
+  // raw q -> A tiles, raw k -> B tiles (rows = keys; keys >= n_tok are zero rows, masked in the softmax)
+  {
+    const bf16* qb = q + (long)b * T * D + h * HD;
+    uint8_t* dstq = Qs + (sub >> 2) * (TP * 128);
+#pragma unroll 1
+    for (int t = rr; t < TP; t += 32) {
+      uint8_t* d0 = dstq + sw_off(t, (sub & 3) * 16);
+      uint8_t* d1 = dstq + sw_off(t, (sub & 3) * 16 + 8);
+      if (t < T) {
+        const bf16* src = qb + (long)t * D + sub * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d0)), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d1)), "l"(src + 8) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(d0) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(d1) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    const bf16* kb = k + (long)b * Nt_max * D + h * HD;
+    uint8_t* dstk = Kv + (sub >> 2) * (128 * 128);
+#pragma unroll 1
+    for (int n = rr; n < NK; n += 32) {
+      uint8_t* d0 = dstk + sw_off(n, (sub & 3) * 16);
+      uint8_t* d1 = dstk + sw_off(n, (sub & 3) * 16 + 8);
+      if (n < n_tok) {
+        const bf16* src = kb + (long)n * D + sub * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d0)), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(d1)), "l"(src + 8) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(d0) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(d1) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t qs_a = smem_u32(Qs), kv_a = smem_u32(Kv);
+  if (tid == 0) {                        // S[mt] = Q[mt] . K^T   (N = NK keys)
+    const uint32_t id = make_idesc_bf16(128, NK);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        const uint64_t ad = make_sw128_kmajor_desc(qs_a + kc * (TP * 128) + mt * (128 * 128));
+        const uint64_t bd = make_sw128_kmajor_desc(kv_a + kc * (128 * 128));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base + mt * 128, ad + 2 * kk, bd + 2 * kk, id, (kc | kk) != 0);
+      }
+    }
+    umma_commit(&bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  tc_fence_after();
+  // v^T over the K region (S has retired): V^T[l][n], zero columns for the masked keys
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    const int n = rr + 32 * p;
+    if (n < NK) {
+      uint8_t* dcol = Kv + (n >> 6) * (128 * 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<uint16_t*>(dcol + sw_off(2 * sub + 16 * j, n & 63)) = (uint16_t)(vraw[p][j] & 0xffffu);
+        *reinterpret_cast<uint16_t*>(dcol + sw_off(2 * sub + 16 * j + 1, n & 63)) = (uint16_t)(vraw[p][j] >> 16);
+      }
+    }
+  }
+  // masked softmax over the keys of the thread's own frame -> P (bf16) over Q
+  const int quad = warp & 3, hi = warp >> 2;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+  if (hi < MT) {
+    const int t = hi * 128 + quad * 32 + lane;
+    const uint32_t t_row = t_lane + hi * 128;
+    const float sl2 = scale * 1.4426950408889634f;
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < NK / 32; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(t_row + c * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (c * 32 + e < n_tok) mx = fmaxf(mx, __uint_as_float(raw[e]));
+    }
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < NK / 32; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(t_row + c * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        float ev;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ev) : "f"((__uint_as_float(raw[e]) - mx) * sl2));
+        sum += (c * 32 + e < n_tok) ? ev : 0.f;
+      }
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll 1
+    for (int c = 0; c < NK / 32; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(t_row + c * 32, raw);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float e0, e1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"((__uint_as_float(raw[2 * e]) - mx) * sl2));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"((__uint_as_float(raw[2 * e + 1]) - mx) * sl2));
+        e0 = (c * 32 + 2 * e < n_tok) ? e0 * inv : 0.f;
+        e1 = (c * 32 + 2 * e + 1 < n_tok) ? e1 * inv : 0.f;
+        pk[e] = pack2u(e0, e1);
+      }
+      uint8_t* dst = Qs + (c >> 1) * (TP * 128);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(dst + sw_off(t, (c & 1) * 32 + 8 * j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {                        // O[mt] = P[mt] . V   (K = NK keys)
+    constexpr uint32_t id = make_idesc_bf16(128, 128);
+    const int ksteps = NK / 16;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int kc = ks >> 2, kk = ks & 3;
+        const uint64_t ad = make_sw128_kmajor_desc(qs_a + kc * (TP * 128) + mt * (128 * 128));
+        const uint64_t bd = make_sw128_kmajor_desc(kv_a + kc * (128 * 128));
+        umma_bf16(tmem_base + mt * 128, ad + 2 * kk, bd + 2 * kk, id, ks != 0);
+      }
+    }
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  constexpr int PITCH = 272;
+  {
+    constexpr int CH = MT == 2 ? 4 : 2;
+    const int mt = MT == 2 ? hi : 0, c0 = MT == 2 ? 0 : hi * 2;
+    const int t = mt * 128 + quad * 32 + lane;
+    const uint32_t t_row = t_lane + mt * 128;
+#pragma unroll 1
+    for (int c = c0; c < c0 + CH; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(t_row + c * 32, raw);
+      tmem_ld_wait();
+      if (t < T) {
+        uint4* dst = reinterpret_cast<uint4*>(Qs + t * PITCH + c * 64);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_uint4(pack2u(__uint_as_float(raw[8 * j]), __uint_as_float(raw[8 * j + 1])),
+                              pack2u(__uint_as_float(raw[8 * j + 2]), __uint_as_float(raw[8 * j + 3])),
+                              pack2u(__uint_as_float(raw[8 * j + 4]), __uint_as_float(raw[8 * j + 5])),
+                              pack2u(__uint_as_float(raw[8 * j + 6]), __uint_as_float(raw[8 * j + 7])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  for (int i = tid; i < T * 16; i += NTHR) {
+    const int r = i >> 4, c = i & 15;
+    *reinterpret_cast<uint4*>(o + ((long)(b * T + r)) * D + h * HD + c * 8) =
+        *reinterpret_cast<const uint4*>(Qs + r * PITCH + c * 16);
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TP);
+  }
+}
+
+template <int TP>
+int launch_sc(const bf16* q, const bf16* k, const bf16* v, const int* nt, int B, int H, int T, int Nt_max, float scale,
+              bf16* o, cudaStream_t st) {
+  using L = SmemLC<TP>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(softmax_cross_umma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+        cudaSuccess)
+      return MDM_ERR_CUDA;
+    attr = true;
+  }
+  const int NK = (Nt_max + 31) / 32 * 32;
+  softmax_cross_umma_kernel<TP><<<B * H, NTHR, L::TOTAL, st>>>(q, k, v, nt, H, T, Nt_max, NK, scale, o);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
 }  // namespace
 
 // hd == M == 128, bf16, T <= 256, with the pre-transposed bf16 projection matrix; MDM_ERR_UNSUPPORTED otherwise
@@ -777,4 +1007,18 @@ int mdm_lincross_apply_umma(const void* q, const void* ctxT_bf16, int B, int T, 
   bf16* yy = reinterpret_cast<bf16*>(y);
   if (T <= 128) return launch_lc<128>(qq, cc, B, H, T, yy, st);
   return launch_lc<256>(qq, cc, B, H, T, yy, st);
+}
+
+// hd == 128, bf16, T <= 256, at most 96 keys; MDM_ERR_UNSUPPORTED otherwise.
+int mdm_softmax_cross_umma(const void* q, const void* k, const void* v, const int* nt, int B, int T, int Nt_max, int H,
+                           int hd, float scale, void* o, cudaStream_t st) {
+  if (hd != HD || T > 256 || Nt_max > 96 || Nt_max < 1) return MDM_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) ||
+      (reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(o) & 15))
+    return MDM_ERR_UNSUPPORTED;
+  const bf16 *qq = reinterpret_cast<const bf16*>(q), *kk = reinterpret_cast<const bf16*>(k),
+             *vv = reinterpret_cast<const bf16*>(v);
+  bf16* oo = reinterpret_cast<bf16*>(o);
+  if (T <= 128) return launch_sc<128>(qq, kk, vv, nt, B, H, T, Nt_max, scale, oo, st);
+  return launch_sc<256>(qq, kk, vv, nt, B, H, T, Nt_max, scale, oo, st);
 }

@@ -210,6 +210,34 @@ def test_step_host_pipelined_copies_equal_device_steps():
     del net.encode_text
 
 
+def test_trainer_generate_mirrors_reference_entry_point(tmp_path):
+    """DDPMTrainer.generate / generate_batch / load (trainers/ddpm_trainer.py:145-199, 277-289): the call the reference's
+    evaluation / visualisation tools make; here with the strided DDIM loop so that the test stays short."""
+    import types
+    case = "tiny_b3"
+    cfg_name, _, T = cases.CASES[case]
+    cfg, p, net = build(case, "bf16")
+    net.encode_text = lambda text, device: mo.stub_text(text, cfg.text_latent_dim, device)
+    opt = types.SimpleNamespace(device=DEV, diffusion_steps=1000, is_train=False, cfg_scale=7.5)
+    tr = mdm.DDPMTrainer(opt, net, sampler="ddim", num_inference_steps=4)
+    caps = ["a person walks", "a person jumps", "a person sits down", "someone waves", "a man runs"]
+    lens = torch.tensor([8, 6, 8, 4, 8])
+    torch.manual_seed(5)
+    outs = tr.generate(caps, lens, cfg.input_feats, batch_size=2)
+    assert len(outs) == 5 and all(o.shape == (T, cfg.input_feats) and torch.isfinite(o).all() for o in outs)
+    torch.manual_seed(5)
+    first = tr.generate_batch(caps[:2], lens[:2], cfg.input_feats)
+    assert torch.equal(first[0], outs[0]) and torch.equal(first[1], outs[1])
+    path = str(tmp_path / "ckpt_e001.tar")
+    tr.save(path, 1, 77)
+    assert tr.load(path) == (1, 77)
+    with pytest.raises(NotImplementedError):
+        tr.update()
+    with pytest.raises(NotImplementedError):
+        mdm.DDPMTrainer(types.SimpleNamespace(device=DEV, diffusion_steps=1000, is_train=True), net)
+    del net.encode_text
+
+
 def test_full_1000_step_sample_matches_oracle_loop():
     """north_star: 'the final 1000-step sample within a stated tolerance'.  All 1000 reverse steps of
     p_sample_loop_with_cfg (CUDA-graph replay) against the oracle's loop (two forwards + update per
