@@ -101,6 +101,15 @@ MDM_API int mdm_gemm_f32(const float* A, int lda, long a_rows, const float* W, i
 
 /* ---- row-wise normalisation / FiLM ----------------------------------------------------------- */
 MDM_API int mdm_rowop(const MdmRowOp* op, long rows, int D, int out_dt, void* stream);
+/* The row pipeline fused into the GEMM that consumes it (no intermediate in global memory):
+ *   out_f32[m, :] = beta * resid[m, :] + alpha * ( pipeline(in[m, :]) . W[N, D]^T + bias )
+ * with the stage set of `op` (its outputs are ignored).  The eight epilogue warps build the bf16 A operand of each
+ * 128-row tile in shared memory in the tensor core's swizzled K-major layout, W streams by TMA, accumulators in TMEM,
+ * fp32 + residual epilogue by TMA.  D == 512, N in {256, 512}, bf16 input rows and weights, fp32 residual / output;
+ * stage sets: LN1+L2+LN2+FiLM+SiLU (stylization.py:29-30 after fast_attention.py:169-172) and LN2+FiLM+SiLU.
+ * Anything else returns MDM_ERR_UNSUPPORTED (status 3) and the caller uses mdm_rowop + mdm_gemm_bf16. */
+MDM_API int mdm_gemm_rowop(const MdmRowOp* op, long rows, int D, const void* W, int ldw, long w_rows, int N,
+                           const MdmGemmEpi* epi, void* stream);
 
 /* ---- FastAttention core, models/fast_attention.py:29-92 (PerformerSelfAttention :155-160) ----
  * qkv: [B*T, 3*H*hd] (q | k | v, already multiplied by nothing: the 0.1 pre-scale of :155-157 is

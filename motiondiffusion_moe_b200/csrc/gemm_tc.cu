@@ -16,6 +16,7 @@
 
 #include <stdlib.h>
 #include "gemm_epilogue.cuh"
+#include "rowmath.cuh"
 
 #ifdef MDM_GEMM_PROFILE
 // bring-up instrumentation: per CTA {epilogue wait cycles, epilogue work cycles, MMA-thread cycles waiting
@@ -598,6 +599,272 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
+
+// =============================================================================================
+// Row pipeline fused into the GEMM that consumes it (K = D = 512): the A operand is never in global memory.
+//   out[m, :] = beta * resid[m, :] + alpha * ( rowop(in[m, :]) . W^T + bias )
+// rowop = the stage set of mdm_rowop (LayerNorm -> L2 norm * sqrt(D) -> LayerNorm -> FiLM -> SiLU, each optional).
+// Per 128-row tile the eight epilogue warps first BUILD the A operand: 16 rows each, row pipeline in registers
+// (warp per row, two rows interleaved), result written as bf16 straight into the eight 128B-swizzled K-major
+// k-block tiles the tensor core reads (128 KB).  Meanwhile warp 0 streams the weight tiles by TMA through a 3-stage
+// ring and warp 1 issues the tcgen05.mma chains for the N / 256 accumulators (TMEM columns 0..N-1).  When the
+// accumulators are complete the A region is dead and becomes the staging area of the fp32 + residual epilogue
+// (EPI_F32T: residual in / sum out by TMA).  Replaces rowop + GEMM pairs whose intermediate has one consumer:
+// the StylizationBlock chains of the two Performer blocks and of the linear cross-attention (a2 -> s_out / ca_out).
+constexpr int RD = 512;                 // row width == K
+constexpr int RKB = RD / BK;            // k-blocks of the A operand
+constexpr int RSTAGES = 3;              // weight ring
+constexpr int RBN = 256;
+struct RowGemmSmem {
+  static constexpr int A_OFF = 0;                               // RKB x [128 rows x 128 B]; later epilogue staging
+  static constexpr int B_OFF = RKB * BM * BK * 2;               // RSTAGES x [256 rows x 128 B]
+  static constexpr int BAR_OFF = B_OFF + RSTAGES * RBN * BK * 2;
+  // full / empty ring, a_ready, acc_full, tmem_empty, 16 residual barriers, TMEM pointer; + alignment slack
+  static constexpr int TOTAL = BAR_OFF + (2 * RSTAGES + 3 + 16) * 8 + 16 + 1024;
+};
+static_assert(RowGemmSmem::TOTAL <= 227 * 1024, "shared memory budget");
+static_assert(tr_bytes(EPI_F32T) <= RowGemmSmem::B_OFF, "epilogue staging fits the dead A operand");
+
+enum { RF_LN1 = 1, RF_L2 = 2, RF_LN2 = 4, RF_FILM = 8, RF_SILU = 16 };
+
+__device__ __forceinline__ float silu_mufu_g(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-x * 1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+
+template <typename TI, int FLAGS>
+__global__ void __launch_bounds__(num_threads(EPI_F32T), 1)
+gemm_rowop_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmF,
+                  const TI* __restrict__ in, const float* __restrict__ ln1_w, const float* __restrict__ ln1_b,
+                  const float* __restrict__ ln2_w, const float* __restrict__ ln2_b, const float* __restrict__ film,
+                  int rows_per_seq, int M, int N, const GemmEpi epi) {
+  using L = RowGemmSmem;
+  constexpr int VPT = RD / 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* As = smem + L::A_OFF;
+  uint8_t* Bs = smem + L::B_OFF;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + RSTAGES;
+  uint64_t* a_ready = empty_bar + RSTAGES;
+  uint64_t* acc_full = a_ready + 1;
+  uint64_t* tmem_empty = acc_full + 1;
+  uint64_t* res_bar = tmem_empty + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NT = N / RBN;
+  const int num_m_tiles = (M + BM - 1) / BM;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int s = 0; s < RSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(a_ready, 8);
+    mbar_init(acc_full, 1);
+    mbar_init(tmem_empty, 8);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mbar_init(&res_bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < FIRST_EPI_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------ weight tiles by TMA
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_m_tiles; t += gridDim.x) {
+        for (int nt = 0; nt < NT; ++nt) {
+          for (int kb = 0; kb < RKB; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], RBN * BK * 2);
+            tma_load_2d(&tmB, &full_bar[stage], Bs + stage * (RBN * BK * 2), kb * BK, nt * RBN);
+            if (++stage == RSTAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(BM, RBN);
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      const uint32_t a_addr = smem_u32(As), b_addr = smem_u32(Bs);
+      long long w_a = 0, w_op = 0;
+      const long long t_begin = PROF_T();
+      (void)t_begin;
+      for (int t = blockIdx.x; t < num_m_tiles; t += gridDim.x, ++it) {
+        long long c0 = PROF_T();
+        mbar_wait(tmem_empty, (it & 1) ^ 1);        // the previous tile's epilogue has drained the accumulators
+        mbar_wait(a_ready, it & 1);                 // the A operand of this tile is in shared memory
+        w_a += PROF_T() - c0;
+        tc_fence_after();
+        for (int nt = 0; nt < NT; ++nt) {
+          for (int kb = 0; kb < RKB; ++kb) {
+            c0 = PROF_T();
+            mbar_wait(&full_bar[stage], phase);
+            w_op += PROF_T() - c0;
+            tc_fence_after();
+            const uint64_t adesc = make_sw128_kmajor_desc(a_addr + kb * (BM * BK * 2));
+            const uint64_t bdesc = make_sw128_kmajor_desc(b_addr + stage * (RBN * BK * 2));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16(tmem_base + nt * RBN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(&empty_bar[stage]);
+            if (++stage == RSTAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(acc_full);
+      }
+#ifdef MDM_GEMM_PROFILE
+      g_gemm_prof[blockIdx.x * 8 + 2] = w_a;
+      g_gemm_prof[blockIdx.x * 8 + 3] = w_op;
+      g_gemm_prof[blockIdx.x * 8 + 4] = PROF_T() - t_begin;
+#endif
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ------------------------------------------------------------ A builder + epilogue (8 warps)
+    const int widx = warp - FIRST_EPI_WARP;
+    const int quad = warp & 3, cpar = widx >> 2;
+    uint4* tr = reinterpret_cast<uint4*>(As) + widx * 512;
+    uint32_t rphase = 0;
+    const EpiTma tm{&tmC, &tmR, &tmF, res_bar + 2 * widx, &rphase};
+    float w1[VPT], b1[VPT], w2[VPT], b2[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT / 4; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 a = (FLAGS & RF_LN1) ? __ldg(reinterpret_cast<const float4*>(ln1_w + c)) : z;
+      const float4 bq = (FLAGS & RF_LN1) ? __ldg(reinterpret_cast<const float4*>(ln1_b + c)) : z;
+      const float4 cc = (FLAGS & RF_LN2) ? __ldg(reinterpret_cast<const float4*>(ln2_w + c)) : z;
+      const float4 d = (FLAGS & RF_LN2) ? __ldg(reinterpret_cast<const float4*>(ln2_b + c)) : z;
+      w1[4 * j] = a.x; w1[4 * j + 1] = a.y; w1[4 * j + 2] = a.z; w1[4 * j + 3] = a.w;
+      b1[4 * j] = bq.x; b1[4 * j + 1] = bq.y; b1[4 * j + 2] = bq.z; b1[4 * j + 3] = bq.w;
+      w2[4 * j] = cc.x; w2[4 * j + 1] = cc.y; w2[4 * j + 2] = cc.z; w2[4 * j + 3] = cc.w;
+      b2[4 * j] = d.x; b2[4 * j + 1] = d.y; b2[4 * j + 2] = d.z; b2[4 * j + 3] = d.w;
+    }
+    // the row pipeline on one row held as v[VPT] (lane owns columns (j*32 + lane)*4 + c)
+    auto pipeline = [&](float (&v)[VPT], long m) {
+      if (FLAGS & RF_LN1) {
+        float mean, rstd;
+        row_stats<VPT>(v, RD, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) v[i] = (v[i] - mean) * rstd * w1[i] + b1[i];
+      }
+      if (FLAGS & RF_L2) l2norm_row<VPT>(v, RD);
+      if (FLAGS & RF_LN2) {
+        float mean, rstd;
+        row_stats<VPT>(v, RD, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) v[i] = (v[i] - mean) * rstd * w2[i] + b2[i];
+      }
+      if (FLAGS & RF_FILM) film_row<VPT>(v, film + (m / rows_per_seq) * 2 * RD, lane, RD);
+      if (FLAGS & RF_SILU) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) v[i] = silu_mufu_g(v[i]);
+      }
+    };
+    auto store_a = [&](const float (&v)[VPT], int r) {     // bf16 row r -> the swizzled k-block tiles
+#pragma unroll
+      for (int j = 0; j < VPT / 4; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        uint2 pk;
+        pk.x = pack2(v[4 * j], v[4 * j + 1]);
+        pk.y = pack2(v[4 * j + 2], v[4 * j + 3]);
+        *reinterpret_cast<uint2*>(As + (c >> 6) * (BM * BK * 2) + r * 128 + (((((c & 63) >> 3) ^ r) & 7) << 4) + ((c & 7) << 1)) = pk;
+      }
+    };
+    uint32_t it = 0;
+    long long p_build = 0, p_wait = 0, p_epi = 0;
+    for (int t = blockIdx.x; t < num_m_tiles; t += gridDim.x, ++it) {
+      const long long q0 = PROF_T();
+      if (it > 0) {      // the staging tiles of the previous epilogue live in the A region: every store must have read them
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      // ---- build A: rows widx*16 .. +15, two at a time
+      const long row0 = (long)t * BM + widx * 16;
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        const long ma = row0 + i, mb = row0 + i + 8;
+        float va[VPT], vb[VPT];
+        if (ma < M) load_row<VPT, TI>(in + ma * RD, lane, va);
+        else {
+#pragma unroll
+          for (int e = 0; e < VPT; ++e) va[e] = 0.f;
+        }
+        if (mb < M) load_row<VPT, TI>(in + mb * RD, lane, vb);
+        else {
+#pragma unroll
+          for (int e = 0; e < VPT; ++e) vb[e] = 0.f;
+        }
+        pipeline(va, ma < M ? ma : 0);
+        pipeline(vb, mb < M ? mb : 0);
+        store_a(va, widx * 16 + i);
+        store_a(vb, widx * 16 + i + 8);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+      const long long q1 = PROF_T();
+      // ---- epilogue once the accumulators are complete (the MMAs have finished reading A)
+      mbar_wait(acc_full, it & 1);
+      tc_fence_after();
+      const long long q2 = PROF_T();
+      const int c_row0 = t * BM, rows_valid = M - t * BM;
+      for (int nt = 0; nt < NT; ++nt)
+        epilogue_tile<RBN, EPI_F32T, MDM_ACT_NONE>(epi, tm, N, nt, c_row0, 0, rows_valid,
+                                                   tmem_base + ((uint32_t)(quad * 32) << 16) + nt * RBN, acc_full, it & 1, tr,
+                                                   quad, cpar, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+      p_build += q1 - q0; p_wait += q2 - q1; p_epi += PROF_T() - q2;
+    }
+#ifdef MDM_GEMM_PROFILE
+    if (warp == FIRST_EPI_WARP && lane == 0) {
+      g_gemm_prof[blockIdx.x * 8 + 0] = p_build;
+      g_gemm_prof[blockIdx.x * 8 + 1] = p_wait;
+      g_gemm_prof[blockIdx.x * 8 + 6] = p_epi;
+      g_gemm_prof[blockIdx.x * 8 + 5] = it;
+    }
+#endif
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <typename TI, int FLAGS>
+int launch_rowop_gemm(const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr, const CUtensorMap& tf,
+                      const MdmRowOp& op, int M, int N, const GemmEpi& epi, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(gemm_rowop_kernel<TI, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             RowGemmSmem::TOTAL) != cudaSuccess)
+      return MDM_ERR_CUDA;
+    attr = true;
+  }
+  const int tiles = (M + BM - 1) / BM, sms = num_sms();
+  gemm_rowop_kernel<TI, FLAGS><<<tiles < sms ? tiles : sms, num_threads(EPI_F32T), RowGemmSmem::TOTAL, st>>>(
+      tb, tc, tr, tf, reinterpret_cast<const TI*>(op.in), op.ln1_w, op.ln1_b, op.ln2_w, op.ln2_b, op.film, op.rows_per_seq, M, N,
+      epi);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
 }  // namespace
 
 // C-ABI: see include/mdm_b200.h
@@ -701,4 +968,32 @@ extern "C" MDM_API int mdm_gemm_bf16(const void* A, int lda, long a_rows, const 
   if (kind == EPI_F32 && act == MDM_ACT_GELU) MDM_GO(EPI_F32, MDM_ACT_GELU);
   MDM_GO(EPI_ANY, -1);
 #undef MDM_GO
+}
+
+// C-ABI: see include/mdm_b200.h
+extern "C" MDM_API int mdm_gemm_rowop(const MdmRowOp* op, long rows, int D, const void* W, int ldw, long w_rows, int N,
+                                      const GemmEpi* epi, void* stream) {
+  if (!op || !op->in || !W || !epi) return MDM_ERR_ARG;
+  if (D != RD || N % RBN != 0 || N < RBN || N > 512 || rows <= 0 || rows > 0x7fffffffL) return MDM_ERR_UNSUPPORTED;
+  if (!epi->out_f32 || !epi->resid || epi->resid_mod > 0 || epi->act != MDM_ACT_NONE || epi->rowscale || epi->rowmask ||
+      epi->out_bf16)
+    return MDM_ERR_UNSUPPORTED;
+  if ((ldw & 7) || (epi->ld_f32 & 3) || (epi->ld_resid & 3)) return MDM_ERR_UNSUPPORTED;
+  auto al = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+  if (!al(W, 16) || !al(op->in, 16) || !al(epi->out_f32, 16) || !al(epi->resid, 16)) return MDM_ERR_UNSUPPORTED;
+  if ((op->film != nullptr) && op->rows_per_seq <= 0) return MDM_ERR_ARG;
+  const int M = (int)rows;
+  CUtensorMap tb, tr, tf;
+  if (!make_map(&tb, W, w_rows, D, ldw, RBN)) return MDM_ERR_CUDA;
+  if (!make_f32_map(&tr, epi->resid, M, N, epi->ld_resid) || !make_f32_map(&tf, epi->out_f32, M, N, epi->ld_f32))
+    return MDM_ERR_CUDA;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int flags = (op->ln1_w ? RF_LN1 : 0) | (op->l2norm ? RF_L2 : 0) | (op->ln2_w ? RF_LN2 : 0) | (op->film ? RF_FILM : 0) |
+                    (op->silu ? RF_SILU : 0);
+  // the stage sets of MotionTransformer._layer that feed a residual-stream GEMM
+  if (op->in_dt == MDM_BF16 && flags == (RF_LN1 | RF_L2 | RF_LN2 | RF_FILM | RF_SILU))
+    return launch_rowop_gemm<bf16, RF_LN1 | RF_L2 | RF_LN2 | RF_FILM | RF_SILU>(tb, tb, tr, tf, *op, M, N, *epi, st);
+  if (op->in_dt == MDM_BF16 && flags == (RF_LN2 | RF_FILM | RF_SILU))
+    return launch_rowop_gemm<bf16, RF_LN2 | RF_FILM | RF_SILU>(tb, tb, tr, tf, *op, M, N, *epi, st);
+  return MDM_ERR_UNSUPPORTED;
 }

@@ -97,6 +97,36 @@ def rowop(x, rows, D, out_dt, *, ln1=None, l2norm=False, out1_f32=None, out1_a=N
     _lib.check(_lib.load().mdm_rowop(C.byref(op), rows, D, out_dt, _stream()), "mdm_rowop")
 
 
+def gemm_rowop(x, rows, D, W, bias, *, ln1=None, l2norm=False, ln2=None, film=None, rows_per_seq=0, silu=False,
+               out_f32=None, resid=None, alpha=1.0, beta=1.0):
+    """out_f32 = beta * resid + alpha * (rowop(x) @ W^T + bias) with the row pipeline of `rowop` fused into the GEMM's
+    A-operand construction (mdm_gemm_rowop: D == 512, N in {256, 512}, bf16 weights).  Raises MdmError with status
+    Returns False (nothing launched) for shapes / stage sets outside the fused kernel: the caller then runs rowop + gemm."""
+    _c(x, film, W, bias, out_f32, resid)
+    for pair in (ln1, ln2):
+        if pair is not None:
+            _c(*pair)
+    op = _lib.RowOp()
+    op.inp, op.in_dt = x.data_ptr(), _dt(x)
+    if ln1 is not None:
+        op.ln1_w, op.ln1_b = ln1[0].data_ptr(), ln1[1].data_ptr()
+    op.l2norm = 1 if l2norm else 0
+    if ln2 is not None:
+        op.ln2_w, op.ln2_b = ln2[0].data_ptr(), ln2[1].data_ptr()
+    op.film, op.rows_per_seq, op.silu = _ptr(film), rows_per_seq, 1 if silu else 0
+    e = _lib.GemmEpi()
+    e.bias, e.resid = _ptr(bias), _ptr(resid)
+    e.ld_resid = resid.stride(0) if resid is not None else 0
+    e.alpha, e.beta, e.act = alpha, beta, ACT_NONE
+    e.out_f32, e.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    st = _lib.load().mdm_gemm_rowop(C.byref(op), rows, D, W.data_ptr(), W.stride(0), W.shape[0], W.shape[0], C.byref(e),
+                                    _stream())
+    if st == 3:             # MDM_ERR_UNSUPPORTED: shape / stage set outside the fused kernel
+        return False
+    _lib.check(st, "mdm_gemm_rowop")
+    return True
+
+
 def fastattn(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out, seq_order=None, Pt=None):
     _c(qkv, P, norm_w, norm_b, length, out, seq_order, Pt)
     if Pt is not None and (Pt.dtype != torch.bfloat16 or tuple(Pt.shape) != (P.shape[1], P.shape[0])):

@@ -21,6 +21,8 @@ Deliberate, documented differences from the reference:
 import math
 from typing import List, Optional
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -82,6 +84,9 @@ class MotionTransformer(nn.Module):
         self.last_routing = []
         if text_encoder is not None:
             self.text_encoder = text_encoder
+        # mdm_gemm_rowop (row pipeline fused into the GEMM's A-operand construction) is correct and tested but slower
+        # than rowop + GEMM today (profiles/README.md, step 22): opt-in with MDM_FUSE_ROWOP=1
+        self._fuse_rowop = os.environ.get("MDM_FUSE_ROWOP", "0") == "1"
         self._packed = None
         self._ws = {}
         self._film_tiles = {}
@@ -599,9 +604,14 @@ class MotionTransformer(nn.Module):
                      seq_order=order, Pt=Pk["Pt"])
         self._lin(a1, Pk["p0"], out_a=a2, act=ACT_GELU)
         self._lin(a2, Pk["p3"], out_a=a1)
-        ops.rowop(a1, N, D, ops._dt(a2), ln1=Pk["post"], l2norm=True, ln2=Pk["s_norm"], film=film,
-                  rows_per_seq=T, silu=True, out2_a=a2)
-        self._lin(a2, Pk["s_out"], out_f32=out, resid=resid, alpha=0.1, beta=1.0)
+        # post LN -> L2 norm -> StylizationBlock (LN, FiLM, SiLU) -> its output Linear, + residual: one kernel in bf16
+        # mode (the row pipeline builds the GEMM's A operand in shared memory), rowop + GEMM otherwise
+        if not (self._fuse_rowop and adt == torch.bfloat16 and
+                ops.gemm_rowop(a1, N, D, Pk["s_out"][0], Pk["s_out"][1], ln1=Pk["post"], l2norm=True, ln2=Pk["s_norm"],
+                               film=film, rows_per_seq=T, silu=True, out_f32=out, resid=resid, alpha=0.1, beta=1.0)):
+            ops.rowop(a1, N, D, ops._dt(a2), ln1=Pk["post"], l2norm=True, ln2=Pk["s_norm"], film=film,
+                      rows_per_seq=T, silu=True, out2_a=a2)
+            self._lin(a2, Pk["s_out"], out_f32=out, resid=resid, alpha=0.1, beta=1.0)
 
     def _layer(self, li, x, ctx, film_all, Bpad, Bn, T, length, shift):
         """MoEExtendedDecoderLayer.forward (transformer.py:55-64); x [Bn*T, D] fp32 is updated in place."""
@@ -633,8 +643,11 @@ class MotionTransformer(nn.Module):
         # ---- GatedCrossAttention (fast_attention.py:242-272)
         self._lin(a0, L["ca_q"], out_a=a1)
         ops.lincross_apply(a1, ctx.lin_ctx[li], Bn, T, H, D // H, a2, ctxT=ctx.lin_ctxT[li])
-        ops.rowop(a2, N, D, adti, ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T, silu=True, out2_a=a1)
-        self._lin(a1, L["ca_out"], out_f32=x2, resid=x1, alpha=1.0, beta=1.0)
+        if not (self._fuse_rowop and adt == torch.bfloat16 and
+                ops.gemm_rowop(a2, N, D, L["ca_out"][0], L["ca_out"][1], ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T,
+                               silu=True, out_f32=x2, resid=x1, alpha=1.0, beta=1.0)):
+            ops.rowop(a2, N, D, adti, ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T, silu=True, out2_a=a1)
+            self._lin(a1, L["ca_out"], out_f32=x2, resid=x1, alpha=1.0, beta=1.0)
         # ---- MoEMultiBranchFFN (multi_branch.py:52-61, switch_moe.py:44-111)
         if self._ep_on:
             ep = self._ep_for(N)

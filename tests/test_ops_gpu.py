@@ -137,6 +137,42 @@ def test_gemm_grouped_device_tile_count(dtype):
         assert torch.all(out[pad] == 7.0)      # padding rows are never written
 
 
+@pytest.mark.parametrize("stages", ["full", "ln2_film_silu"])
+@pytest.mark.parametrize("M,T", [(196 * 3, 196), (128, 8), (1000, 100), (25, 5)])
+def test_gemm_rowop_fused(stages, M, T):
+    """mdm_gemm_rowop (row pipeline fused into the A-operand construction of the residual-stream GEMM) against
+    torch and against the unfused rowop + gemm pair."""
+    D = N = 512
+    x = randn(M, D, seed=1, scale=1.5).bfloat16()
+    W = randn(N, D, seed=2, scale=D ** -0.5).bfloat16()
+    b, R = randn(N, seed=3), randn(M, N, seed=4)
+    ln1 = (torch.rand(D, generator=gen(5)).to(DEV) + 0.5, randn(D, seed=6, scale=0.1))
+    ln2 = (torch.rand(D, generator=gen(7)).to(DEV) + 0.5, randn(D, seed=8, scale=0.1))
+    film = randn((M + T - 1) // T, 2 * D, seed=9, scale=0.3)
+    full = stages == "full"
+    kw = dict(ln1=ln1 if full else None, l2norm=full, ln2=ln2, film=film, rows_per_seq=T, silu=True)
+    out = torch.full((M + 8, N), 3.0, device=DEV)
+    assert ops.gemm_rowop(x, M, D, W, b, out_f32=out[:M], resid=R, alpha=0.1, beta=1.0, **kw)
+    assert torch.all(out[M:] == 3.0)
+    a2 = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    ops.rowop(x, M, D, ops._dt(a2), out2_a=a2, **kw)
+    unf = torch.empty(M, N, device=DEV)
+    ops.gemm(a2, W, b, out_f32=unf, resid=R, alpha=0.1, beta=1.0)
+    v = x.float()
+    if full:
+        v = F.layer_norm(v, (D,), ln1[0], ln1[1])
+        v = F.normalize(v, dim=-1) * math.sqrt(D)
+    v = F.layer_norm(v, (D,), ln2[0], ln2[1])
+    sc, sh = film[:, :D], film[:, D:]
+    seq = torch.arange(M, device=DEV) // T
+    v = F.silu(v * (1 + sc[seq]) + sh[seq]).bfloat16().float()
+    ref = R + 0.1 * (v @ W.float().t() + b)
+    assert rel(out[:M], ref) < 2e-3
+    assert rel(out[:M], unf) < 2e-3
+    # shapes outside the fused kernel are declined without launching anything
+    assert not ops.gemm_rowop(x[:, :256].contiguous(), M, 256, W[:, :256].contiguous(), b, out_f32=out[:M], resid=R, **kw)
+
+
 # ------------------------------------------------------------------------------------------ row pipeline
 @pytest.mark.parametrize("D", [128, 256, 512, 1024])
 @pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),

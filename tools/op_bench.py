@@ -84,6 +84,17 @@ timeit("rowop f32->f32+bf16+bf16 ln,ln", lambda i: ops.rowop(xf[i], N, D, MDM_BF
        out0_a=ob2[i]), nset, N * D * 12, "GB/s")
 timeit("rowop f32->bf16 ln", lambda i: ops.rowop(xf[i], N, D, MDM_BF16, ln1=ln, out1_a=ob[i]), nset, N * D * 6, "GB/s")
 
+# ---- row pipeline fused into the residual-stream GEMM (a1 -> LN, L2, LN, FiLM, SiLU -> s_out Linear + residual)
+Wf = (torch.randn(D, D, device=dev) / D ** 0.5).to(bf)
+bfv = torch.randn(D, device=dev)
+kwf = dict(ln1=ln, l2norm=True, ln2=ln2, film=film, rows_per_seq=T, silu=True)
+timeit("gemm_rowop fused (rowop31 + s_out)", lambda i: ops.gemm_rowop(xb[i], N, D, Wf, bfv, out_f32=of[i], resid=xf[i], alpha=0.1, beta=1.0, **kwf),
+       nset, 2.0 * N * D * D, "TFLOP/s")
+def _unfused(i):
+    ops.rowop(xb[i], N, D, MDM_BF16, out2_a=ob[i], **kwf)
+    ops.gemm(ob[i], Wf, bfv, out_f32=of[i], resid=xf[i], alpha=0.1, beta=1.0)
+timeit("rowop31 + gemm s_out (unfused pair)", _unfused, nset, 2.0 * N * D * D, "TFLOP/s")
+
 # ---- MoE routing
 E, NB = 8, 2
 G = NB * E
