@@ -32,9 +32,100 @@ __device__ __forceinline__ float tree_sum(const float (&a)[VPT]) {
     for (int i = 0; i < n; ++i) t[i] += t[i + n];
   return t[0];
 }
+// Packed (FFMA2 / FMUL2 / FADD2) versions for the bf16-operand specialisations: the row kernels are issue-bound
+// (~650 instructions per row for the five-stage pipeline), two elements per issue slot.
+template <int VPT>
+__device__ __forceinline__ float2 pair_sum(const float (&a)[VPT]) {       // two interleaved partial sums, tree order
+  float2 t[VPT / 2];
+#pragma unroll
+  for (int i = 0; i < VPT / 2; ++i) t[i] = make_float2(a[2 * i], a[2 * i + 1]);
+#pragma unroll
+  for (int n = VPT / 4; n >= 1; n >>= 1)
+#pragma unroll
+    for (int i = 0; i < n; ++i) t[i] = add2(t[i], t[i + n]);
+  return t[0];
+}
+template <int VPT>
+__device__ __forceinline__ void ln_regs_packed(float (&v)[VPT], const float* __restrict__ w_s, const float* __restrict__ b_s,
+                                               int lane, int D) {
+  const float inv_d = 1.0f / (float)D;
+  const float2 s2 = pair_sum<VPT>(v);
+  const float mean = warp_sum(s2.x + s2.y) * inv_d;
+  const float2 nm = make_float2(-mean, -mean);
+  float2 q2 = make_float2(0.f, 0.f), q3 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < VPT / 2; i += 2) {
+    const float2 d0 = add2(make_float2(v[2 * i], v[2 * i + 1]), nm), d1 = add2(make_float2(v[2 * i + 2], v[2 * i + 3]), nm);
+    v[2 * i] = d0.x; v[2 * i + 1] = d0.y; v[2 * i + 2] = d1.x; v[2 * i + 3] = d1.y;
+    q2 = fma2(d0, d0, q2);
+    q3 = fma2(d1, d1, q3);
+  }
+  const float rstd = rsqrtf(warp_sum((q2.x + q3.x) + (q2.y + q3.y)) * inv_d + 1e-5f);
+  const float2 r2 = make_float2(rstd, rstd);
+#pragma unroll
+  for (int j = 0; j < VPT / 4; ++j) {
+    const float4 w4 = *reinterpret_cast<const float4*>(w_s + (j * 32 + lane) * 4);
+    const float4 b4 = *reinterpret_cast<const float4*>(b_s + (j * 32 + lane) * 4);
+    const float2 y0 = fma2(make_float2(v[4 * j], v[4 * j + 1]), mul2(make_float2(w4.x, w4.y), r2), make_float2(b4.x, b4.y));
+    const float2 y1 = fma2(make_float2(v[4 * j + 2], v[4 * j + 3]), mul2(make_float2(w4.z, w4.w), r2), make_float2(b4.z, b4.w));
+    v[4 * j] = y0.x; v[4 * j + 1] = y0.y; v[4 * j + 2] = y1.x; v[4 * j + 3] = y1.y;
+  }
+}
+template <int VPT>
+__device__ __forceinline__ void l2norm_packed(float (&v)[VPT], int D) {
+  float2 q2 = make_float2(0.f, 0.f), q3 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < VPT / 2; i += 2) {
+    const float2 a = make_float2(v[2 * i], v[2 * i + 1]), b = make_float2(v[2 * i + 2], v[2 * i + 3]);
+    q2 = fma2(a, a, q2);
+    q3 = fma2(b, b, q3);
+  }
+  const float denom = fmaxf(sqrtf(warp_sum((q2.x + q3.x) + (q2.y + q3.y))), 1e-12f);
+  const float sc = sqrtf((float)D) / denom;
+  const float2 s2 = make_float2(sc, sc);
+#pragma unroll
+  for (int i = 0; i < VPT / 2; ++i) {
+    const float2 y = mul2(make_float2(v[2 * i], v[2 * i + 1]), s2);
+    v[2 * i] = y.x; v[2 * i + 1] = y.y;
+  }
+}
+template <int VPT>
+__device__ __forceinline__ void film_packed(float (&v)[VPT], const float* __restrict__ film, int lane, int D) {
+  const float2 one = make_float2(1.f, 1.f);
+#pragma unroll
+  for (int j = 0; j < VPT / 4; ++j) {
+    const float4 sc = *reinterpret_cast<const float4*>(film + (j * 32 + lane) * 4);
+    const float4 sh = *reinterpret_cast<const float4*>(film + D + (j * 32 + lane) * 4);
+    const float2 y0 = fma2(make_float2(v[4 * j], v[4 * j + 1]), add2(make_float2(sc.x, sc.y), one), make_float2(sh.x, sh.y));
+    const float2 y1 = fma2(make_float2(v[4 * j + 2], v[4 * j + 3]), add2(make_float2(sc.z, sc.w), one), make_float2(sh.z, sh.w));
+    v[4 * j] = y0.x; v[4 * j + 1] = y0.y; v[4 * j + 2] = y1.x; v[4 * j + 3] = y1.y;
+  }
+}
+template <int VPT>
+__device__ __forceinline__ void silu_packed(float (&v)[VPT]) {
+  const float2 nl2e = make_float2(-1.4426950408889634f, -1.4426950408889634f), one = make_float2(1.f, 1.f);
+#pragma unroll
+  for (int i = 0; i < VPT / 2; ++i) {
+    const float2 x = make_float2(v[2 * i], v[2 * i + 1]);
+    const float2 a = mul2(x, nl2e);
+    float2 e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+    e = add2(e, one);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(e.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(e.y));
+    const float2 y = mul2(x, r);
+    v[2 * i] = y.x; v[2 * i + 1] = y.y;
+  }
+}
+
 template <int VPT, bool TREE>
 __device__ __forceinline__ void ln_regs(float (&v)[VPT], const float* __restrict__ w_s, const float* __restrict__ b_s,
                                         int lane, int D) {
+  if (TREE) {
+    ln_regs_packed<VPT>(v, w_s, b_s, lane, D);
+    return;
+  }
   float mean, rstd;
   if (TREE) {
     const float inv_d = 1.0f / (float)D;
@@ -136,14 +227,20 @@ __global__ void __launch_bounds__(256, (VPT >= 32 ? 1 : 3)) rowop_kernel(const R
       if (r + PF * stride < rows) ring[j].load(in + (r + PF * stride) * D, lane);
       if (op.out0_a) store_row<VPT, TO>(reinterpret_cast<TO*>(op.out0_a) + r * D, lane, v);
       if (do_ln1) ln_regs<VPT, FAST>(v, prm[0], prm[1], lane, D);
-      if (do_l2) l2norm_row<VPT>(v, D);
+      if (do_l2) { if (FAST) l2norm_packed<VPT>(v, D); else l2norm_row<VPT>(v, D); }
       if (op.out1_f32) store_row<VPT, float>(op.out1_f32 + r * D, lane, v);
       if (op.out1_a) store_row<VPT, TO>(reinterpret_cast<TO*>(op.out1_a) + r * D, lane, v);
       if (do_ln2) ln_regs<VPT, FAST>(v, prm[2], prm[3], lane, D);
-      if (do_film) film_row<VPT>(v, op.film + (r / op.rows_per_seq) * 2 * D, lane, D);
+      if (do_film) {
+        if (FAST) film_packed<VPT>(v, op.film + (r / op.rows_per_seq) * 2 * D, lane, D);
+        else film_row<VPT>(v, op.film + (r / op.rows_per_seq) * 2 * D, lane, D);
+      }
       if (do_silu) {
+        if (FAST) silu_packed<VPT>(v);
+        else {
 #pragma unroll
-        for (int i = 0; i < VPT; ++i) v[i] = FAST ? silu_mufu(v[i]) : silu_f(v[i]);
+          for (int i = 0; i < VPT; ++i) v[i] = silu_f(v[i]);
+        }
       }
       if (op.out2_f32) store_row<VPT, float>(op.out2_f32 + r * D, lane, v);
       if (op.out2_a) store_row<VPT, TO>(reinterpret_cast<TO*>(op.out2_a) + r * D, lane, v);
