@@ -392,6 +392,52 @@ def test_shape_variants_match_oracle(name, precision, tol):
                 assert torch.equal(idx[:, br].long().cpu(), routing[2 * i + br][1].long().cpu()), (i, br)
 
 
+def test_full_size_permutation_equivariance_and_determinism():
+    """BASELINE.json configs[1] at its full size (default model, 64 sequences x 196 frames, bf16), through properties
+    that do not need an oracle run: (1) two forwards of the same batch are bit-identical (no atomics, no
+    order-dependent reductions in the data path); (2) permuting the sequences of the batch permutes the output, bit for
+    bit - every kernel (grouped expert GEMM tiles, token permute / combine, attention CTAs in longest-first order)
+    treats a sequence independently of where it sits in the batch; (3) the routing of a token does not depend on
+    the batch it is in."""
+    case = "default_b2"
+    cfg, p, net = build(case, "bf16")
+    B, T = 64, 196
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(B, T, cfg.input_feats, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+    length = torch.randint(40, T + 1, (B,), generator=g).to(DEV)
+    xf_out = torch.nn.functional.gelu(torch.randn(B, 20, cfg.text_latent_dim, generator=g)).to(DEV)
+    xf_proj = xf_out.mean(1)
+    net.record_routing = True
+    y1 = net(x, t, length, None, xf_proj, xf_out)
+    r1 = [r[0].clone() for r in net.last_routing]
+    y2 = net(x, t, length, None, xf_proj, xf_out)
+    assert torch.isfinite(y1).all()
+    assert torch.equal(y1, y2)
+    perm = torch.randperm(B, generator=g).to(DEV)
+    ctx = net.prepare_text(xf_proj[perm].contiguous(), xf_out[perm].contiguous())
+    ctx.seq_order = torch.argsort(length[perm], descending=True, stable=True).to(torch.int32)
+    yp = net(x[perm].contiguous(), t[perm].contiguous(), length[perm].contiguous(), text_ctx=ctx)
+    assert torch.equal(yp, y1[perm])
+    n_low = cfg.num_layers
+    for li, (a, b_) in enumerate(zip(r1, [r[0] for r in net.last_routing])):
+        Tl = T // 2 if li < n_low else T
+        assert torch.equal(b_.view(B, Tl, 2, 2), a.view(B, Tl, 2, 2)[perm]), li
+    net.record_routing = False
+    # (4) classifier-free guidance batching: cond (20 text tokens) and uncond (10) as ONE forward of 2B sequences with
+    # per-sequence token counts gives exactly the two separate forwards
+    u_out = torch.nn.functional.gelu(torch.randn(B, 10, cfg.text_latent_dim, generator=g)).to(DEV)
+    y_u = net(x, t, length, None, u_out.mean(1), u_out)
+    xo = torch.zeros(2 * B, 20, cfg.text_latent_dim, device=DEV)
+    xo[:B] = xf_out
+    xo[B:, :10] = u_out
+    nt = torch.cat([torch.full((B,), 20), torch.full((B,), 10)]).to(device=DEV, dtype=torch.int32)
+    ctx2 = net.prepare_text(torch.cat([xf_proj, u_out.mean(1)]), xo, nt)
+    y12 = net(torch.cat([x, x]), torch.cat([t, t]), torch.cat([length, length]), text_ctx=ctx2)
+    assert torch.equal(y12[:B], y1)
+    assert torch.equal(y12[B:], y_u)
+
+
 def test_state_dict_roundtrip_and_errors():
     cfg, p, net = build("tiny_b3", "fp32")
     sd = net.state_dict()
