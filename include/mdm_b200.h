@@ -235,6 +235,13 @@ MDM_API int mdm_ddim_update(const float* x, const float* eps_c, const float* eps
 MDM_API int mdm_recover_from_ric(const float* x, const float* mean, const float* stdv, int B, int T, int F,
                                  int joints, float* out, void* stream);
 
+/* Masked reconstruction loss of DDPMTrainer.backward_G (trainers/ddpm_trainer.py:207-214): mean over features of
+ * (pred - target)^2 per frame, summed over the frames t < min(T, length[b]) and divided by the number of such frames
+ * (src_mask of models/transformer.py:284-289).  pred / target [B, T, F] fp32; partial [B] fp32 and counter [1] u32
+ * (zero before the first call; reset by the kernel) are scratch; loss [1] fp32.  Deterministic. */
+MDM_API int mdm_masked_mse(const float* pred, const float* target, const int64_t* length, int B, int T, int F,
+                           float* partial, unsigned* counter, float* loss, void* stream);
+
 /* ---- expert-parallel MoE over NVLink peer memory (BASELINE.json configs[3]) -------------------------
  * The reference has no expert parallelism (experts are a local nn.ModuleList: models/switch_moe.py:
  * 19-25, looped at :97-109); these entry points replace that loop when the E experts of every branch are

@@ -238,6 +238,42 @@ __global__ void transpose_cast_kernel(const float* __restrict__ src, int R, int 
   dst[i] = __float2bfloat16_rn(src[(n * R + r) * Cc + c]);
 }
 
+// The reconstruction term of DDPMTrainer.backward_G (trainers/ddpm_trainer.py:207-214):
+//   per_frame[b, t] = mean_f (pred - target)^2 ;  loss = sum_{t < min(T, len_b)} per_frame / sum_b min(T, len_b)
+// One block per sequence (fixed reduction order inside the block), per-sequence sums to `partial[B]`; the block that
+// finishes last adds them in index order, so the scalar is deterministic from launch to launch.
+__global__ void masked_mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                  const int64_t* __restrict__ length, int T, int F, int B, float* __restrict__ partial,
+                                  unsigned* __restrict__ counter, float* __restrict__ loss) {
+  __shared__ float red[32];
+  __shared__ bool last;
+  const int b = blockIdx.x;
+  const int len = (int)min((long)T, (long)length[b]);
+  const float* p = pred + (long)b * T * F;
+  const float* q = target + (long)b * T * F;
+  float acc = 0.f;
+  const long n = (long)len * F;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) { const float d = p[i] - q[i]; acc = fmaf(d, d, acc); }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    partial[b] = s / (float)F;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == (unsigned)(B - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    float s = 0.f;
+    long cnt = 0;
+    for (int i = 0; i < B; ++i) { s += partial[i]; cnt += min((long)T, (long)length[i]); }
+    *loss = s / (float)cnt;
+    *counter = 0u;
+  }
+}
+
 inline unsigned blocks(long n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
@@ -332,5 +368,13 @@ extern "C" MDM_API int mdm_transpose_cast_bf16(const float* src, long n, int R, 
   if (total == 0) return MDM_OK;
   transpose_cast_kernel<<<blocks(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, R, Cc, total,
                                                                                          reinterpret_cast<bf16*>(dst));
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_masked_mse(const float* pred, const float* target, const int64_t* length, int B, int T, int F,
+                                      float* partial, unsigned* counter, float* loss, void* stream) {
+  if (!pred || !target || !length || !partial || !counter || !loss || B <= 0 || T <= 0 || F <= 0) return MDM_ERR_ARG;
+  masked_mse_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, target, length, T, F, B, partial, counter,
+                                                                         loss);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }

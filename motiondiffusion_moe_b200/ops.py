@@ -260,6 +260,14 @@ def recover_from_ric(x, joints, out, mean=None, std=None):
                                                 _stream()), "mdm_recover_from_ric")
 
 
+def masked_mse(pred, target, length, partial, counter, loss):
+    _c(pred, target, length, partial, counter, loss)
+    B, T, F = pred.shape
+    _lib.check(_lib.load().mdm_masked_mse(pred.data_ptr(), target.data_ptr(), length.data_ptr(), B, T, F,
+                                          partial.data_ptr(), counter.data_ptr(), loss.data_ptr(), _stream()),
+               "mdm_masked_mse")
+
+
 def q_sample(x0, noise, t, tables2, n_steps, x_t):
     _c(x0, noise, t, tables2, x_t)
     B = x0.shape[0]

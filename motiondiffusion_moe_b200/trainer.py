@@ -7,8 +7,12 @@ tools/evaluation.py and tools/visualization.py call to turn captions into motion
 
 `generate_batch` (:145-174) is `p_sample_loop_with_cfg` on the CUDA-graph step runner.  Extras (keyword-only /
 optional attributes, absent from the reference): `sampler="ddim"` with `num_inference_steps` runs the strided DDIM
-loop instead of the 1000-step ancestral one.  The training half (forward / backward_G / update / train, :97-143,
-201-360) is not built: there are no backward kernels yet, and the methods say so loudly."""
+loop instead of the 1000-step ancestral one.  `forward` / `backward_G` (:97-143, 201-225) compute the training-step
+VALUES (noise prediction, masked reconstruction loss, MoE balance loss) on the kernels; `update` / `train` (:227-360)
+are not built: there are no backward / optimizer kernels yet, and they say so loudly."""
+from collections import OrderedDict
+
+import numpy as np
 import torch
 
 from .gaussian_diffusion import GaussianDiffusion, LossType, ModelMeanType, ModelVarType, get_named_beta_schedule
@@ -86,9 +90,45 @@ class DDPMTrainer(object):
             cur_idx += batch_size
         return all_output
 
-    # ------------------------------------------------------------------ training half: not built
-    def _no_training(self, *a, **kw):
-        raise NotImplementedError("DDPMTrainer.forward / backward_G / update / train need the backward and optimizer "
-                                  "kernels of the training step, which are not built (DESIGN.md section 7)")
+    # ------------------------------------------------------------------ training forward (loss VALUES; no backward yet)
+    def forward(self, batch_data, eval_mode=False):                                       # :97-143
+        """q_sample at a uniformly drawn timestep, one model forward, noise prediction vs noise, MoE balance loss, mask:
+        the values the reference computes before `update` back-propagates.  Uses numpy's global RNG for the timesteps
+        (UniformSampler.sample, models/gaussian_diffusion.py:108-133) and torch's for the noise, like the reference."""
+        caption, motions, m_lens = batch_data
+        motions = motions.detach().to(self.device).float()
+        self.caption, self.motions = caption, motions
+        B, T = motions.shape[:2]
+        cur_len = torch.LongTensor([min(T, int(m)) for m in m_lens]).to(self.device)
+        p = np.ones([self.diffusion.num_timesteps]) / self.diffusion.num_timesteps
+        t = torch.from_numpy(np.random.choice(len(p), size=(B,), p=p)).long().to(self.device)
+        output = self.diffusion.training_losses(model=self._model(), x_start=motions, t=t,
+                                                model_kwargs={"text": caption, "length": cur_len})
+        self.real_noise, self.fake_noise = output["target"], output["pred"]
+        self.moe_loss = output.get("moe_loss", 0.0)
+        self.cur_len = cur_len
+        self.src_mask = self._model().generate_src_mask(T, cur_len).to(motions.device)
 
-    forward = backward_G = update = train = _no_training
+    def backward_G(self):                                                                 # :201-225 (values only)
+        """loss_mot_rec = sum(mse_per_frame * src_mask) / sum(src_mask) (one kernel: mdm_masked_mse) + moe_loss."""
+        pred, target = self.fake_noise.float().contiguous(), self.real_noise.float().contiguous()
+        dev = pred.device
+        if not hasattr(self, "_loss_ws") or self._loss_ws[0].numel() < pred.shape[0]:
+            self._loss_ws = (torch.zeros(pred.shape[0], device=dev), torch.zeros(1, dtype=torch.int32, device=dev),
+                             torch.zeros(1, device=dev))
+        partial, counter, loss = self._loss_ws
+        from . import ops
+        ops.masked_mse(pred, target, self.cur_len.contiguous(), partial, counter, loss)
+        loss_mot_rec = loss[0].clone()
+        total = loss_mot_rec + (self.moe_loss if isinstance(self.moe_loss, torch.Tensor) else 0.0)
+        self.loss_mot_rec = total
+        return OrderedDict({"loss_mot_rec": loss_mot_rec.item(),
+                            "loss_moe": float(self.moe_loss) if isinstance(self.moe_loss, torch.Tensor) else self.moe_loss,
+                            "loss_total": total.item()})
+
+    # ------------------------------------------------------------------ optimisation: not built
+    def _no_training(self, *a, **kw):
+        raise NotImplementedError("DDPMTrainer.update / train need the backward and optimizer kernels of the training "
+                                  "step, which are not built (DESIGN.md section 7)")
+
+    update = train = _no_training

@@ -231,6 +231,19 @@ def test_trainer_generate_mirrors_reference_entry_point(tmp_path):
     path = str(tmp_path / "ckpt_e001.tar")
     tr.save(path, 1, 77)
     assert tr.load(path) == (1, 77)
+    # training-step VALUES (forward + backward_G of the reference trainer): masked loss kernel vs torch
+    import numpy as np
+    np.random.seed(3)
+    torch.manual_seed(3)
+    motions = torch.randn(3, T, cfg.input_feats, generator=torch.Generator().manual_seed(8))
+    tr.forward((caps[:3], motions, [8, 5, 2]))
+    logs = tr.backward_G()
+    per = ((tr.fake_noise - tr.real_noise) ** 2).mean(-1)
+    mask = tr.src_mask.float().view(per.shape)
+    want = float((per * mask).sum() / mask.sum())
+    assert abs(logs["loss_mot_rec"] - want) < 1e-5 * max(1.0, abs(want))
+    assert abs(logs["loss_total"] - (want + float(tr.moe_loss))) < 1e-4 * max(1.0, abs(want))
+    assert logs == tr.backward_G()                  # deterministic; the scratch counter resets itself
     with pytest.raises(NotImplementedError):
         tr.update()
     with pytest.raises(NotImplementedError):
