@@ -242,6 +242,16 @@ MDM_API int mdm_recover_from_ric(const float* x, const float* mean, const float*
 MDM_API int mdm_masked_mse(const float* pred, const float* target, const int64_t* length, int B, int T, int F,
                            float* partial, unsigned* counter, float* loss, void* stream);
 
+/* ---- first building blocks of the training step's backward (the full backward is
+ * not built): the two gradient GEMMs of a Linear y = x W^T + b (models/*: every nn.Linear) run on mdm_gemm_bf16.
+ *   dX = dY . W     -> mdm_gemm_bf16 with W^T [in, out] as the weight (mdm_transpose_split_bf16, S = 1)
+ *   dW = dY^T . X   -> contraction over the tokens: operands transposed AND split into S token slabs laid out as the row
+ *                      groups of a grouped GEMM (dst[s*C + c][m'] = src[s*Ks + m'][c], zero padded to Ks), fp32 partial
+ *                      products [S, out, in] summed by mdm_sum_partials; db = column sums (mdm_colsum_bf16 + sum). */
+MDM_API int mdm_transpose_split_bf16(const void* src, long M, int C, int S, int Ks, void* dst, void* stream);
+MDM_API int mdm_sum_partials(const float* part, int S, long n, int accumulate, float* out, void* stream);
+MDM_API int mdm_colsum_bf16(const void* src, long M, int C, int slabs, float* part, void* stream);
+
 /* ---- expert-parallel MoE over NVLink peer memory (BASELINE.json configs[3]) -------------------------
  * The reference has no expert parallelism (experts are a local nn.ModuleList: models/switch_moe.py:
  * 19-25, looped at :97-109); these entry points replace that loop when the E experts of every branch are

@@ -274,6 +274,63 @@ __global__ void masked_mse_kernel(const float* __restrict__ pred, const float* _
   }
 }
 
+// Backward building blocks of a Linear (y = x W^T + b) on the forward GEMM kernel:
+//   dX = dY . W          : the forward GEMM with W^T ([in, out], mdm_transpose_split_bf16 with S = 1) as its weight
+//   dW = dY^T . X        : contraction over the M tokens.  Both operands must be K-major in the token index, i.e.
+//                          transposed, and a 512 x 512 result alone would occupy 8 of 148 SMs, so the token range is
+//                          split in S slabs: dst[s*C + c][m'] = src[s*Ks + m'][c] lays the slabs out as the row groups
+//                          of a grouped GEMM (one group per slab, partial products [S, out, in] in fp32), which
+//                          mdm_sum_partials then adds up (+ the bias gradient as column sums of dY).
+// 32 x 32 tiles through shared memory: coalesced 64-byte reads and writes.
+__global__ void transpose_split_kernel(const bf16* __restrict__ src, long M, int Cc, int Ks, bf16* __restrict__ dst) {
+  __shared__ bf16 tile[32][33];
+  const int s = blockIdx.z;
+  const long m0 = (long)s * Ks + (long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty + 8 * i;
+    const long m = m0 + r;
+    const bool ok = m < M && (blockIdx.x * 32 + r) < Ks && c0 + tx < Cc;
+    tile[r][tx] = ok ? src[m * Cc + c0 + tx] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = ty + 8 * i;
+    const int ml = blockIdx.x * 32 + tx;
+    if (c0 + c < Cc && ml < Ks) dst[((long)s * Cc + c0 + c) * Ks + ml] = tile[tx][c];
+  }
+}
+
+// out[i] (+)= sum_s part[s][i]; fixed order
+__global__ void sum_partials_kernel(const float* __restrict__ part, int S, long n, int accumulate, float* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = accumulate ? out[i] : 0.f;
+  for (int s = 0; s < S; ++s) a += part[(long)s * n + i];
+  out[i] = a;
+}
+
+// column sums of a [M, C] bf16 matrix (bias gradient): block per 32 columns x slab of rows, partials [slabs, C]
+__global__ void colsum_kernel(const bf16* __restrict__ src, long M, int Cc, int rows_per_blk, float* __restrict__ part) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
+  const long r0 = (long)blockIdx.y * rows_per_blk, r1 = min(M, r0 + rows_per_blk);
+  float a = 0.f;
+  if (c < Cc)
+    for (long r = r0 + ty; r < r1; r += 8) a += __bfloat162float(src[r * Cc + c]);
+  red[ty][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (ty == 0 && c < Cc) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x & 31];
+    part[(long)blockIdx.y * Cc + c] = s;
+  }
+}
+
 inline unsigned blocks(long n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
@@ -376,5 +433,29 @@ extern "C" MDM_API int mdm_masked_mse(const float* pred, const float* target, co
   if (!pred || !target || !length || !partial || !counter || !loss || B <= 0 || T <= 0 || F <= 0) return MDM_ERR_ARG;
   masked_mse_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, target, length, T, F, B, partial, counter,
                                                                          loss);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_transpose_split_bf16(const void* src, long M, int Cc, int S, int Ks, void* dst, void* stream) {
+  if (!src || !dst || M <= 0 || Cc <= 0 || S <= 0 || Ks <= 0 || (long)S * Ks < M) return MDM_ERR_ARG;
+  dim3 grid((Ks + 31) / 32, (Cc + 31) / 32, S);
+  transpose_split_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(src), M, Cc, Ks,
+                                                                                  reinterpret_cast<bf16*>(dst));
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_sum_partials(const float* part, int S, long n, int accumulate, float* out, void* stream) {
+  if (!part || !out || S <= 0) return MDM_ERR_ARG;
+  if (n == 0) return MDM_OK;
+  sum_partials_kernel<<<blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part, S, n, accumulate, out);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_colsum_bf16(const void* src, long M, int Cc, int slabs, float* part, void* stream) {
+  if (!src || !part || M <= 0 || Cc <= 0 || slabs <= 0) return MDM_ERR_ARG;
+  const int rows_per_blk = (int)((M + slabs - 1) / slabs);
+  dim3 grid((Cc + 31) / 32, slabs);
+  colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(src), M, Cc, rows_per_blk,
+                                                                         part);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }

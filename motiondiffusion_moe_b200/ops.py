@@ -273,3 +273,63 @@ def q_sample(x0, noise, t, tables2, n_steps, x_t):
     B = x0.shape[0]
     _lib.check(_lib.load().mdm_q_sample(x0.data_ptr(), noise.data_ptr(), t.data_ptr(), tables2.data_ptr(), n_steps,
                                         B, x0.numel() // B, x_t.data_ptr(), _stream()), "mdm_q_sample")
+
+
+# ------------------------------------------------------------------ backward building blocks (training step, round 2)
+_SLAB_TILES = {}
+
+def linear_backward(x, W, dy, *, dx=None, dW=None, db=None, accumulate=False, splits=None):
+    """Gradients of y = x @ W^T + b on the tcgen05 GEMM: x [M, in], W [out, in], dy [M, out] (bf16) ->
+    dx [M, in] (bf16, optional), dW [out, in] / db [out] (fp32, optional; `accumulate` adds to them).
+    dW contracts over the M tokens: both operands are transposed into S token slabs that form the row groups of one
+    grouped GEMM (fp32 partial products), so that the small [out, in] result still fills the machine."""
+    _c(x, W, dy, dx, dW, db)
+    lib = _lib.load()
+    M, K_in = x.shape
+    N_out = W.shape[0]
+    dev = x.device
+    if dx is not None:
+        Wt = torch.empty(K_in, N_out, dtype=torch.bfloat16, device=dev)        # W^T: the weight of dX = dY . W
+        _lib.check(lib.mdm_transpose_split_bf16(W.data_ptr(), N_out, K_in, 1, N_out, Wt.data_ptr(), _stream()),
+                   "mdm_transpose_split_bf16")
+        gemm(dy, Wt, None, out_a=dx)
+    if dW is not None:
+        tiles_out = (N_out + 127) // 128
+        S = splits or max(1, min(64, (2 * _lib.load().mdm_num_sms()) // max(1, tiles_out * ((K_in + 255) // 256))))
+        Ks = ((M + S - 1) // S + 63) // 64 * 64
+        rows_a = tiles_out * 128                                                # slab rows padded to the GEMM tile
+        dyT = torch.zeros(S * rows_a, Ks, dtype=torch.bfloat16, device=dev) if rows_a != N_out else \
+            torch.empty(S * N_out, Ks, dtype=torch.bfloat16, device=dev)
+        xT = torch.empty(S * K_in, Ks, dtype=torch.bfloat16, device=dev)
+        if rows_a == N_out:
+            _lib.check(lib.mdm_transpose_split_bf16(dy.data_ptr(), M, N_out, S, Ks, dyT.data_ptr(), _stream()), "transpose dY")
+        else:
+            tmp = torch.empty(S * N_out, Ks, dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.mdm_transpose_split_bf16(dy.data_ptr(), M, N_out, S, Ks, tmp.data_ptr(), _stream()), "transpose dY")
+            dyT.view(S, rows_a, Ks)[:, :N_out].copy_(tmp.view(S, N_out, Ks))
+        _lib.check(lib.mdm_transpose_split_bf16(x.data_ptr(), M, K_in, S, Ks, xT.data_ptr(), _stream()), "transpose X")
+        key = (S, tiles_out, rows_a, K_in, N_out, str(dev))
+        tt = _SLAB_TILES.get(key)
+        if tt is None:                                   # one tile table per shape, built once
+            rows = [[s_ * rows_a + i * 128, s_ * rows_a + i * 128, s_ * K_in, min(128, N_out - i * 128)]
+                    for s_ in range(S) for i in range(tiles_out)]
+            tt = _SLAB_TILES[key] = torch.tensor(rows, dtype=torch.int32).to(dev)
+        part = torch.empty(S * rows_a, K_in, dtype=torch.float32, device=dev)
+        gemm(dyT, xT, None, out_f32=part, N=K_in, M=S * rows_a, tiles=tt, num_tiles=S * tiles_out, a_rows=S * rows_a,
+             w_rows=S * K_in)
+        if rows_a == N_out:
+            _lib.check(lib.mdm_sum_partials(part.data_ptr(), S, N_out * K_in, 1 if accumulate else 0, dW.data_ptr(), _stream()),
+                       "mdm_sum_partials")
+        else:
+            red = torch.empty(rows_a, K_in, dtype=torch.float32, device=dev)
+            _lib.check(lib.mdm_sum_partials(part.data_ptr(), S, rows_a * K_in, 0, red.data_ptr(), _stream()), "mdm_sum_partials")
+            if accumulate:
+                dW.add_(red[:N_out])
+            else:
+                dW.copy_(red[:N_out])
+    if db is not None:
+        slabs = 64
+        part = torch.empty(slabs, N_out, dtype=torch.float32, device=dev)
+        _lib.check(lib.mdm_colsum_bf16(dy.data_ptr(), M, N_out, slabs, part.data_ptr(), _stream()), "mdm_colsum_bf16")
+        _lib.check(lib.mdm_sum_partials(part.data_ptr(), slabs, N_out, 1 if accumulate else 0, db.data_ptr(), _stream()),
+                   "mdm_sum_partials")

@@ -173,6 +173,25 @@ def test_gemm_rowop_fused(stages, M, T):
     assert not ops.gemm_rowop(x[:, :256].contiguous(), M, 256, W[:, :256].contiguous(), b, out_f32=out[:M], resid=R, **kw)
 
 
+@pytest.mark.parametrize("M,K_in,N_out", [(1000, 512, 512), (25088, 512, 1536), (300, 264, 128), (4097, 1024, 512)])
+def test_linear_backward_building_blocks(M, K_in, N_out):
+    """dX = dY W, dW = dY^T X (token slabs as the groups of one grouped GEMM + fp32 partial sums), db = column sums:
+    the gradient GEMMs of a Linear on the forward tcgen05 kernel, against torch in fp32 on the same bf16 operands."""
+    x = randn(M, K_in, seed=1).bfloat16()
+    W = randn(N_out, K_in, seed=2, scale=K_in ** -0.5).bfloat16()
+    dy = randn(M, N_out, seed=3).bfloat16()
+    dx = torch.empty(M, K_in, device=DEV, dtype=torch.bfloat16)
+    dW = torch.empty(N_out, K_in, device=DEV)
+    db = torch.empty(N_out, device=DEV)
+    ops.linear_backward(x, W, dy, dx=dx, dW=dW, db=db)
+    assert rel(dx, dy.float() @ W.float()) < 4e-3                       # bf16 output rounding
+    assert rel(dW, dy.float().t() @ x.float()) < 1e-5
+    assert rel(db, dy.float().sum(0)) < 1e-5
+    dW2, db2 = dW.clone(), db.clone()
+    ops.linear_backward(x, W, dy, dW=dW2, db=db2, accumulate=True)
+    assert rel(dW2, 2 * dW) < 1e-6 and rel(db2, 2 * db) < 1e-6
+
+
 # ------------------------------------------------------------------------------------------ row pipeline
 @pytest.mark.parametrize("D", [128, 256, 512, 1024])
 @pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),

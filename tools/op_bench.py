@@ -131,3 +131,22 @@ k2 = torch.randn(NSEQ * Nt, D, device=dev).to(bf)
 v2 = torch.randn(NSEQ * Nt, D, device=dev).to(bf)
 nt = torch.full((NSEQ,), Nt, dtype=torch.int32, device=dev)
 timeit("softmax_cross", lambda i: ops.softmax_cross(xb[i], k2, v2, nt, NSEQ, T, Nt, H, hd, ob[i]), nset, N * D * 4, "GB/s")
+
+# ---- backward building blocks of a Linear (dX, dW with token slabs, db)
+xg = torch.randn(N, D, device=dev).to(bf)
+Wg = (torch.randn(D, D, device=dev) / D ** 0.5).to(bf)
+dyg = torch.randn(N, D, device=dev).to(bf)
+dxg = torch.empty(N, D, device=dev, dtype=bf)
+dWg, dbg = torch.empty(D, D, device=dev), torch.empty(D, device=dev)
+if not ONLY or "linear_backward" in ONLY:
+    for _ in range(2):
+        ops.linear_backward(xg, Wg, dyg, dx=dxg, dW=dWg, db=dbg)
+    torch.cuda.synchronize()
+    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_.record()
+    for _ in range(10):
+        ops.linear_backward(xg, Wg, dyg, dx=dxg, dW=dWg, db=dbg)
+    e_.record()
+    torch.cuda.synchronize()
+    us = s_.elapsed_time(e_) / 10 * 1e3
+    print("%-44s %8.1f us  %8.1f TFLOP/s (dX + dW + db: 4 N D^2 FLOP; 8 eager launches incl. the three transposes)" % ("linear_backward N x512x512", us, 4.0 * N * D * D / us / 1e6))
