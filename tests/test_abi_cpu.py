@@ -118,3 +118,35 @@ def test_reference_checkpoint_roundtrip(tmp_path):
         mdm.load_reference_checkpoint(b, {"model": {}})
     with pytest.raises(mdm.MdmError):
         mdm.recover_from_ric(torch.zeros(1, 4, 263), 22)       # CPU tensor: no CPU path
+
+
+def test_ddim_schedule_and_trainer_host_logic():
+    """Host-side logic that needs no GPU: the strided DDIM schedule, the diffusion tables against the oracle's, and the
+    training half of DDPMTrainer refusing loudly."""
+    import types
+    import motiondiffusion_moe_b200 as mdm
+    from oracle import motion_oracle as mo
+    d = mdm.GaussianDiffusion(betas=mdm.get_named_beta_schedule("linear", 1000))
+    for S in (1, 2, 7, 50, 333, 1000):
+        order, prev = d.ddim_timesteps(S)
+        assert order == sorted(set(order), reverse=True) and order[-1] == 0 and 0 <= max(order) < 1000
+        assert len(order) <= S and (S > 500 or len(order) == S)
+        assert prev == order[1:] + [-1]
+    assert d.ddim_timesteps(1000)[0] == list(range(999, -1, -1))          # the reference's full-length loop
+    with pytest.raises(ValueError):
+        d.ddim_timesteps(0)
+    tab = mo.diffusion_tables(1000)
+    for k in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
+              "posterior_log_variance_clipped", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "alphas_cumprod"):
+        assert np.array_equal(getattr(d, k), tab[k]), k
+    cfg = dict(input_feats=12, num_frames=8, latent_dim=128, ff_size=256, num_layers=1, num_heads=4, text_latent_dim=128,
+               moe_num_experts=4)
+    net = mdm.MotionTransformer(**cfg)
+    with pytest.raises(NotImplementedError):
+        mdm.DDPMTrainer(types.SimpleNamespace(device="cpu", diffusion_steps=1000, is_train=True), net)
+    tr = mdm.DDPMTrainer(types.SimpleNamespace(device="cpu", diffusion_steps=100, is_train=False), net, sampler="ddim")
+    assert tr.diffusion.num_timesteps == 100 and tr.cfg_scale == 7.5
+    with pytest.raises(NotImplementedError):
+        tr.train(None)
+    with pytest.raises(ValueError):
+        mdm.DDPMTrainer(types.SimpleNamespace(device="cpu", diffusion_steps=100, is_train=False), net, sampler="euler")
