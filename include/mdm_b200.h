@@ -248,6 +248,15 @@ MDM_API int mdm_masked_mse(const float* pred, const float* target, const int64_t
  *   dW = dY^T . X   -> contraction over the tokens: operands transposed AND split into S token slabs laid out as the row
  *                      groups of a grouped GEMM (dst[s*C + c][m'] = src[s*Ks + m'][c], zero padded to Ks), fp32 partial
  *                      products [S, out, in] summed by mdm_sum_partials; db = column sums (mdm_colsum_bf16 + sum). */
+/* Backward twin of mdm_rowop: `op` describes the FORWARD pipeline (in, in_dt, ln1, l2norm, ln2, film, rows_per_seq, silu;
+ * its outputs are ignored); dout / din [rows, D] (grad_dt: MDM_F32 or MDM_BF16) are the gradients of the pipeline's final
+ * output and of its input.  The forward intermediates are recomputed in registers.  Parameter gradients come as per-CTA
+ * partial sums to be added up by mdm_sum_partials (fixed order, deterministic):
+ *   dparam_part [n_param_parts, 4, D]   (ln1_w, ln1_b, ln2_w, ln2_b)
+ *   dfilm_part  [n_film_chunks, n_seq, 2*D]   (scale | shift of every sequence)
+ * Called with dout == NULL it only reports n_param_parts / n_film_chunks.  D == 512. */
+MDM_API int mdm_rowop_bwd(const MdmRowOp* op, long rows, int D, int grad_dt, const void* dout, void* din,
+                          float* dparam_part, float* dfilm_part, int* n_param_parts, int* n_film_chunks, void* stream);
 MDM_API int mdm_transpose_split_bf16(const void* src, long M, int C, int S, int Ks, void* dst, void* stream);
 MDM_API int mdm_sum_partials(const float* part, int S, long n, int accumulate, float* out, void* stream);
 MDM_API int mdm_colsum_bf16(const void* src, long M, int C, int slabs, float* part, void* stream);

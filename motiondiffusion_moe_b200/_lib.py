@@ -76,6 +76,7 @@ _SIGS = {
     "mdm_p_mean_variance": [_P, _P, _P, _P, _P, _I, _I, _I, _L, _P, _P, _P, _P],
     "mdm_recover_from_ric": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "mdm_masked_mse": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "mdm_rowop_bwd": [C.POINTER(RowOp), _L, _I, _I, _P, _P, _P, _P, C.POINTER(C.c_int), C.POINTER(C.c_int), _P],
     "mdm_transpose_split_bf16": [_P, _L, _I, _I, _I, _P, _P],
     "mdm_sum_partials": [_P, _I, _L, _I, _P, _P],
     "mdm_colsum_bf16": [_P, _L, _I, _I, _P, _P],

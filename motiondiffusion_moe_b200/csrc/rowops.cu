@@ -277,6 +277,140 @@ int dispatch(const RowOp& op, long rows, int D, int out_dt, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Backward twin of the row pipeline (training step): given the gradient of the
+// pipeline's final output, the gradient of its input plus per-CTA partial gradients of the LayerNorm affine vectors
+// and of the FiLM (scale | shift) rows.  The forward intermediates are recomputed in registers from the input row
+// (cheaper than storing five [N, D] tensors).  One warp per row, 32 rows of ONE sequence per CTA, so that the FiLM
+// gradient of a sequence is a fixed-order sum of per-CTA partials (mdm_sum_partials): no atomics, deterministic.
+//   a = LN1(x)      b = a * sqrt(D) / max(|a|, eps)      c = LN2(b)      d = c * (1 + sc) + sh      e = SiLU(d)
+constexpr int BWD_ROWS = 32;
+template <int VPT, typename TI, typename TG>
+__global__ void __launch_bounds__(256, 1)
+rowop_bwd_kernel(const RowOp op, long rows, int D, int rows_per_seq, int chunks, int n_seq, const TG* __restrict__ dout,
+                 TG* __restrict__ din, float* __restrict__ dparam_part, float* __restrict__ dfilm_part) {
+  __shared__ float red[8][VPT * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seq = blockIdx.x / chunks, ch = blockIdx.x - seq * chunks;
+  const bool do_ln1 = op.ln1_w != nullptr, do_l2 = op.l2norm != 0, do_ln2 = op.ln2_w != nullptr, do_film = op.film != nullptr,
+             do_silu = op.silu != 0;
+  float w1[VPT], w2[VPT], sc[VPT];
+  float gw1[VPT], gb1[VPT], gw2[VPT], gb2[VPT], gsc[VPT], gsh[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) { gw1[i] = gb1[i] = gw2[i] = gb2[i] = gsc[i] = gsh[i] = 0.f; w1[i] = w2[i] = 1.f; sc[i] = 0.f; }
+  float b1[VPT], b2[VPT], sh[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) b1[i] = b2[i] = sh[i] = 0.f;
+  if (do_ln1) { load_vec<VPT>(op.ln1_w, lane, w1); load_vec<VPT>(op.ln1_b, lane, b1); }
+  if (do_ln2) { load_vec<VPT>(op.ln2_w, lane, w2); load_vec<VPT>(op.ln2_b, lane, b2); }
+  if (do_film) { load_vec<VPT>(op.film + (long)seq * 2 * D, lane, sc); load_vec<VPT>(op.film + (long)seq * 2 * D + D, lane, sh); }
+  const float inv_d = 1.0f / (float)D;
+  const long seq_row0 = (long)seq * rows_per_seq;
+  const int r_begin = ch * BWD_ROWS, r_end = min(rows_per_seq, r_begin + BWD_ROWS);
+  for (int rl = r_begin + warp; rl < r_end; rl += 8) {
+    const long r = seq_row0 + rl;
+    if (r >= rows) break;
+    float x[VPT], g[VPT];
+    load_row<VPT, TI>(reinterpret_cast<const TI*>(op.in) + r * D, lane, x);
+    load_row<VPT, TG>(dout + r * D, lane, g);
+    // ---- forward recompute
+    float xh1[VPT], r1 = 1.f;                 // LN1: normalised input, rstd
+    if (do_ln1) {
+      float mean;
+      row_stats<VPT>(x, D, mean, r1);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) { xh1[i] = (x[i] - mean) * r1; x[i] = xh1[i] * w1[i] + b1[i]; }
+    }
+    float a[VPT], s_l2 = 1.f, n2 = 1.f;       // a = LN1 output (input of the L2 stage)
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) a[i] = x[i];
+    if (do_l2) {
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) q = fmaf(a[i], a[i], q);
+      n2 = warp_sum(q);
+      s_l2 = sqrtf((float)D) / fmaxf(sqrtf(n2), 1e-12f);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) x[i] = a[i] * s_l2;
+    }
+    float xh2[VPT], r2 = 1.f;
+    if (do_ln2) {
+      float mean;
+      row_stats<VPT>(x, D, mean, r2);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) { xh2[i] = (x[i] - mean) * r2; x[i] = xh2[i] * w2[i] + b2[i]; }
+    }
+    // x = c (LN2 output); d = c * (1 + sc) + sh
+    // ---- backward
+    if (do_silu) {
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const float d = do_film ? x[i] * (1.f + sc[i]) + sh[i] : x[i];
+        const float sg = 1.f / (1.f + expf(-d));
+        g[i] *= sg * (1.f + d * (1.f - sg));
+      }
+    }
+    if (do_film) {
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) { gsc[i] = fmaf(g[i], x[i], gsc[i]); gsh[i] += g[i]; g[i] *= 1.f + sc[i]; }
+    }
+    if (do_ln2) {
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        gw2[i] = fmaf(g[i], xh2[i], gw2[i]); gb2[i] += g[i];
+        g[i] *= w2[i];
+        m1 += g[i]; m2 = fmaf(g[i], xh2[i], m2);
+      }
+      m1 = warp_sum(m1) * inv_d; m2 = warp_sum(m2) * inv_d;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) g[i] = r2 * (g[i] - m1 - xh2[i] * m2);
+    }
+    if (do_l2) {                               // b = a * s,  s = sqrt(D) / |a|   (|a| > eps assumed, as in the forward)
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) dot = fmaf(a[i], g[i], dot);
+      dot = warp_sum(dot) / fmaxf(n2, 1e-24f);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) g[i] = s_l2 * (g[i] - a[i] * dot);
+    }
+    if (do_ln1) {
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        gw1[i] = fmaf(g[i], xh1[i], gw1[i]); gb1[i] += g[i];
+        g[i] *= w1[i];
+        m1 += g[i]; m2 = fmaf(g[i], xh1[i], m2);
+      }
+      m1 = warp_sum(m1) * inv_d; m2 = warp_sum(m2) * inv_d;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) g[i] = r1 * (g[i] - m1 - xh1[i] * m2);
+    }
+    store_row<VPT, TG>(din + r * D, lane, g);
+  }
+  // ---- per-CTA partial sums of the parameter gradients (fixed order over the 8 warps)
+  auto reduce_to = [&](const float (&v)[VPT], float* dst) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < VPT / 4; ++j)
+      *reinterpret_cast<float4*>(&red[warp][(j * 32 + lane) * 4]) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += 256) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sacc += red[w][c];
+      dst[c] = sacc;
+    }
+  };
+  float* pp = dparam_part + (long)blockIdx.x * 4 * D;
+  reduce_to(gw1, pp); reduce_to(gb1, pp + D); reduce_to(gw2, pp + 2 * D); reduce_to(gb2, pp + 3 * D);
+  if (do_film) {
+    float* fp = dfilm_part + ((long)ch * n_seq + seq) * 2 * D;
+    reduce_to(gsc, fp); reduce_to(gsh, fp + D);
+  }
+}
+
 }  // namespace
 
 extern "C" MDM_API int mdm_rowop(const MdmRowOp* op, long rows, int D, int out_dt, void* stream) {
@@ -291,4 +425,31 @@ extern "C" MDM_API int mdm_rowop(const MdmRowOp* op, long rows, int D, int out_d
     case 1024: return dispatch<32>(*op, rows, D, out_dt, st);
     default: return MDM_ERR_UNSUPPORTED;
   }
+}
+
+// C-ABI: see include/mdm_b200.h
+extern "C" MDM_API int mdm_rowop_bwd(const MdmRowOp* op, long rows, int D, int grad_dt, const void* dout, void* din,
+                                     float* dparam_part, float* dfilm_part, int* n_param_parts, int* n_film_chunks,
+                                     void* stream) {
+  if (!op || !op->in || !n_param_parts || !n_film_chunks) return MDM_ERR_ARG;
+  if (D != 512) return MDM_ERR_UNSUPPORTED;              // VPT = 16 only (the default model); other widths: round 2
+  if (op->film && op->rows_per_seq <= 0) return MDM_ERR_ARG;
+  const int rps = op->film ? op->rows_per_seq : (int)(rows < 0x7fffffffL ? rows : 0x7fffffff);
+  const int n_seq = (int)((rows + rps - 1) / rps), chunks = (rps + BWD_ROWS - 1) / BWD_ROWS;
+  *n_param_parts = n_seq * chunks;
+  *n_film_chunks = chunks;
+  if (!dout || !din || !dparam_part) return MDM_OK;       // size query
+  if (op->film && !dfilm_part) return MDM_ERR_ARG;
+  if (rows == 0) return MDM_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)(n_seq * chunks);
+#define BWD(TI_, TG_) rowop_bwd_kernel<16, TI_, TG_><<<grid, 256, 0, st>>>(*op, rows, D, rps, chunks, n_seq, \
+      reinterpret_cast<const TG_*>(dout), reinterpret_cast<TG_*>(din), dparam_part, dfilm_part)
+  if (op->in_dt == MDM_BF16 && grad_dt == MDM_BF16) BWD(bf16, bf16);
+  else if (op->in_dt == MDM_BF16 && grad_dt == MDM_F32) BWD(bf16, float);
+  else if (op->in_dt == MDM_F32 && grad_dt == MDM_F32) BWD(float, float);
+  else if (op->in_dt == MDM_F32 && grad_dt == MDM_BF16) BWD(float, bf16);
+  else return MDM_ERR_ARG;
+#undef BWD
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }

@@ -333,3 +333,45 @@ def linear_backward(x, W, dy, *, dx=None, dW=None, db=None, accumulate=False, sp
         _lib.check(lib.mdm_colsum_bf16(dy.data_ptr(), M, N_out, slabs, part.data_ptr(), _stream()), "mdm_colsum_bf16")
         _lib.check(lib.mdm_sum_partials(part.data_ptr(), slabs, N_out, 1 if accumulate else 0, db.data_ptr(), _stream()),
                    "mdm_sum_partials")
+
+
+def rowop_bwd(x, rows, D, dout, *, ln1=None, l2norm=False, ln2=None, film=None, rows_per_seq=0, silu=False):
+    """Backward of the row pipeline `rowop(x, ...)` (final output only): returns (din, grads) with grads = {"ln1_w", "ln1_b",
+    "ln2_w", "ln2_b"} [D] fp32 and "film" [n_seq, 2D] fp32 (those of the stages that are present)."""
+    _c(x, dout, film)
+    for pair in (ln1, ln2):
+        if pair is not None:
+            _c(*pair)
+    lib = _lib.load()
+    op = _lib.RowOp()
+    op.inp, op.in_dt = x.data_ptr(), _dt(x)
+    if ln1 is not None:
+        op.ln1_w, op.ln1_b = ln1[0].data_ptr(), ln1[1].data_ptr()
+    op.l2norm = 1 if l2norm else 0
+    if ln2 is not None:
+        op.ln2_w, op.ln2_b = ln2[0].data_ptr(), ln2[1].data_ptr()
+    op.film, op.rows_per_seq, op.silu = _ptr(film), rows_per_seq, 1 if silu else 0
+    npp, nfc = C.c_int(0), C.c_int(0)
+    st = lib.mdm_rowop_bwd(C.byref(op), rows, D, _dt(dout), None, None, None, None, C.byref(npp), C.byref(nfc), _stream())
+    if st != 0:
+        raise _lib.MdmError("mdm_rowop_bwd: status %d" % st)
+    dev = x.device
+    din = torch.empty_like(dout)
+    ppart = torch.empty(npp.value, 4, D, dtype=torch.float32, device=dev)
+    n_seq = film.shape[0] if film is not None else 1
+    fpart = torch.empty(nfc.value, n_seq, 2 * D, dtype=torch.float32, device=dev) if film is not None else None
+    _lib.check(lib.mdm_rowop_bwd(C.byref(op), rows, D, _dt(dout), dout.data_ptr(), din.data_ptr(), ppart.data_ptr(),
+                                 _ptr(fpart), C.byref(npp), C.byref(nfc), _stream()), "mdm_rowop_bwd")
+    psum = torch.empty(4, D, dtype=torch.float32, device=dev)
+    _lib.check(lib.mdm_sum_partials(ppart.data_ptr(), npp.value, 4 * D, 0, psum.data_ptr(), _stream()), "mdm_sum_partials")
+    grads = {}
+    if ln1 is not None:
+        grads["ln1_w"], grads["ln1_b"] = psum[0], psum[1]
+    if ln2 is not None:
+        grads["ln2_w"], grads["ln2_b"] = psum[2], psum[3]
+    if film is not None:
+        fsum = torch.empty(n_seq, 2 * D, dtype=torch.float32, device=dev)
+        _lib.check(lib.mdm_sum_partials(fpart.data_ptr(), nfc.value, n_seq * 2 * D, 0, fsum.data_ptr(), _stream()),
+                   "mdm_sum_partials")
+        grads["film"] = fsum
+    return din, grads

@@ -353,6 +353,50 @@ def test_softmax_cross_attention(dtype, B, H, T, hd, Nt):
 
 
 # ------------------------------------------------------------------------------------------ routing
+@pytest.mark.parametrize("stages", ["full", "ln", "ln2_film_silu", "l2"])
+@pytest.mark.parametrize("gdt", [torch.float32, torch.bfloat16])
+def test_rowop_backward_matches_autograd(stages, gdt):
+    """mdm_rowop_bwd (backward twin of the row pipeline, intermediates recomputed) against torch autograd of the same chain:
+    input gradient, LayerNorm affine gradients, per-sequence FiLM gradients."""
+    D, T, B = 512, 50, 5
+    M = B * T - 7                                  # the last sequence is ragged
+    x = randn(M, D, seed=1, scale=1.5)
+    ln1 = (torch.rand(D, generator=gen(5)).to(DEV) + 0.5, randn(D, seed=6, scale=0.1))
+    ln2 = (torch.rand(D, generator=gen(7)).to(DEV) + 0.5, randn(D, seed=8, scale=0.1))
+    film = randn(B, 2 * D, seed=9, scale=0.3)
+    dout = randn(M, D, seed=10).to(gdt)
+    kw = {"full": dict(ln1=ln1, l2norm=True, ln2=ln2, film=film, rows_per_seq=T, silu=True),
+          "ln": dict(ln1=ln1), "ln2_film_silu": dict(ln2=ln2, film=film, rows_per_seq=T, silu=True),
+          "l2": dict(l2norm=True)}[stages]
+    din, grads = ops.rowop_bwd(x, M, D, dout, **kw)
+    xr = x.clone().requires_grad_(True)
+    leaves = {}
+    v = xr
+    if "ln1" in kw:
+        w, b_ = (t.clone().requires_grad_(True) for t in ln1)
+        leaves["ln1_w"], leaves["ln1_b"] = w, b_
+        v = F.layer_norm(v, (D,), w, b_)
+    if kw.get("l2norm"):
+        v = F.normalize(v, dim=-1) * math.sqrt(D)
+    if "ln2" in kw:
+        w, b_ = (t.clone().requires_grad_(True) for t in ln2)
+        leaves["ln2_w"], leaves["ln2_b"] = w, b_
+        v = F.layer_norm(v, (D,), w, b_)
+    if "film" in kw:
+        fl = film.clone().requires_grad_(True)
+        leaves["film"] = fl
+        seq = torch.arange(M, device=DEV) // T
+        v = v * (1 + fl[seq, :D]) + fl[seq, D:]
+    if kw.get("silu"):
+        v = F.silu(v)
+    v.backward(dout.float())
+    tol = 1e-4 if gdt == torch.float32 else 6e-3
+    assert rel(din, xr.grad) < tol
+    for k, leaf in leaves.items():
+        assert rel(grads[k], leaf.grad) < 1e-4, k
+    assert set(grads) == set(leaves)
+
+
 @pytest.mark.parametrize("E", [4, 8])
 def test_softmax_topk_bit_exact_vs_torch_cuda(E):
     """Expert routing indices bit-exact against torch.softmax + torch.topk ON CUDA (the reference's
