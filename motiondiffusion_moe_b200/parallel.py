@@ -39,10 +39,12 @@ def slice_kwargs(model_kwargs: dict, lo: int, hi: int) -> dict:
 
 
 def sample_dp(make_stepper: Callable, shape, model_kwargs: dict, num_timesteps: int, seed: int = 0,
-              group=None, num_steps: Optional[int] = None, device=None) -> torch.Tensor:
+              group=None, num_steps: Optional[int] = None, device=None, schedule=None) -> torch.Tensor:
     """Sharded p_sample_loop_with_cfg.  make_stepper(local_shape, local_kwargs) must return an object with
     `.x` (the local state tensor) and `.step(t, noise)` (GaussianDiffusion.make_cfg_stepper does).  Returns
-    the full [B, T, F] sample on every rank."""
+    the full [B, T, F] sample on every rank.  schedule (optional): the (t, t_prev) pairs of a strided DDIM loop
+    (zip(*GaussianDiffusion.ddim_timesteps(n)) with a stepper built with sampler="ddim"): each step is then
+    `.step(t, noise, ts_prev=t_prev)`."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -51,11 +53,15 @@ def sample_dp(make_stepper: Callable, shape, model_kwargs: dict, num_timesteps: 
     st = make_stepper((hi - lo,) + tuple(shape[1:]), slice_kwargs(model_kwargs, lo, hi))
     dev = device if device is not None else st.x.device
     st.x.copy_(global_noise(shape, seed, -1, dev)[lo:hi])
-    steps = list(reversed(range(num_timesteps)))
-    if num_steps is not None:
-        steps = steps[:num_steps]
-    for t in steps:
-        st.step(t, global_noise(shape, seed, t, dev)[lo:hi])
+    if schedule is not None:
+        for t, t_prev in schedule:
+            st.step(t, global_noise(shape, seed, t, dev)[lo:hi], ts_prev=t_prev)
+    else:
+        steps = list(reversed(range(num_timesteps)))
+        if num_steps is not None:
+            steps = steps[:num_steps]
+        for t in steps:
+            st.step(t, global_noise(shape, seed, t, dev)[lo:hi])
     local = st.x.contiguous()
     if world == 1:
         return local.clone()

@@ -29,17 +29,21 @@ class ToyStepper:
         self.x = torch.zeros(*shape)
         self.length = kw["length"].float().view(-1, 1, 1)
 
-    def step(self, t, noise):
-        self.x.copy_(0.9 * self.x + 0.01 * (t % 7) * torch.tanh(self.x) / self.length + 0.1 * noise)
+    def step(self, t, noise, ts_prev=None):
+        jump = 1.0 if ts_prev is None else float(t - ts_prev)          # strided (DDIM-style) schedules pass ts_prev
+        self.x.copy_(0.9 * self.x + 0.01 * (t % 7) * jump * torch.tanh(self.x) / self.length + 0.1 * noise)
         return self.x
 
 
-def _dp_worker(rank, world, port, B, ret):
+SCHEDULE = [(11, 7), (7, 4), (4, 0), (0, -1)]        # a strided schedule as GaussianDiffusion.ddim_timesteps returns it
+
+
+def _dp_worker(rank, world, port, B, ret, schedule=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     shape = (B, 6, 5)
     kw = {"length": torch.arange(1, B + 1), "text": ["t%d" % i for i in range(B)]}
-    full = parallel.sample_dp(lambda s, k: ToyStepper(s, k), shape, kw, num_timesteps=12, seed=3)
+    full = parallel.sample_dp(lambda s, k: ToyStepper(s, k), shape, kw, num_timesteps=12, seed=3, schedule=schedule)
     if rank == 0:
         ret.put(full)
     dist.destroy_process_group()
@@ -63,7 +67,28 @@ def test_dp_sampling_equals_single_rank(B):
     assert torch.equal(got, single)
 
 
-def test_shard_range_covers_batch():
+def test_dp_ddim_schedule_equals_single_rank():
+    """The strided (DDIM) schedule through sample_dp: sharded == unsharded, and different from the full-length loop."""
+    B = 5
+    shape = (B, 6, 5)
+    kw = {"length": torch.arange(1, B + 1), "text": ["t%d" % i for i in range(B)]}
+    single = parallel.sample_dp(lambda s, k: ToyStepper(s, k), shape, kw, num_timesteps=12, seed=3, schedule=SCHEDULE)
+    full_len = parallel.sample_dp(lambda s, k: ToyStepper(s, k), shape, kw, num_timesteps=12, seed=3)
+    assert not torch.equal(single, full_len)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, B, q, SCHEDULE)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert torch.equal(got, single)
+
+
+def test_shard_range_covers_batch():def test_shard_range_covers_batch():
     for B in (1, 7, 64, 65):
         for W in (1, 2, 4, 8):
             spans = [parallel.shard_range(B, W, r) for r in range(W)]
