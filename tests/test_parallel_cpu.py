@@ -88,7 +88,7 @@ def test_dp_ddim_schedule_equals_single_rank():
     assert torch.equal(got, single)
 
 
-def test_shard_range_covers_batch():def test_shard_range_covers_batch():
+def test_shard_range_covers_batch():
     for B in (1, 7, 64, 65):
         for W in (1, 2, 4, 8):
             spans = [parallel.shard_range(B, W, r) for r in range(W)]
