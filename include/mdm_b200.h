@@ -56,6 +56,11 @@ typedef struct MdmGemmEpi {
   int bf16_pre_resid; /* 1: the secondary output omits the residual term */
   int pair_tiles;     /* grouped GEMM only: 1 = tiles 2i and 2i+1 of the table share w_row0 (segments padded
                          to 256 rows), which lets the CTA-pair (cta_group::2) kernel take them together */
+  const int* tile_k;  /* grouped GEMM only, optional (device): {k0, klen} per tile - the tile contracts over the columns
+                         [k0, k0 + klen) of A and W instead of [0, K) (k0 % 64 == 0; klen > 0, rounded up to 64 with
+                         whatever the buffers hold there: pad with zeros).  This is what the weight gradient of an
+                         expert needs: dW_e = dY_e^T X_e contracts over the rows of the expert's segment, whose
+                         offset and length only exist on the device.  Selects the single-CTA kernel. */
 } MdmGemmEpi;
 
 /* One 128-row tile of a grouped GEMM: rows [a_row0, a_row0+128) of A times the weight rows starting

@@ -96,6 +96,7 @@ extern "C" MDM_API int mdm_gemm_f32(const float* A, int lda, long a_rows, const 
                                     long w_rows, int M, int N, int K, const void* mtiles,
                                     int num_m_tiles, const int* num_m_tiles_dev, const MdmGemmEpi* epi,
                                     void* stream) {
+  if (epi && epi->tile_k) return MDM_ERR_UNSUPPORTED;   // per-tile K ranges: tcgen05 kernel only
   if (!A || !W || !epi || M < 0 || N <= 0 || K <= 0) return MDM_ERR_ARG;
   if (!mtiles) num_m_tiles = (M + 127) / 128;
   if (num_m_tiles <= 0) return MDM_OK;

@@ -105,13 +105,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           a_row0 = mi.a_row0;
           w_row0 = mi.w_row0;
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int k0 = 0, nkb = num_kb;
+        if (epi.tile_k) { k0 = epi.tile_k[2 * mt]; nkb = (epi.tile_k[2 * mt + 1] + BK - 1) / BK; }
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, a_row0);
-          tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, w_row0 + nt * BN);
+          tma_load_2d(&tmA, &full_bar[stage], sa, k0 + kb * BK, a_row0);
+          tma_load_2d(&tmB, &full_bar[stage], sb, k0 + kb * BK, w_row0 + nt * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -131,7 +133,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         w_acc += PROF_T() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int nkb = epi.tile_k ? (epi.tile_k[2 * (t / num_n_tiles) + 1] + BK - 1) / BK : num_kb;
+        for (int kb = 0; kb < nkb; ++kb) {
           c0 = PROF_T();
           mbar_wait(&full_bar[stage], phase);
           w_op += PROF_T() - c0;
@@ -893,7 +896,9 @@ extern "C" MDM_API int mdm_gemm_bf16(const void* A, int lda, long a_rows, const 
   // epilogue, where the pair kernel is ~8 % slower; from K = 1024 up (operand-feed bound) it wins
   // (N x 512 x 2048: 56.8 -> 53.8 us).  MDM_GEMM_PAIR=0/1 forces it off / on for A/B runs.
   static const int pair_env = [] { const char* e = getenv("MDM_GEMM_PAIR"); return e ? atoi(e) : -1; }();
-  const bool pair_fit = wide && (num_m_tiles_dev || num_m_tiles >= 2) && (!mtiles || epi->pair_tiles) && max_ctas >= 2;
+  if (epi->tile_k && !mtiles) return MDM_ERR_ARG;
+  const bool pair_fit = wide && (num_m_tiles_dev || num_m_tiles >= 2) && (!mtiles || epi->pair_tiles) && max_ctas >= 2 &&
+                        !epi->tile_k;
   const bool pair = pair_fit && (pair_env == 1 || (pair_env < 0 && K >= 1024));
   CUtensorMap ta, tb;
   if (!make_map(&ta, A, a_rows, K, lda, BM)) return MDM_ERR_CUDA;

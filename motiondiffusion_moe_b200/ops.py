@@ -44,11 +44,11 @@ def _c(*ts):
 
 def gemm(A, W, bias=None, *, act=ACT_NONE, alpha=1.0, beta=0.0, resid=None, resid_mod=0, rowscale=None,
          rowmask=None, out_f32=None, out_a=None, a_pre_resid=False, N=None, M=None, tiles=None,
-         num_tiles=0, num_tiles_dev=None, a_rows=None, w_rows=None, pair_tiles=False):
+         num_tiles=0, num_tiles_dev=None, a_rows=None, w_rows=None, pair_tiles=False, tile_k=None):
     """C = epi(A @ W^T).  A [rows,K] (row stride may exceed K), W [w_rows,K]; both bf16 (tcgen05 path)
     or both fp32.  out_f32: fp32 output; out_a: secondary output in the operand dtype."""
     _req_cuda(A, W, out_f32, out_a, resid)
-    _c(bias, rowscale, rowmask, tiles, num_tiles_dev)
+    _c(bias, rowscale, rowmask, tiles, num_tiles_dev, tile_k)
     for t_ in (A, W, out_f32, out_a, resid):
         if t_ is not None and (t_.dim() != 2 or t_.stride(1) != 1):
             raise _lib.MdmError("GEMM operands/outputs must be 2-D with unit inner stride")
@@ -67,6 +67,7 @@ def gemm(A, W, bias=None, *, act=ACT_NONE, alpha=1.0, beta=0.0, resid=None, resi
         e.out_bf16, e.ld_bf16 = out_a.data_ptr(), out_a.stride(0)
     e.bf16_pre_resid = 1 if a_pre_resid else 0
     e.pair_tiles = 1 if pair_tiles else 0
+    e.tile_k = _ptr(tile_k)
     a_rows = A.shape[0] if a_rows is None else a_rows
     w_rows = W.shape[0] if w_rows is None else w_rows
     if A.dtype == torch.bfloat16:

@@ -192,6 +192,30 @@ def test_linear_backward_building_blocks(M, K_in, N_out):
     assert rel(dW2, 2 * dW) < 1e-6 and rel(db2, 2 * db) < 1e-6
 
 
+def test_gemm_grouped_per_tile_k_range():
+    """Grouped GEMM whose tiles contract over different column ranges (MdmGemmEpi.tile_k, device-resident): the shape of
+    an expert's weight gradient dW_e = dY_e^T X_e, where the expert's rows are a segment of the permuted buffers."""
+    F_, D_, cap = 256, 128, 1024
+    offs, lens = [0, 256, 640], [200, 384, 100]
+    dyT = torch.zeros(F_, cap, device=DEV, dtype=torch.bfloat16)
+    xT = torch.zeros(D_, cap, device=DEV, dtype=torch.bfloat16)
+    for e, (o, n) in enumerate(zip(offs, lens)):          # padding columns of a segment stay zero
+        dyT[:, o:o + n] = randn(F_, n, seed=10 + e).bfloat16()
+        xT[:, o:o + n] = randn(D_, n, seed=20 + e).bfloat16()
+    tiles, tk = [], []
+    for e, (o, n) in enumerate(zip(offs, lens)):
+        for mt in range(F_ // 128):
+            tiles.append([mt * 128, e * F_ + mt * 128, 0, 128])
+            tk.append([o, n])
+    tt = torch.tensor(tiles, dtype=torch.int32, device=DEV)
+    tkd = torch.tensor(tk, dtype=torch.int32, device=DEV)
+    out = torch.full((3 * F_, D_), 7.0, device=DEV)
+    ops.gemm(dyT, xT, None, out_f32=out, N=D_, M=3 * F_, tiles=tt, num_tiles=len(tiles), a_rows=F_, w_rows=D_, tile_k=tkd)
+    for e, (o, n) in enumerate(zip(offs, lens)):
+        ref = dyT[:, o:o + n].float() @ xT[:, o:o + n].float().t()
+        assert rel(out[e * F_:(e + 1) * F_], ref) < 1e-5, e
+
+
 # ------------------------------------------------------------------------------------------ row pipeline
 @pytest.mark.parametrize("D", [128, 256, 512, 1024])
 @pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
