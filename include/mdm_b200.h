@@ -262,6 +262,14 @@ MDM_API int mdm_masked_mse(const float* pred, const float* target, const int64_t
  * Called with dout == NULL it only reports n_param_parts / n_film_chunks.  D == 512. */
 MDM_API int mdm_rowop_bwd(const MdmRowOp* op, long rows, int D, int grad_dt, const void* dout, void* din,
                           float* dparam_part, float* dfilm_part, int* n_param_parts, int* n_film_chunks, void* stream);
+/* Elementwise / segment helpers of the expert FFN's backward (models/switch_moe.py:19-25: Linear -> GELU -> Linear per
+ * expert): exact-erf GELU forward on the saved pre-activation and its derivative; row scaling by the gate weights; bias
+ * gradients as column sums over each expert's row segment [seg_off[g], seg_off[g] + seg_cnt[g]) -> out [G, C] fp32. */
+MDM_API int mdm_gelu_fwd(const void* pre, long n, void* h, void* stream);
+MDM_API int mdm_gelu_bwd(const void* pre, const void* dh, long n, void* dp, void* stream);
+MDM_API int mdm_rowscale_bf16(const void* src, const float* scale, long rows, int C, void* dst, void* stream);
+MDM_API int mdm_seg_colsum_bf16(const void* src, int C, const int* seg_off, const int* seg_cnt, int G, float* out,
+                                void* stream);
 MDM_API int mdm_transpose_split_bf16(const void* src, long M, int C, int S, int Ks, void* dst, void* stream);
 MDM_API int mdm_sum_partials(const float* part, int S, long n, int accumulate, float* out, void* stream);
 MDM_API int mdm_colsum_bf16(const void* src, long M, int C, int slabs, float* part, void* stream);

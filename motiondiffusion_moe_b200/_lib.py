@@ -78,6 +78,10 @@ _SIGS = {
     "mdm_recover_from_ric": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "mdm_masked_mse": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "mdm_rowop_bwd": [C.POINTER(RowOp), _L, _I, _I, _P, _P, _P, _P, C.POINTER(C.c_int), C.POINTER(C.c_int), _P],
+    "mdm_gelu_fwd": [_P, _L, _P, _P],
+    "mdm_gelu_bwd": [_P, _P, _L, _P, _P],
+    "mdm_rowscale_bf16": [_P, _P, _L, _I, _P, _P],
+    "mdm_seg_colsum_bf16": [_P, _I, _P, _P, _I, _P, _P],
     "mdm_transpose_split_bf16": [_P, _L, _I, _I, _I, _P, _P],
     "mdm_sum_partials": [_P, _I, _L, _I, _P, _P],
     "mdm_colsum_bf16": [_P, _L, _I, _I, _P, _P],

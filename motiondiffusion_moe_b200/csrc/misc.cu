@@ -331,6 +331,47 @@ __global__ void colsum_kernel(const bf16* __restrict__ src, long M, int Cc, int 
   }
 }
 
+// Exact-erf GELU forward / backward on bf16 rows (training keeps the pre-activation of the expert up-projection):
+//   h = gelu(p)           dp = dh * (Phi(p) + p * phi(p))
+__global__ void gelu_fwd_kernel(const bf16* __restrict__ pre, long n, bf16* __restrict__ h) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) h[i] = __float2bfloat16_rn(gelu_erf(__bfloat162float(pre[i])));
+}
+__global__ void gelu_bwd_kernel(const bf16* __restrict__ pre, const bf16* __restrict__ dh, long n, bf16* __restrict__ dp) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float p = __bfloat162float(pre[i]);
+  const float cdf = 0.5f * (1.0f + erff(p * 0.70710678118654752440f));
+  const float pdf = 0.3989422804014327f * expf(-0.5f * p * p);
+  dp[i] = __float2bfloat16_rn(__bfloat162float(dh[i]) * (cdf + p * pdf));
+}
+// dst[r, :] = src[r, :] * scale[r]   (the gate weight / NB of a routed row: gradient of the down-projection output)
+__global__ void rowscale_kernel(const bf16* __restrict__ src, const float* __restrict__ scale, long rows, int Cc,
+                                bf16* __restrict__ dst) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Cc) return;
+  dst[i] = __float2bfloat16_rn(__bfloat162float(src[i]) * scale[i / Cc]);
+}
+// out[g, c] = sum of src[r, c] over the rows r of segment g = [seg_off[g], seg_off[g] + seg_cnt[g])  (bias gradients
+// of the experts); one block per (32 columns, segment), fixed order
+__global__ void seg_colsum_kernel(const bf16* __restrict__ src, int Cc, const int* __restrict__ seg_off,
+                                  const int* __restrict__ seg_cnt, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int g = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
+  const long r0 = seg_off[g], r1 = r0 + seg_cnt[g];
+  float a = 0.f;
+  if (c < Cc)
+    for (long r = r0 + ty; r < r1; r += 8) a += __bfloat162float(src[r * Cc + c]);
+  red[ty][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (ty == 0 && c < Cc) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x & 31];
+    out[(long)g * Cc + c] = s;
+  }
+}
+
 inline unsigned blocks(long n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
@@ -457,5 +498,35 @@ extern "C" MDM_API int mdm_colsum_bf16(const void* src, long M, int Cc, int slab
   dim3 grid((Cc + 31) / 32, slabs);
   colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(src), M, Cc, rows_per_blk,
                                                                          part);
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_gelu_fwd(const void* pre, long n, void* h, void* stream) {
+  if (!pre || !h) return MDM_ERR_ARG;
+  if (n == 0) return MDM_OK;
+  gelu_fwd_kernel<<<blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(pre), n,
+                                                                               reinterpret_cast<bf16*>(h));
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+extern "C" MDM_API int mdm_gelu_bwd(const void* pre, const void* dh, long n, void* dp, void* stream) {
+  if (!pre || !dh || !dp) return MDM_ERR_ARG;
+  if (n == 0) return MDM_OK;
+  gelu_bwd_kernel<<<blocks(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(pre), reinterpret_cast<const bf16*>(dh), n, reinterpret_cast<bf16*>(dp));
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+extern "C" MDM_API int mdm_rowscale_bf16(const void* src, const float* scale, long rows, int Cc, void* dst, void* stream) {
+  if (!src || !scale || !dst || Cc <= 0) return MDM_ERR_ARG;
+  if (rows == 0) return MDM_OK;
+  rowscale_kernel<<<blocks(rows * Cc), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(src), scale, rows, Cc, reinterpret_cast<bf16*>(dst));
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+extern "C" MDM_API int mdm_seg_colsum_bf16(const void* src, int Cc, const int* seg_off, const int* seg_cnt, int G, float* out,
+                                           void* stream) {
+  if (!src || !seg_off || !seg_cnt || !out || Cc <= 0 || G <= 0) return MDM_ERR_ARG;
+  dim3 grid((Cc + 31) / 32, G);
+  seg_colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(src), Cc, seg_off,
+                                                                            seg_cnt, out);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }

@@ -376,3 +376,74 @@ def rowop_bwd(x, rows, D, dout, *, ln1=None, l2norm=False, ln2=None, film=None, 
                    "mdm_sum_partials")
         grads["film"] = fsum
     return din, grads
+
+
+def expert_ffn_backward(xp, pre, W1, W2, rowscale, d_yp, seg_off, seg_cnt, tiles_rows, *, F, D):
+    """Backward of the grouped expert FFN  yp = rowscale * (gelu(xp W1_g^T + b1_g) W2_g^T + b2_g)  over expert-sorted rows
+    (models/switch_moe.py:97-109 with the gate weight folded into the down-projection).  Inputs, all on the device:
+      xp [cap, D] bf16 (padding rows of every segment ZERO), pre [cap, F] bf16 = saved pre-activation,
+      W1 [G*F, D], W2 [G*D, F] bf16 stacked expert weights, rowscale [cap] fp32, d_yp [cap, D] bf16,
+      seg_off / seg_cnt [G] int32 (128-aligned offsets, valid rows), tiles_rows: list of (row0, group) 128-row tiles.
+    Returns d_xp [cap, D] bf16, dW1 [G*F, D], dW2 [G*D, F], db1 [G, F], db2 [G, D] fp32 (the gradient of the gate weights,
+    <d_yp[r], z[r]>, belongs to the gate's backward and is not computed here).
+    Every product runs on the tcgen05 grouped GEMM: the data gradients with the transposed stacked weights, the weight
+    gradients as contractions over each expert's row segment (MdmGemmEpi.tile_k) of the transposed activations."""
+    _c(xp, pre, W1, W2, rowscale, d_yp, seg_off, seg_cnt)
+    lib = _lib.load()
+    dev = xp.device
+    cap = xp.shape[0]
+    G = seg_off.shape[0]
+    bf = torch.bfloat16
+    st = _stream
+
+    def tr(src, rows, cols, groups=1):        # [groups*rows, cols] -> [groups*cols, rows] (per group transposed)
+        dst = torch.empty(groups * cols, rows, dtype=bf, device=dev)
+        for g_ in range(groups):
+            _lib.check(lib.mdm_transpose_split_bf16(src[g_ * rows:].data_ptr(), rows, cols, 1, rows, dst[g_ * cols:].data_ptr(),
+                                                    st()), "mdm_transpose_split_bf16")
+        return dst
+
+    # tile tables (built once per routing on the device by moe_scan in the fused path; here from the host description)
+    def table(w_rows_per_group):
+        return torch.tensor([[r0, r0, g_ * w_rows_per_group, 128] for r0, g_ in tiles_rows], dtype=torch.int32, device=dev)
+
+    nt = len(tiles_rows)
+    # dz = rowscale * d_yp
+    dz = torch.empty_like(d_yp)
+    _lib.check(lib.mdm_rowscale_bf16(d_yp.data_ptr(), rowscale.data_ptr(), cap, D, dz.data_ptr(), st()), "mdm_rowscale_bf16")
+    hp = torch.empty_like(pre)
+    _lib.check(lib.mdm_gelu_fwd(pre.data_ptr(), pre.numel(), hp.data_ptr(), st()), "mdm_gelu_fwd")
+    # d_hp = dz . W2_g   (weight operand: W2_g^T [F, D] stacked)
+    W2t = tr(W2, D, F, G)                                                   # [G*F, D]
+    d_hp = torch.empty(cap, F, dtype=bf, device=dev)
+    gemm(dz, W2t, None, out_a=d_hp, N=F, M=cap, tiles=table(F), num_tiles=nt, a_rows=cap, w_rows=G * F)
+    d_pre = torch.empty_like(pre)
+    _lib.check(lib.mdm_gelu_bwd(pre.data_ptr(), d_hp.data_ptr(), pre.numel(), d_pre.data_ptr(), st()), "mdm_gelu_bwd")
+    # d_xp = d_pre . W1_g   (weight operand: W1_g^T [D, F] stacked)
+    W1t = tr(W1, F, D, G)                                                   # [G*D, F]
+    d_xp = torch.empty(cap, D, dtype=bf, device=dev)
+    gemm(d_pre, W1t, None, out_a=d_xp, N=D, M=cap, tiles=table(D), num_tiles=nt, a_rows=cap, w_rows=G * D)
+    # weight gradients: contraction over each expert's segment
+    def wgrad(dy_rows, x_rows, out_dim, in_dim):
+        dyT, xT = tr(dy_rows, cap, out_dim), tr(x_rows, cap, in_dim)        # [out, cap], [in, cap]
+        mt = (out_dim + 127) // 128
+        rows = [[i * 128, g_ * out_dim + i * 128, 0, min(128, out_dim - i * 128)] for g_ in range(G) for i in range(mt)]
+        tt = torch.tensor(rows, dtype=torch.int32, device=dev)
+        off, cnt = seg_off.tolist(), seg_cnt.tolist()
+        tk = torch.tensor([[off[g_], max(cnt[g_], 1)] for g_ in range(G) for _ in range(mt)], dtype=torch.int32, device=dev)
+        out = torch.zeros(G * out_dim, in_dim, dtype=torch.float32, device=dev)
+        gemm(dyT, xT, None, out_f32=out, N=in_dim, M=G * out_dim, tiles=tt, num_tiles=len(rows), a_rows=out_dim, w_rows=in_dim,
+             tile_k=tk)
+        empty = [g_ for g_ in range(G) if cnt[g_] == 0]
+        for g_ in empty:
+            out[g_ * out_dim:(g_ + 1) * out_dim].zero_()
+        return out
+    dW2 = wgrad(dz, hp, D, F)
+    dW1 = wgrad(d_pre, xp, F, D)
+    db2 = torch.empty(G, D, dtype=torch.float32, device=dev)
+    db1 = torch.empty(G, F, dtype=torch.float32, device=dev)
+    _lib.check(lib.mdm_seg_colsum_bf16(dz.data_ptr(), D, seg_off.data_ptr(), seg_cnt.data_ptr(), G, db2.data_ptr(), st()),
+               "mdm_seg_colsum_bf16")
+    _lib.check(lib.mdm_seg_colsum_bf16(d_pre.data_ptr(), F, seg_off.data_ptr(), seg_cnt.data_ptr(), G, db1.data_ptr(), st()),
+               "mdm_seg_colsum_bf16")
+    return d_xp, dW1, dW2, db1, db2

@@ -216,6 +216,59 @@ def test_gemm_grouped_per_tile_k_range():
         assert rel(out[e * F_:(e + 1) * F_], ref) < 1e-5, e
 
 
+def test_expert_ffn_backward_building_block():
+    """Backward of the grouped expert FFN (Linear -> GELU -> Linear per expert, gate weight folded into the second Linear)
+    on the tcgen05 grouped GEMM, including an expert that received no token, against torch autograd."""
+    G, D, Fd = 3, 128, 256
+    cnt = [200, 0, 130]
+    off, tiles_rows, o = [], [], 0
+    for g_, c in enumerate(cnt):
+        off.append(o)
+        for i in range((c + 127) // 128):
+            tiles_rows.append((o + i * 128, g_))
+        o += (c + 127) // 128 * 128
+    cap = o + 128
+    bf = torch.bfloat16
+    W1 = randn(G * Fd, D, seed=1, scale=D ** -0.5).to(bf)
+    b1 = randn(G * Fd, seed=2, scale=0.1)
+    W2 = randn(G * D, Fd, seed=3, scale=Fd ** -0.5).to(bf)
+    xp = torch.zeros(cap, D, device=DEV, dtype=bf)
+    d_yp = torch.zeros(cap, D, device=DEV, dtype=bf)
+    rs = torch.zeros(cap, device=DEV)
+    for g_, c in enumerate(cnt):
+        xp[off[g_]:off[g_] + c] = randn(c, D, seed=10 + g_).to(bf)
+        d_yp[off[g_]:off[g_] + c] = randn(c, D, seed=20 + g_).to(bf)
+        rs[off[g_]:off[g_] + c] = torch.rand(c, generator=gen(30 + g_)).to(DEV) * 0.5
+    # forward pre-activation as the training forward would save it (grouped GEMM without activation)
+    tt = torch.tensor([[r0, r0, g_ * Fd, 128] for r0, g_ in tiles_rows], dtype=torch.int32, device=DEV)
+    pre = torch.zeros(cap, Fd, device=DEV, dtype=bf)
+    ops.gemm(xp, W1, b1, out_a=pre, N=Fd, M=cap, tiles=tt, num_tiles=len(tiles_rows), a_rows=cap, w_rows=G * Fd)
+    for g_, c in enumerate(cnt):                          # rows of a tile beyond the segment's count carry the bias: clear
+        pre[off[g_] + c:off[g_] + (c + 127) // 128 * 128] = 0
+    seg_off = torch.tensor(off, dtype=torch.int32, device=DEV)
+    seg_cnt = torch.tensor(cnt, dtype=torch.int32, device=DEV)
+    d_xp, dW1, dW2, db1, db2 = ops.expert_ffn_backward(xp, pre, W1, W2, rs, d_yp, seg_off, seg_cnt, tiles_rows, F=Fd, D=D)
+    for g_, c in enumerate(cnt):
+        sl = slice(off[g_], off[g_] + c)
+        w1 = W1[g_ * Fd:(g_ + 1) * Fd].float().requires_grad_(True)
+        bb1 = b1[g_ * Fd:(g_ + 1) * Fd].clone().requires_grad_(True)
+        w2 = W2[g_ * D:(g_ + 1) * D].float().requires_grad_(True)
+        bb2 = torch.zeros(D, device=DEV, requires_grad=True)
+        xin = xp[sl].float().requires_grad_(True)
+        if c:
+            q_ = xin @ w1.t() + bb1
+            p_ = q_ + (q_.to(bf).float() - q_).detach()   # the saved pre-activation is bf16 (straight-through rounding)
+            y = (F.gelu(p_) @ w2.t() + bb2) * rs[sl, None]
+            y.backward(d_yp[sl].float())
+            assert rel(d_xp[sl], xin.grad) < 2e-2, g_
+            assert rel(dW1[g_ * Fd:(g_ + 1) * Fd], w1.grad) < 2e-2, g_
+            assert rel(dW2[g_ * D:(g_ + 1) * D], w2.grad) < 2e-2, g_
+            assert rel(db1[g_], bb1.grad) < 2e-2 and rel(db2[g_], bb2.grad) < 2e-2, g_
+        else:
+            assert dW1[g_ * Fd:(g_ + 1) * Fd].abs().max() == 0 and dW2[g_ * D:(g_ + 1) * D].abs().max() == 0
+            assert db1[g_].abs().max() == 0 and db2[g_].abs().max() == 0
+
+
 # ------------------------------------------------------------------------------------------ row pipeline
 @pytest.mark.parametrize("D", [128, 256, 512, 1024])
 @pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
