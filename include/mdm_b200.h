@@ -163,6 +163,13 @@ MDM_API int mdm_softmax_cross(const void* q, const void* k, const void* v, int d
 MDM_API int mdm_moe_gate(const float* x, long N, int D, int NB, int E, int K, const float* ln_w,
                          const float* ln_b, const float* gate_w, const float* gate_b, int* idx,
                          float* vals, float* stats, int* blk_hist, float* blk_imp, void* stream);
+/* Parity hook (tests): same kernel, but the expert INDICES are taken from forced_idx [N,NB,K] int32 (e.g. the routing
+ * the fp32 reference chose for the same tokens, models/switch_moe.py:57) instead of the top-k search; vals are still this
+ * kernel's own softmax probabilities of those experts.  Lets a bf16 run be compared with the fp32 reference "with identical
+ * routing"  without a flipped near-tie changing a token discontinuously. */
+MDM_API int mdm_moe_gate_forced(const float* x, long N, int D, int NB, int E, int K, const float* ln_w,
+                                const float* ln_b, const float* gate_w, const float* gate_b, const int* forced_idx,
+                                int* idx, float* vals, float* stats, int* blk_hist, float* blk_imp, void* stream);
 /* Scan: expert segment offsets (each padded to 128 rows), per-block bases, the two grouped-GEMM tile
  * tables (up: w_row0 = g*F, down: w_row0 = g*D), the tile count, and the usage / importance
  * counters (expert_usage, expert_importance buffers of switch_moe.py:32-34,72-92), updated in place. */
@@ -202,7 +209,7 @@ MDM_API int mdm_pad_cast(const float* x, long rows, int F, void* out, int ld_out
  *   mean = coef1*x0 + coef2*x ; x_prev = mean + (t != 0) * exp(0.5*logvar) * noise
  * tables: [5, n_steps] fp32 rows = sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod,
  * posterior_mean_coef1, posterior_mean_coef2, posterior_log_variance_clipped.
- * clip != 0 clamps each branch's x0 to [-1, 1] (clip_denoised). */
+ * clip != 0 clamps each branch's x0 to [-1, 1] (clip_denoised).  x_prev may be the same buffer as x (in-place step). */
 MDM_API int mdm_cfg_update(const float* x, const float* eps_c, const float* eps_u, const float* noise,
                            const int64_t* t, const float* tables, int n_steps, float cfg_scale,
                            int clip, int B, long per_sample, float* x_prev, float* x0, void* stream);
@@ -320,7 +327,8 @@ MDM_API int mdm_ep_combine_film(const MdmEpPeers* peers, int dt, const int* perm
                                 int rows_per_seq, void* out, void* stream);
 /* Flag barrier of the R ranks in stream order.  *epoch_ctr (device memory, start at 0, private to this
  * rank) is incremented by the kernel, so the call can be captured in a CUDA graph and replayed; every rank
- * must execute the same number of barriers.  *err is set to 1 if a peer does not arrive within ~2 s. */
+ * must execute the same number of barriers.  If a peer does not arrive within ~2 s, *err is set to 1 and the kernel
+ * traps: the stream reports a launch failure at its next synchronisation (a missed barrier is fatal, never silent). */
 MDM_API int mdm_ep_barrier(const MdmEpPeers* peers, int R, int me, unsigned* epoch_ctr, int* err, void* stream);
 /* CUDA IPC: 64-byte handle of the allocation containing ptr (+ byte offset of ptr inside it); open /
  * close a peer's handle (returns the base of the mapped allocation). */
@@ -329,6 +337,11 @@ MDM_API int mdm_ipc_open_handle(const void* handle64, void** base);
 MDM_API int mdm_ipc_close_handle(void* base);
 
 MDM_API int mdm_num_sms(void);
+/* sizeof() of the structs above as this library was compiled: a binding checks its own struct definitions against them
+ * (a short MdmGemmEpi would make the kernel read garbage as the tile_k device pointer). */
+MDM_API int mdm_sizeof_gemm_epi(void);
+MDM_API int mdm_sizeof_rowop(void);
+MDM_API int mdm_sizeof_ep_peers(void);
 MDM_API const char* mdm_version(void);
 
 #ifdef __cplusplus

@@ -65,6 +65,7 @@ _SIGS = {
     "mdm_transpose_cast_bf16": [_P, _L, _I, _I, _P, _P],
     "mdm_softmax_cross": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P],
     "mdm_moe_gate": [_P, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "mdm_moe_gate_forced": [_P, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "mdm_moe_scan": [_P, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "mdm_moe_permute": [_P, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "mdm_moe_combine_film": [_P, _I, _P, _L, _I, _I, _P, _P, _P, _I, _P, _P],
@@ -95,6 +96,9 @@ _SIGS = {
     "mdm_ipc_open_handle": [_P, C.POINTER(C.c_void_p)],
     "mdm_ipc_close_handle": [_P],
     "mdm_num_sms": [],
+    "mdm_sizeof_gemm_epi": [],
+    "mdm_sizeof_rowop": [],
+    "mdm_sizeof_ep_peers": [],
 }
 
 _lib = None
@@ -117,6 +121,10 @@ def load():
         fn.restype = C.c_int
     lib.mdm_version.restype = C.c_char_p
     lib.mdm_version.argtypes = []
+    for fn, st in ((lib.mdm_sizeof_gemm_epi, GemmEpi), (lib.mdm_sizeof_rowop, RowOp), (lib.mdm_sizeof_ep_peers, EpPeers)):
+        if fn() != C.sizeof(st):     # a stale .so or a drifted binding: refuse to pass short structs to the kernels
+            raise MdmError("struct layout mismatch between _lib.py and %s: %s is %d bytes here, %d in the library"
+                           % (LIB_PATH, st.__name__, C.sizeof(st), fn()))
     _lib = lib
     return lib
 

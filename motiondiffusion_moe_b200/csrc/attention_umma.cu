@@ -553,11 +553,12 @@ int launch(const bf16* qkv, const bf16* Pt, const float* nw, const float* nb, co
            int H, int T, bf16* out, const int* seq_order, cudaStream_t st) {
   using L = Smem<TP>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;   // one bit per device ordinal: the attribute is per (function, device)
+  const unsigned long long dev_bit = 1ull << mdm_cur_dev();
+  if (!(attr & dev_bit)) {
     if (cudaFuncSetAttribute(fastattn_umma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
       return MDM_ERR_CUDA;
-    attr = true;
+    attr |= dev_bit;
   }
   fastattn_umma_kernel<TP><<<B * H, NTHR, L::TOTAL, st>>>(qkv, Pt, nw, nb, length, shift, H, T, out, seq_order);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
@@ -738,11 +739,12 @@ lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, 
 template <int TP>
 int launch_lc(const bf16* q, const bf16* ctxT, int B, int H, int T, bf16* y, cudaStream_t st) {
   using L = SmemLC<TP>;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;   // one bit per device ordinal: the attribute is per (function, device)
+  const unsigned long long dev_bit = 1ull << mdm_cur_dev();
+  if (!(attr & dev_bit)) {
     if (cudaFuncSetAttribute(lincross_umma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
       return MDM_ERR_CUDA;
-    attr = true;
+    attr |= dev_bit;
   }
   lincross_umma_kernel<TP><<<B * H, NTHR, L::TOTAL, st>>>(q, ctxT, H, T, y);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
@@ -966,12 +968,13 @@ template <int TP>
 int launch_sc(const bf16* q, const bf16* k, const bf16* v, const int* nt, int B, int H, int T, int Nt_max, float scale,
               bf16* o, cudaStream_t st) {
   using L = SmemLC<TP>;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;   // one bit per device ordinal: the attribute is per (function, device)
+  const unsigned long long dev_bit = 1ull << mdm_cur_dev();
+  if (!(attr & dev_bit)) {
     if (cudaFuncSetAttribute(softmax_cross_umma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
         cudaSuccess)
       return MDM_ERR_CUDA;
-    attr = true;
+    attr |= dev_bit;
   }
   const int NK = (Nt_max + 31) / 32 * 32;
   softmax_cross_umma_kernel<TP><<<B * H, NTHR, L::TOTAL, st>>>(q, k, v, nt, H, T, Nt_max, NK, scale, o);

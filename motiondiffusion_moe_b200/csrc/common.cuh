@@ -10,6 +10,9 @@ typedef __nv_bfloat16 bf16;
 
 #include "mdm_b200.h"
 
+// current device ordinal (kernel attributes / SM counts are cached per device, not per process)
+inline int mdm_cur_dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+
 typedef MdmGemmEpi GemmEpi;
 typedef MdmMTile MTile;
 typedef MdmRowOp RowOp;

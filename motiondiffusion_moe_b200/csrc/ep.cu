@@ -193,7 +193,7 @@ ep_combine_film_kernel(MdmEpPeers peers, const int* __restrict__ perm, long N, i
 // Flag barrier across the R ranks of one node.  Thread p publishes `epoch` into slot [me] of rank p's
 // flag array (release, system scope) and then waits until rank p has published >= epoch into this
 // rank's slot [p].  Epochs only grow (a device-side counter per rank), so no reset is needed.  The spin is bounded (~2 s): on expiry the
-// error word is set and the kernel returns, so a dead peer cannot hang the GPU.
+// error word is set and the kernel traps (fatal, loud), so a dead peer can neither hang the GPU nor corrupt a sample.
 __global__ void __launch_bounds__(32)
 ep_barrier_kernel(MdmEpPeers peers, int R, int me, unsigned* __restrict__ epoch_ctr, int* __restrict__ err) {
   const int p = threadIdx.x;
@@ -213,8 +213,15 @@ ep_barrier_kernel(MdmEpPeers peers, int R, int me, unsigned* __restrict__ epoch_
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
       if ((int)(v - epoch) >= 0) break;
       __nanosleep(200);
-    } while (++spins < 10000000L);
-    if ((int)(v - epoch) < 0) atomicExch(err, 1);
+    } while (++spins < 40000000L);   // ~10 s
+    if ((int)(v - epoch) < 0) {
+      // a peer did not arrive: its buffers are not ready, so nothing after this barrier may run on them.  Record the
+      // reason, then abort the grid: the stream fails with a launch error at the next synchronisation instead of
+      // producing silently wrong samples (the error is sticky for the context, i.e. fatal for this process).
+      atomicExch(err, 1);
+      __threadfence_system();
+      __trap();
+    }
   }
   __syncwarp();
   __threadfence_system();

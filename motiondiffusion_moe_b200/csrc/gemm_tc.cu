@@ -546,14 +546,11 @@ bool make_f32_map(CUtensorMap* map, const void* ptr, long rows, long cols, long 
   return r == CUDA_SUCCESS;
 }
 
-int g_num_sms = 0;
+int g_num_sms[64] = {0};   // per device ordinal
 int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return g_num_sms;
+  const int dev = mdm_cur_dev();
+  if (!g_num_sms[dev]) cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return g_num_sms[dev];
 }
 
 template <int BN, int STAGES, int EPI, int ACT>
@@ -563,12 +560,13 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
            cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES, EPI>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;   // one bit per device ordinal: the attribute is per (function, device)
+  const unsigned long long dev_bit = 1ull << mdm_cur_dev();
+  if (!(attr_set & dev_bit)) {
     if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              L::TOTAL) != cudaSuccess)
       return MDM_ERR_CUDA;
-    attr_set = true;
+    attr_set |= dev_bit;
   }
   const int num_n_tiles = (N + BN - 1) / BN;
   long tiles = (long)num_m_tiles * num_n_tiles;
@@ -586,12 +584,13 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
             const int* num_m_tiles_dev, const MTile* mtiles, const GemmEpi& epi, int max_ctas, cudaStream_t stream) {
   using L = SmemLayout2<STAGES, EPI>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;   // one bit per device ordinal: the attribute is per (function, device)
+  const unsigned long long dev_bit = 1ull << mdm_cur_dev();
+  if (!(attr_set & dev_bit)) {
     if (cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
         cudaSuccess)
       return MDM_ERR_CUDA;
-    attr_set = true;
+    attr_set |= dev_bit;
   }
   const long work = (long)((num_m_tiles + 1) / 2) * ((N + BN2 - 1) / BN2);
   long clusters = max_ctas / 2;
@@ -854,12 +853,13 @@ gemm_rowop_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
 template <typename TI, int FLAGS>
 int launch_rowop_gemm(const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr, const CUtensorMap& tf,
                       const MdmRowOp& op, int M, int N, const GemmEpi& epi, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;   // one bit per device ordinal: the attribute is per (function, device)
+  const unsigned long long dev_bit = 1ull << mdm_cur_dev();
+  if (!(attr & dev_bit)) {
     if (cudaFuncSetAttribute(gemm_rowop_kernel<TI, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              RowGemmSmem::TOTAL) != cudaSuccess)
       return MDM_ERR_CUDA;
-    attr = true;
+    attr |= dev_bit;
   }
   const int tiles = (M + BM - 1) / BM, sms = num_sms();
   gemm_rowop_kernel<TI, FLAGS><<<tiles < sms ? tiles : sms, num_threads(EPI_F32T), RowGemmSmem::TOTAL, st>>>(

@@ -39,10 +39,12 @@ __global__ void pad_cast_kernel(const float* __restrict__ x, long rows, int F, T
 
 // torch-eager arithmetic order, no FMA contraction, so that the update is bit-identical to
 // p_sample_with_cfg given the same eps.
-__global__ void cfg_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_c,
+// x and x_prev may be the same buffer (CFGStepper updates its state in place: every thread reads element i before it
+// writes element i), so neither carries __restrict__.
+__global__ void cfg_update_kernel(const float* x, const float* __restrict__ eps_c,
                                   const float* __restrict__ eps_u, const float* __restrict__ noise,
                                   const int64_t* __restrict__ t, const float* __restrict__ tables, int n_steps,
-                                  float s, int clip, long per_sample, long total, float* __restrict__ x_prev,
+                                  float s, int clip, long per_sample, long total, float* x_prev,
                                   float* __restrict__ x0_out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -103,11 +105,11 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
 // t_prev == NULL: alpha_bar_prev = alphas_cumprod_prev[t] (the reference's 1000-step loop); otherwise the
 // previous timestep of a strided schedule (alpha_bar_prev = alphas_cumprod[t_prev], 1 for t_prev < 0).
 // tables: [4][n_steps] = sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, alphas_cumprod, alphas_cumprod_prev.
-__global__ void ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_c,
+__global__ void ddim_update_kernel(const float* x /* may alias x_prev */, const float* __restrict__ eps_c,
                                    const float* __restrict__ eps_u, const float* __restrict__ noise,
                                    const int64_t* __restrict__ t, const int64_t* __restrict__ t_prev,
                                    const float* __restrict__ tables, int n_steps, float s, float eta, int clip,
-                                   long per_sample, long total, float* __restrict__ x_prev, float* __restrict__ x0_out) {
+                                   long per_sample, long total, float* x_prev, float* __restrict__ x0_out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int b = (int)(i / per_sample);

@@ -49,11 +49,13 @@ __device__ __forceinline__ void softmax_top2(const float (&logits)[E], float (&p
 #pragma unroll
   for (int e = 1; e < E; ++e)
     if (probs[e] > pa) { a = e; pa = probs[e]; }
-  int b = -1;
-  float pb = -1.f;
+  // b starts at a valid index (not -1): with non-finite probabilities no comparison succeeds and the indices must
+  // still stay inside [0, E) - a numerical blow-up may not turn into an out-of-bounds scatter in permute / dispatch
+  int b = (a == 0) ? 1 : 0;
+  float pb = probs[b];
 #pragma unroll
   for (int e = 0; e < E; ++e)
-    if (e != a && probs[e] > pb) { b = e; pb = probs[e]; }
+    if (e != a && e != ((a == 0) ? 1 : 0) && probs[e] > pb) { b = e; pb = probs[e]; }
   if (pa == pb) { i0 = b; i1 = a; v0 = pb; v1 = pa; }  // b > a here: tie => higher index first
   else { i0 = a; i1 = b; v0 = pa; v1 = pb; }
 }
@@ -87,12 +89,16 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&p)[GP], int lane) {
 //     current pair is evaluated) when there are fewer blocks than SMs: the parallelism has to come from
 //     inside the block (N = 12 544: 32.5 -> 25.6 us);
 //   GATE_WARPS = 8 (16 tokens per warp, two blocks per SM) otherwise (N = 25 088: 37 us; 16 warps: 49 us).
-template <int VPT, int E, int NB, int GATE_WARPS>
-__global__ void __launch_bounds__(GATE_WARPS * 32, (GATE_WARPS == 8 && VPT <= 16 && NB * E <= 16) ? 2 : 1)
+// FORCED (parity hook, mdm_moe_gate_forced): the expert INDICES come from `forced_idx` [N, NB, 2] (e.g. the routing of
+// the fp32 reference run) instead of the top-2 search; the gate weights are still this kernel's own softmax
+// probabilities of those experts, so LayerNorm, gate GEMV and softmax stay under test.
+template <int VPT, int E, int NB, int GATE_WARPS, bool FORCED = false>
+__global__ void __launch_bounds__(GATE_WARPS * 32, (GATE_WARPS == 8 && VPT <= 16 && NB * E <= 16 && !FORCED) ? 2 : 1)
 moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restrict__ ln_w,
                 const float* __restrict__ ln_b, const float* __restrict__ gate_w,
                 const float* __restrict__ gate_b, int* __restrict__ idx, float* __restrict__ vals,
-                float* __restrict__ stats, int* __restrict__ blk_hist, float* __restrict__ blk_imp) {
+                float* __restrict__ stats, int* __restrict__ blk_hist, float* __restrict__ blk_imp,
+                const int* __restrict__ forced_idx = nullptr) {
   constexpr int G = NB * E;
   constexpr int LG = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : (G == 4) ? 2 : 1;
   constexpr int TT = 2;
@@ -189,6 +195,12 @@ moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restr
     int i0, i1;
     float v0, v1;
     softmax_top2<E>(logits, probs, i0, i1, v0, v1);
+    if (FORCED && lane < TT * NB && (my_t == 0 || two)) {
+      const int2 f = *reinterpret_cast<const int2*>(forced_idx + ((tok + my_t) * NB + my_br) * 2);
+      i0 = min(max(f.x, 0), E - 1); i1 = min(max(f.y, 0), E - 1);
+#pragma unroll
+      for (int e = 0; e < E; ++e) { if (e == i0) v0 = probs[e]; if (e == i1) v1 = probs[e]; }
+    }
     if (lane < TT * NB && (my_t == 0 || two)) {
       const long o = ((tok + my_t) * NB + my_br) * 2;
       *reinterpret_cast<int2*>(idx + o) = make_int2(i0, i1);
@@ -429,17 +441,24 @@ __global__ void softmax_topk_kernel(const float* __restrict__ logits, long N, fl
 template <int VPT, int E, int NB>
 int launch_gate(const float* x, long N, int D, const float* ln_w, const float* ln_b, const float* gate_w,
                 const float* gate_b, int* idx, float* vals, float* stats, int* blk_hist, float* blk_imp,
-                cudaStream_t st) {
+                cudaStream_t st, const int* forced_idx = nullptr) {
   const int nblk = (int)((N + TOK_PER_BLK - 1) / TOK_PER_BLK);
   const size_t smem = sizeof(float) * ((size_t)NB * E * D + 2 * (size_t)NB * D);
+  if (forced_idx) {
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB, 8, true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return MDM_ERR_CUDA;
+    moe_gate_kernel<VPT, E, NB, 8, true><<<nblk, 256, smem, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
+                                                                  blk_hist, blk_imp, forced_idx);
+    return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+  }
   if (smem > 48 * 1024 &&
       (cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
            cudaSuccess ||
        cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
            cudaSuccess))
     return MDM_ERR_CUDA;
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int sms = mdm_num_sms();
   if (nblk <= sms)
     moe_gate_kernel<VPT, E, NB, 16><<<nblk, 512, smem, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
                                                              blk_hist, blk_imp);
@@ -452,30 +471,44 @@ int launch_gate(const float* x, long N, int D, const float* ln_w, const float* l
 template <int VPT>
 int gate_dispatch(int NB, int E, const float* x, long N, int D, const float* ln_w, const float* ln_b,
                   const float* gate_w, const float* gate_b, int* idx, float* vals, float* stats, int* blk_hist,
-                  float* blk_imp, cudaStream_t st) {
+                  float* blk_imp, cudaStream_t st, const int* forced_idx = nullptr) {
 #define GATE_CASE(e, nb) \
-  if (E == e && NB == nb) return launch_gate<VPT, e, nb>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st);
+  if (E == e && NB == nb) return launch_gate<VPT, e, nb>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st, forced_idx);
   GATE_CASE(2, 1) GATE_CASE(4, 1) GATE_CASE(8, 1) GATE_CASE(16, 1)
   GATE_CASE(2, 2) GATE_CASE(4, 2) GATE_CASE(8, 2) GATE_CASE(16, 2)
 #undef GATE_CASE
   return MDM_ERR_UNSUPPORTED;  // the expert count must be a power of two <= 16 (reference uses 4 / 8)
 }
 
-extern "C" MDM_API int mdm_moe_gate(const float* x, long N, int D, int NB, int E, int K, const float* ln_w,
-                                    const float* ln_b, const float* gate_w, const float* gate_b, int* idx,
-                                    float* vals, float* stats, int* blk_hist, float* blk_imp, void* stream) {
+static int moe_gate_impl(const float* x, long N, int D, int NB, int E, int K, const float* ln_w,
+                         const float* ln_b, const float* gate_w, const float* gate_b, int* idx,
+                         float* vals, float* stats, int* blk_hist, float* blk_imp, const int* forced, void* stream) {
   if (!x || !ln_w || !ln_b || !gate_w || !gate_b || !idx || !vals || !stats || !blk_hist || !blk_imp)
     return MDM_ERR_ARG;
   if (K != 2 || E < 2 || E > MAX_E || NB * E > MAX_G || NB < 1) return MDM_ERR_UNSUPPORTED;
   if (N == 0) return MDM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (D) {
-    case 128: return gate_dispatch<4>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st);
-    case 256: return gate_dispatch<8>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st);
-    case 512: return gate_dispatch<16>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st);
-    case 1024: return gate_dispatch<32>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st);
+    case 128: return gate_dispatch<4>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st, forced);
+    case 256: return gate_dispatch<8>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st, forced);
+    case 512: return gate_dispatch<16>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st, forced);
+    case 1024: return gate_dispatch<32>(NB, E, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, st, forced);
     default: return MDM_ERR_UNSUPPORTED;
   }
+}
+
+extern "C" MDM_API int mdm_moe_gate(const float* x, long N, int D, int NB, int E, int K, const float* ln_w,
+                                    const float* ln_b, const float* gate_w, const float* gate_b, int* idx,
+                                    float* vals, float* stats, int* blk_hist, float* blk_imp, void* stream) {
+  return moe_gate_impl(x, N, D, NB, E, K, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, nullptr, stream);
+}
+
+extern "C" MDM_API int mdm_moe_gate_forced(const float* x, long N, int D, int NB, int E, int K, const float* ln_w,
+                                           const float* ln_b, const float* gate_w, const float* gate_b,
+                                           const int* forced_idx, int* idx, float* vals, float* stats, int* blk_hist,
+                                           float* blk_imp, void* stream) {
+  if (!forced_idx) return MDM_ERR_ARG;
+  return moe_gate_impl(x, N, D, NB, E, K, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, forced_idx, stream);
 }
 
 extern "C" MDM_API int mdm_moe_scan(const int* blk_hist, const float* blk_imp, const int* idx, long N, int NB,

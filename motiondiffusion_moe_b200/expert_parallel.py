@@ -145,8 +145,15 @@ class ExpertParallelFFN:
             off = C.c_long(0)
             _lib.check(lib.mdm_ipc_get_handle(getattr(self, k).data_ptr(), h, C.byref(off)), "mdm_ipc_get_handle")
             mine[k] = (bytes(h), off.value)
+        mine["_shape"] = (int(n_tokens), int(self.cap), D, F, E, NB, str(dtype))
         everyone = [None] * R
         dist.all_gather_object(everyone, mine, group=group)
+        # every rank must use the same token count / buffer capacity: dispatch bounds rows by the SENDER's cap while writing
+        # into the OWNER's buffers, so a rank with a larger shard would write out of bounds on a peer
+        shapes = [e.pop("_shape") for e in everyone]
+        if any(sh != shapes[0] for sh in shapes):
+            raise MdmError("expert parallelism needs identical shapes on every rank (n_tokens, cap, D, F, E, NB, dtype); "
+                           "got %s - shard the batch evenly (B %% world == 0)" % (shapes,))
         ptrs, opened = [], {}
         for p in range(R):
             if p == me:

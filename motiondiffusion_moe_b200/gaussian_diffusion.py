@@ -264,7 +264,9 @@ class GaussianDiffusion:
             steps = tqdm(steps, desc="Sampling")
         for ts in steps:
             st.step(ts, None if step_noise is None else step_noise(ts))
-        return st.x.clone()
+        out = st.x.clone()
+        model.check_health()             # expert parallelism: barrier time-outs / overflows are raised here (synchronises)
+        return out
 
     # ------------------------------------------------------------------ DDIM
     def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
@@ -373,7 +375,9 @@ class GaussianDiffusion:
             steps = tqdm(steps, desc="DDIM sampling")
         for ts, tp in steps:
             st.step(ts, ts_prev=tp)
-        return st.x.clone()
+        out = st.x.clone()
+        model.check_health()
+        return out
 
     # ------------------------------------------------------------------ training losses (forward value)
     def training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
@@ -409,7 +413,11 @@ class CFGStepper:
             raise ValueError(sampler)
         self.sampler, self.eta = sampler, float(eta)
         self.d, self.model = diffusion, model
-        self.device = device if device is not None else next(model.parameters()).device
+        self.device = torch.device(device if device is not None else next(model.parameters()).device)
+        if self.device.type != "cuda":
+            raise MdmError("CFGStepper needs a CUDA device: there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.B = shape[0]
         self.cfg_scale, self.clip = cfg_scale, clip_denoised
         self.ctx = diffusion._cfg_inputs(model, self.B, model_kwargs, self.device)
@@ -426,6 +434,10 @@ class CFGStepper:
         self.graph = None
 
     def _run(self):
+        with torch.cuda.device(self.device):
+            self._run_on_device()
+
+    def _run_on_device(self):
         if self.sampler == "ddim":
             self.d._cfg_ddim_step(self.model, self.ctx, self.x, self.t, self.t_prev, self.length2, self.noise,
                                   self.cfg_scale, self.eta, self.clip, self.x, self.x0)
@@ -434,10 +446,15 @@ class CFGStepper:
                          self.x, self.x0)
 
     def _capture(self):
+        with torch.cuda.device(self.device):
+            self._capture_on_device()
+
+    def _capture_on_device(self):
         pk = self.model._packed or self.model._pack()
         keep = (self.x.clone(), pk["usage"].clone(), pk["importance"].clone())
         self._run()                                   # warm-up: allocates workspaces, sets kernel attributes
         torch.cuda.synchronize(self.device)
+        self.model.check_health()                     # expert parallelism: a barrier time-out / overflow is fatal here
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._run()
@@ -448,6 +465,10 @@ class CFGStepper:
     def step(self, ts, noise=None, ts_prev=None):
         """Advance x from timestep ts to ts-1 (DDIM: to ts_prev, default ts-1).  noise=None draws torch's
         normal_ (== randn_like, :1094); a DDIM step with eta == 0 uses no noise."""
+        with torch.cuda.device(self.device):
+            return self._step(ts, noise, ts_prev)
+
+    def _step(self, ts, noise, ts_prev):
         if self.use_graph and self.graph is None:
             self._capture()
         self.t.fill_(int(ts))
@@ -467,9 +488,15 @@ class CFGStepper:
         """One step on HOST data: x_host (pinned, [B,T,F] fp32) -> device, step(ts), result -> out_host (pinned).
         The copies run on two side streams through double-buffered device staging tensors, so the upload of the next
         call and the download of the previous result overlap the compute of the current step (PCIe and the SMs work
-        concurrently; a call returns as soon as its work is enqueued).  Call flush() before reading out_host."""
+        concurrently; a call returns as soon as its work is enqueued).  Call flush() before reading out_host.
+        x_host is read asynchronously: it must not be modified until `input_consumed()` has returned (or flush()),
+        which waits for the upload of the most recent call."""
         if not (x_host.is_pinned() and out_host.is_pinned()):
             raise ValueError("step_host needs pinned host tensors (the copies are asynchronous)")
+        with torch.cuda.device(self.device):
+            self._step_host(x_host, ts, out_host, noise, ts_prev)
+
+    def _step_host(self, x_host, ts, out_host, noise, ts_prev):
         if not hasattr(self, "_hp"):
             mk = lambda: [torch.empty_like(self.x) for _ in range(2)]
             ev = lambda: [torch.cuda.Event() for _ in range(2)]
@@ -499,6 +526,13 @@ class CFGStepper:
             hp["s_out"].wait_event(hp["out_ready"][k])
             out_host.copy_(hp["xout"][k], non_blocking=True)
             hp["out_free"][k].record(hp["s_out"])
+
+    def input_consumed(self):
+        """Block the host until the uploads of every step_host() call so far have read their x_host."""
+        hp = getattr(self, "_hp", None)
+        if hp is not None:
+            for k in range(min(2, hp["i"])):
+                hp["in_ready"][k].synchronize()
 
     def flush(self):
         """Make the current stream wait for every download issued by step_host()."""

@@ -24,19 +24,36 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _dev_check(t):
+    """The C library launches on the CURRENT device and stream: a tensor that lives on another GPU would be reached
+    through peer access (or fault).  The model / stepper entry points select the tensors' device
+    (torch.cuda.device(...)); a direct ops call from the wrong device is refused."""
+    if t.device.index != torch.cuda.current_device():
+        raise _lib.MdmError("tensor on %s but the current CUDA device is cuda:%d: wrap the call in "
+                            "torch.cuda.device(tensor.device)" % (t.device, torch.cuda.current_device()))
+
+
 def _req_cuda(*ts):
+    first = True
     for t in ts:
         if t is not None and not t.is_cuda:
             raise _lib.MdmError("mdm_b200 kernels need CUDA tensors; there is no CPU path")
+        if t is not None and first:
+            _dev_check(t)
+            first = False
 
 
 def _c(*ts):
-    """The C-ABI takes raw pointers: every tensor must be CUDA and dense row-major."""
+    """The C-ABI takes raw pointers: every tensor must be CUDA (on the current device) and dense row-major."""
+    first = True
     for t in ts:
         if t is None:
             continue
         if not t.is_cuda:
             raise _lib.MdmError("mdm_b200 kernels need CUDA tensors; there is no CPU path")
+        if first:
+            _dev_check(t)
+            first = False
         if not t.is_contiguous():
             raise _lib.MdmError("non-contiguous tensor (shape %s, strides %s) passed to a raw-pointer kernel"
                                 % (tuple(t.shape), t.stride()))
@@ -164,8 +181,17 @@ def softmax_cross(q, k, v, nt, B, T, Nt_max, H, hd, o):
                                              Nt_max, H, hd, o.data_ptr(), _stream()), "mdm_softmax_cross")
 
 
-def moe_gate(x, N, D, NB, E, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp):
-    _c(x, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp)
+def moe_gate(x, N, D, NB, E, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, forced_idx=None):
+    _c(x, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp, forced_idx)
+    if forced_idx is not None:
+        if forced_idx.dtype != torch.int32 or tuple(forced_idx.shape) != (N, NB, 2):
+            raise _lib.MdmError("forced_idx must be int32 [N, NB, 2]")
+        _lib.check(_lib.load().mdm_moe_gate_forced(x.data_ptr(), N, D, NB, E, 2, ln_w.data_ptr(), ln_b.data_ptr(),
+                                                   gate_w.data_ptr(), gate_b.data_ptr(), forced_idx.data_ptr(),
+                                                   idx.data_ptr(), vals.data_ptr(), stats.data_ptr(),
+                                                   blk_hist.data_ptr(), blk_imp.data_ptr(), _stream()),
+                   "mdm_moe_gate_forced")
+        return
     _lib.check(_lib.load().mdm_moe_gate(x.data_ptr(), N, D, NB, E, 2, ln_w.data_ptr(), ln_b.data_ptr(),
                                         gate_w.data_ptr(), gate_b.data_ptr(), idx.data_ptr(), vals.data_ptr(),
                                         stats.data_ptr(), blk_hist.data_ptr(), blk_imp.data_ptr(), _stream()),

@@ -82,6 +82,9 @@ class MotionTransformer(nn.Module):
         self.precision = precision
         self.record_routing = False
         self.last_routing = []
+        # parity hook (tests): per-layer expert indices [N_l, 2 branches, 2] int32 that replace the top-2 search of the
+        # gate (set_forced_routing); None = the gate routes, as in production
+        self.force_routing = None
         if text_encoder is not None:
             self.text_encoder = text_encoder
         # mdm_gemm_rowop (row pipeline fused into the GEMM's A-operand construction) is correct and tested but slower
@@ -359,6 +362,31 @@ class MotionTransformer(nn.Module):
             self._ep_inst[n_tokens] = ep
         return ep
 
+    def set_forced_routing(self, routing):
+        """Parity hook: make every SwitchMoELayer use the given expert indices instead of its own top-2 search, so that a
+        bf16 (or fp32) run can be compared with the fp32 reference "with identical routing" (reference
+        routing: models/switch_moe.py:53-57).  `routing`: None (off), or one entry per SwitchMoELayer call in execution
+        order (2 per decoder layer: branch 0, branch 1) holding the [N, 2] index tensor (or a tuple whose element [1] is
+        it, as oracle.forward(routing=[...]) records), or one [N, 2, 2] tensor per decoder layer.  The gate weights are
+        still this model's own softmax probabilities of those experts (mdm_moe_gate_forced)."""
+        if routing is None:
+            self.force_routing = None
+            return
+        dev = self._t("sequence_embedding").device
+        ent = [r[1] if isinstance(r, (tuple, list)) else r for r in routing]
+        nl = 2 * self.num_layers
+        if len(ent) == 2 * nl:
+            ent = [torch.stack([ent[2 * i], ent[2 * i + 1]], dim=1) for i in range(nl)]
+        if len(ent) != nl:
+            raise MdmError("forced routing needs %d (per branch) or %d (per layer) entries, got %d" % (2 * nl, nl, len(ent)))
+        self.force_routing = [e.to(device=dev, dtype=torch.int32).contiguous() for e in ent]
+
+    def check_health(self):
+        """Expert parallelism: raise if a peer missed a barrier or a receive buffer overflowed (reads two device words per
+        token count: synchronises).  Called by the sampling loops at their synchronisation points; no-op otherwise."""
+        for ep in self._ep_inst.values():
+            ep.check_health()
+
     def repack(self):
         """Call after modifying parameters in place (the packed kernel layouts are cached)."""
         self._packed = None
@@ -542,10 +570,16 @@ class MotionTransformer(nn.Module):
         return r
 
     # ------------------------------------------------------------------ text side
-    @torch.no_grad()
     def prepare_text(self, xf_proj, xf_out, nt=None):
         """Project the text tokens for every layer once (they do not depend on x or t):
         fast_attention.py:249-252 (linear cross-attention state) and :306-307 (K/V)."""
+        if not xf_out.is_cuda:
+            raise MdmError("prepare_text needs CUDA tensors: there is no CPU fallback")
+        with torch.cuda.device(xf_out.device):      # the C library launches on the current device
+            return self._prepare_text(xf_proj, xf_out, nt)
+
+    @torch.no_grad()
+    def _prepare_text(self, xf_proj, xf_out, nt=None):
         pk = self._packed or self._pack()
         adt, D, H, Dt = self._adt(), self.latent_dim, self.num_heads, self.text_latent_dim
         hd = D // H
@@ -649,6 +683,13 @@ class MotionTransformer(nn.Module):
             ops.rowop(a2, N, D, adti, ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T, silu=True, out2_a=a1)
             self._lin(a1, L["ca_out"], out_f32=x2, resid=x1, alpha=1.0, beta=1.0)
         # ---- MoEMultiBranchFFN (multi_branch.py:52-61, switch_moe.py:44-111)
+        forced = None
+        if self.force_routing is not None:
+            forced = self.force_routing[li]
+            if self._ep_on:
+                raise MdmError("forced routing (parity hook) is not wired into the expert-parallel path")
+            if tuple(forced.shape) != (N, 2, 2):
+                raise MdmError("forced routing of layer %d has shape %s, expected %s" % (li, tuple(forced.shape), (N, 2, 2)))
         if self._ep_on:
             ep = self._ep_for(N)
             if "ep_w" not in L:
@@ -681,7 +722,7 @@ class MotionTransformer(nn.Module):
         hp = self._buf("moe_hp", (cap, Fd), adt)
         yp = self._buf("moe_yp", (cap, D), adt)
         ops.moe_gate(x2, N, D, NB, E, L["moe_ln_w"], L["moe_ln_b"], L["gate_w"], L["gate_b"], idx, vals, stats,
-                     hist, imp)
+                     hist, imp, forced_idx=forced)
         ops.moe_scan(hist, imp, idx, N, NB, E, Fd, D, base, seg, t_up, t_dn, ntile, pk["usage"][li],
                      pk["importance"][li])
         ops.moe_permute(x2, N, D, NB, E, L["moe_ln_w"], L["moe_ln_b"], idx, vals, stats, base, seg, xp, perm,
@@ -773,6 +814,12 @@ class MotionTransformer(nn.Module):
         [B,T,input_feats] fp32.  T must be even and <= num_frames (the reference fails on odd T, H8)."""
         if not x.is_cuda:
             raise MdmError("MotionTransformer.forward needs CUDA tensors: there is no CPU fallback")
+        if x.device != self._t("sequence_embedding").device:
+            raise MdmError("input on %s but the model lives on %s" % (x.device, self._t("sequence_embedding").device))
+        with torch.cuda.device(x.device):           # the C library launches on the current device / stream
+            return self._forward(x, timesteps, length, text, xf_proj, xf_out, nt, text_ctx)
+
+    def _forward(self, x, timesteps, length, text, xf_proj, xf_out, nt, text_ctx):
         Bn, T, Fin = x.shape
         if Fin != self.input_feats:
             raise RuntimeError("expected %d input features, got %d" % (self.input_feats, Fin))

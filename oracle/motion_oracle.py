@@ -241,7 +241,7 @@ def _ln(p, name, x):
 
 def top2_cuda_order(probs):
     """(vals, idx) of torch.topk(probs, 2, dim=1) with the tie order torch 2.11 shows on CUDA
-    (measured on B200, tools/probe_gemm.py): the lowest indices among equal values are selected,
+    (measured on B200 by tests/test_ops_gpu.py::test_softmax_topk_bit_exact_vs_torch_cuda): the lowest indices among equal values are selected,
     and two equal selected values are emitted higher index first.  models/switch_moe.py:57."""
     n, e = probs.shape
     ar = torch.arange(e, device=probs.device)
@@ -328,12 +328,17 @@ def gated_cross_attention(p, name, x, xf, emb, H, nt=None):
     return x + torch.sigmoid(p[name + ".gate"]).view(1, 1, -1) * (ca - x)
 
 
-def switch_moe(p, name, x, E, counters=None, tie_order="cuda"):
-    """SwitchMoELayer.forward, models/switch_moe.py:44-111.  Returns (y, idx[N,2], vals[N,2])."""
+def switch_moe(p, name, x, E, counters=None, tie_order="cuda", forced_idx=None):
+    """SwitchMoELayer.forward, models/switch_moe.py:44-111.  Returns (y, idx[N,2], vals[N,2]).
+    forced_idx [N,2] (test hook, not in the reference): use these expert indices instead of the top-k search; the
+    weights are the softmax probabilities of those experts ("identical routing" comparisons)."""
     B, T, D = x.shape
     xf = x.reshape(-1, D)
-    probs = F.softmax(_lin(p, name + ".gate", xf), dim=1)         # :53-54
-    if tie_order == "cuda":
+    probs = F.softmax(_lin(p, name + ".gate", xf).float(), dim=1)  # :53-54 (softmax runs in fp32 under autocast too)
+    if forced_idx is not None:
+        idx = forced_idx.to(device=x.device, dtype=torch.long)
+        vals = probs.gather(1, idx)
+    elif tie_order == "cuda":
         vals, idx = top2_cuda_order(probs)
     else:
         vals, idx = torch.topk(probs, k=2, dim=1)                 # :57 (host tie order)
@@ -352,12 +357,14 @@ def switch_moe(p, name, x, E, counters=None, tie_order="cuda"):
     return y.view(B, T, D), idx, vals
 
 
-def moe_multibranch_ffn(p, name, x, emb, E, routing=None, counters=None, tie_order="cuda"):
-    """MoEMultiBranchFFN.forward, models/multi_branch.py:52-61."""
+def moe_multibranch_ffn(p, name, x, emb, E, routing=None, counters=None, tie_order="cuda", forced=None):
+    """MoEMultiBranchFFN.forward, models/multi_branch.py:52-61.  forced: optional iterator over per-call [N,2]
+    expert indices (test hook)."""
     out = 0
     for b in range(2):
         br = "%s.branches.%d" % (name, b)
-        h, idx, vals = switch_moe(p, br + ".moe", _ln(p, br + ".layernorm", x), E, counters, tie_order)
+        h, idx, vals = switch_moe(p, br + ".moe", _ln(p, br + ".layernorm", x), E, counters, tie_order,
+                                  None if forced is None else next(forced))
         if routing is not None:
             routing.append((br + ".moe", idx, vals))
         out = out + h
@@ -383,12 +390,12 @@ def sd_cross_attention(p, name, x, xf, H, nt=None):
     return x + (o + f)
 
 
-def decoder_layer(p, blk, x, xf, emb, mask, cfg, nt=None, routing=None, counters=None, tie_order="cuda"):
+def decoder_layer(p, blk, x, xf, emb, mask, cfg, nt=None, routing=None, counters=None, tie_order="cuda", forced=None):
     """MoEExtendedDecoderLayer.forward, models/transformer.py:55-64."""
     H, E = cfg.num_heads, cfg.moe_num_experts
     x = dual_self_attention(p, blk + ".dual_self_attn", x, emb, mask, H)
     x = gated_cross_attention(p, blk + ".cross_attn", x, xf, emb, H, nt)
-    x = moe_multibranch_ffn(p, blk + ".ffn", x, emb, E, routing, counters, tie_order)
+    x = moe_multibranch_ffn(p, blk + ".ffn", x, emb, E, routing, counters, tie_order, forced)
     return sd_cross_attention(p, blk + ".sd_cross_attn", x, xf, H, nt)
 
 
@@ -421,8 +428,10 @@ def fused_embedding(p, cfg, timesteps, xf_proj):
 
 
 def forward(p, cfg, x, timesteps, length, xf_proj, xf_out, nt=None, routing=None, counters=None,
-            tie_order="cuda"):
-    """MotionTransformer.forward, models/transformer.py:291-361 (eval mode, text embeddings given)."""
+            tie_order="cuda", force_routing=None):
+    """MotionTransformer.forward, models/transformer.py:291-361 (eval mode, text embeddings given).
+    force_routing (test hook): the `routing` list of an earlier call (or its [N,2] index tensors), replayed."""
+    forced = None if force_routing is None else iter([r[1] if isinstance(r, (tuple, list)) else r for r in force_routing])
     B, T, _ = x.shape
     if T % 2:
         raise RuntimeError("odd T: the reference's h_up + h fails (H8), T=%d" % T)
@@ -436,12 +445,12 @@ def forward(p, cfg, x, timesteps, length, xf_proj, xf_out, nt=None, routing=None
     mask_low = src_mask(h_low.shape[1], (length / 2).long())
     blks = block_prefixes(cfg)
     for blk in blks[:cfg.num_layers]:
-        h_low = decoder_layer(p, blk, h_low, xf_out, emb, mask_low, cfg, nt, routing, counters, tie_order)
+        h_low = decoder_layer(p, blk, h_low, xf_out, emb, mask_low, cfg, nt, routing, counters, tie_order, forced)
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
         h_up = F.conv_transpose1d(h_low.permute(0, 2, 1), p["upsample.weight"], p["upsample.bias"], stride=2)
     hc = h_up.permute(0, 2, 1) + h
     for blk in blks[cfg.num_layers:]:
-        hc = decoder_layer(p, blk, hc, xf_out, emb, mask, cfg, nt, routing, counters, tie_order)
+        hc = decoder_layer(p, blk, hc, xf_out, emb, mask, cfg, nt, routing, counters, tie_order, forced)
     return _lin(p, "out", hc)
 
 

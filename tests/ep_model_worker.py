@@ -9,15 +9,14 @@ import torch.distributed as dist
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+from dist_common import init_dist, all_max  # noqa: E402
 import motiondiffusion_moe_b200 as mdm  # noqa: E402
 from oracle import cases, motion_oracle as mo  # noqa: E402
 
 
 def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    rank, world, dev, shared = init_dist()
     cfg, p = cases.case_params("small_b4")            # 4 layers x 2 scales, D256, 4 experts (divisible by 2 / 4 ranks)
     B, T = 3, 60
 
@@ -57,8 +56,7 @@ def main():
     ok &= torch.equal(outs[0], outs[1])
     for ep in epn._ep_inst.values():
         ep.check_health()
-    flag = torch.tensor([0.0 if ok else 1.0], device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    flag = all_max([0.0 if ok else 1.0], dev, shared)[0]
     if rank == 0:
         print("EP_MODEL_OK" if float(flag) == 0.0 else "EP_MODEL_MISMATCH")
     for ep in epn._ep_inst.values():

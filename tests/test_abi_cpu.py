@@ -23,6 +23,28 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.mdm_version()
 
 
+def test_struct_mirrors_match_the_library_and_the_docs():
+    """a binding that mirrors MdmGemmEpi without `tile_k` passes a short struct and the kernel reads
+    garbage as a device pointer.  The library exports the sizeof of every struct of the C-ABI; _lib.py checks them at
+    load time, and the stub printed in INTEGRATION.md must declare the same fields as _lib.GemmEpi."""
+    import ctypes as C
+    from motiondiffusion_moe_b200 import _lib
+    lib = _lib.load()
+    assert lib.mdm_sizeof_gemm_epi() == C.sizeof(_lib.GemmEpi)
+    assert lib.mdm_sizeof_rowop() == C.sizeof(_lib.RowOp)
+    assert lib.mdm_sizeof_ep_peers() == C.sizeof(_lib.EpPeers)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = doc[doc.index("class MdmGemmEpi(C.Structure)"):]
+    stub = stub[:stub.index("lib.mdm_gemm_bf16.restype")]
+    doc_fields = re.findall(r'\("(\w+)", C\.c_\w+\)', stub)
+    assert doc_fields == [f[0] for f in _lib.GemmEpi._fields_]
+    hdr = open(os.path.join(ROOT, "include", "mdm_b200.h")).read()
+    body = hdr[hdr.index("typedef struct MdmGemmEpi {"):hdr.index("} MdmGemmEpi;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    hdr_fields = [n for decl in re.findall(r"[\w\* ]+?([\w ,\*]+);", body) for n in re.findall(r"(\w+)\s*(?:,|$)", decl)]
+    assert hdr_fields == doc_fields, (hdr_fields, doc_fields)
+
+
 def test_sass_is_blackwell_native():
     """tcgen05 / TMA must be in the shipped cubin (UTCHMMA, UTMALDG, LDTM) — no legacy-only build."""
     import shutil

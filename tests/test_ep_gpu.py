@@ -43,28 +43,40 @@ def test_emulated_ranks_match_local_moe_bit_exact(dtype, R, E, n_seq, T):
     assert total_rows == R * n_seq * T * 4
 
 
-@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_distributed_ranks_match_local_moe(world):
-    if torch.cuda.device_count() < world:
-        pytest.skip("needs %d GPUs" % world)
+def _run_workers(script, world, port, timeout, token):
+    """One process per GPU (NCCL) when the box has `world` GPUs; world == 2 on a single-GPU box: both ranks share
+    cuda:0 (gloo plumbing, CUDA IPC between the two processes: tests/dist_common.py), so that the multi-rank paths run
+    under the driver's 1-GPU test tier too.  Larger worlds need the GPUs."""
+    ngpu = torch.cuda.device_count()
+    env = dict(os.environ)
+    if ngpu < world:
+        if world != 2:
+            pytest.skip("needs %d GPUs" % world)
+        env["MDM_TEST_SHARED_GPU"] = "1"
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
-           "--master-addr", "127.0.0.1", "--master-port", "29%03d" % (500 + world), os.path.join(here, "ep_dist_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    print(r.stdout[-2000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "EP_DIST_OK" in r.stdout
+    assert token in r.stdout
 
 
-@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_distributed_ranks_match_local_moe(world):
+    """EP parity compares the expert-parallel path with the repo's own single-GPU MoE kernels on the same tokens; that
+    is a valid oracle check because the single-GPU MoE path is itself checked against oracle.switch_moe
+    (tests/test_ops_gpu.py::test_moe_multibranch) and the whole model against the reference goldens."""
+    _run_workers("ep_dist_worker.py", world, 29500 + world, 600, "EP_DIST_OK")
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_model_with_expert_parallelism_is_bit_identical(world):
     """MotionTransformer.enable_expert_parallel(): forward, routing, counters and graph-captured CFG steps."""
-    if torch.cuda.device_count() < world:
-        pytest.skip("needs %d GPUs" % world)
-    here = os.path.dirname(os.path.abspath(__file__))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
-           "--master-addr", "127.0.0.1", "--master-port", "29%03d" % (600 + world), os.path.join(here, "ep_model_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "EP_MODEL_OK" in r.stdout
+    _run_workers("ep_model_worker.py", world, 29600 + world, 900, "EP_MODEL_OK")
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_cfg_sampling_equals_single_gpu_bit_for_bit(world):
+    """parallel.sample_dp on the real model: N-rank sharded CFG sampling == the unsharded loop, bit for bit."""
+    _run_workers("dp_model_worker.py", world, 29700 + world, 900, "DP_MODEL_OK")

@@ -5,10 +5,13 @@ Tolerances (relative L2 unless noted), and why:
   fp32 path, 2- and 8-layer models : 1e-5  (north_star)
   fp32 path, 16-layer default      : 2e-2  when a handful of near-tie routing decisions flip (measured:
       2e-4 of tokens, each flip is a discontinuous change), 1e-4 on sequences without flips
-  bf16 path: per-layer 2e-2 (north_star) with teacher-forced inputs; whole-model error is reported next to
-      the error of the oracle itself under torch.autocast(bfloat16) — the reference's own bf16 path — and
-      must not exceed 1.5x of it (a random-init 16-layer MoE amplifies any bf16 rounding through routing
-      flips; SURVEY.md H7 measured 4.7 % for the reference's autocast path on the small model).
+  bf16 path: whole model 2e-2 (north_star) against the fp32 reference WITH IDENTICAL ROUTING: the
+      expert indices of the fp32 reference run are injected (MotionTransformer.set_forced_routing ->
+      mdm_moe_gate_forced; the gate weights are still the kernel's own probabilities), so a near-tie that flips
+      under bf16 rounding does not change a token discontinuously.  Tested on all three golden cases and on the
+      benchmarked full-size batch (64 x 196).  Without injection the whole-model error is reported next to the
+      error of the oracle itself under torch.autocast(bfloat16) - the reference's own bf16 path.
+  fp32 path, 16-layer default, identical routing: 1e-4 (the fp32 noise floor between two evaluation orders).
 """
 import os
 
@@ -137,6 +140,153 @@ def test_layers_teacher_forced(precision, tol):
     print("\n[%s] worst per-layer rel err %.3e" % (precision, worst))
 
 
+def _layer_routing(routing):
+    """oracle routing list (one (name, idx[N,2], vals) per SwitchMoELayer call) -> per decoder layer [N, 2, 2]."""
+    return [torch.stack([routing[2 * i][1], routing[2 * i + 1][1]], dim=1) for i in range(len(routing) // 2)]
+
+
+@pytest.mark.parametrize("case", ["tiny_b3", "small_b4", "default_b2"])
+def test_whole_model_parity_with_identical_routing(case):
+    """north_star: per-step denoised output within 2e-2 relative error in bf16 (1e-5 in fp32; 1e-4 for the 16-layer
+    model) of the reference path, routing identical.  The reference routing is the oracle's fp32
+    run on this device (checked against the golden routing of the unmodified reference first)."""
+    cfg_name, B, T = cases.CASES[case]
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    ref = torch.from_numpy(g["y"]).to(DEV)
+    cfg, p, net32 = build(case, "fp32")
+    x, t, length, xf_proj, xf_out = cases.make_inputs(cfg, B, T, seed=3, device=DEV)
+    routing = []
+    with torch.no_grad():
+        y_o = mo.forward(p, cfg, x, t, length, xf_proj, xf_out, routing=routing)
+    assert rel(y_o, ref) < (1e-4 if cfg_name == "default" else 1e-5)
+    n_low = cfg.num_layers * 2
+    gold_idx = np.concatenate([g["routing_low"].reshape(n_low, -1, 2).reshape(-1, 2),
+                               g["routing_high"].reshape(n_low, -1, 2).reshape(-1, 2)])
+    ora_idx = torch.cat([r[1] for r in routing]).cpu().numpy()
+    flips_oracle = float((ora_idx != gold_idx).any(-1).mean())
+    assert flips_oracle < 1e-3                      # the GPU oracle routes like the CPU reference (near-ties aside)
+    forced = _layer_routing(routing)
+    # fp32, identical routing
+    net32.set_forced_routing(forced)
+    net32.record_routing = True
+    y32 = net32(x, t, length, None, xf_proj, xf_out)
+    for li, (idx, _) in enumerate(net32.last_routing):
+        assert torch.equal(idx.long(), forced[li].long())            # zero flips by construction: the hook works
+    net32.set_forced_routing(None)
+    net32.record_routing = False
+    e32 = rel(y32, y_o)
+    # natural (un-forced) fp32 routing: how many decisions differ
+    net32.record_routing = True
+    net32(x, t, length, None, xf_proj, xf_out)
+    bad = torch.cat([(r[0].long() != f.long()).any(-1).reshape(-1) for r, f in zip(net32.last_routing, forced)])
+    flips32 = float(bad.float().mean())
+    net32.record_routing = False
+    # bf16, identical routing
+    cfg, p, net16 = build(case, "bf16")
+    net16.set_forced_routing(forced)
+    y16 = net16(x, t, length, None, xf_proj, xf_out)
+    net16.set_forced_routing(None)
+    e16 = rel(y16, y_o)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y_ac = mo.forward(p, cfg, x, t, length, xf_proj, xf_out, force_routing=routing).float()
+    e_ac = rel(y_ac, y_o)
+    print("\n[%s] identical routing: fp32 rel %.3e (natural fp32 flips %.2e), bf16 rel %.3e; reference under "
+          "autocast(bf16), same routing: %.3e" % (case, e32, flips32, e16, e_ac))
+    assert torch.isfinite(y16).all()
+    assert e32 < (1e-4 if cfg_name == "default" else 1e-5)
+    assert e16 < 2e-2
+
+
+def test_full_size_bf16_parity_with_identical_routing():
+    """BASELINE.json configs[1] at its benchmarked size: default model, 64 sequences x 196 frames, bf16, against the
+    oracle's fp32 forward of the same batch on this device with the oracle's routing injected: whole-model relative
+    L2 error <= 2e-2 (north_star), per sequence <= 4e-2."""
+    case = "default_b2"
+    cfg, p, net = build(case, "bf16")
+    B, T = 64, 196
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, T, cfg.input_feats, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+    length = torch.randint(40, T + 1, (B,), generator=g).to(DEV)
+    xf_out = torch.nn.functional.gelu(torch.randn(B, 20, cfg.text_latent_dim, generator=g)).to(DEV)
+    xf_proj = xf_out.mean(1)
+    routing = []
+    with torch.no_grad():
+        y_o = mo.forward(p, cfg, x, t, length, xf_proj, xf_out, routing=routing)
+    net.set_forced_routing(_layer_routing(routing))
+    y = net(x, t, length, None, xf_proj, xf_out)
+    net.set_forced_routing(None)
+    e = rel(y, y_o)
+    per_seq = ((y - y_o).flatten(1).norm(dim=1) / y_o.flatten(1).norm(dim=1))
+    y_nat = net(x, t, length, None, xf_proj, xf_out)
+    print("\n[default 64x196 bf16] identical routing: rel %.3e (worst sequence %.3e); own routing: rel %.3e"
+          % (e, per_seq.max().item(), rel(y_nat, y_o)))
+    assert torch.isfinite(y).all()
+    assert e < 2e-2
+    assert per_seq.max().item() < 4e-2
+
+
+def test_multi_step_cfg_sampling_small_model_matches_oracle_loop():
+    """north_star: 'the final 1000-step sample within a stated tolerance', on a non-toy model: BASELINE configs[0]
+    (small: 8 decoder layers, 196 frames x 263 features), 120 consecutive CFG steps t = 999..880 of
+    p_sample_loop_with_cfg against the oracle's loop (two forwards + update per step,
+    gaussian_diffusion.py:1100-1141), same injected initial / per-step noise.
+      fp32, own routing, CUDA-graph replay: <= 1e-3 relative L2 of the final state (measured ~1e-6);
+      bf16 with the oracle's per-step routing injected: <= 2e-2;
+      bf16, own routing: reported, bounded by 4x the injected-routing error + 2e-2 (routing flips are the difference)."""
+    case = "small_b4"
+    cfg_name, B, T = cases.CASES[case]
+    steps = 120
+    cfg, p, net = build(case, "fp32")
+    stub = lambda text, device: mo.stub_text(text, cfg.text_latent_dim, device)
+    net.encode_text = stub
+    _, _, length, xf_proj, xf_out = cases.make_inputs(cfg, B, T, seed=3, device=DEV)
+    gen = torch.Generator().manual_seed(78)
+    x_T = torch.randn(B, T, cfg.input_feats, generator=gen).to(DEV)
+    noises = torch.randn(steps, B, T, cfg.input_feats, generator=gen).to(DEV)
+    kw = {"text": ["a person walks"] * B, "length": length, "xf_proj": xf_proj, "xf_out": xf_out}
+    d = mdm.GaussianDiffusion(betas=mdm.get_named_beta_schedule("linear", 1000))
+    shape = (B, T, cfg.input_feats)
+    got32 = d.p_sample_loop_with_cfg(net, shape, noise=x_T, clip_denoised=False, model_kwargs=kw, cfg_scale=7.5,
+                                     num_steps=steps, step_noise=lambda ts: noises[999 - ts])
+    del net.encode_text
+    # oracle loop, recording the routing of both branches of every step
+    tab = mo.diffusion_tables(1000)
+    unc = stub([""] * B, DEV)
+    x = x_T.clone()
+    per_step = []
+    with torch.no_grad():
+        for i in range(steps):
+            tt = torch.full((B,), 999 - i, dtype=torch.long, device=DEV)
+            rc, ru = [], []
+            eps_c = mo.forward(p, cfg, x, tt, length, xf_proj, xf_out, routing=rc)
+            eps_u = mo.forward(p, cfg, x, tt, length, unc[0], unc[1], routing=ru)
+            per_step.append([torch.stack([torch.cat([rc[2 * l][1], ru[2 * l][1]]),
+                                          torch.cat([rc[2 * l + 1][1], ru[2 * l + 1][1]])], dim=1).to(torch.int32)
+                             for l in range(len(rc) // 2)])
+            x, _ = mo.cfg_update(tab, x, tt, eps_c, eps_u, noises[i], 7.5, False)
+    err32 = rel(got32, x)
+    cfg, p, net16 = build(case, "bf16")
+    net16.encode_text = stub
+    got16 = d.p_sample_loop_with_cfg(net16, shape, noise=x_T, clip_denoised=False, model_kwargs=kw, cfg_scale=7.5,
+                                     num_steps=steps, step_noise=lambda ts: noises[999 - ts])
+    err16 = rel(got16, x)
+    st = d.make_cfg_stepper(net16, shape, kw, cfg_scale=7.5, clip_denoised=False, device=DEV, use_cuda_graph=False)
+    st.x.copy_(x_T)
+    for i in range(steps):
+        net16.set_forced_routing(per_step[i])
+        st.step(999 - i, noises[i])
+    net16.set_forced_routing(None)
+    err16f = rel(st.x, x)
+    del net16.encode_text
+    print("\n%d-step CFG sampling, small model, vs oracle loop: fp32 rel %.3e; bf16 rel %.3e with the oracle's routing, "
+          "%.3e with its own" % (steps, err32, err16f, err16))
+    assert torch.isfinite(got32).all() and torch.isfinite(got16).all() and torch.isfinite(st.x).all()
+    assert err32 < 1e-3
+    assert err16f < 2e-2
+    assert err16 < 4 * err16f + 2e-2
+
+
 def test_cfg_step_fp32_matches_oracle_and_batched_branches():
     """p_sample_with_cfg (cond + uncond batched as one 2B forward with per-sequence text lengths)
     against the oracle's two separate forwards + update, pinned ephemerals, injected noise."""
@@ -256,8 +406,9 @@ def test_full_1000_step_sample_matches_oracle_loop():
     p_sample_loop_with_cfg (CUDA-graph replay) against the oracle's loop (two forwards + update per
     step, gaussian_diffusion.py:1100-1141) on the same injected initial / per-step noise.
     Stated tolerance: 1e-3 relative L2 in fp32 (measured 8.5e-7 on B200: the sampler re-injects the same noise
-    every step, so fp32 rounding differences do not grow); the bf16 path is reported (measured 4.1e-2) and bounded by 0.25
-    (routing flips of a random-init MoE change individual frames discontinuously)."""
+    every step, so fp32 rounding differences do not grow); the bf16 path (own routing) is reported (measured 4.1e-2) and
+    bounded by 0.1; the non-toy version of this test, with the routing injected, is
+    test_multi_step_cfg_sampling_small_model_matches_oracle_loop."""
     case = "tiny_b3"
     cfg_name, B, T = cases.CASES[case]
     cfg, p, net = build(case, "fp32")
@@ -287,7 +438,7 @@ def test_full_1000_step_sample_matches_oracle_loop():
     print("1000-step CFG sample vs oracle loop: fp32 rel %.3e, bf16 rel %.3e" % (err32, err16))
     assert torch.isfinite(got).all() and torch.isfinite(got16).all()
     assert err32 < 1e-3
-    assert err16 < 0.25
+    assert err16 < 0.1
 
 
 def test_p_mean_variance_and_p_sample_match_oracle():
