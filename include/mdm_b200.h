@@ -266,9 +266,15 @@ MDM_API int mdm_masked_mse(const float* pred, const float* target, const int64_t
  * partial sums to be added up by mdm_sum_partials (fixed order, deterministic):
  *   dparam_part [n_param_parts, 4, D]   (ln1_w, ln1_b, ln2_w, ln2_b)
  *   dfilm_part  [n_film_chunks, n_seq, 2*D]   (scale | shift of every sequence)
- * Called with dout == NULL it only reports n_param_parts / n_film_chunks.  D == 512. */
+ * Called with dout == NULL it only reports n_param_parts / n_film_chunks. */
 MDM_API int mdm_rowop_bwd(const MdmRowOp* op, long rows, int D, int grad_dt, const void* dout, void* din,
                           float* dparam_part, float* dfilm_part, int* n_param_parts, int* n_film_chunks, void* stream);
+/* Generalised form (D in {128, 256, 512, 1024}): dmid (optional, fp32 [rows, D]) is a second gradient arriving at the out1
+ * point of the pipeline (after LN1 / L2, before LN2: e.g. the residual-stream gradient of x1 = LN(pre), whose other consumer
+ * is LN2); din_flags bit 0 = type of din (MDM_F32 / MDM_BF16), bit 1 = accumulate into din instead of overwriting it. */
+MDM_API int mdm_rowop_bwd2(const MdmRowOp* op, long rows, int D, int grad_dt, const void* dout, const void* dmid, int dmid_dt,
+                           void* din, float* dparam_part, float* dfilm_part, int din_flags, int* n_param_parts,
+                           int* n_film_chunks, void* stream);
 /* Elementwise / segment helpers of the expert FFN's backward (models/switch_moe.py:19-25: Linear -> GELU -> Linear per
  * expert): exact-erf GELU forward on the saved pre-activation and its derivative; row scaling by the gate weights; bias
  * gradients as column sums over each expert's row segment [seg_off[g], seg_off[g] + seg_cnt[g]) -> out [G, C] fp32. */
@@ -335,6 +341,107 @@ MDM_API int mdm_ep_barrier(const MdmEpPeers* peers, int R, int me, unsigned* epo
 MDM_API int mdm_ipc_get_handle(const void* ptr, void* handle64, long* offset);
 MDM_API int mdm_ipc_open_handle(const void* handle64, void** base);
 MDM_API int mdm_ipc_close_handle(void* base);
+
+
+/* ================================================================================================================
+ * Training step (BASELINE.json configs[4]; reference: GaussianDiffusion.training_losses models/gaussian_diffusion.py:923-992,
+ * DDPMTrainer.backward_G / update trainers/ddpm_trainer.py:201-244, torch autograd through models/transformer.py:291-361).
+ * Every token-level GEMM of the backward pass runs on mdm_gemm_bf16 / mdm_gemm_f32 (dX with the transposed weight, dW as a
+ * grouped contraction over token slabs); the entry points below are what those cannot express.  dt arguments select fp32
+ * or bf16 activations; parameter gradients are fp32 and deterministic (fixed-order partial sums). */
+
+/* Strided batched GEMM over z = (z1, z2) (e.g. sequence, head):
+ *   C[z][m][n] (+)= alpha * sum_k A[z][m][k] * B[z][k][n]
+ * element (z, i, j) of X lives at X + z1 * x_z1 + z2 * x_z2 + i * x_rs + j * x_cs.  The small per-head products of the
+ * attention cores' backward passes (operands are slices of token-major [N, H*hd] tensors or head-major fp32 scratch).
+ * m_limit / k_limit (optional, int64 per z1, shifted right by limit_shift): rows >= limit are written as zero /
+ * contraction stops at the limit (sequence lengths). */
+typedef struct MdmBgemm {
+  const void* A; int a_dt; long a_z1, a_z2, a_rs, a_cs;
+  const void* B; int b_dt; long b_z1, b_z2, b_rs, b_cs;
+  void* C; int c_dt; long c_z1, c_z2, c_rs, c_cs;
+  int Z1, Z2, M, N, K;
+  float alpha; int accumulate;
+  const int64_t* m_limit; const int64_t* k_limit; int limit_shift;
+} MdmBgemm;
+MDM_API int mdm_bgemm(const MdmBgemm* g, void* stream);
+MDM_API int mdm_sizeof_bgemm(void);
+
+/* FastAttention backward (models/fast_attention.py:29-92 with the 0.1 pre-scale of :155-157 and the gradient clamp of
+ * :150-152), recomputed from the saved raw qkv [N, 3*H*hd].  Scratch is fp32, head-major [B, H, T, *]:
+ *   mdm_fa_prep      qh = L2(LN(0.1 q)), kh = L2(LN(0.1 k)), vn = LN(0.1 v)
+ *   (mdm_bgemm)      uq = qh P, uk = kh P
+ *   mdm_fa_feat      qp = 0.1 exp(clamp(uq)), kp = 0.1 exp(clamp(uk)) * [t < length >> shift]
+ *   (mdm_bgemm)      kv = 0.1 kp^T vn ; o = 0.1 qp kv
+ *   mdm_fa_out_bwd   den = max(<qp, kp>, 1e-6); out = LN(o / den): from dout -> d_o (over o), dden; LN affine partials
+ *   (mdm_bgemm)      dqp = 0.1 d_o kv^T ; dkv = 0.1 qp^T d_o ; dkp = 0.1 vn dkv^T ; dvn = 0.1 kp dkv
+ *   mdm_fa_feat_bwd  duq, duk (in place over dqp, dkp; adds the denominator terms)
+ *   (mdm_bgemm)      dqh = duq P^T ; dkh = duk P^T
+ *   mdm_fa_prep_bwd  L2 / LN backward, * 0.1, clamp to [-1, 1] -> dqkv [N, 3*H*hd]; LN affine partials
+ * Partials are [n_parts, 2, hd] (dw | db), to be summed with mdm_sum_partials; a call with the first pointer NULL only
+ * reports n_parts. */
+MDM_API int mdm_fa_prep(const void* qkv, int dt, const float* nw, const float* nb, int B, int H, int T, int hd, float* qh,
+                        float* kh, float* vn, void* stream);
+MDM_API int mdm_fa_feat(const float* uq, const float* uk, const int64_t* length, int shift, int B, int H, int T, int M,
+                        float* qp, float* kp, void* stream);
+MDM_API int mdm_fa_out_bwd(float* o, const float* qp, const float* kp, const void* dout, int dt, const float* nw, int B, int H,
+                           int T, int hd, float* dden, float* part, int* n_parts, void* stream);
+MDM_API int mdm_fa_feat_bwd(const float* uq, const float* uk, const float* qp, const float* kp, const float* dden, int B, int H,
+                            int T, int M, float* dqp, float* dkp, void* stream);
+MDM_API int mdm_fa_prep_bwd(const void* qkv, int dt, const float* nw, const float* nb, int B, int H, int T, int hd,
+                            const float* dqh, const float* dkh, const float* dvn, void* dqkv, float* part, int* n_parts,
+                            void* stream);
+/* softmax pieces of the two cross-attention backward passes (fast_attention.py:242-258, 305-325):
+ *   head softmax over hd (q of LinearTemporalCrossAttention): token-major q -> head-major P fp32, and its backward;
+ *   key softmax over <= 96 text tokens with per-sequence count nt[b] (in place on fp32 [B*H, T, NK]) and its backward;
+ *   column softmax over the text tokens of k [B, Nt, C] (:251) and its backward. */
+MDM_API int mdm_head_softmax(const void* q, int dt, int B, int H, int T, int hd, float* P, void* stream);
+MDM_API int mdm_head_softmax_bwd(const float* P, const float* dP, int B, int H, int T, int hd, void* dq, int dt, void* stream);
+MDM_API int mdm_key_softmax(float* S, const int* nt, int B, int H, int T, int NK, void* stream);
+MDM_API int mdm_key_softmax_bwd(const float* P, float* dP, int B, int H, int T, int NK, void* stream);
+MDM_API int mdm_col_softmax(const void* k, int dt, const int* nt, int B, int Nt, int C, float* Ks, void* stream);
+MDM_API int mdm_col_softmax_bwd(const float* Ks, const float* dKs, int B, int Nt, int C, void* dk, int dt, void* stream);
+/* MoE (models/switch_moe.py:53-109, multi_branch.py:52-61).  The training forward keeps the un-scaled expert outputs z:
+ *   mdm_moe_combine_sum      m[token] = sum_j rowscale[pos_j] * z[pos_j]
+ *   mdm_moe_combine_bwd      dz[pos_j] = rowscale[pos_j] * dm[token]; drs[pos_j] = <dm[token], z[pos_j]>
+ *   mdm_moe_gate_bwd_logits  vals = probs[idx] (not renormalised): dlogits [N, NB*E] from drs (probabilities recomputed)
+ *   mdm_moe_unpermute_bwd    dh_br[token] = d_xp[pos0] + d_xp[pos1] + dlogits[token, br, :] Wg_br
+ *   mdm_moe_wgrad_tables     per-group row counts and the MdmGemmEpi.tile_k tables of the experts' weight gradients (an empty
+ *                            expert contracts over `zero_row0`, a zero region of the buffers: its gradient is exactly 0) */
+MDM_API int mdm_moe_combine_sum(const void* z, int dt, const float* rowscale, const int* perm, long N, int D, int NBK, void* m,
+                                void* stream);
+MDM_API int mdm_moe_combine_bwd(const void* z, int dt, const float* rowscale, const int* perm, long N, int D, int NBK,
+                                const void* dm, void* dz, float* drs, void* stream);
+MDM_API int mdm_moe_gate_bwd_logits(const float* x, const float* stats, const float* ln_w, const float* ln_b,
+                                    const float* gate_w, const float* gate_b, const int* idx, const int* perm, const float* drs,
+                                    long N, int D, int NB, int E, float* dlogits, void* stream);
+MDM_API int mdm_moe_unpermute_bwd(const void* dxp, int dt, const int* perm, const float* dlogits, const float* gate_w, long N,
+                                  int D, int NB, int E, int br, void* dh, void* stream);
+MDM_API int mdm_moe_wgrad_tables(const int* seg_off, const int* idx, long N, int NB, int E, int mt_up, int mt_down,
+                                 int zero_row0, int* seg_cnt, int* tile_k_up, int* tile_k_down, void* stream);
+/* elementwise / reductions (any dt): activation forward / derivative on a saved pre-activation (GELU exact-erf, SiLU);
+ * out = a x + b y; GatedFusion mix backward (models/gate.py:18-19); gradient of the masked reconstruction loss
+ * (ddpm_trainer.py:207-214) times `scale`; column sums (bias gradients) as [slabs, C] partials; column sums of
+ * a * (b - c); tiled transpose with token-slab split (see mdm_transpose_split_bf16); per-segment column sums. */
+MDM_API int mdm_act_fwd(const void* pre, int dt, long n, int act, void* out, void* stream);
+MDM_API int mdm_act_bwd(const void* pre, const void* dy, int dt, long n, int act, void* dx, void* stream);
+MDM_API int mdm_axpby(const void* x, int x_dt, float a, const void* y, int y_dt, float b, long n, void* out, int out_dt,
+                      void* stream);
+MDM_API int mdm_gated_mix_bwd(const float* t, const float* x, const float* dout, long n, float* dt_, float* dx, void* stream);
+MDM_API int mdm_masked_mse_grad(const float* pred, const float* target, const int64_t* length, int B, int T, int F, float scale,
+                                float* dpred, void* stream);
+MDM_API int mdm_colsum(const void* src, int dt, long M, int C, long ld, int slabs, float* part, void* stream);
+MDM_API int mdm_colsum_prod(const float* a, const float* b, const float* c, long M, int C, int slabs, float* part, void* stream);
+MDM_API int mdm_transpose_split(const void* src, int dt, long M, int C, long ld, int S, int Ks, void* dst, void* stream);
+MDM_API int mdm_seg_colsum(const void* src, int dt, int C, const int* seg_off, const int* seg_cnt, int G, float* out,
+                           void* stream);
+/* clip_grad_norm_(max_norm) + Adam (ddpm_trainer.py:228-244; torch.optim.Adam defaults, no weight decay) on flat fp32
+ * buffers, no host synchronisation: mdm_grad_clip_coef writes norm_coef = {global L2 norm, min(1, max_norm / (norm + 1e-6))}
+ * (part: n_part floats of scratch); mdm_adam_step scales the gradient by norm_coef[1] in place (as clip_grad_norm_ does)
+ * and applies bias-corrected Adam step number `step` (1-based). */
+MDM_API int mdm_grad_clip_coef(const float* g, long n, float max_norm, float* part, int n_part, float* norm_coef, void* stream);
+MDM_API int mdm_adam_step(float* p, float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps, int step,
+                          const float* norm_coef, void* stream);
 
 MDM_API int mdm_num_sms(void);
 /* sizeof() of the structs above as this library was compiled: a binding checks its own struct definitions against them

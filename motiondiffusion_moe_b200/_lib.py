@@ -41,6 +41,15 @@ class RowOp(C.Structure):
     ]
 
 
+class Bgemm(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("a_dt", C.c_int), ("a_z1", C.c_long), ("a_z2", C.c_long), ("a_rs", C.c_long), ("a_cs", C.c_long),
+                ("B", C.c_void_p), ("b_dt", C.c_int), ("b_z1", C.c_long), ("b_z2", C.c_long), ("b_rs", C.c_long), ("b_cs", C.c_long),
+                ("C", C.c_void_p), ("c_dt", C.c_int), ("c_z1", C.c_long), ("c_z2", C.c_long), ("c_rs", C.c_long), ("c_cs", C.c_long),
+                ("Z1", C.c_int), ("Z2", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("alpha", C.c_float), ("accumulate", C.c_int),
+                ("m_limit", C.c_void_p), ("k_limit", C.c_void_p), ("limit_shift", C.c_int)]
+
+
 EP_MAX_RANKS = 8
 
 
@@ -79,6 +88,7 @@ _SIGS = {
     "mdm_recover_from_ric": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "mdm_masked_mse": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "mdm_rowop_bwd": [C.POINTER(RowOp), _L, _I, _I, _P, _P, _P, _P, C.POINTER(C.c_int), C.POINTER(C.c_int), _P],
+    "mdm_rowop_bwd2": [C.POINTER(RowOp), _L, _I, _I, _P, _P, _I, _P, _P, _P, _I, C.POINTER(C.c_int), C.POINTER(C.c_int), _P],
     "mdm_gelu_fwd": [_P, _L, _P, _P],
     "mdm_gelu_bwd": [_P, _P, _L, _P, _P],
     "mdm_rowscale_bf16": [_P, _P, _L, _I, _P, _P],
@@ -95,6 +105,35 @@ _SIGS = {
     "mdm_ipc_get_handle": [_P, _P, C.POINTER(C.c_long)],
     "mdm_ipc_open_handle": [_P, C.POINTER(C.c_void_p)],
     "mdm_ipc_close_handle": [_P],
+    "mdm_bgemm": [C.POINTER(Bgemm), _P],
+    "mdm_sizeof_bgemm": [],
+    "mdm_fa_prep": [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "mdm_fa_feat": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "mdm_fa_out_bwd": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, C.POINTER(C.c_int), _P],
+    "mdm_fa_feat_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "mdm_fa_prep_bwd": [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, C.POINTER(C.c_int), _P],
+    "mdm_head_softmax": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "mdm_head_softmax_bwd": [_P, _P, _I, _I, _I, _I, _P, _I, _P],
+    "mdm_key_softmax": [_P, _P, _I, _I, _I, _I, _P],
+    "mdm_key_softmax_bwd": [_P, _P, _I, _I, _I, _I, _P],
+    "mdm_col_softmax": [_P, _I, _P, _I, _I, _I, _P, _P],
+    "mdm_col_softmax_bwd": [_P, _P, _I, _I, _I, _P, _I, _P],
+    "mdm_moe_combine_sum": [_P, _I, _P, _P, _L, _I, _I, _P, _P],
+    "mdm_moe_combine_bwd": [_P, _I, _P, _P, _L, _I, _I, _P, _P, _P, _P],
+    "mdm_moe_gate_bwd_logits": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P],
+    "mdm_moe_unpermute_bwd": [_P, _I, _P, _P, _P, _L, _I, _I, _I, _I, _P, _P],
+    "mdm_moe_wgrad_tables": [_P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "mdm_act_fwd": [_P, _I, _L, _I, _P, _P],
+    "mdm_act_bwd": [_P, _P, _I, _L, _I, _P, _P],
+    "mdm_axpby": [_P, _I, _F, _P, _I, _F, _L, _P, _I, _P],
+    "mdm_gated_mix_bwd": [_P, _P, _P, _L, _P, _P, _P],
+    "mdm_masked_mse_grad": [_P, _P, _P, _I, _I, _I, _F, _P, _P],
+    "mdm_colsum": [_P, _I, _L, _I, _L, _I, _P, _P],
+    "mdm_colsum_prod": [_P, _P, _P, _L, _I, _I, _P, _P],
+    "mdm_transpose_split": [_P, _I, _L, _I, _L, _I, _I, _P, _P],
+    "mdm_seg_colsum": [_P, _I, _I, _P, _P, _I, _P, _P],
+    "mdm_grad_clip_coef": [_P, _L, _F, _P, _I, _P, _P],
+    "mdm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P, _P],
     "mdm_num_sms": [],
     "mdm_sizeof_gemm_epi": [],
     "mdm_sizeof_rowop": [],
@@ -121,7 +160,8 @@ def load():
         fn.restype = C.c_int
     lib.mdm_version.restype = C.c_char_p
     lib.mdm_version.argtypes = []
-    for fn, st in ((lib.mdm_sizeof_gemm_epi, GemmEpi), (lib.mdm_sizeof_rowop, RowOp), (lib.mdm_sizeof_ep_peers, EpPeers)):
+    for fn, st in ((lib.mdm_sizeof_gemm_epi, GemmEpi), (lib.mdm_sizeof_rowop, RowOp), (lib.mdm_sizeof_ep_peers, EpPeers),
+                   (lib.mdm_sizeof_bgemm, Bgemm)):
         if fn() != C.sizeof(st):     # a stale .so or a drifted binding: refuse to pass short structs to the kernels
             raise MdmError("struct layout mismatch between _lib.py and %s: %s is %d bytes here, %d in the library"
                            % (LIB_PATH, st.__name__, C.sizeof(st), fn()))

@@ -29,21 +29,23 @@ gemm_f32_kernel(const float* __restrict__ A, int lda, long a_rows, const float* 
   float acc[4][4] = {};
   const int lr = threadIdx.x >> 2;         // 0..63: tile row loaded by this thread
   const int lk = (threadIdx.x & 3) * 4;    // 0,4,8,12
-  for (int k0 = 0; k0 < K; k0 += TK) {
+  int kb = 0, ke = K;                      // per-tile contraction range (MdmGemmEpi.tile_k), exact here (no rounding to 64)
+  if (epi.tile_k) { kb = epi.tile_k[2 * mt]; ke = min(K, kb + epi.tile_k[2 * mt + 1]); }
+  for (int k0 = kb; k0 < ke; k0 += TK) {
     {
       const long ar = a_row0 + lr;
       const bool ok = lr < rows_valid && ar < a_rows;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = k0 + lk + j;
-        As[lk + j][lr] = (ok && k < K) ? A[ar * lda + k] : 0.f;
+        As[lk + j][lr] = (ok && k < ke) ? A[ar * lda + k] : 0.f;
       }
       const long wr = (long)w_row0 + n_base + lr;
       const bool wok = (n_base + lr) < N && wr < w_rows;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = k0 + lk + j;
-        Ws[lk + j][lr] = (wok && k < K) ? W[wr * ldw + k] : 0.f;
+        Ws[lk + j][lr] = (wok && k < ke) ? W[wr * ldw + k] : 0.f;
       }
     }
     __syncthreads();
@@ -96,7 +98,7 @@ extern "C" MDM_API int mdm_gemm_f32(const float* A, int lda, long a_rows, const 
                                     long w_rows, int M, int N, int K, const void* mtiles,
                                     int num_m_tiles, const int* num_m_tiles_dev, const MdmGemmEpi* epi,
                                     void* stream) {
-  if (epi && epi->tile_k) return MDM_ERR_UNSUPPORTED;   // per-tile K ranges: tcgen05 kernel only
+  if (epi && epi->tile_k && !mtiles) return MDM_ERR_ARG;
   if (!A || !W || !epi || M < 0 || N <= 0 || K <= 0) return MDM_ERR_ARG;
   if (!mtiles) num_m_tiles = (M + 127) / 128;
   if (num_m_tiles <= 0) return MDM_OK;

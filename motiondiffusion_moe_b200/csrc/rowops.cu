@@ -286,10 +286,13 @@ int dispatch(const RowOp& op, long rows, int D, int out_dt, cudaStream_t st) {
 // gradient of a sequence is a fixed-order sum of per-CTA partials (mdm_sum_partials): no atomics, deterministic.
 //   a = LN1(x)      b = a * sqrt(D) / max(|a|, eps)      c = LN2(b)      d = c * (1 + sc) + sh      e = SiLU(d)
 constexpr int BWD_ROWS = 32;
-template <int VPT, typename TI, typename TG>
+// dmid (optional, fp32): a gradient that arrives at the out1 point (after LN1 / L2, before LN2), e.g. the residual-stream
+// gradient of x1 = LN(pre) whose second consumer is LN2.  din may have its own type (TD) and may be accumulated into.
+template <int VPT, typename TI, typename TG, typename TD>
 __global__ void __launch_bounds__(256, 1)
 rowop_bwd_kernel(const RowOp op, long rows, int D, int rows_per_seq, int chunks, int n_seq, const TG* __restrict__ dout,
-                 TG* __restrict__ din, float* __restrict__ dparam_part, float* __restrict__ dfilm_part) {
+                 const float* __restrict__ dmid, TD* din, int accumulate, float* __restrict__ dparam_part,
+                 float* __restrict__ dfilm_part) {
   __shared__ float red[8][VPT * 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seq = blockIdx.x / chunks, ch = blockIdx.x - seq * chunks;
@@ -367,6 +370,12 @@ rowop_bwd_kernel(const RowOp op, long rows, int D, int rows_per_seq, int chunks,
 #pragma unroll
       for (int i = 0; i < VPT; ++i) g[i] = r2 * (g[i] - m1 - xh2[i] * m2);
     }
+    if (dmid) {
+      float gm[VPT];
+      load_row<VPT, float>(dmid + r * D, lane, gm);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) g[i] += gm[i];
+    }
     if (do_l2) {                               // b = a * s,  s = sqrt(D) / |a|   (|a| > eps assumed, as in the forward)
       float dot = 0.f;
 #pragma unroll
@@ -387,7 +396,13 @@ rowop_bwd_kernel(const RowOp op, long rows, int D, int rows_per_seq, int chunks,
 #pragma unroll
       for (int i = 0; i < VPT; ++i) g[i] = r1 * (g[i] - m1 - xh1[i] * m2);
     }
-    store_row<VPT, TG>(din + r * D, lane, g);
+    if (accumulate) {
+      float old[VPT];
+      load_row<VPT, TD>(din + r * D, lane, old);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) g[i] += old[i];
+    }
+    store_row<VPT, TD>(din + r * D, lane, g);
   }
   // ---- per-CTA partial sums of the parameter gradients (fixed order over the 8 warps)
   auto reduce_to = [&](const float (&v)[VPT], float* dst) {
@@ -428,28 +443,52 @@ extern "C" MDM_API int mdm_rowop(const MdmRowOp* op, long rows, int D, int out_d
 }
 
 // C-ABI: see include/mdm_b200.h
-extern "C" MDM_API int mdm_rowop_bwd(const MdmRowOp* op, long rows, int D, int grad_dt, const void* dout, void* din,
-                                     float* dparam_part, float* dfilm_part, int* n_param_parts, int* n_film_chunks,
-                                     void* stream) {
+template <int VPT>
+static int launch_rowop_bwd(const MdmRowOp* op, long rows, int D, int grad_dt, const void* dout, const float* dmid, void* din,
+                            int din_dt, int accumulate, float* dparam_part, float* dfilm_part, int rps, int n_seq, int chunks,
+                            cudaStream_t st) {
+  const unsigned grid = (unsigned)(n_seq * chunks);
+#define BWD(TI_, TG_, TD_) rowop_bwd_kernel<VPT, TI_, TG_, TD_><<<grid, 256, 0, st>>>(*op, rows, D, rps, chunks, n_seq, \
+      reinterpret_cast<const TG_*>(dout), dmid, reinterpret_cast<TD_*>(din), accumulate, dparam_part, dfilm_part)
+  if (op->in_dt == MDM_BF16 && grad_dt == MDM_BF16 && din_dt == MDM_BF16) BWD(bf16, bf16, bf16);
+  else if (op->in_dt == MDM_F32 && grad_dt == MDM_BF16 && din_dt == MDM_F32) BWD(float, bf16, float);
+  else if (op->in_dt == MDM_F32 && grad_dt == MDM_F32 && din_dt == MDM_F32) BWD(float, float, float);
+  else if (op->in_dt == MDM_BF16 && grad_dt == MDM_F32 && din_dt == MDM_F32) BWD(bf16, float, float);
+  else if (op->in_dt == MDM_F32 && grad_dt == MDM_BF16 && din_dt == MDM_BF16) BWD(float, bf16, bf16);
+  else return MDM_ERR_UNSUPPORTED;
+#undef BWD
+  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+}
+
+extern "C" MDM_API int mdm_rowop_bwd2(const MdmRowOp* op, long rows, int D, int grad_dt, const void* dout, const void* dmid,
+                                      int dmid_dt, void* din, float* dparam_part, float* dfilm_part, int din_flags,
+                                      int* n_param_parts, int* n_film_chunks, void* stream) {
   if (!op || !op->in || !n_param_parts || !n_film_chunks) return MDM_ERR_ARG;
-  if (D != 512) return MDM_ERR_UNSUPPORTED;              // VPT = 16 only (the default model); other widths: round 2
   if (op->film && op->rows_per_seq <= 0) return MDM_ERR_ARG;
   const int rps = op->film ? op->rows_per_seq : (int)(rows < 0x7fffffffL ? rows : 0x7fffffff);
+  // without FiLM the rows need no per-sequence grouping: chunk the whole range
   const int n_seq = (int)((rows + rps - 1) / rps), chunks = (rps + BWD_ROWS - 1) / BWD_ROWS;
   *n_param_parts = n_seq * chunks;
   *n_film_chunks = chunks;
   if (!dout || !din || !dparam_part) return MDM_OK;       // size query
   if (op->film && !dfilm_part) return MDM_ERR_ARG;
+  if (dmid && dmid_dt != MDM_F32) return MDM_ERR_UNSUPPORTED;
   if (rows == 0) return MDM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const unsigned grid = (unsigned)(n_seq * chunks);
-#define BWD(TI_, TG_) rowop_bwd_kernel<16, TI_, TG_><<<grid, 256, 0, st>>>(*op, rows, D, rps, chunks, n_seq, \
-      reinterpret_cast<const TG_*>(dout), reinterpret_cast<TG_*>(din), dparam_part, dfilm_part)
-  if (op->in_dt == MDM_BF16 && grad_dt == MDM_BF16) BWD(bf16, bf16);
-  else if (op->in_dt == MDM_BF16 && grad_dt == MDM_F32) BWD(bf16, float);
-  else if (op->in_dt == MDM_F32 && grad_dt == MDM_F32) BWD(float, float);
-  else if (op->in_dt == MDM_F32 && grad_dt == MDM_BF16) BWD(float, bf16);
-  else return MDM_ERR_ARG;
-#undef BWD
-  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+  const int din_dt = din_flags & 1, acc = (din_flags >> 1) & 1;
+  const float* dm = reinterpret_cast<const float*>(dmid);
+  switch (D) {
+    case 128: return launch_rowop_bwd<4>(op, rows, D, grad_dt, dout, dm, din, din_dt, acc, dparam_part, dfilm_part, rps, n_seq, chunks, st);
+    case 256: return launch_rowop_bwd<8>(op, rows, D, grad_dt, dout, dm, din, din_dt, acc, dparam_part, dfilm_part, rps, n_seq, chunks, st);
+    case 512: return launch_rowop_bwd<16>(op, rows, D, grad_dt, dout, dm, din, din_dt, acc, dparam_part, dfilm_part, rps, n_seq, chunks, st);
+    case 1024: return launch_rowop_bwd<32>(op, rows, D, grad_dt, dout, dm, din, din_dt, acc, dparam_part, dfilm_part, rps, n_seq, chunks, st);
+    default: return MDM_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" MDM_API int mdm_rowop_bwd(const MdmRowOp* op, long rows, int D, int grad_dt, const void* dout, void* din,
+                                     float* dparam_part, float* dfilm_part, int* n_param_parts, int* n_film_chunks,
+                                     void* stream) {
+  return mdm_rowop_bwd2(op, rows, D, grad_dt, dout, nullptr, MDM_F32, din, dparam_part, dfilm_part, grad_dt & 1, n_param_parts,
+                        n_film_chunks, stream);
 }

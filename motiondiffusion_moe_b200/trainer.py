@@ -7,9 +7,13 @@ tools/evaluation.py and tools/visualization.py call to turn captions into motion
 
 `generate_batch` (:145-174) is `p_sample_loop_with_cfg` on the CUDA-graph step runner.  Extras (keyword-only /
 optional attributes, absent from the reference): `sampler="ddim"` with `num_inference_steps` runs the strided DDIM
-loop instead of the 1000-step ancestral one.  `forward` / `backward_G` (:97-143, 201-225) compute the training-step
-VALUES (noise prediction, masked reconstruction loss, MoE balance loss) on the kernels; `update` / `train` (:227-360)
-are not built: there are no backward / optimizer kernels yet, and they say so loudly."""
+loop instead of the 1000-step ancestral one.
+
+Training (args.is_train): `forward` / `backward_G` / `update` / `train` (:97-143, 201-244, 290-360) run on the hand-written
+backward and optimizer kernels through `training.TrainEngine` (flat fp32 master parameters + bf16 operand mirror, fused
+global-norm clipping + Adam).  With torch.distributed initialised and world size > 1, `update` all-reduces the flat
+gradient buffer (average) before the optimizer step: the data-parallel semantics the reference intends with its DDP
+wrapper, whose reducer never fires because the trainer calls the unwrapped module."""
 from collections import OrderedDict
 
 import numpy as np
@@ -29,14 +33,15 @@ class DDPMTrainer(object):
         self.diffusion = GaussianDiffusion(betas=betas, model_mean_type=ModelMeanType.EPSILON,
                                            model_var_type=ModelVarType.FIXED_SMALL, loss_type=LossType.MSE)
         self.sampler_name = "uniform"
-        if getattr(args, "is_train", False):
-            raise NotImplementedError("the DDPM training step (backward + Adam) has no CUDA kernels yet: "
-                                      "construct the trainer with is_train=False for sampling")
         if sampler not in ("ddpm", "ddim"):
             raise ValueError(sampler)
         self.sampling, self.num_inference_steps, self.eta = sampler, num_inference_steps, eta
         self.to(self.device)
         self.cfg_scale = getattr(args, "cfg_scale", 7.5)                                    # :67
+        self.engine = None
+        if getattr(args, "is_train", False):                                                # :52-53, :297 (Adam, lr = opt.lr)
+            from .training import TrainEngine
+            self.engine = TrainEngine(self._model(), lr=getattr(args, "lr", 2e-4), max_grad_norm=1.0)
 
     def _model(self):                                                                      # :69-77
         return self.encoder.module if hasattr(self.encoder, "module") else self.encoder
@@ -90,7 +95,7 @@ class DDPMTrainer(object):
             cur_idx += batch_size
         return all_output
 
-    # ------------------------------------------------------------------ training forward (loss VALUES; no backward yet)
+    # ------------------------------------------------------------------ training step
     def forward(self, batch_data, eval_mode=False):                                       # :97-143
         """q_sample at a uniformly drawn timestep, one model forward, noise prediction vs noise, MoE balance loss, mask:
         the values the reference computes before `update` back-propagates.  Uses numpy's global RNG for the timesteps
@@ -102,10 +107,23 @@ class DDPMTrainer(object):
         cur_len = torch.LongTensor([min(T, int(m)) for m in m_lens]).to(self.device)
         p = np.ones([self.diffusion.num_timesteps]) / self.diffusion.num_timesteps
         t = torch.from_numpy(np.random.choice(len(p), size=(B,), p=p)).long().to(self.device)
-        output = self.diffusion.training_losses(model=self._model(), x_start=motions, t=t,
-                                                model_kwargs={"text": caption, "length": cur_len})
-        self.real_noise, self.fake_noise = output["target"], output["pred"]
-        self.moe_loss = output.get("moe_loss", 0.0)
+        if self.engine is not None and not eval_mode:
+            # training_losses (gaussian_diffusion.py:923-992) with the activations kept for the backward kernels
+            m = self._model()
+            with torch.cuda.device(self.engine.dev):
+                xf_proj, xf_out = m.encode_text(caption, self.device)
+                noise = torch.randn_like(motions)
+                x_t = self.diffusion.q_sample(motions, t, noise=noise)
+                m.reset_all_moe_counters(m)
+                pred, self._saved = self.engine.forward_train(x_t, t, cur_len, xf_proj, xf_out)
+            self.real_noise, self.fake_noise = noise, pred
+            self.moe_loss = 0.0 + m.get_moe_loss(m)
+        else:
+            output = self.diffusion.training_losses(model=self._model(), x_start=motions, t=t,
+                                                    model_kwargs={"text": caption, "length": cur_len})
+            self.real_noise, self.fake_noise = output["target"], output["pred"]
+            self.moe_loss = output.get("moe_loss", 0.0)
+            self._saved = None
         self.cur_len = cur_len
         self.src_mask = self._model().generate_src_mask(T, cur_len).to(motions.device)
 
@@ -126,9 +144,63 @@ class DDPMTrainer(object):
                             "loss_moe": float(self.moe_loss) if isinstance(self.moe_loss, torch.Tensor) else self.moe_loss,
                             "loss_total": total.item()})
 
-    # ------------------------------------------------------------------ optimisation: not built
-    def _no_training(self, *a, **kw):
-        raise NotImplementedError("DDPMTrainer.update / train need the backward and optimizer kernels of the training "
-                                  "step, which are not built (DESIGN.md section 7)")
+    # ------------------------------------------------------------------ optimisation
+    def update(self):                                                                     # :227-244
+        """zero_grad, backward_G, backward (hand-written kernels), clip_grad_norm_(1.0), Adam step."""
+        if self.engine is None:
+            raise RuntimeError("DDPMTrainer.update needs a trainer constructed with args.is_train = True")
+        if getattr(self, "_saved", None) is None:
+            raise RuntimeError("call forward(batch_data) before update()")
+        from . import train_ops as T
+        eng = self.engine
+        with torch.cuda.device(eng.dev):
+            eng.zero_grad()
+            loss_logs = self.backward_G()
+            d_pred = T.masked_mse_grad(self.fake_noise.float().contiguous(), self.real_noise.float().contiguous(),
+                                       self.cur_len.contiguous())
+            eng.backward(self._saved, d_pred)                    # the MoE balance loss carries no gradient (SURVEY.md H9)
+            self._saved = None
+            self._all_reduce_gradients()
+            eng.optimizer_step()
+        return loss_logs
 
-    update = train = _no_training
+    def _all_reduce_gradients(self):
+        """Data-parallel training (BASELINE.json configs[4] at N > 1): average the flat gradient buffer over the ranks.
+        One collective over one contiguous buffer (NCCL reduces in-switch over NVLS on an NVSwitch node)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.engine.grad, op=dist.ReduceOp.SUM)
+            self.engine.grad.mul_(1.0 / dist.get_world_size())
+
+    def train(self, train_dataset):                                                       # :290-360
+        """Main loop of the reference: per batch one update with the captions and one with empty captions (the
+        unconditional branch of classifier-free guidance); MoE counters reset per epoch; checkpoints as the reference."""
+        from os.path import join as pjoin
+        import os
+        it, cur_epoch = 0, 0
+        latest = pjoin(self.opt.model_dir, "latest.tar")
+        if os.path.exists(latest):
+            cur_epoch, it = self.load(latest)
+            self.engine.refresh()
+        logs = OrderedDict()
+        for epoch in range(cur_epoch, self.opt.num_epochs):
+            self.train_mode()
+            self.maybe_reset_all_moe_counters()
+            for i, batch_data in enumerate(train_dataset):
+                self.forward(batch_data)
+                loss_logs = self.update()
+                caption, motions, m_lens = batch_data
+                self.forward(([""] * len(caption), motions, m_lens))
+                for k, v in self.update().items():
+                    loss_logs["uncond_" + k] = v
+                for k, v in loss_logs.items():
+                    logs[k] = logs.get(k, 0.0) + v
+                it += 1
+                if it % getattr(self.opt, "log_every", 50) == 0:
+                    print("epoch %d it %d " % (epoch, it) + " ".join("%s: %.4f" % (k, v / self.opt.log_every) for k, v in logs.items()))
+                    logs = OrderedDict()
+                if it % getattr(self.opt, "save_latest", 500) == 0:
+                    self.save(latest, epoch, it)
+            self.save(latest, epoch, it)
+            if epoch % getattr(self.opt, "save_every_e", 5) == 0:
+                self.save(pjoin(self.opt.model_dir, "ckpt_e%03d.tar" % epoch), epoch, total_it=it)

@@ -288,7 +288,11 @@ def performer_self_attention(p, name, x, emb, mask, H):
     hd = D // H
     h = _ln(p, name + ".pre_norm", x)
     split = lambda t: t.reshape(B, T, H, hd).permute(0, 2, 1, 3) * 0.1     # :155-157
-    q, k, v = split(_lin(p, name + ".query", h)), split(_lin(p, name + ".key", h)), split(_lin(p, name + ".value", h))
+    q, k, v = _lin(p, name + ".query", h), _lin(p, name + ".key", h), _lin(p, name + ".value", h)
+    for tensor in (q, k, v):                                              # :150-152 (training: gradients clamped to [-1, 1])
+        if tensor.requires_grad:
+            tensor.register_hook(lambda grad: torch.clamp(grad, -1, 1))
+    q, k, v = split(q), split(k), split(v)
     a = fast_attention(p, name + ".fast_attention", q, k, v, mask)
     a = a.permute(0, 2, 1, 3).reshape(B, T, D)                    # :162
     a = _lin(p, name + ".proj_out.3", F.gelu(_lin(p, name + ".proj_out.0", a)))   # :165
@@ -428,9 +432,11 @@ def fused_embedding(p, cfg, timesteps, xf_proj):
 
 
 def forward(p, cfg, x, timesteps, length, xf_proj, xf_out, nt=None, routing=None, counters=None,
-            tie_order="cuda", force_routing=None):
+            tie_order="cuda", force_routing=None, skip_layers=()):
     """MotionTransformer.forward, models/transformer.py:291-361 (eval mode, text embeddings given).
-    force_routing (test hook): the `routing` list of an earlier call (or its [N,2] index tensors), replayed."""
+    force_routing (test hook): the `routing` list of an earlier call (or its [N,2] index tensors), replayed.
+    skip_layers: indices (execution order, 0..2L-1) of the decoder layers that StochasticDepth skips in train mode
+    (models/time.py:41-49: the block returns its input unchanged)."""
     forced = None if force_routing is None else iter([r[1] if isinstance(r, (tuple, list)) else r for r in force_routing])
     B, T, _ = x.shape
     if T % 2:
@@ -444,12 +450,16 @@ def forward(p, cfg, x, timesteps, length, xf_proj, xf_out, nt=None, routing=None
         h_low = F.conv1d(h.permute(0, 2, 1), p["downsample.weight"], p["downsample.bias"], stride=2).permute(0, 2, 1)
     mask_low = src_mask(h_low.shape[1], (length / 2).long())
     blks = block_prefixes(cfg)
-    for blk in blks[:cfg.num_layers]:
+    for li, blk in enumerate(blks[:cfg.num_layers]):
+        if li in skip_layers:
+            continue
         h_low = decoder_layer(p, blk, h_low, xf_out, emb, mask_low, cfg, nt, routing, counters, tie_order, forced)
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
         h_up = F.conv_transpose1d(h_low.permute(0, 2, 1), p["upsample.weight"], p["upsample.bias"], stride=2)
     hc = h_up.permute(0, 2, 1) + h
-    for blk in blks[cfg.num_layers:]:
+    for li, blk in enumerate(blks[cfg.num_layers:]):
+        if li + cfg.num_layers in skip_layers:
+            continue
         hc = decoder_layer(p, blk, hc, xf_out, emb, mask, cfg, nt, routing, counters, tie_order, forced)
     return _lin(p, "out", hc)
 

@@ -25,9 +25,27 @@ def _import():
         return _mods["t"], _mods["g"]
     if not available():
         raise RuntimeError("oracle/_ref is not built: run `python -m oracle.build_ref` where /root/reference exists")
-    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
-    if root not in sys.path:
-        sys.path.insert(0, root)
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "models")
+    import importlib.abc
+    import importlib.machinery
+    import importlib.util
+
+    class RefFinder(importlib.abc.MetaPathFinder):
+        """Resolves the package `models` (the reference's text2motion/models) to the byte code under oracle/_ref."""
+        def find_spec(self, fullname, path=None, target=None):
+            if fullname == "models":
+                f = os.path.join(root, "__init__.refbc")
+                return importlib.util.spec_from_file_location(fullname, f, loader=importlib.machinery.SourcelessFileLoader(fullname, f),
+                                                              submodule_search_locations=[root])
+            if fullname.startswith("models."):
+                f = os.path.join(root, fullname.split(".", 1)[1] + ".refbc")
+                if os.path.exists(f):
+                    return importlib.util.spec_from_file_location(fullname, f,
+                                                                  loader=importlib.machinery.SourcelessFileLoader(fullname, f))
+            return None
+
+    if not any(type(f).__name__ == "RefFinder" for f in sys.meta_path):
+        sys.meta_path.insert(0, RefFinder())
     import models.transformer as mt            # noqa: E402  (the reference, sourceless)
     import models.gaussian_diffusion as gd     # noqa: E402
 

@@ -25,7 +25,13 @@ def main():
     net.load_state_dict({k: p[k] for k in net.state_dict()})
     net.load_extras(p)
     net.to(dev)
-    net.encode_text = lambda text, device: mo.stub_text(text, cfg.text_latent_dim, device)
+
+    def encode(text, device):
+        # like a real encoder, the embedding of a sequence depends on its own string only (not on its position in the
+        # batch): every "" row gets the same embedding, so a shard sees exactly the rows of the global batch
+        pooled, tok = mo.stub_text(text[:1], cfg.text_latent_dim, device)
+        return pooled.expand(len(text), -1).contiguous(), tok.expand(len(text), -1, -1).contiguous()
+    net.encode_text = encode
     _, _, length, xf_proj, xf_out = cases.make_inputs(cfg, B, T, seed=40, device=dev)     # same global batch on every rank
     d = mdm.GaussianDiffusion(betas=mdm.get_named_beta_schedule("linear", 1000))
     kw = {"text": ["a person walks"] * B, "length": length, "xf_proj": xf_proj, "xf_out": xf_out}

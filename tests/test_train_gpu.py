@@ -1,0 +1,330 @@
+"""GPU parity of the DDPM training step (BASELINE.json configs[4]): the
+hand-written backward / optimizer kernels (csrc/train.cu, training.py) against torch autograd through the oracle
+(which is itself pinned to the unmodified reference's gradients by tests/golden/train_tiny.npz, test_oracle_golden.py).
+Tolerances: fp32 path 1e-4 (relative L2 over all parameter gradients), bf16 path 2e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import motiondiffusion_moe_b200 as mdm  # noqa: E402
+from motiondiffusion_moe_b200 import train_ops as T, ops  # noqa: E402
+from motiondiffusion_moe_b200.training import TrainEngine  # noqa: E402
+from oracle import cases, motion_oracle as mo  # noqa: E402
+
+DEV = torch.device("cuda")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+f32, bf16 = torch.float32, torch.bfloat16
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def test_bgemm_strided_batches():
+    g = gen(1)
+    B, H, Tn, hd = 3, 4, 50, 64
+    D = H * hd
+    x = torch.randn(B * Tn, D, generator=g).to(DEV)                  # token-major
+    w = torch.randn(B, H, hd, 40, generator=g).to(DEV)
+    out = torch.empty(B * H, Tn, 40, device=DEV)
+    T.bgemm(x, (Tn * D, hd, D, 1), w, (H * hd * 40, hd * 40, 40, 1), out, (H * Tn * 40, Tn * 40, 40, 1), B, H, Tn, 40, hd, alpha=0.5)
+    ref = 0.5 * torch.einsum("bthd,bhdn->bhtn", x.view(B, Tn, H, hd), w).reshape(B * H, Tn, 40)
+    assert rel(out, ref) < 1e-5
+    # transposed operands, contraction over the frames, bf16 inputs, accumulate
+    xb = x.bfloat16()
+    acc = torch.ones(B, H, hd, hd, device=DEV)
+    T.bgemm(xb, (Tn * D, hd, 1, D), xb, (Tn * D, hd, D, 1), acc, (H * hd * hd, hd * hd, hd, 1), B, H, hd, hd, Tn, accumulate=True)
+    xf = xb.float().view(B, Tn, H, hd)
+    ref = 1.0 + torch.einsum("bthd,bthe->bhde", xf, xf)
+    assert rel(acc, ref) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(f32, 2e-4), (bf16, 2e-2)])
+@pytest.mark.parametrize("B,H,Tn,hd,scale", [(2, 4, 60, 64, 1.0), (3, 4, 98, 128, 1.0), (2, 4, 8, 32, 300.0)])
+def test_fastattn_backward_matches_autograd(dtype, tol, B, H, Tn, hd, scale):
+    """fastattn_bwd against autograd through oracle.fast_attention with the 0.1 pre-scale and the [-1, 1] gradient clamp of
+    PerformerSelfAttention (scale = 300 makes the clamp active)."""
+    g = gen(2)
+    D = H * hd
+    qkv = (torch.randn(B * Tn, 3 * D, generator=g) * 2).to(DEV).to(dtype)
+    P = torch.nn.functional.normalize(torch.linalg.qr(torch.randn(hd, 256, generator=g), mode="reduced")[0], dim=0) * hd ** -0.25
+    P = P.to(DEV).contiguous()
+    nw, nb = (1 + 0.1 * torch.randn(hd, generator=g)).to(DEV), (0.05 * torch.randn(hd, generator=g)).to(DEV)
+    length = torch.tensor([Tn, max(2, Tn // 3), Tn - 1][:B]).to(DEV)
+    dout = (torch.randn(B * Tn, D, generator=g) * scale).to(DEV).to(dtype)
+    # reference
+    x = qkv.float().clone().requires_grad_(True)
+    w_, b_ = nw.clone().requires_grad_(True), nb.clone().requires_grad_(True)
+    p = {"fa.projection_matrix": P, "fa.norm.weight": w_, "fa.norm.bias": b_}
+    lin = x.view(B, Tn, 3, D)
+    parts = []
+    for s in range(3):
+        t = lin[:, :, s]
+        t.register_hook(lambda grad: torch.clamp(grad, -1, 1))
+        parts.append(t.reshape(B, Tn, H, hd).permute(0, 2, 1, 3) * 0.1)
+    mask = mo.src_mask(Tn, length)
+    out = mo.fast_attention(p, "fa", parts[0], parts[1], parts[2], mask).permute(0, 2, 1, 3).reshape(B * Tn, D)
+    out.backward(dout.float())
+    gn = (torch.zeros(hd, device=DEV), torch.zeros(hd, device=DEV))
+    dqkv = T.fastattn_bwd(qkv, P, nw, nb, length, 0, B, H, Tn, hd, dout, gn)
+    print("\n fastattn bwd %s hd=%d: dqkv rel %.2e, dnorm_w rel %.2e, dnorm_b rel %.2e" % (dtype, hd, rel(dqkv, x.grad), rel(gn[0], w_.grad), rel(gn[1], b_.grad)))
+    assert rel(dqkv, x.grad) < tol
+    assert rel(gn[0], w_.grad) < tol and rel(gn[1], b_.grad) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(f32, 1e-4), (bf16, 2e-2)])
+def test_cross_attention_cores_backward_match_autograd(dtype, tol):
+    g = gen(3)
+    B, H, Tn, hd, Nt = 3, 4, 60, 64, 20
+    D = H * hd
+    nt = torch.tensor([20, 11, 1], dtype=torch.int32).to(DEV)
+    mk = lambda *s: torch.randn(*s, generator=g).to(DEV).to(dtype)
+    q, k, v, dy = mk(B * Tn, D), mk(B * Nt, D), mk(B * Nt, D), mk(B * Tn, D)
+    pad = (torch.arange(Nt, device=DEV)[None, :] >= nt[:, None])
+    # LinearTemporalCrossAttention (fast_attention.py:249-253)
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    qs = torch.softmax(qr.view(B, Tn, H, hd), dim=-1)
+    ks = torch.softmax(kr.view(B, Nt, H, hd).masked_fill(pad[:, :, None, None], float("-inf")), dim=1)
+    att = torch.einsum("bnhd,bnhl->bhdl", ks, vr.view(B, Nt, H, hd).masked_fill(pad[:, :, None, None], 0.0))
+    y = torch.einsum("bnhd,bhdl->bnhl", qs, att).reshape(B * Tn, D)
+    y.backward(dy.float())
+    ctx = torch.empty(B, H, hd, hd, device=DEV)
+    ops.lincross_ctx(k, v, nt, B, Nt, H, hd, ctx)
+    assert rel(ctx, att) < tol
+    dq, dctx = T.lincross_apply_bwd(q, ctx, B, Tn, H, hd, dy)
+    dk, dv = T.lincross_ctx_bwd(k, v, nt, B, Nt, H, hd, dctx)
+    print("\n lincross bwd %s: dq %.2e dk %.2e dv %.2e" % (dtype, rel(dq, qr.grad), rel(dk, kr.grad), rel(dv, vr.grad)))
+    assert rel(dq, qr.grad) < tol and rel(dk, kr.grad) < tol and rel(dv, vr.grad) < tol
+    # MemoryEfficientCrossAttentionBlock core (fast_attention.py:305-325)
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("bqhd,bkhd->bhqk", qr.view(B, Tn, H, hd) * hd ** -0.5, kr.view(B, Nt, H, hd))
+    s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    o = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, dim=-1), vr.view(B, Nt, H, hd)).reshape(B * Tn, D)
+    o.backward(dy.float())
+    dq, dk, dv = T.softmax_cross_bwd(q, k, v, nt, B, Tn, Nt, H, hd, dy)
+    print(" softmax-cross bwd %s: dq %.2e dk %.2e dv %.2e" % (dtype, rel(dq, qr.grad), rel(dk, kr.grad), rel(dv, vr.grad)))
+    assert rel(dq, qr.grad) < tol and rel(dk, kr.grad) < tol and rel(dv, vr.grad) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(f32, 1e-5), (bf16, 1e-2)])
+@pytest.mark.parametrize("M,K_in,N_out", [(3000, 256, 512), (37, 264, 8), (6, 128, 263)])
+def test_linear_backward_any_dtype(dtype, tol, M, K_in, N_out):
+    g = gen(4)
+    x = torch.randn(M, K_in, generator=g).to(DEV).to(dtype)
+    W = (torch.randn(N_out, K_in, generator=g) / K_in ** 0.5).to(DEV).to(dtype)
+    Np = (N_out + 7) // 8 * 8
+    dy = torch.zeros(M, Np, device=DEV, dtype=dtype)
+    dy[:, :N_out] = torch.randn(M, N_out, generator=g).to(DEV).to(dtype)
+    Wt = torch.zeros(K_in, Np, device=DEV, dtype=dtype)
+    Wt[:, :N_out] = W.t()
+    dx = torch.empty(M, K_in, device=DEV, dtype=dtype)
+    dW = torch.ones(Np, K_in, device=DEV)
+    db = torch.ones(Np, device=DEV)
+    T.linear_bwd(x, Wt, dy, dx_a=dx, dW=dW, db=db)
+    dyf, xf = dy.float()[:, :N_out], x.float()
+    assert rel(dx, dyf @ W.float()) < tol
+    assert rel(dW[:N_out], 1 + dyf.t() @ xf) < tol                     # accumulated into
+    assert rel(db[:N_out], 1 + dyf.sum(0)) < tol
+    r = torch.randn(M, K_in, generator=g).to(DEV)
+    out = r.clone()
+    T.linear_bwd(x, Wt, dy, dx_f32=out, dx_resid=out)                  # in-place residual accumulation
+    assert rel(out, r + dyf @ W.float()) < tol
+
+
+def test_rowop_backward_mid_gradient_and_accumulate():
+    g = gen(5)
+    for D in (128, 256, 512):
+        N = 77
+        x = torch.randn(N, D, generator=g).to(DEV)
+        ln1 = ((1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV))
+        ln2 = ((1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV))
+        dout = torch.randn(N, D, generator=g).to(DEV).bfloat16()
+        dmid = torch.randn(N, D, generator=g).to(DEV)
+        base = torch.randn(N, D, generator=g).to(DEV)
+        xr = x.clone().requires_grad_(True)
+        leaves = [t.clone().requires_grad_(True) for t in (*ln1, *ln2)]
+        mid = torch.nn.functional.layer_norm(xr, (D,), leaves[0], leaves[1])
+        fin = torch.nn.functional.layer_norm(mid, (D,), leaves[2], leaves[3])
+        (fin * dout.float()).sum().backward(retain_graph=True)
+        (mid * dmid).sum().backward()
+        din = base.clone()
+        g1 = (torch.zeros(D, device=DEV), torch.zeros(D, device=DEV))
+        g2 = (torch.zeros(D, device=DEV), torch.zeros(D, device=DEV))
+        T.rowop_bwd(x, N, D, dout, ln1=ln1, ln2=ln2, dmid=dmid, din=din, accumulate=True, g_ln1=g1, g_ln2=g2)
+        assert rel(din, base + xr.grad) < 1e-4
+        for got, leaf in zip((*g1, *g2), leaves):
+            assert rel(got, leaf.grad) < 1e-4
+
+
+def test_clip_and_adam_match_torch():
+    g = gen(6)
+    n = 100_003
+    p0 = torch.randn(n, generator=g).to(DEV)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=2e-4)
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    part, nc = torch.empty(256, device=DEV), torch.zeros(2, device=DEV)
+    lib = T._lib.load()
+    for step in range(1, 4):
+        gr = (torch.randn(n, generator=g) * (5.0 if step == 1 else 0.001)).to(DEV)      # step 1 clips, later steps do not
+        ref.grad = gr.clone()
+        norm = torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        opt.step()
+        gg = gr.clone()
+        T._chk(lib.mdm_grad_clip_coef(gg.data_ptr(), n, 1.0, part.data_ptr(), 256, nc.data_ptr(), ops._stream()), "clip")
+        T._chk(lib.mdm_adam_step(p.data_ptr(), gg.data_ptr(), m.data_ptr(), v.data_ptr(), n, 2e-4, 0.9, 0.999, 1e-8, step, nc.data_ptr(),
+                                 ops._stream()), "adam")
+        assert abs(float(nc[0]) - float(norm)) < 1e-4 * float(norm)
+        assert rel(gg, ref.grad) < 1e-6                                # clip_grad_norm_ scales .grad in place
+        assert rel(p, ref.detach()) < 1e-6
+
+
+def _oracle_grads(cfg, p, x0, t, length, xf_proj, xf_out, noise, skip=()):
+    names = [k for k in mo.param_shapes(cfg) if "expert_usage" not in k and "expert_importance" not in k]
+    pr = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in p.items()}
+    tab = mo.diffusion_tables(1000)
+    x_t = mo.q_sample(tab, x0, t, noise)
+    routing, counters = [], {}
+    pred = mo.forward(pr, cfg, x_t, t, length, xf_proj, xf_out, routing=routing, counters=counters, skip_layers=skip)
+    per_frame = ((pred - noise) ** 2).mean(-1)
+    mask = mo.src_mask(x0.shape[1], length).view(per_frame.shape).float()
+    loss = (per_frame * mask).sum() / mask.sum()
+    loss.backward()
+    moe = sum(mo.load_balancing_loss(counters[r[0] + ".expert_usage"], counters[r[0] + ".expert_importance"], cfg.moe_num_experts)
+              for r in routing)
+    grads = {k: (pr[k].grad if pr[k].grad is not None else torch.zeros_like(pr[k])) for k in names}
+    return loss.item(), float(moe), pred.detach(), grads, routing
+
+
+def _engine(case, precision):
+    cfg, p = cases.case_params(case)
+    net = mdm.MotionTransformer(precision=precision, dropout=0.0, **cfg)
+    net.load_state_dict({k: p[k] for k in net.state_dict()})
+    net.load_extras(p)
+    net.to(DEV)
+    return cfg, {k: v.to(DEV) for k, v in p.items()}, net, TrainEngine(net)
+
+
+@pytest.mark.parametrize("case,precision,tol", [("tiny_b3", "fp32", 1e-4), ("small_b4", "fp32", 1e-4),
+                                                ("tiny_b3", "bf16", 2e-2), ("small_b4", "bf16", 2e-2)])
+def test_training_step_gradients_match_oracle_autograd(case, precision, tol):
+    """One DDPM training-step evaluation (q_sample, forward, masked noise-prediction loss, backward): loss values and every
+    parameter gradient against autograd through the oracle on the same device.  bf16: the oracle's routing is injected
+    (identical routing)."""
+    cfg_name, B, Tn = cases.CASES[case]
+    if case == "small_b4":
+        Tn = 60                                                        # keep the autograd reference light
+    cfg, p, net, eng = _engine(case, precision)
+    x0, t, length, xf_proj, xf_out = cases.make_inputs(cfg, B, Tn, seed=5, device=DEV)
+    noise = torch.randn(x0.shape, generator=gen(6)).to(DEV)
+    loss_ref, moe_ref, pred_ref, gref, routing = _oracle_grads(cfg, p, x0, t, length, xf_proj, xf_out, noise)
+    d = mdm.GaussianDiffusion(betas=mdm.get_named_beta_schedule("linear", 1000))
+    if precision == "bf16":
+        net.set_forced_routing(routing)
+    eng.zero_grad()
+    out = eng.loss_and_grads(x0, t, length, xf_proj, xf_out, noise, d)
+    net.set_forced_routing(None)
+    torch.cuda.synchronize()
+    assert rel(out["pred"], pred_ref) < (1e-5 if precision == "fp32" else 3e-2)
+    assert abs(float(out["loss_mot_rec"]) - loss_ref) < (1e-5 if precision == "fp32" else 3e-2) * abs(loss_ref)
+    assert abs(float(out["moe_loss"]) - moe_ref) < 1e-3 * max(1.0, abs(moe_ref))
+    rows, num, den = [], 0.0, 0.0
+    for n, gr in gref.items():
+        got = dict(net.named_parameters())[n].grad
+        e = (got.float() - gr).norm().item()
+        num += e * e
+        den += gr.norm().item() ** 2
+        rows.append((e / max(gr.norm().item(), 1e-12), gr.norm().item(), n))
+    total = (num / den) ** 0.5
+    rows.sort(reverse=True)
+    print("\n[%s %s] all-gradient rel L2 %.3e; worst parameters:" % (case, precision, total))
+    for e, nrm, n in rows[:12]:
+        print("   %.3e  |g|=%.3e  %s" % (e, nrm, n))
+    gmax = max(r[1] for r in rows)
+    bad = [(e, nrm, n) for e, nrm, n in rows if nrm > 1e-4 * gmax and e > 20 * tol]
+    assert total < tol, total
+    assert not bad, bad[:5]
+    if case == "tiny_b3" and precision == "fp32":                     # and against the unmodified reference's golden gradients
+        g = np.load(os.path.join(GOLD, "train_tiny.npz"))
+        assert abs(float(out["loss_mot_rec"]) - float(g["loss_rec"])) < 1e-4 * abs(float(g["loss_rec"]))
+        want = dict(zip([str(n) for n in g["names"]], g["grad_norms"]))
+        params = dict(net.named_parameters())
+        for n, w in want.items():
+            if w > 1e-6:
+                assert abs(float(params[n].grad.norm()) - w) < 2e-4 * w + 1e-7, n
+        for k in g.files:
+            if k.startswith("grad::"):
+                assert rel(params[k[6:]].grad, torch.from_numpy(g[k]).to(DEV)) < 2e-4, k
+
+
+def test_stochastic_depth_skips_layers_like_the_reference():
+    """StochasticDepth in train mode (models/time.py:41-49): a skipped block is the identity; its parameters get no
+    gradient.  The skip pattern is injected (the reference draws it from the CPU generator interleaved with its ephemeral
+    Linears, which are pinned here, so the stream itself cannot be replayed)."""
+    case = "small_b4"
+    cfg, p, net, eng = _engine(case, "fp32")
+    B, Tn = 2, 40
+    x0, t, length, xf_proj, xf_out = cases.make_inputs(cfg, B, Tn, seed=7, device=DEV)
+    noise = torch.randn(x0.shape, generator=gen(8)).to(DEV)
+    skip = [False] * (2 * cfg.num_layers)
+    skip[2], skip[5] = True, True
+    loss_ref, _, pred_ref, gref, _ = _oracle_grads(cfg, p, x0, t, length, xf_proj, xf_out, noise, skip=(2, 5))
+    d = mdm.GaussianDiffusion(betas=mdm.get_named_beta_schedule("linear", 1000))
+    eng.zero_grad()
+    out = eng.loss_and_grads(x0, t, length, xf_proj, xf_out, noise, d, sd_skip=skip)
+    assert rel(out["pred"], pred_ref) < 1e-5
+    params = dict(net.named_parameters())
+    num = sum(((params[n].grad - gr).norm() ** 2).item() for n, gr in gref.items())
+    den = sum((gr.norm() ** 2).item() for gr in gref.values())
+    assert (num / den) ** 0.5 < 1e-4
+    assert all(float(params[n].grad.abs().max()) == 0.0 for n in gref if n.startswith("decoder_blocks_low.2.module."))
+    # train() mode draws the pattern itself: survival probabilities linspace(1, 0.8, L), CPU generator
+    net.train()
+    torch.manual_seed(3)
+    surv = torch.linspace(1.0, 0.8, steps=cfg.num_layers).tolist()
+    torch.manual_seed(3)
+    want = []
+    for i in range(2 * cfg.num_layers):
+        pr = surv[i % cfg.num_layers]
+        want.append(bool(pr != 1.0 and not (torch.rand(1).item() < pr)))
+    torch.manual_seed(3)
+    _, S = eng.forward_train(x0, t, length, xf_proj, xf_out)
+    assert S["sd_skip"] == want
+    net.eval()
+
+
+def test_trainer_update_runs_and_learns():
+    """DDPMTrainer.update (trainers/ddpm_trainer.py:227-244): zero_grad, backward_G, backward, clip_grad_norm_(1.0), Adam step.
+    On a fixed batch the loss must go down; the parameters must change; everything stays finite."""
+    import types
+    case = "tiny_b3"
+    cfg, p = cases.case_params(case)
+    net = mdm.MotionTransformer(precision="bf16", dropout=0.0, **cfg)
+    net.load_state_dict({k: p[k] for k in net.state_dict()})
+    net.load_extras(p)
+    net.encode_text = lambda text, device: mo.stub_text(text, cfg.text_latent_dim, device)
+    opt = types.SimpleNamespace(device=DEV, diffusion_steps=1000, is_train=True, lr=2e-3)
+    tr = mdm.DDPMTrainer(opt, net)
+    caps = ["a person walks", "a person jumps", "a person sits down"]
+    motions = torch.randn(3, 8, cfg.input_feats, generator=gen(8))
+    before = net.state_dict()["out.weight"].clone()
+    losses = []
+    for it in range(12):
+        np.random.seed(3)
+        torch.manual_seed(3)                                            # same timesteps / noise: a fixed objective
+        tr.forward((caps, motions, [8, 5, 2]))
+        logs = tr.update()
+        losses.append(logs["loss_mot_rec"])
+        assert np.isfinite(logs["loss_total"])
+    print("\n trainer losses:", ["%.4f" % l for l in losses])
+    assert losses[-1] < 0.9 * losses[0]
+    assert not torch.equal(before, net.state_dict()["out.weight"])
+    assert float(tr.engine.norm_coef[0]) > 0
