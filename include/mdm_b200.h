@@ -363,6 +363,7 @@ typedef struct MdmBgemm {
   int Z1, Z2, M, N, K;
   float alpha; int accumulate;
   const int64_t* m_limit; const int64_t* k_limit; int limit_shift;
+  int tensor_cores; /* 1: operands rounded to bf16 in shared memory, mma.sync m16n8k16 (bf16 training path); 0: fp32 FMA */
 } MdmBgemm;
 MDM_API int mdm_bgemm(const MdmBgemm* g, void* stream);
 MDM_API int mdm_sizeof_bgemm(void);
@@ -433,8 +434,8 @@ MDM_API int mdm_masked_mse_grad(const float* pred, const float* target, const in
 MDM_API int mdm_colsum(const void* src, int dt, long M, int C, long ld, int slabs, float* part, void* stream);
 MDM_API int mdm_colsum_prod(const float* a, const float* b, const float* c, long M, int C, int slabs, float* part, void* stream);
 MDM_API int mdm_transpose_split(const void* src, int dt, long M, int C, long ld, int S, int Ks, void* dst, void* stream);
-MDM_API int mdm_seg_colsum(const void* src, int dt, int C, const int* seg_off, const int* seg_cnt, int G, float* out,
-                           void* stream);
+MDM_API int mdm_seg_colsum(const void* src, int dt, int C, const int* seg_off, const int* seg_cnt, int G, int slabs, float* out,
+                           void* stream);      /* out: [slabs, G, C] partials over `slabs` row slabs of every segment */
 /* clip_grad_norm_(max_norm) + Adam (ddpm_trainer.py:228-244; torch.optim.Adam defaults, no weight decay) on flat fp32
  * buffers, no host synchronisation: mdm_grad_clip_coef writes norm_coef = {global L2 norm, min(1, max_norm / (norm + 1e-6))}
  * (part: n_part floats of scratch); mdm_adam_step scales the gradient by norm_coef[1] in place (as clip_grad_norm_ does)

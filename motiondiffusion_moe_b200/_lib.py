@@ -47,7 +47,7 @@ class Bgemm(C.Structure):
                 ("C", C.c_void_p), ("c_dt", C.c_int), ("c_z1", C.c_long), ("c_z2", C.c_long), ("c_rs", C.c_long), ("c_cs", C.c_long),
                 ("Z1", C.c_int), ("Z2", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
                 ("alpha", C.c_float), ("accumulate", C.c_int),
-                ("m_limit", C.c_void_p), ("k_limit", C.c_void_p), ("limit_shift", C.c_int)]
+                ("m_limit", C.c_void_p), ("k_limit", C.c_void_p), ("limit_shift", C.c_int), ("tensor_cores", C.c_int)]
 
 
 EP_MAX_RANKS = 8
@@ -131,7 +131,7 @@ _SIGS = {
     "mdm_colsum": [_P, _I, _L, _I, _L, _I, _P, _P],
     "mdm_colsum_prod": [_P, _P, _P, _L, _I, _I, _P, _P],
     "mdm_transpose_split": [_P, _I, _L, _I, _L, _I, _I, _P, _P],
-    "mdm_seg_colsum": [_P, _I, _I, _P, _P, _I, _P, _P],
+    "mdm_seg_colsum": [_P, _I, _I, _P, _P, _I, _I, _P, _P],
     "mdm_grad_clip_coef": [_P, _L, _F, _P, _I, _P, _P],
     "mdm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P, _P],
     "mdm_num_sms": [],

@@ -147,6 +147,107 @@ bgemm_kernel(const MdmBgemm g) {
   }
 }
 
+// Tensor-core flavour for the bf16 training path: the same contract, operands rounded to bf16 while they are staged in
+// shared memory (whatever their storage type), mma.sync.m16n8k16 with fp32 accumulators.  These products are 1-2 % of the
+// step's FLOPs and have no fixed operand layout (slices of token-major tensors, transposed head-major scratch), so they
+// use register-fragment MMAs on generic strided tiles rather than TMA-fed tcgen05 tiles.  64 x 64 x 32 tiles, 8 warps
+// (2 x 4), the next k-tile prefetched into registers while the current one is multiplied.
+constexpr int TBK = 32, TPITCH = TBK + 8;      // bf16 row pitch 80 B: conflict-free 32-bit fragment loads
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <typename TA, typename TB, typename TC>
+__global__ void __launch_bounds__(256)
+bgemm_tc_kernel(const MdmBgemm g) {
+  __shared__ __align__(16) bf16 As[BT][TPITCH];     // [m][k]
+  __shared__ __align__(16) bf16 Bs[BT][TPITCH];     // [n][k]
+  const int z = blockIdx.z, z1 = z / g.Z2, z2 = z - z1 * g.Z2;
+  const TA* A = reinterpret_cast<const TA*>(g.A) + z1 * g.a_z1 + z2 * g.a_z2;
+  const TB* B = reinterpret_cast<const TB*>(g.B) + z1 * g.b_z1 + z2 * g.b_z2;
+  TC* C = reinterpret_cast<TC*>(g.C) + z1 * g.c_z1 + z2 * g.c_z2;
+  int M = g.M, K = g.K;
+  if (g.m_limit) M = min(M, max(0, (int)g.m_limit[z1] >> g.limit_shift));
+  if (g.k_limit) K = min(K, max(0, (int)g.k_limit[z1] >> g.limit_shift));
+  const int m0 = blockIdx.y * BT, n0 = blockIdx.x * BT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;      // warp tile 32 x 16
+  const int gq = lane >> 2, tq = lane & 3;
+  const bool a_kfast = g.a_cs == 1, b_nfast = g.b_cs == 1;
+  float acc[2][2][4] = {};
+  float ra[8], rb[8];                                           // 64 x 32 elements / 256 threads = 8 each
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m, k;
+      if (a_kfast) { k = tid & 31; m = (tid >> 5) + 8 * i; } else { m = tid & 63; k = (tid >> 6) + 4 * i; }
+      const int gm = m0 + m, gk = k0 + k;
+      ra[i] = (gm < M && gk < K) ? ldf<TA>(A + (long)gm * g.a_rs + (long)gk * g.a_cs) : 0.f;
+      int n, kb;
+      if (b_nfast) { n = tid & 63; kb = (tid >> 6) + 4 * i; } else { kb = tid & 31; n = (tid >> 5) + 8 * i; }
+      const int gn = n0 + n, gkb = k0 + kb;
+      rb[i] = (gn < g.N && gkb < K) ? ldf<TB>(B + (long)gkb * g.b_rs + (long)gn * g.b_cs) : 0.f;
+    }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m, k;
+      if (a_kfast) { k = tid & 31; m = (tid >> 5) + 8 * i; } else { m = tid & 63; k = (tid >> 6) + 4 * i; }
+      As[m][k] = __float2bfloat16_rn(ra[i]);
+      int n, kb;
+      if (b_nfast) { n = tid & 63; kb = (tid >> 6) + 4 * i; } else { kb = tid & 31; n = (tid >> 5) + 8 * i; }
+      Bs[n][kb] = __float2bfloat16_rn(rb[i]);
+    }
+  };
+  if (m0 < g.M) {
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += TBK) {
+      stage();
+      __syncthreads();
+      if (k0 + TBK < K) fetch(k0 + TBK);
+#pragma unroll
+      for (int kk = 0; kk < TBK; kk += 16) {
+        uint32_t af[2][4], bfr[2][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const bf16* ap = &As[wm + 16 * i + gq][kk + 2 * tq];
+          af[i][0] = *reinterpret_cast<const uint32_t*>(ap);
+          af[i][1] = *reinterpret_cast<const uint32_t*>(ap + 8 * TPITCH);
+          af[i][2] = *reinterpret_cast<const uint32_t*>(ap + 8);
+          af[i][3] = *reinterpret_cast<const uint32_t*>(ap + 8 * TPITCH + 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const bf16* bp = &Bs[wn + 8 * j + gq][kk + 2 * tq];
+          bfr[j][0] = *reinterpret_cast<const uint32_t*>(bp);
+          bfr[j][1] = *reinterpret_cast<const uint32_t*>(bp + 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) mma_bf16_16816(acc[i][j], af[i], bfr[j]);
+      }
+      __syncthreads();
+    }
+  }
+  if (m0 >= g.M) return;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int m = m0 + wm + 16 * i + gq + (r >> 1) * 8, n = n0 + wn + 8 * j + 2 * tq + (r & 1);
+        if (m >= g.M || n >= g.N) continue;
+        TC* c = C + (long)m * g.c_rs + (long)n * g.c_cs;
+        float v = (m < M) ? g.alpha * acc[i][j][r] : 0.f;
+        if (g.accumulate) v += ldf<TC>(c);
+        stf<TC>(c, v);
+      }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // FastAttention backward pieces (fast_attention.py:29-92 with the pre-scale of :155-157)
 // ---------------------------------------------------------------------------------------------------------------
@@ -566,25 +667,66 @@ __global__ void moe_group_counts_kernel(const int* __restrict__ idx, long N, int
 // ---------------------------------------------------------------------------------------------------------------
 // elementwise
 // ---------------------------------------------------------------------------------------------------------------
+// 16-byte vectors: 8 bf16 / 4 fp32 per thread (the scalar versions moved 2 bytes per thread: 37 ms of a 400 ms step)
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec16<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+__device__ __forceinline__ float act_f(float p, int act) { return act == MDM_ACT_GELU ? gelu_erf(p) : silu_f(p); }
+__device__ __forceinline__ float act_df(float p, int act) {
+  if (act == MDM_ACT_GELU) {
+    const float cdf = 0.5f * (1.0f + erff(p * 0.70710678118654752440f));
+    return cdf + p * 0.3989422804014327f * expf(-0.5f * p * p);
+  }
+  const float sg = 1.f / (1.f + expf(-p));
+  return sg * (1.f + p * (1.f - sg));
+}
 template <typename T>
 __global__ void act_fwd_kernel(const T* __restrict__ pre, long n, int act, T* __restrict__ out) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) stf<T>(out + i, act == MDM_ACT_GELU ? gelu_erf(ldf<T>(pre + i)) : silu_f(ldf<T>(pre + i)));
+  constexpr int V = Vec16<T>::N;
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (i + V <= n) {
+    float v[V];
+    Vec16<T>::load(pre + i, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = act_f(v[j], act);
+    Vec16<T>::store(out + i, v);
+  } else {
+    for (long j = i; j < n; ++j) stf<T>(out + j, act_f(ldf<T>(pre + j), act));
+  }
 }
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ pre, const T* __restrict__ dy, long n, int act, T* __restrict__ dx) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float p = ldf<T>(pre + i);
-  float d;
-  if (act == MDM_ACT_GELU) {
-    const float cdf = 0.5f * (1.0f + erff(p * 0.70710678118654752440f));
-    d = cdf + p * 0.3989422804014327f * expf(-0.5f * p * p);
+  constexpr int V = Vec16<T>::N;
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (i + V <= n) {
+    float p[V], g[V];
+    Vec16<T>::load(pre + i, p);
+    Vec16<T>::load(dy + i, g);
+#pragma unroll
+    for (int j = 0; j < V; ++j) g[j] *= act_df(p[j], act);
+    Vec16<T>::store(dx + i, g);
   } else {
-    const float sg = 1.f / (1.f + expf(-p));
-    d = sg * (1.f + p * (1.f - sg));
+    for (long j = i; j < n; ++j) stf<T>(dx + j, ldf<T>(dy + j) * act_df(ldf<T>(pre + j), act));
   }
-  stf<T>(dx + i, ldf<T>(dy + i) * d);
 }
 template <typename TX, typename TY, typename TO>
 __global__ void axpby_kernel(const TX* __restrict__ x, float a, const TY* __restrict__ y, float b, long n, TO* __restrict__ out) {
@@ -656,6 +798,42 @@ __global__ void colsum_prod_kernel(const float* __restrict__ a, const float* __r
     part[(long)blockIdx.y * Cc + c] = t;
   }
 }
+// 64 x 64 tiles, two elements per access on both sides (C, ld and Ks even): the 32 x 32 scalar version moved 2 bytes per
+// thread per access (38 ms of a 400 ms training step)
+template <typename T> struct Pair;
+template <> struct Pair<float> { typedef float2 V; static __device__ __forceinline__ float2 mk(float a, float b) { return make_float2(a, b); }
+  static __device__ __forceinline__ float lo(float2 v) { return v.x; } static __device__ __forceinline__ float hi(float2 v) { return v.y; } };
+template <> struct Pair<bf16> { typedef __nv_bfloat162 V; static __device__ __forceinline__ __nv_bfloat162 mk(float a, float b) { return __floats2bfloat162_rn(a, b); }
+  static __device__ __forceinline__ float lo(__nv_bfloat162 v) { return __low2float(v); } static __device__ __forceinline__ float hi(__nv_bfloat162 v) { return __high2float(v); } };
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_split_pair_kernel(const T* __restrict__ src, long M, int Cc, long ld, int Ks, T* __restrict__ dst) {
+  typedef typename Pair<T>::V V2;
+  __shared__ float tile[64][65];
+  const int s = blockIdx.z;
+  const int ml0 = blockIdx.x * 64;                               // row inside the slab
+  const long m0 = (long)s * Ks + ml0;
+  const int c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = ty + 8 * i, c = c0 + 2 * tx;
+    const long m = m0 + r;
+    float a = 0.f, b = 0.f;
+    if (m < M && ml0 + r < Ks && c < Cc) {                       // Cc even: c + 1 < Cc too
+      const V2 v = *reinterpret_cast<const V2*>(src + m * ld + c);
+      a = Pair<T>::lo(v); b = Pair<T>::hi(v);
+    }
+    tile[r][2 * tx] = a; tile[r][2 * tx + 1] = b;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = ty + 8 * i, ml = ml0 + 2 * tx;
+    if (c0 + c < Cc && ml < Ks)
+      *reinterpret_cast<V2*>(dst + ((long)s * Cc + c0 + c) * Ks + ml) = Pair<T>::mk(tile[2 * tx][c], tile[2 * tx + 1][c]);
+  }
+}
 // 32 x 32 tiled transpose with optional split in S token slabs (see misc.cu: transpose_split_kernel), any dtype
 template <typename T>
 __global__ void transpose_split_any_kernel(const T* __restrict__ src, long M, int Cc, long ld, int Ks, T* __restrict__ dst) {
@@ -679,13 +857,16 @@ __global__ void transpose_split_any_kernel(const T* __restrict__ src, long M, in
     if (c0 + c < Cc && ml < Ks) stf<T>(dst + ((long)s * Cc + c0 + c) * Ks + ml, tile[tx][c]);
   }
 }
-// out[g, c] = sum of src[r, c] over rows [seg_off[g], seg_off[g] + seg_cnt[g])
+// out[g, c] = sum of src[r, c] over rows [seg_off[g], seg_off[g] + seg_cnt[g]); blockIdx.z = row slab of the segment
+// (gridDim.z slabs -> out is [slabs, G, C] partials; one slab: the sums themselves)
 template <typename T>
 __global__ void seg_colsum_any_kernel(const T* __restrict__ src, int Cc, const int* __restrict__ seg_off,
                                       const int* __restrict__ seg_cnt, float* __restrict__ out) {
   __shared__ float red[8][33];
   const int g = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
-  const long r0 = seg_off[g], r1 = r0 + seg_cnt[g];
+  const int cnt = seg_cnt[g], per = (cnt + gridDim.z - 1) / gridDim.z;
+  const long r0 = (long)seg_off[g] + (long)blockIdx.z * per, r1 = min((long)seg_off[g] + cnt, r0 + per);
+  out += (long)blockIdx.z * gridDim.y * Cc;
   float a = 0.f;
   if (c < Cc)
     for (long r = r0 + ty; r < r1; r += 8) a += ldf<T>(src + r * Cc + c);
@@ -761,7 +942,11 @@ extern "C" MDM_API int mdm_bgemm(const MdmBgemm* g, void* stream) {
   TRY(g && g->A && g->B && g->C && g->Z1 > 0 && g->Z2 > 0 && g->M > 0 && g->N > 0 && g->K >= 0);
   dim3 grid((g->N + BT - 1) / BT, (g->M + BT - 1) / BT, g->Z1 * g->Z2);
   cudaStream_t st = ST(stream);
-#define BG(TA_, TB_, TC_) bgemm_kernel<TA_, TB_, TC_><<<grid, 256, 0, st>>>(*g)
+#define BG(TA_, TB_, TC_)                                                     \
+  do {                                                                        \
+    if (g->tensor_cores) bgemm_tc_kernel<TA_, TB_, TC_><<<grid, 256, 0, st>>>(*g); \
+    else bgemm_kernel<TA_, TB_, TC_><<<grid, 256, 0, st>>>(*g);               \
+  } while (0)
   const int key = g->a_dt * 4 + g->b_dt * 2 + g->c_dt;
   switch (key) {
     case 0: BG(float, float, float); break;
@@ -928,14 +1113,16 @@ extern "C" MDM_API int mdm_moe_wgrad_tables(const int* seg_off, const int* idx, 
 
 extern "C" MDM_API int mdm_act_fwd(const void* pre, int dt, long n, int act, void* out, void* stream) {
   TRY(pre && out && (act == MDM_ACT_GELU || act == MDM_ACT_SILU));
-  if (dt == MDM_F32) act_fwd_kernel<float><<<blocks_for(n, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(pre), n, act, reinterpret_cast<float*>(out));
-  else act_fwd_kernel<bf16><<<blocks_for(n, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(pre), n, act, reinterpret_cast<bf16*>(out));
+  if ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(out)) & 15) return MDM_ERR_ARG;   // 16-byte vectors
+  if (dt == MDM_F32) act_fwd_kernel<float><<<blocks_for(n, 256 * 4), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(pre), n, act, reinterpret_cast<float*>(out));
+  else act_fwd_kernel<bf16><<<blocks_for(n, 256 * 8), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(pre), n, act, reinterpret_cast<bf16*>(out));
   DONE();
 }
 extern "C" MDM_API int mdm_act_bwd(const void* pre, const void* dy, int dt, long n, int act, void* dx, void* stream) {
   TRY(pre && dy && dx && (act == MDM_ACT_GELU || act == MDM_ACT_SILU));
-  if (dt == MDM_F32) act_bwd_kernel<float><<<blocks_for(n, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(pre), reinterpret_cast<const float*>(dy), n, act, reinterpret_cast<float*>(dx));
-  else act_bwd_kernel<bf16><<<blocks_for(n, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(pre), reinterpret_cast<const bf16*>(dy), n, act, reinterpret_cast<bf16*>(dx));
+  if ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) return MDM_ERR_ARG;
+  if (dt == MDM_F32) act_bwd_kernel<float><<<blocks_for(n, 256 * 4), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(pre), reinterpret_cast<const float*>(dy), n, act, reinterpret_cast<float*>(dx));
+  else act_bwd_kernel<bf16><<<blocks_for(n, 256 * 8), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(pre), reinterpret_cast<const bf16*>(dy), n, act, reinterpret_cast<bf16*>(dx));
   DONE();
 }
 extern "C" MDM_API int mdm_axpby(const void* x, int x_dt, float a, const void* y, int y_dt, float b, long n, void* out, int out_dt,
@@ -989,15 +1176,22 @@ extern "C" MDM_API int mdm_colsum_prod(const float* a, const float* b, const flo
 }
 extern "C" MDM_API int mdm_transpose_split(const void* src, int dt, long M, int C, long ld, int S, int Ks, void* dst, void* stream) {
   TRY(src && dst && S > 0 && Ks > 0);
+  const int esz = dt == MDM_F32 ? 4 : 2;
+  if (!((C | Ks) & 1) && !(ld & 1) && !((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & (2 * esz - 1))) {
+    dim3 g2((Ks + 63) / 64, (C + 63) / 64, S);
+    if (dt == MDM_F32) transpose_split_pair_kernel<float><<<g2, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(src), M, C, ld, Ks, reinterpret_cast<float*>(dst));
+    else transpose_split_pair_kernel<bf16><<<g2, 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), M, C, ld, Ks, reinterpret_cast<bf16*>(dst));
+    DONE();
+  }
   dim3 grid((Ks + 31) / 32, (C + 31) / 32, S);
   if (dt == MDM_F32) transpose_split_any_kernel<float><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(src), M, C, ld, Ks, reinterpret_cast<float*>(dst));
   else transpose_split_any_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), M, C, ld, Ks, reinterpret_cast<bf16*>(dst));
   DONE();
 }
-extern "C" MDM_API int mdm_seg_colsum(const void* src, int dt, int C, const int* seg_off, const int* seg_cnt, int G, float* out,
-                                      void* stream) {
-  TRY(src && seg_off && seg_cnt && out);
-  dim3 grid((C + 31) / 32, G);
+extern "C" MDM_API int mdm_seg_colsum(const void* src, int dt, int C, const int* seg_off, const int* seg_cnt, int G, int slabs,
+                                      float* out, void* stream) {
+  TRY(src && seg_off && seg_cnt && out && slabs >= 1);
+  dim3 grid((C + 31) / 32, G, slabs);
   if (dt == MDM_F32) seg_colsum_any_kernel<float><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(src), C, seg_off, seg_cnt, out);
   else seg_colsum_any_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), C, seg_off, seg_cnt, out);
   DONE();

@@ -17,9 +17,14 @@ def _chk(st, what):
     _lib.check(st, what)
 
 
-def bgemm(A, a_str, B, b_str, Cm, c_str, Z1, Z2, M, N, K, alpha=1.0, accumulate=False):
-    """C[z][m][n] (+)= alpha * sum_k A[z][m][k] B[z][k][n]; *_str = (z1, z2, row, col) element strides."""
+TENSOR_CORES = [False]      # set by the bf16 training path (fastattn_bwd & co. pass tc=...): see csrc/train.cu bgemm_tc_kernel
+
+
+def bgemm(A, a_str, B, b_str, Cm, c_str, Z1, Z2, M, N, K, alpha=1.0, accumulate=False, tc=None):
+    """C[z][m][n] (+)= alpha * sum_k A[z][m][k] B[z][k][n]; *_str = (z1, z2, row, col) element strides.
+    tc: True = bf16 tensor-core flavour (operands rounded to bf16 on the fly), False = fp32 FMA, None = TENSOR_CORES[0]."""
     g = _lib.Bgemm()
+    g.tensor_cores = 1 if (TENSOR_CORES[0] if tc is None else tc) else 0
     g.A, g.a_dt = A.data_ptr(), _dt(A)
     g.a_z1, g.a_z2, g.a_rs, g.a_cs = a_str
     g.B, g.b_dt = B.data_ptr(), _dt(B)
@@ -171,6 +176,7 @@ def fastattn_bwd(qkv, P, norm_w, norm_b, length, shift, B, H, T, hd, dout, g_nor
     qkv's type (with the reference's [-1, 1] gradient clamp); adds the shared LayerNorm(hd) gradients to g_norm = (dw, db)."""
     lib = _lib.load()
     dev = qkv.device
+    TENSOR_CORES[0] = qkv.dtype == bf16
     M = P.shape[1]
     BH, st = B * H, _stream
     z = lambda *s: torch.empty(*s, dtype=f32, device=dev)
@@ -225,6 +231,7 @@ def lincross_apply_bwd(q, ctx, B, T, H, hd, dy):
     y = softmax_hd(q) @ ctx[b, h].  Returns (dq [N, D] in q's type, dctx [B, H, hd, hd] fp32)."""
     lib = _lib.load()
     dev, D = q.device, H * hd
+    TENSOR_CORES[0] = q.dtype == bf16
     Pm = torch.empty(B * H, T, hd, dtype=f32, device=dev)
     _chk(lib.mdm_head_softmax(q.data_ptr(), _dt(q), B, H, T, hd, Pm.data_ptr(), _stream()), "mdm_head_softmax")
     hm = (H * T * hd, T * hd, hd, 1)
@@ -244,6 +251,7 @@ def lincross_ctx_bwd(k, v, nt, B, Nt, H, hd, dctx):
     [B*Nt, D] in k's type."""
     lib = _lib.load()
     dev, D = k.device, H * hd
+    TENSOR_CORES[0] = k.dtype == bf16
     Ks = torch.empty(B, Nt, D, dtype=f32, device=dev)
     _chk(lib.mdm_col_softmax(k.data_ptr(), _dt(k), _ptr(nt), B, Nt, D, Ks.data_ptr(), _stream()), "mdm_col_softmax")
     txt = (Nt * D, hd, D, 1)
@@ -262,6 +270,7 @@ def softmax_cross_bwd(q, k, v, nt, B, T, Nt, H, hd, do):
     o = softmax_n(q k^T hd^-0.5) v.  Returns (dq [N, D], dk, dv [B*Nt, D]) in the operand type."""
     lib = _lib.load()
     dev, D = q.device, H * hd
+    TENSOR_CORES[0] = q.dtype == bf16
     scale = hd ** -0.5
     tok, txt = (T * D, hd, D, 1), (Nt * D, hd, D, 1)
     sm = (H * T * Nt, T * Nt, Nt, 1)
@@ -344,12 +353,13 @@ def expert_ffn_bwd(xp, pre, hp, W1t, W2t, dz, seg_off, idx, N, NB, E, tiles_up, 
         axpby(part, 1.0, g_w, 1.0, g_w)
     wgrad(dz, hp, D, F, tk_dn, mt_dn, g_w2)
     wgrad(d_pre, xp, F, D, tk_up, mt_up, g_w1)
-    db2 = torch.empty(G, D, dtype=f32, device=dev)
-    db1 = torch.empty(G, F, dtype=f32, device=dev)
-    _chk(lib.mdm_seg_colsum(dz.data_ptr(), _dt(dz), D, seg_off.data_ptr(), seg_cnt.data_ptr(), G, db2.data_ptr(), _stream()), "mdm_seg_colsum")
-    _chk(lib.mdm_seg_colsum(d_pre.data_ptr(), _dt(d_pre), F, seg_off.data_ptr(), seg_cnt.data_ptr(), G, db1.data_ptr(), _stream()), "mdm_seg_colsum")
-    axpby(db2.view(-1), 1.0, g_b2, 1.0, g_b2)
-    axpby(db1.view(-1), 1.0, g_b1, 1.0, g_b1)
+    SL = 16                                                    # row slabs per segment: [SL, G, C] partials, summed in a fixed order
+    pb2 = torch.empty(SL, G, D, dtype=f32, device=dev)
+    pb1 = torch.empty(SL, G, F, dtype=f32, device=dev)
+    _chk(lib.mdm_seg_colsum(dz.data_ptr(), _dt(dz), D, seg_off.data_ptr(), seg_cnt.data_ptr(), G, SL, pb2.data_ptr(), _stream()), "mdm_seg_colsum")
+    _chk(lib.mdm_seg_colsum(d_pre.data_ptr(), _dt(d_pre), F, seg_off.data_ptr(), seg_cnt.data_ptr(), G, SL, pb1.data_ptr(), _stream()), "mdm_seg_colsum")
+    sum_partials(pb2, SL, G * D, g_b2)
+    sum_partials(pb1, SL, G * F, g_b1)
     return d_xp
 
 

@@ -80,3 +80,9 @@ def test_model_with_expert_parallelism_is_bit_identical(world):
 def test_sharded_cfg_sampling_equals_single_gpu_bit_for_bit(world):
     """parallel.sample_dp on the real model: N-rank sharded CFG sampling == the unsharded loop, bit for bit."""
     _run_workers("dp_model_worker.py", world, 29700 + world, 900, "DP_MODEL_OK")
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_data_parallel_training_keeps_replicas_identical(world):
+    """DDPMTrainer.update with torch.distributed initialised: flat gradient all-reduce (average) before clip + Adam."""
+    _run_workers("dp_train_worker.py", world, 29800 + world, 600, "DP_TRAIN_OK")

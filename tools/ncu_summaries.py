@@ -2,6 +2,9 @@
 
   python tools/ncu_summaries.py shares  gpurun_out/launches_X.csv  profiles/launch_shares_X.csv  "<command>"
   python tools/ncu_summaries.py metrics gpurun_out/Y.ncu-rep       profiles/Y_ncu.txt            "<command>"
+  python tools/ncu_summaries.py side    gpurun_out/expert_ffn.ncu-rep profiles/expert_ffn_ncu_latest.json "<command>"
+      (the roofline side-data bench.py attaches to its line: DRAM traffic + tensor-pipe utilisation of the two grouped
+       expert GEMMs, tagged with the commit the capture was taken at)
 """
 import csv, gzip, io, re, subprocess, sys
 
@@ -56,5 +59,28 @@ def metrics(src, dst, cmd):
                     f.write("  %-78s %s %s\n" % (short, row[i], units[i]))
 
 
+def side(src, dst, cmd):
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(out)))
+    head, body = rd[0], rd[2:]
+    col = lambda name: next(i for i, h in enumerate(head) if h.endswith(name))
+    num = lambda v: float(v.replace(",", ""))
+    rows = []
+    for row in body[:2]:                      # the up- and the down-projection launch of one expert FFN
+        rows.append({"kernel": row[head.index("Kernel Name")][:60],
+                     "dram_bytes": num(row[col("dram__bytes_read.sum")]) + num(row[col("dram__bytes_write.sum")]),
+                     "dram_unit": rd[1][col("dram__bytes_read.sum")],
+                     "tensor_pipe_pct": num(row[col("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")]),
+                     "duration": num(row[col("gpu__time_duration.sum")]), "duration_unit": rd[1][col("gpu__time_duration.sum")]})
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    json.dump({"commit": commit, "source": dst.replace(".json", ".txt") + " (ncu --set full, " + cmd + ")",
+               "traffic": sum(r["dram_bytes"] * scale.get(r["dram_unit"], 1.0) for r in rows),
+               "tensor_pipe_active_pct": {"up": rows[0]["tensor_pipe_pct"], "down": rows[1]["tensor_pipe_pct"],
+                                          "source": "ncu sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"},
+               "launches": rows}, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"shares": shares, "metrics": metrics}[sys.argv[1]](*sys.argv[2:5])
+    {"shares": shares, "metrics": metrics, "side": side}[sys.argv[1]](*sys.argv[2:5])
