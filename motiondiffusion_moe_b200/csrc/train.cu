@@ -308,12 +308,12 @@ fa_out_bwd_kernel(float* __restrict__ o, const float* __restrict__ qp, const flo
                   float* __restrict__ dden, float* __restrict__ part) {
   constexpr int W = 32 * VPT;
   __shared__ float red[8 * W];
-  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);       // head-major row (b, h, t)
   const int lane = threadIdx.x & 31;
   float acc[2][VPT];
 #pragma unroll
   for (int i = 0; i < VPT; ++i) acc[0][i] = acc[1][i] = 0.f;
-  if (r < (long)B * H * Tn) {
+  // capped grid, fixed row -> CTA assignment: one partial per CTA (deterministic), a few thousand instead of rows / 8
+  for (long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5); r < (long)B * H * Tn; r += (long)gridDim.x * 8) {
     const int t = (int)(r % Tn);
     const long bh = r / Tn;
     const int h = (int)(bh % H), b = (int)(bh / H);
@@ -360,12 +360,11 @@ fa_prep_bwd_kernel(const T* __restrict__ qkv, const float* __restrict__ nw, cons
                    T* __restrict__ dqkv, float* __restrict__ part) {
   constexpr int W = 32 * VPT;
   __shared__ float red[8 * W];
-  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);       // (token, head)
   const int lane = threadIdx.x & 31;
   float acc[2][VPT];
 #pragma unroll
   for (int i = 0; i < VPT; ++i) acc[0][i] = acc[1][i] = 0.f;
-  if (r < (long)B * Tn * H) {
+  for (long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5); r < (long)B * Tn * H; r += (long)gridDim.x * 8) {   // (token, head)
     const long tok = r / H;
     const int h = (int)(r - tok * H);
     const int b = (int)(tok / Tn), t = (int)(tok - (long)b * Tn);
@@ -983,7 +982,7 @@ extern "C" MDM_API int mdm_fa_feat(const float* uq, const float* uk, const int64
 extern "C" MDM_API int mdm_fa_out_bwd(float* o, const float* qp, const float* kp, const void* dout, int dt, const float* nw,
                                       int B, int H, int T, int hd, float* dden, float* part, int* n_parts, void* stream) {
   TRY(n_parts);
-  const unsigned grid = blocks_for((long)B * H * T, 8);
+  const unsigned grid = min(blocks_for((long)B * H * T, 8), 2048u);
   *n_parts = (int)grid;
   if (!o) return MDM_OK;                                 // size query
   TRY(qp && kp && dout && nw && dden && part);
@@ -1004,7 +1003,7 @@ extern "C" MDM_API int mdm_fa_prep_bwd(const void* qkv, int dt, const float* nw,
                                        const float* dqh, const float* dkh, const float* dvn, void* dqkv, float* part,
                                        int* n_parts, void* stream) {
   TRY(n_parts);
-  const unsigned grid = blocks_for((long)B * T * H, 8);
+  const unsigned grid = min(blocks_for((long)B * T * H, 8), 2048u);
   *n_parts = (int)grid;
   if (!qkv) return MDM_OK;
   TRY(nw && nb && dqh && dkh && dvn && dqkv && part);

@@ -61,11 +61,25 @@ class DDPMTrainer(object):
         self._model().eval()
 
     def save(self, file_name, ep, total_it):                                               # :260-275
-        save_reference_checkpoint(self._model(), file_name, ep=ep, total_it=total_it)
+        opt_state = None
+        if self.engine is not None:     # Adam moments in the flat layout of TrainEngine (the reference stores torch's opt.state_dict())
+            opt_state = {"mdm_b200_flat_adam": True, "step": self.engine.step_count, "offset": dict(self.engine.offset),
+                         "exp_avg": self.engine.exp_avg.cpu(), "exp_avg_sq": self.engine.exp_avg_sq.cpu()}
+        save_reference_checkpoint(self._model(), file_name, ep=ep, total_it=total_it, opt_state=opt_state)
 
     def load(self, model_dir):                                                             # :277-289
-        ep, total_it, _, _ = load_reference_checkpoint(self._model(), model_dir, map_location="cpu")
-        self._model().to(self.device)
+        import torch as _t
+        ckpt = _t.load(model_dir, map_location="cpu", weights_only=False) if not isinstance(model_dir, dict) else model_dir
+        ep, total_it, _, _ = load_reference_checkpoint(self._model(), ckpt, map_location="cpu")
+        if self.engine is None:
+            self._model().to(self.device)
+        else:                            # parameters are views of the engine's flat buffer: loaded in place; re-derive the mirrors
+            opt = ckpt.get("opt_encoder") or {}
+            if opt.get("mdm_b200_flat_adam") and opt.get("offset") == self.engine.offset:
+                self.engine.exp_avg.copy_(opt["exp_avg"])
+                self.engine.exp_avg_sq.copy_(opt["exp_avg_sq"])
+                self.engine.step_count = int(opt["step"])
+            self.engine.refresh()
         return ep, total_it
 
     def generate_batch(self, caption, m_lens, dim_pose):                                   # :145-174

@@ -34,10 +34,17 @@ def main():
     for it in range(2):
         y0 = ref(x, t, length, None, xf_proj, xf_out)
         y1 = epn(x, t, length, None, xf_proj, xf_out)
-        ok &= torch.equal(y0, y1)
-        ok &= all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(ref.last_routing, epn.last_routing))
+        same_y = torch.equal(y0, y1)
+        same_r = all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(ref.last_routing, epn.last_routing))
+        if not (same_y and same_r):
+            print("rank %d forward %d: outputs equal %s (rel %.3e), routing equal %s" %
+                  (rank, it, same_y, ((y0 - y1).norm() / y0.norm()).item(), same_r), flush=True)
+        ok &= same_y and same_r
     sd0, sd1 = ref.state_dict(), epn.state_dict()
-    ok &= all(torch.equal(sd0[k], sd1[k]) for k in sd0 if "expert_usage" in k)
+    same_c = all(torch.equal(sd0[k], sd1[k]) for k in sd0 if "expert_usage" in k)
+    if not same_c:
+        print("rank %d: usage counters differ" % rank, flush=True)
+    ok &= same_c
     for ep in epn._ep_inst.values():
         ep.check_health()
     # CFG sampling steps with the step captured in a CUDA graph
@@ -53,6 +60,8 @@ def main():
     for net in (ref, epn):
         outs.append(d.p_sample_loop_with_cfg(net, (B, T, cfg.input_feats), noise=x_T, clip_denoised=False, model_kwargs=kw,
                                              cfg_scale=7.5, num_steps=8, step_noise=lambda ts: noises[999 - ts]))
+    if not torch.equal(outs[0], outs[1]):
+        print("rank %d: graph-captured CFG steps differ (rel %.3e)" % (rank, ((outs[0] - outs[1]).norm() / outs[0].norm()).item()), flush=True)
     ok &= torch.equal(outs[0], outs[1])
     for ep in epn._ep_inst.values():
         ep.check_health()
