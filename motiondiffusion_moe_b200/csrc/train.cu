@@ -11,6 +11,7 @@
 // All kernels take fp32 or bf16 activations (MDM_F32 / MDM_BF16) and accumulate in fp32; parameter gradients are
 // deterministic (fixed-order partial sums, no float atomics).
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -177,28 +178,137 @@ bgemm_tc_kernel(const MdmBgemm g) {
   const bool a_kfast = g.a_cs == 1, b_nfast = g.b_cs == 1;
   float acc[2][2][4] = {};
   float ra[8], rb[8];                                           // 64 x 32 elements / 256 threads = 8 each
+  // Loads: 4 consecutive elements of the operand's contiguous dimension per access when strides / alignment allow
+  // (every product of the attention backward does: row pitches and batch strides are multiples of 4 elements);
+  // element by element otherwise.  A tile = 64 (m) x 32 (k), B tile = 32 (k) x 64 (n).
+  constexpr int VA = 16 / sizeof(TA) >= 4 ? 4 : 1, VB = 16 / sizeof(TB) >= 4 ? 4 : 1;
+  auto al = [](const void* p, long a, long b, long c, int esz) {
+    return ((reinterpret_cast<uintptr_t>(p) | (uintptr_t)(a * esz) | (uintptr_t)(b * esz) | (uintptr_t)(c * esz)) & (4 * esz - 1)) == 0;
+  };
+  const bool a_vec = VA == 4 && (a_kfast ? al(g.A, g.a_z1, g.a_z2, g.a_rs, sizeof(TA)) : (g.a_rs == 1 && al(g.A, g.a_z1, g.a_z2, g.a_cs, sizeof(TA))));
+  const bool b_vec = VB == 4 && (b_nfast ? al(g.B, g.b_z1, g.b_z2, g.b_rs, sizeof(TB)) : (g.b_rs == 1 && al(g.B, g.b_z1, g.b_z2, g.b_cs, sizeof(TB))));
+  auto ld4 = [](const auto* p, float (&v)[4]) {
+    typedef typename std::remove_cv<typename std::remove_pointer<decltype(p)>::type>::type E;
+    if constexpr (sizeof(E) == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+      const uint2 t = *reinterpret_cast<const uint2*>(p);
+      const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&t.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+      v[0] = __low2float(lo); v[1] = __high2float(lo); v[2] = __low2float(hi); v[3] = __high2float(hi);
+    }
+  };
+  // index maps: (i-th access of this thread) -> (slow index, first fast index); vector form covers 4 fast indices
   auto fetch = [&](int k0) {
+    if (a_vec) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int m, k;
-      if (a_kfast) { k = tid & 31; m = (tid >> 5) + 8 * i; } else { m = tid & 63; k = (tid >> 6) + 4 * i; }
-      const int gm = m0 + m, gk = k0 + k;
-      ra[i] = (gm < M && gk < K) ? ldf<TA>(A + (long)gm * g.a_rs + (long)gk * g.a_cs) : 0.f;
-      int n, kb;
-      if (b_nfast) { n = tid & 63; kb = (tid >> 6) + 4 * i; } else { kb = tid & 31; n = (tid >> 5) + 8 * i; }
-      const int gn = n0 + n, gkb = k0 + kb;
-      rb[i] = (gn < g.N && gkb < K) ? ldf<TB>(B + (long)gkb * g.b_rs + (long)gn * g.b_cs) : 0.f;
+      for (int i = 0; i < 2; ++i) {
+        const int q = tid + 256 * i;                            // 512 vectors
+        float v[4];
+        if (a_kfast) {                                          // 8 vectors per row of 32 k
+          const int m = q >> 3, k = (q & 7) * 4, gm = m0 + m, gk = k0 + k;
+          const TA* p = A + (long)gm * g.a_rs + gk;
+          if (gm < M && gk + 3 < K) ld4(p, v);
+          else
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = (gm < M && gk + e < K) ? ldf<TA>(p + e) : 0.f;
+        } else {                                                // m fast: 16 vectors per k row of 64 m
+          const int k = q >> 4, m = (q & 15) * 4, gm = m0 + m, gk = k0 + k;
+          const TA* p = A + (long)gk * g.a_cs + gm;
+          if (gk < K && gm + 3 < M) ld4(p, v);
+          else
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = (gk < K && gm + e < M) ? ldf<TA>(p + e) : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ra[4 * i + e] = v[e];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int m, k;
+        if (a_kfast) { k = tid & 31; m = (tid >> 5) + 8 * i; } else { m = tid & 63; k = (tid >> 6) + 4 * i; }
+        const int gm = m0 + m, gk = k0 + k;
+        ra[i] = (gm < M && gk < K) ? ldf<TA>(A + (long)gm * g.a_rs + (long)gk * g.a_cs) : 0.f;
+      }
+    }
+    if (b_vec) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = tid + 256 * i;
+        float v[4];
+        if (b_nfast) {                                          // 16 vectors per k row of 64 n
+          const int k = q >> 4, n = (q & 15) * 4, gn = n0 + n, gk = k0 + k;
+          const TB* p = B + (long)gk * g.b_rs + gn;
+          if (gk < K && gn + 3 < g.N) ld4(p, v);
+          else
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = (gk < K && gn + e < g.N) ? ldf<TB>(p + e) : 0.f;
+        } else {                                                // k fast: 8 vectors per n row of 32 k
+          const int n = q >> 3, k = (q & 7) * 4, gn = n0 + n, gk = k0 + k;
+          const TB* p = B + (long)gn * g.b_cs + gk;
+          if (gn < g.N && gk + 3 < K) ld4(p, v);
+          else
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = (gn < g.N && gk + e < K) ? ldf<TB>(p + e) : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rb[4 * i + e] = v[e];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int n, kb;
+        if (b_nfast) { n = tid & 63; kb = (tid >> 6) + 4 * i; } else { kb = tid & 31; n = (tid >> 5) + 8 * i; }
+        const int gn = n0 + n, gkb = k0 + kb;
+        rb[i] = (gn < g.N && gkb < K) ? ldf<TB>(B + (long)gkb * g.b_rs + (long)gn * g.b_cs) : 0.f;
+      }
     }
   };
   auto stage = [&]() {
+    if (a_vec) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int m, k;
-      if (a_kfast) { k = tid & 31; m = (tid >> 5) + 8 * i; } else { m = tid & 63; k = (tid >> 6) + 4 * i; }
-      As[m][k] = __float2bfloat16_rn(ra[i]);
-      int n, kb;
-      if (b_nfast) { n = tid & 63; kb = (tid >> 6) + 4 * i; } else { kb = tid & 31; n = (tid >> 5) + 8 * i; }
-      Bs[n][kb] = __float2bfloat16_rn(rb[i]);
+      for (int i = 0; i < 2; ++i) {
+        const int q = tid + 256 * i;
+        if (a_kfast) {
+          const int m = q >> 3, k = (q & 7) * 4;
+          *reinterpret_cast<__nv_bfloat162*>(&As[m][k]) = __floats2bfloat162_rn(ra[4 * i], ra[4 * i + 1]);
+          *reinterpret_cast<__nv_bfloat162*>(&As[m][k + 2]) = __floats2bfloat162_rn(ra[4 * i + 2], ra[4 * i + 3]);
+        } else {
+          const int k = q >> 4, m = (q & 15) * 4;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) As[m + e][k] = __float2bfloat16_rn(ra[4 * i + e]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int m, k;
+        if (a_kfast) { k = tid & 31; m = (tid >> 5) + 8 * i; } else { m = tid & 63; k = (tid >> 6) + 4 * i; }
+        As[m][k] = __float2bfloat16_rn(ra[i]);
+      }
+    }
+    if (b_vec) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = tid + 256 * i;
+        if (b_nfast) {
+          const int k = q >> 4, n = (q & 15) * 4;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) Bs[n + e][k] = __float2bfloat16_rn(rb[4 * i + e]);
+        } else {
+          const int n = q >> 3, k = (q & 7) * 4;
+          *reinterpret_cast<__nv_bfloat162*>(&Bs[n][k]) = __floats2bfloat162_rn(rb[4 * i], rb[4 * i + 1]);
+          *reinterpret_cast<__nv_bfloat162*>(&Bs[n][k + 2]) = __floats2bfloat162_rn(rb[4 * i + 2], rb[4 * i + 3]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int n, kb;
+        if (b_nfast) { n = tid & 63; kb = (tid >> 6) + 4 * i; } else { kb = tid & 31; n = (tid >> 5) + 8 * i; }
+        Bs[n][kb] = __float2bfloat16_rn(rb[i]);
+      }
     }
   };
   if (m0 < g.M) {

@@ -170,6 +170,12 @@ class ExpertParallelFFN:
                 d[k] = opened[h] + off
             ptrs.append(d)
         self._fill_peers(ptrs)
+        # The zero-fills of this rank's peer-visible buffers (cnt, flags, xp, ...) are asynchronous on its stream; a peer that
+        # runs ahead writes its count row / barrier flag into them through NVLink as soon as its first MoE call starts.  Make
+        # sure every rank's buffers are initialised ON THE DEVICE before any rank leaves this constructor (a host barrier
+        # alone does not order the GPUs: found with two ranks time-sliced on one GPU, where the first forward occasionally
+        # routed with a zeroed count table).
+        torch.cuda.synchronize(device)
         dist.barrier(group=group)
         return self
 
