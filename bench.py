@@ -214,7 +214,27 @@ def ncu_side_data():
         return None
 
 
+_REAL_STDOUT = [None]
+
+
+def own_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, the reference's
+    constructors): from here on fd 1 goes to stderr and the line is written to the saved descriptor by emit()."""
+    if _REAL_STDOUT[0] is None:
+        sys.stdout.flush()
+        _REAL_STDOUT[0] = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _REAL_STDOUT[0] or sys.__stdout__
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -248,13 +268,12 @@ def main():
         randomize_zero_init(net)
         k = max(1, min(args.steps, 2))
         cb = cpu_reference_leg(net.state_dict(), net.extras_state(), steps=k, warmup=1)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
-                          "n_gpus": args.gpus, "steps": k, "warmup": 1, "ms_per_step": cb["ms_per_step"],
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": {"workload": WORKLOAD, "reference_sample": cb["sample"]},
-                          "cpu_baseline": cb,
-                          "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
-                                  "d2h_bytes_per_step": 0}}))
+        emit({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+              "n_gpus": args.gpus, "steps": k, "warmup": 1, "ms_per_step": cb["ms_per_step"],
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+              "data": "synthetic", "config": {"workload": WORKLOAD, "reference_sample": cb["sample"]},
+              "cpu_baseline": cb,
+              "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     if not torch.cuda.is_available():
@@ -486,7 +505,7 @@ def main():
             line["gpu_eager_baseline"] = gpu_eager_leg(state_cpu, extras_cpu, dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_leg(state_cpu, extras_cpu, steps=1, warmup=1)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -71,11 +71,11 @@ def main(args, rank, world, local):
         net = mdm.MotionTransformer(precision="bf16", dropout=0.0, **CFG)
         B_.randomize_zero_init(net)
         cb = cpu_train_leg(net.state_dict(), net.extras_state(), batch=2, steps=max(1, min(args.steps, 2)))
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-                          "steps": max(1, min(args.steps, 2)), "warmup": 1, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": WORKLOAD, "reference_sample": cb["sample"]}, "cpu_baseline": cb,
-                          "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        B_.emit({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                 "steps": max(1, min(args.steps, 2)), "warmup": 1, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                 "config": {"workload": WORKLOAD, "reference_sample": cb["sample"]}, "cpu_baseline": cb,
+                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -176,7 +176,7 @@ def main(args, rank, world, local):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_train_leg(state_cpu, extras_cpu, batch=2, steps=1)
-        print(json.dumps(line))
+        B_.emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

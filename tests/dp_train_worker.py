@@ -41,11 +41,12 @@ def main():
     eng.backward(tr._saved, T.masked_mse_grad(tr.fake_noise.contiguous(), tr.real_noise.contiguous(), tr.cur_len.contiguous()))
     local = eng.grad.clone()
     tr._all_reduce_gradients()
-    mine = local.cpu()
+    gather_dev = "cpu" if shared else dev                     # gloo (shared GPU) gathers host tensors, NCCL device tensors
+    mine = local.to(gather_dev)
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine)
     want = torch.stack(parts).sum(0) / world
-    ok &= bool(torch.allclose(eng.grad.cpu(), want, rtol=1e-5, atol=1e-8))
+    ok &= bool(torch.allclose(eng.grad.to(gather_dev), want, rtol=1e-5, atol=1e-8))
     ok &= not torch.equal(local, eng.grad)
     # (2) replicas stay bit-identical through updates
     for it in range(3):
@@ -54,7 +55,7 @@ def main():
         tr.forward((caps, motions, [8, 6, 4]))
         logs = tr.update()
         ok &= bool(np.isfinite(logs["loss_total"]))
-    flat = eng.flat.cpu()
+    flat = eng.flat.to(gather_dev)
     parts = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(parts, flat)
     ok &= all(torch.equal(parts[0], q) for q in parts[1:])
