@@ -258,6 +258,7 @@ def main():
 
     if args.workload == "train":
         import bench_train
+        bench_train.B_._REAL_STDOUT = _REAL_STDOUT      # `import bench` inside bench_train is a second module instance: share the real stdout
         return bench_train.main(args, rank, world, local)
 
     if args.impl == "reference":

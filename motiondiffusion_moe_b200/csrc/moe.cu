@@ -107,7 +107,13 @@ moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restr
   float* lw = gw + G * D;       // [NB][D] LayerNorm weight
   float* lb = lw + NB * D;      // [NB][D] LayerNorm bias
   constexpr int TPW = TOK_PER_BLK / GATE_WARPS;   // tokens per warp
-  constexpr bool PREFETCH = GATE_WARPS == 16;     // (the 8-warp shape has no registers to spare)
+  constexpr bool PREFETCH = GATE_WARPS == 16;     // rows of the next token pair prefetched into registers
+  // The 8-warp shape (two blocks per SM, 128 registers per thread) has no registers for that: its next token pair
+  // arrives by cp.async in a per-warp shared-memory staging buffer (2 stages x 2 tokens x D floats) while the current
+  // pair is evaluated, every lane copying exactly the 16-byte chunks it reads back.  Same arithmetic, same bits; the
+  // global-load latency (the kernel ran at 1.1 TB/s of its 51 MB, 17 % warps active) leaves the critical path.
+  constexpr bool ASYNC = GATE_WARPS == 8;
+  float* my_stg = lb + NB * D + (threadIdx.x >> 5) * (2 * TT * D);
   __shared__ int w_all[GATE_WARPS][MAX_G], w_top1[GATE_WARPS][MAX_G];
   __shared__ float w_imp[GATE_WARPS][MAX_G];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,7 +125,23 @@ moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restr
       load_row<VPT, float>(x + (tok + 1 < N ? tok + 1 : tok) * D, lane, nxt[1]);
     }
   };
+  auto issue = [&](long tok, int stage) {
+    if (tok < N) {
+      const float* s0 = x + tok * D;
+      const float* s1 = x + (tok + 1 < N ? tok + 1 : tok) * D;
+      float* d0 = my_stg + (stage * TT) * D;
+#pragma unroll
+      for (int j = 0; j < VPT / 4; ++j) {
+        const int o = (j * 32 + lane) * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d0 + o)), "l"(s0 + o));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d0 + D + o)), "l"(s1 + o));
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");     // always: the group count stays uniform
+  };
   if (PREFETCH) fetch(tok0);
+  if (ASYNC) issue(tok0, 0);
+  int stage = 0;
   for (int i = threadIdx.x; i < G * D / 4; i += GATE_WARPS * 32)
     reinterpret_cast<float4*>(gw)[i] = __ldg(reinterpret_cast<const float4*>(gate_w) + i);
   for (int i = threadIdx.x; i < NB * D; i += GATE_WARPS * 32) { lw[i] = ln_w[i]; lb[i] = ln_b[i]; }
@@ -132,7 +154,15 @@ moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restr
     if (tok >= N) break;
     const bool two = tok + 1 < N;
     float v[TT][VPT];
-    if (!PREFETCH) fetch(tok);
+    if (ASYNC) {
+      issue(it + TT < TPW ? tok + TT : N, stage ^ 1);         // next pair (an empty group past the end)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");    // the current pair has landed
+#pragma unroll
+      for (int t = 0; t < TT; ++t) load_row<VPT, float>(my_stg + (stage * TT + t) * D, lane, nxt[t]);
+      stage ^= 1;
+    } else if (!PREFETCH) {
+      fetch(tok);
+    }
 #pragma unroll
     for (int t = 0; t < TT; ++t)
 #pragma unroll
@@ -217,6 +247,7 @@ moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restr
       }
     }
   }
+  if (ASYNC) asm volatile("cp.async.wait_group 0;" ::: "memory");
   w_all[warp][lane] = cnt_all;
   w_top1[warp][lane] = cnt_top1;
   w_imp[warp][lane] = imp;
@@ -444,16 +475,17 @@ int launch_gate(const float* x, long N, int D, const float* ln_w, const float* l
                 cudaStream_t st, const int* forced_idx = nullptr) {
   const int nblk = (int)((N + TOK_PER_BLK - 1) / TOK_PER_BLK);
   const size_t smem = sizeof(float) * ((size_t)NB * E * D + 2 * (size_t)NB * D);
+  const size_t smem8 = smem + sizeof(float) * 8 * 2 * 2 * (size_t)D;     // + cp.async staging: 8 warps x 2 stages x 2 tokens
   if (forced_idx) {
-    if (smem > 48 * 1024 && cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB, 8, true>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (smem8 > 48 * 1024 && cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB, 8, true>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8) != cudaSuccess)
       return MDM_ERR_CUDA;
-    moe_gate_kernel<VPT, E, NB, 8, true><<<nblk, 256, smem, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
-                                                                  blk_hist, blk_imp, forced_idx);
+    moe_gate_kernel<VPT, E, NB, 8, true><<<nblk, 256, smem8, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
+                                                                   blk_hist, blk_imp, forced_idx);
     return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
   }
-  if (smem > 48 * 1024 &&
-      (cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+  if (smem8 > 48 * 1024 &&
+      (cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8) !=
            cudaSuccess ||
        cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
            cudaSuccess))
@@ -463,8 +495,8 @@ int launch_gate(const float* x, long N, int D, const float* ln_w, const float* l
     moe_gate_kernel<VPT, E, NB, 16><<<nblk, 512, smem, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
                                                              blk_hist, blk_imp);
   else
-    moe_gate_kernel<VPT, E, NB, 8><<<nblk, 256, smem, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
-                                                            blk_hist, blk_imp);
+    moe_gate_kernel<VPT, E, NB, 8><<<nblk, 256, smem8, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
+                                                             blk_hist, blk_imp);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
