@@ -172,11 +172,42 @@ class DDPMTrainer(object):
             loss_logs = self.backward_G()
             d_pred = T.masked_mse_grad(self.fake_noise.float().contiguous(), self.real_noise.float().contiguous(),
                                        self.cur_len.contiguous())
-            eng.backward(self._saved, d_pred)                    # the MoE balance loss carries no gradient
+            # the MoE balance loss carries no gradient.  Data parallel: every decoder layer's gradient bucket is
+            # all-reduced on a side stream as soon as its backward is done, overlapped with the layers still to come
+            eng.backward(self._saved, d_pred, grad_ready=self._bucket_all_reduce if self._dp_world() > 1 else None)
             self._saved = None
-            self._all_reduce_gradients()
+            self._finish_all_reduce()
             eng.optimizer_step()
         return loss_logs
+
+    def _dp_world(self):
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _bucket_all_reduce(self, ranges):
+        """Average the given ranges of the flat gradient buffer over the ranks, on a side stream, ordered after the kernels
+        that produced them (bucketed gradient all-reduce overlapped with the backward; the intended semantics of the
+        reference's DDP wrapper, tools/train.py:140-145)."""
+        import torch.distributed as dist
+        eng = self.engine
+        if not hasattr(self, "_ar_stream"):
+            self._ar_stream = torch.cuda.Stream(eng.dev)
+            self._ar_avg = dist.get_backend() == "nccl"              # gloo (tests on a shared GPU) has no AVG
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(eng.dev))
+        self._ar_stream.wait_event(ready)
+        with torch.cuda.stream(self._ar_stream):
+            for lo, hi in ranges:
+                buf = eng.grad[lo:hi]
+                if self._ar_avg:
+                    dist.all_reduce(buf, op=dist.ReduceOp.AVG)
+                else:
+                    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                    buf.mul_(1.0 / dist.get_world_size())
+
+    def _finish_all_reduce(self):
+        if hasattr(self, "_ar_stream") and self._dp_world() > 1:
+            torch.cuda.current_stream(self.engine.dev).wait_stream(self._ar_stream)
 
     def _all_reduce_gradients(self):
         """Data-parallel training (BASELINE.json configs[4] at N > 1): average the flat gradient buffer over the ranks.

@@ -67,20 +67,50 @@ class TrainEngine:
                 groups.append(["%s.moe.experts.%d.%s" % (b, e, leaf) for b in br for e in range(E)])
         return groups
 
-    @torch.no_grad()
-    def _flatten(self):
+    def layout(self):
+        """Pure host logic (no CUDA): the flat layout of the parameters.  Returns (order, offset, numel, block_ranges,
+        rest_ranges): stacked groups first (contiguous, 64-element aligned starts), then the remaining tensors; per
+        decoder layer the (at most two) contiguous ranges holding all of its parameters except the FiLM MLPs, and the ranges
+        of everything else.  block_ranges / rest_ranges are the gradient buckets of data-parallel training: a layer's bucket is
+        final as soon as that layer's backward is done, the rest at the end of the backward."""
         m = self.m
         groups = self._groups()
         grouped = {n for g in groups for n in g}
         order = [n for g in groups for n in g] + [n for n in m._param_names if n not in grouped]
         starts = {g[0] for g in groups}
-        off, self.offset = 0, {}
+        off, offset = 0, {}
         for n in order:
             if n in starts or n not in grouped:
                 off = _round_up(off, 64)
-            self.offset[n] = off
+            offset[n] = off
             off += m._t(n).numel()
-        self.numel = _round_up(off, 64)
+        numel = _round_up(off, 64)
+        block_ranges, covered = [], []
+        for blk in m.block_prefixes():
+            mine = lambda n: n.startswith(blk + ".") and ".emb_layers.1." not in n     # (the FiLM MLPs are a global group)
+            rs = []
+            for names in ([n for n in order if n in grouped and mine(n)], [n for n in order if n not in grouped and mine(n)]):
+                if names:
+                    lo = min(offset[n] for n in names)
+                    hi = max(offset[n] + m._t(n).numel() for n in names)
+                    assert not any(lo <= offset[n] < hi for n in order if not mine(n)), blk
+                    rs.append((lo, hi))
+            block_ranges.append(rs)
+            covered += rs
+        covered.sort()
+        rest_ranges, pos = [], 0
+        for lo, hi in covered:
+            if lo > pos:
+                rest_ranges.append((pos, lo))
+            pos = hi
+        if pos < numel:
+            rest_ranges.append((pos, numel))
+        return order, offset, numel, block_ranges, rest_ranges
+
+    @torch.no_grad()
+    def _flatten(self):
+        m = self.m
+        order, self.offset, self.numel, self.block_ranges, self.rest_ranges = self.layout()
         dev = self.dev
         self.flat = torch.zeros(self.numel, dtype=f32, device=dev)
         self.grad = torch.zeros(self.numel, dtype=f32, device=dev)
@@ -692,9 +722,11 @@ class TrainEngine:
         d_e1p = T.act_bwd(E["e1p"], d_e1, ACT_SILU)
         T.linear_bwd(E["e0"], None, d_e1p, dW=G("learnable_time_embed.mlp.0.weight"), db=G("learnable_time_embed.mlp.0.bias"))
 
-    def backward(self, S, d_out):
+    def backward(self, S, d_out, grad_ready=None):
         """Backward of forward_train: d_out [B, T, feats] fp32 = dLoss/d prediction.  Gradients are ACCUMULATED into the flat
-        gradient buffer (zero_grad() first)."""
+        gradient buffer (zero_grad() first).  grad_ready (optional): called with a list of (lo, hi) ranges of the flat
+        gradient buffer as soon as they are final (one decoder layer at a time, in backward order; the rest at the end):
+        the hook data-parallel training uses to all-reduce buckets while the backward is still running."""
         m, pk = self.m, self.pk
         D = m.latent_dim
         Bn, Tn = S["Bn"], S["Tn"]
@@ -728,6 +760,8 @@ class TrainEngine:
         for li in reversed(range(nl, 2 * nl)):
             if S["layers"][li] is not None:
                 cur = self._layer_bwd(li, S["layers"][li], cur, S["ctx"], S["tx"], g_film, Bpad)
+            if grad_ready is not None:
+                grad_ready(self.block_ranges[li])
         # hc = up(hla) + h   (ConvTranspose1d as a GEMM over row pairs)
         d_h = cur                                                           # gradient of h through the skip connection
         d_up = new(Nl, 2 * D)
@@ -742,6 +776,8 @@ class TrainEngine:
         for li in reversed(range(nl)):
             if S["layers"][li] is not None:
                 cur = self._layer_bwd(li, S["layers"][li], cur, S["ctx"], S["tx"], g_film, Bpad)
+            if grad_ready is not None:
+                grad_ready(self.block_ranges[li])
         # h_low = down(ha pairs): Conv1d(k=2, s=2) as a GEMM over row pairs; h = joint_embed(x) + pos
         d_lowa = new(Nl, D)
         T.axpby(cur, 1.0, None, 0.0, d_lowa)
@@ -756,6 +792,8 @@ class TrainEngine:
         G("joint_embed.weight").add_(gje[:, :Fin])
         T.colsum_into(d_h.view(Bn, Tn * D), Bn, Tn * D, G("sequence_embedding").view(-1)[:Tn * D], slabs=1)   # pos. embedding: sum over the batch
         self._embeddings_bwd(E, g_film, Bn)
+        if grad_ready is not None:
+            grad_ready(self.rest_ranges)
 
     # ------------------------------------------------------------------ optimizer
     def zero_grad(self):

@@ -48,6 +48,16 @@ def main():
     want = torch.stack(parts).sum(0) / world
     ok &= bool(torch.allclose(eng.grad.to(gather_dev), want, rtol=1e-5, atol=1e-8))
     ok &= not torch.equal(local, eng.grad)
+    # (1b) the bucketed path of update(): every layer's bucket all-reduced on a side stream while the backward runs
+    eng.zero_grad()
+    eng.backward(tr._saved, T.masked_mse_grad(tr.fake_noise.contiguous(), tr.real_noise.contiguous(), tr.cur_len.contiguous()),
+                 grad_ready=tr._bucket_all_reduce)
+    tr._finish_all_reduce()
+    torch.cuda.synchronize()
+    ok_b = bool(torch.allclose(eng.grad.to(gather_dev), want, rtol=1e-5, atol=1e-8))
+    if not ok_b and rank == 0:
+        print("bucketed all-reduce differs from the single all-reduce: max abs %.3e" % (eng.grad.to(gather_dev) - want).abs().max().item(), flush=True)
+    ok &= ok_b
     # (2) replicas stay bit-identical through updates
     for it in range(3):
         np.random.seed(10 * it + rank)

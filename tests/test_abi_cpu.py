@@ -144,7 +144,7 @@ def test_reference_checkpoint_roundtrip(tmp_path):
 
 def test_ddim_schedule_and_trainer_host_logic():
     """Host-side logic that needs no GPU: the strided DDIM schedule, the diffusion tables against the oracle's, and the
-    training half of DDPMTrainer refusing loudly."""
+    training half of DDPMTrainer refusing a CPU model loudly."""
     import types
     import motiondiffusion_moe_b200 as mdm
     from oracle import motion_oracle as mo
@@ -164,11 +164,11 @@ def test_ddim_schedule_and_trainer_host_logic():
     cfg = dict(input_feats=12, num_frames=8, latent_dim=128, ff_size=256, num_layers=1, num_heads=4, text_latent_dim=128,
                moe_num_experts=4)
     net = mdm.MotionTransformer(**cfg)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(mdm.MdmError):           # the training engine has no CPU path: a CPU model is refused loudly
         mdm.DDPMTrainer(types.SimpleNamespace(device="cpu", diffusion_steps=1000, is_train=True), net)
     tr = mdm.DDPMTrainer(types.SimpleNamespace(device="cpu", diffusion_steps=100, is_train=False), net, sampler="ddim")
     assert tr.diffusion.num_timesteps == 100 and tr.cfg_scale == 7.5
-    with pytest.raises(NotImplementedError):
-        tr.train(None)
+    with pytest.raises(RuntimeError):           # a sampling-only trainer (is_train=False) has no optimizer state
+        tr.update()
     with pytest.raises(ValueError):
         mdm.DDPMTrainer(types.SimpleNamespace(device="cpu", diffusion_steps=100, is_train=False), net, sampler="euler")

@@ -152,3 +152,35 @@ def test_ep_plan_matches_single_gpu_layout(R):
             assert seg_off[grp] == off and dest[0][grp] == off
             off += (cnt[0][grp] + 127) // 128 * 128
     assert sum(tiles) * 128 == sum((r + 127) // 128 * 128 for r in rows)
+
+
+@pytest.mark.parametrize("case", ["tiny_b3", "small_b4"])
+def test_training_gradient_buckets_partition_the_flat_buffer(case):
+    """Host logic of data-parallel training (training.TrainEngine.layout): the per-layer gradient buckets that
+    DDPMTrainer.update all-reduces while the backward is still running, plus the rest, cover the flat gradient buffer exactly
+    once; every parameter lies inside exactly one bucket; the stacked groups the kernels consume are contiguous."""
+    import motiondiffusion_moe_b200 as mdm
+    from motiondiffusion_moe_b200.training import TrainEngine
+    from oracle import cases
+    cfg, _ = cases.case_params(case)
+    net = mdm.MotionTransformer(**cfg)
+    eng = TrainEngine.__new__(TrainEngine)          # layout() is pure host logic: no CUDA device needed
+    eng.m = net
+    order, offset, numel, block_ranges, rest = eng.layout()
+    assert sorted(order) == sorted(net._param_names) and len(block_ranges) == 2 * cfg.num_layers
+    spans = sorted([r for rs in block_ranges for r in rs] + rest)
+    assert spans[0][0] == 0 and spans[-1][1] == numel
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))                # disjoint, no gaps
+    for li, blk in enumerate(net.block_prefixes()):
+        for n in order:
+            inside = [any(lo <= offset[n] and offset[n] + net._t(n).numel() <= hi for lo, hi in rs) for rs in block_ranges]
+            if n.startswith(blk + ".") and ".emb_layers.1." not in n:
+                assert inside[li] and sum(inside) == 1, n
+    for n in order:                                                             # FiLM MLPs and globals: in the rest
+        if ".emb_layers.1." in n or not n.startswith("decoder_blocks"):
+            assert any(lo <= offset[n] and offset[n] + net._t(n).numel() <= hi for lo, hi in rest), n
+    for g in eng._groups():                                                     # stacked groups are contiguous
+        o = offset[g[0]]
+        for n in g:
+            assert offset[n] == o, n
+            o += net._t(n).numel()
