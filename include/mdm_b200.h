@@ -387,6 +387,11 @@ MDM_API int mdm_fa_feat(const float* uq, const float* uk, const int64_t* length,
                         float* qp, float* kp, void* stream);
 MDM_API int mdm_fa_out_bwd(float* o, const float* qp, const float* kp, const void* dout, int dt, const float* nw, int B, int H,
                            int T, int hd, float* dden, float* part, int* n_parts, void* stream);
+/* Output stage FORWARD of the same decomposition: out[t, h, :] = LN(o / max(<qp, kp>, 1e-6)) token-major [N, H*hd].  With
+ * mdm_fa_prep / mdm_fa_feat / mdm_bgemm it forms the generic FastAttention forward for head sizes the fused kernels do not
+ * cover (hd = 256: model_size="big", models/transformer.py:188-192). */
+MDM_API int mdm_fa_out_fwd(const float* o, const float* qp, const float* kp, const float* nw, const float* nb, int B, int H, int T,
+                           int hd, void* out, int dt, void* stream);
 MDM_API int mdm_fa_feat_bwd(const float* uq, const float* uk, const float* qp, const float* kp, const float* dden, int B, int H,
                             int T, int M, float* dqp, float* dkp, void* stream);
 MDM_API int mdm_fa_prep_bwd(const void* qkv, int dt, const float* nw, const float* nb, int B, int H, int T, int hd,

@@ -110,6 +110,7 @@ _SIGS = {
     "mdm_fa_prep": [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
     "mdm_fa_feat": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "mdm_fa_out_bwd": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, C.POINTER(C.c_int), _P],
+    "mdm_fa_out_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P],
     "mdm_fa_feat_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "mdm_fa_prep_bwd": [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, C.POINTER(C.c_int), _P],
     "mdm_head_softmax": [_P, _I, _I, _I, _I, _I, _P, _P],

@@ -397,8 +397,9 @@ fa_prep_kernel(const T* __restrict__ qkv, const float* __restrict__ nw, const fl
 }
 
 // feature maps: qp = 0.1 exp(clamp(uq, +-15)); kp = 0.1 exp(clamp(uk, +-15)) * [t < length[b] >> shift]
-__global__ void fa_feat_kernel(const float* __restrict__ uq, const float* __restrict__ uk, const int64_t* __restrict__ length,
-                               int shift, int H, int Tn, int M, long total, float* __restrict__ qp, float* __restrict__ kp) {
+// (qp / kp may be the same buffers as uq / uk: no __restrict__ on them)
+__global__ void fa_feat_kernel(const float* uq, const float* uk, const int64_t* __restrict__ length,
+                               int shift, int H, int Tn, int M, long total, float* qp, float* kp) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long row = i / M;                       // (b, h, t)
@@ -447,6 +448,33 @@ fa_out_bwd_kernel(float* __restrict__ o, const float* __restrict__ qp, const flo
     if (lane == 0) dden[r] = dsum > 1e-6f ? -dot / (den * den) : 0.f;
   }
   block_reduce_vectors<VPT, 2, 8>(acc, part, W, red);
+}
+
+// output stage FORWARD (generic head sizes, e.g. hd = 256 of model_size="big"): den = max(sum_m q'k', 1e-6),
+// out = LN(o / den; w, b) written token-major [N, H*hd] (T)
+template <int VPT, typename T>
+__global__ void __launch_bounds__(256)
+fa_out_fwd_kernel(const float* __restrict__ o, const float* __restrict__ qp, const float* __restrict__ kp,
+                  const float* __restrict__ nw, const float* __restrict__ nb, int B, int H, int Tn, T* __restrict__ out) {
+  constexpr int W = 32 * VPT;
+  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);       // head-major row (b, h, t)
+  if (r >= (long)B * H * Tn) return;
+  const int lane = threadIdx.x & 31;
+  const int t = (int)(r % Tn);
+  const long bh = r / Tn;
+  const int h = (int)(bh % H), b = (int)(bh / H);
+  float ov[VPT], q[VPT], k[VPT], w[VPT], bb[VPT];
+  ldrow<VPT, float>(o + r * W, lane, ov);
+  ldrow<VPT, float>(qp + r * W, lane, q);
+  ldrow<VPT, float>(kp + r * W, lane, k);
+  ldrow<VPT, float>(nw, lane, w); ldrow<VPT, float>(nb, lane, bb);
+  const float den = fmaxf(rowdot<VPT>(q, k), 1e-6f);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) ov[i] = ov[i] / den;
+  ln_normalize<VPT>(ov, W);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) ov[i] = ov[i] * w[i] + bb[i];
+  strow<VPT, T>(out + ((long)b * Tn + t) * H * W + h * W, lane, ov);
 }
 
 // feature-map backward (in place): duq = (dqp + dden * kp) * qp * [|uq| <= 15]; duk = (dkp + dden * qp) * kp * [|uk| <= 15]
@@ -1099,6 +1127,16 @@ extern "C" MDM_API int mdm_fa_out_bwd(float* o, const float* qp, const float* kp
   HD_SWITCH(hd, {
     if (dt == MDM_F32) fa_out_bwd_kernel<V, float><<<grid, 256, 0, ST(stream)>>>(o, qp, kp, reinterpret_cast<const float*>(dout), nw, B, H, T, dden, part);
     else fa_out_bwd_kernel<V, bf16><<<grid, 256, 0, ST(stream)>>>(o, qp, kp, reinterpret_cast<const bf16*>(dout), nw, B, H, T, dden, part);
+  });
+  DONE();
+}
+extern "C" MDM_API int mdm_fa_out_fwd(const float* o, const float* qp, const float* kp, const float* nw, const float* nb, int B,
+                                      int H, int T, int hd, void* out, int dt, void* stream) {
+  TRY(o && qp && kp && nw && nb && out);
+  const unsigned grid = blocks_for((long)B * H * T, 8);
+  HD_SWITCH(hd, {
+    if (dt == MDM_F32) fa_out_fwd_kernel<V, float><<<grid, 256, 0, ST(stream)>>>(o, qp, kp, nw, nb, B, H, T, reinterpret_cast<float*>(out));
+    else fa_out_fwd_kernel<V, bf16><<<grid, 256, 0, ST(stream)>>>(o, qp, kp, nw, nb, B, H, T, reinterpret_cast<bf16*>(out));
   });
   DONE();
 }

@@ -149,6 +149,9 @@ def fastattn(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out, seq
     _c(qkv, P, norm_w, norm_b, length, out, seq_order, Pt)
     if Pt is not None and (Pt.dtype != torch.bfloat16 or tuple(Pt.shape) != (P.shape[1], P.shape[0])):
         raise _lib.MdmError("Pt must be P^T in bf16")
+    if hd > 128:       # head sizes outside the fused kernels (model_size="big": 4 heads of 256): the composed generic path
+        from . import train_ops
+        return train_ops.fastattn_generic(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out)
     _lib.check(_lib.load().mdm_fastattn_ordered(qkv.data_ptr(), _dt(qkv), P.data_ptr(), norm_w.data_ptr(),
                                                 norm_b.data_ptr(), _ptr(length), length_shift, B, H, T, hd,
                                                 P.shape[1], out.data_ptr(), _ptr(seq_order), _ptr(Pt), _stream()),
@@ -157,12 +160,18 @@ def fastattn(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out, seq
 
 def lincross_ctx(k, v, nt, B, Nt_max, H, hd, ctx):
     _c(k, v, nt, ctx)
+    if hd > 128:
+        from . import train_ops
+        return train_ops.lincross_ctx_generic(k, v, nt, B, Nt_max, H, hd, ctx)
     _lib.check(_lib.load().mdm_lincross_ctx(k.data_ptr(), v.data_ptr(), _dt(k), _ptr(nt), B, Nt_max, H, hd,
                                             ctx.data_ptr(), _stream()), "mdm_lincross_ctx")
 
 
 def lincross_apply(q, ctx, B, T, H, hd, y, ctxT=None):
     _c(q, ctx, y, ctxT)
+    if hd > 128:
+        from . import train_ops
+        return train_ops.lincross_apply_generic(q, ctx, B, T, H, hd, y)
     _lib.check(_lib.load().mdm_lincross_apply_ex(q.data_ptr(), _dt(q), ctx.data_ptr(), _ptr(ctxT), B, T, H, hd,
                                                  y.data_ptr(), _stream()), "mdm_lincross_apply")
 
@@ -177,6 +186,9 @@ def transpose_cast_bf16(src, dst):
 
 def softmax_cross(q, k, v, nt, B, T, Nt_max, H, hd, o):
     _c(q, k, v, nt, o)
+    if hd > 128:
+        from . import train_ops
+        return train_ops.softmax_cross_generic(q, k, v, nt, B, T, Nt_max, H, hd, o)
     _lib.check(_lib.load().mdm_softmax_cross(q.data_ptr(), k.data_ptr(), v.data_ptr(), _dt(q), _ptr(nt), B, T,
                                              Nt_max, H, hd, o.data_ptr(), _stream()), "mdm_softmax_cross")
 

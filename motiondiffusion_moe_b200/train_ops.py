@@ -226,6 +226,72 @@ def fastattn_bwd(qkv, P, norm_w, norm_b, length, shift, B, H, T, hd, dout, g_nor
     return dqkv
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# generic FORWARD of the three attention cores from the same pieces: head sizes outside the fused kernels (hd = 256 of
+# model_size="big", models/transformer.py:188-192).  ops.fastattn / lincross_* / softmax_cross route here for hd > 128.
+# ---------------------------------------------------------------------------------------------------------------
+def fastattn_generic(qkv, P, norm_w, norm_b, length, shift, B, H, T, hd, out):
+    """FastAttention.forward (models/fast_attention.py:29-92 + the 0.1 pre-scale of :155-157) for any hd in {32 .. 1024}."""
+    lib = _lib.load()
+    dev = qkv.device
+    TENSOR_CORES[0] = qkv.dtype == bf16
+    M = P.shape[1]
+    BH, st = B * H, _stream
+    z = lambda *s: torch.empty(*s, dtype=f32, device=dev)
+    qh, kh, vn = z(BH, T, hd), z(BH, T, hd), z(BH, T, hd)
+    _chk(lib.mdm_fa_prep(qkv.data_ptr(), _dt(qkv), norm_w.data_ptr(), norm_b.data_ptr(), B, H, T, hd, qh.data_ptr(), kh.data_ptr(),
+                         vn.data_ptr(), st()), "mdm_fa_prep")
+    hm = lambda w: (H * T * w, T * w, w, 1)
+    uq, uk = z(BH, T, M), z(BH, T, M)
+    bgemm(qh, hm(hd), P, (0, 0, M, 1), uq, hm(M), B, H, T, M, hd)
+    bgemm(kh, hm(hd), P, (0, 0, M, 1), uk, hm(M), B, H, T, M, hd)
+    _chk(lib.mdm_fa_feat(uq.data_ptr(), uk.data_ptr(), _ptr(length), shift, B, H, T, M, uq.data_ptr(), uk.data_ptr(), st()), "mdm_fa_feat")
+    qp, kp = uq, uk                                                        # feature maps written in place
+    kv = z(BH, M, hd)
+    kvs = (H * M * hd, M * hd, hd, 1)
+    bgemm(kp, (H * T * M, T * M, 1, M), vn, hm(hd), kv, kvs, B, H, M, hd, T, alpha=0.1)
+    o = z(BH, T, hd)
+    bgemm(qp, hm(M), kv, kvs, o, hm(hd), B, H, T, hd, M, alpha=0.1)
+    _chk(lib.mdm_fa_out_fwd(o.data_ptr(), qp.data_ptr(), kp.data_ptr(), norm_w.data_ptr(), norm_b.data_ptr(), B, H, T, hd,
+                            out.data_ptr(), _dt(out), st()), "mdm_fa_out_fwd")
+    return out
+
+
+def lincross_ctx_generic(k, v, nt, B, Nt, H, hd, ctx):
+    """ctx[b, h, d, l] = sum_n softmax_n(k)[n, d] v[n, l], n < nt[b]  (fast_attention.py:249-252)."""
+    lib = _lib.load()
+    D = H * hd
+    TENSOR_CORES[0] = k.dtype == bf16
+    Ks = torch.empty(B, Nt, D, dtype=f32, device=k.device)
+    _chk(lib.mdm_col_softmax(k.data_ptr(), _dt(k), _ptr(nt), B, Nt, D, Ks.data_ptr(), _stream()), "mdm_col_softmax")
+    bgemm(Ks, (Nt * D, hd, 1, D), v, (Nt * D, hd, D, 1), ctx, (H * hd * hd, hd * hd, hd, 1), B, H, hd, hd, Nt)
+    return ctx
+
+
+def lincross_apply_generic(q, ctx, B, T, H, hd, y):
+    """y[t, h, :] = softmax_hd(q[t, h, :]) @ ctx[b, h]  (fast_attention.py:252-253)."""
+    lib = _lib.load()
+    D = H * hd
+    TENSOR_CORES[0] = q.dtype == bf16
+    Pm = torch.empty(B * H, T, hd, dtype=f32, device=q.device)
+    _chk(lib.mdm_head_softmax(q.data_ptr(), _dt(q), B, H, T, hd, Pm.data_ptr(), _stream()), "mdm_head_softmax")
+    bgemm(Pm, (H * T * hd, T * hd, hd, 1), ctx, (H * hd * hd, hd * hd, hd, 1), y, (T * D, hd, D, 1), B, H, T, hd, hd)
+    return y
+
+
+def softmax_cross_generic(q, k, v, nt, B, T, Nt, H, hd, o):
+    """o = softmax_n(q k^T hd^-0.5) v over the n < nt[b] text tokens  (fast_attention.py:309-322)."""
+    lib = _lib.load()
+    D = H * hd
+    TENSOR_CORES[0] = q.dtype == bf16
+    tok, txt, sm = (T * D, hd, D, 1), (Nt * D, hd, D, 1), (H * T * Nt, T * Nt, Nt, 1)
+    S = torch.empty(B * H, T, Nt, dtype=f32, device=q.device)
+    bgemm(q, tok, k, (Nt * D, hd, 1, D), S, sm, B, H, T, Nt, hd, alpha=hd ** -0.5)
+    _chk(lib.mdm_key_softmax(S.data_ptr(), _ptr(nt), B, H, T, Nt, _stream()), "mdm_key_softmax")
+    bgemm(S, sm, v, txt, o, tok, B, H, T, hd, Nt)
+    return o
+
+
 def lincross_apply_bwd(q, ctx, B, T, H, hd, dy):
     """Backward of ops.lincross_apply (motion side of LinearTemporalCrossAttention, fast_attention.py:252-253):
     y = softmax_hd(q) @ ctx[b, h].  Returns (dq [N, D] in q's type, dctx [B, H, hd, hd] fp32)."""

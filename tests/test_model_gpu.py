@@ -567,6 +567,13 @@ VARIANTS = {
     # 16 experts, T not a multiple of 16, short text
     "e16_T50": (dict(input_feats=263, num_frames=60, latent_dim=512, ff_size=512, num_layers=1, num_heads=4,
                      text_latent_dim=256, moe_num_experts=16), 2, 50, 9),
+    # head size 256 (the attention cores composed from the generic strided batched GEMM + row kernels)
+    "hd256_D512": (dict(input_feats=263, num_frames=60, latent_dim=512, ff_size=512, num_layers=1, num_heads=2,
+                        text_latent_dim=256, moe_num_experts=4), 2, 40, 12),
+    # model_size="big" (models/transformer.py:188-192: latent, ff and text widths doubled -> D 1024, 4 heads of 256), the
+    # configuration of the reference's own __main__ smoke (:379); constructed through the ctor flag
+    "big_D1024": (dict(input_feats=263, num_frames=60, latent_dim=1024, ff_size=1024, num_layers=1, num_heads=4,
+                       text_latent_dim=512, moe_num_experts=4), 2, 20, 10),
 }
 
 
@@ -579,7 +586,12 @@ def test_shape_variants_match_oracle(name, precision, tol):
     cfg = mo.Config(**kw)
     p = mo.make_params(cfg, 3)
     p.update(mo.draw_ephemerals(cfg, 5))
-    net = mdm.MotionTransformer(precision=precision, **cfg)
+    if name.startswith("big"):        # halve the widths and let model_size="big" double them, as the reference's ctor does
+        net = mdm.MotionTransformer(precision=precision, model_size="big", **dict(cfg, latent_dim=cfg.latent_dim // 2,
+                                    ff_size=cfg.ff_size // 2, text_latent_dim=cfg.text_latent_dim // 2))
+        assert (net.latent_dim, net.ff_size, net.text_latent_dim) == (cfg.latent_dim, cfg.ff_size, cfg.text_latent_dim)
+    else:
+        net = mdm.MotionTransformer(precision=precision, **cfg)
     net.load_state_dict({k: p[k] for k in net.state_dict()})
     net.load_extras(p)
     net.to(DEV)
