@@ -379,11 +379,13 @@ class GaussianDiffusion:
         model.check_health()
         return out
 
-    # ------------------------------------------------------------------ training losses (forward value)
+    # ------------------------------------------------------------------ training losses
     def training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
-        """:923-992, MSE branch, forward values only: {"mse","target","pred","moe_loss"}.
-        The backward kernels of the training step (BASELINE.json configs[4]) are not built yet, so
-        the returned tensors carry no autograd graph."""
+        """:923-992, MSE branch: {"mse", "target", "pred", "moe_loss"}.
+        The reference back-propagates through these tensors with torch autograd; here the backward is hand-written: when the
+        model has a training engine attached (training.TrainEngine, created by DDPMTrainer with is_train=True) the forward
+        keeps its activations and the returned dict carries them under the extra key "saved", to be handed to
+        `engine.backward(terms["saved"], dLoss/dpred)` (DDPMTrainer.update does).  Without an engine: forward values only."""
         self._check_supported()
         if self.loss_type not in (LossType.MSE, LossType.RESCALED_MSE):
             raise NotImplementedError(self.loss_type)
@@ -393,10 +395,21 @@ class GaussianDiffusion:
             noise = torch.randn_like(x_start)
         x_t = self.q_sample(x_start, t, noise=noise)
         model.reset_all_moe_counters(model)                           # :935
-        out = model(x_t, t, **model_kwargs)                           # :950
+        eng = getattr(model, "_train_engine", None)
+        saved = None
+        if eng is not None:
+            xf_proj, xf_out = model_kwargs.get("xf_proj"), model_kwargs.get("xf_out")
+            if xf_proj is None or xf_out is None:                     # transformer.py:311-312
+                xf_proj, xf_out = model.encode_text(model_kwargs["text"], x_start.device)
+            with torch.cuda.device(eng.dev):
+                out, saved = eng.forward_train(x_t, t, model_kwargs["length"], xf_proj, xf_out)
+        else:
+            out = model(x_t, t, **model_kwargs)                       # :950
         assert out.shape == noise.shape == x_start.shape
         terms = {"mse": ((noise - out) ** 2).mean(dim=list(range(1, out.dim()))).view(-1),
                  "target": noise, "pred": out, "moe_loss": 0.0 + model.get_moe_loss(model)}
+        if saved is not None:
+            terms["saved"] = saved
         return terms
 
 

@@ -121,23 +121,13 @@ class DDPMTrainer(object):
         cur_len = torch.LongTensor([min(T, int(m)) for m in m_lens]).to(self.device)
         p = np.ones([self.diffusion.num_timesteps]) / self.diffusion.num_timesteps
         t = torch.from_numpy(np.random.choice(len(p), size=(B,), p=p)).long().to(self.device)
-        if self.engine is not None and not eval_mode:
-            # training_losses (gaussian_diffusion.py:923-992) with the activations kept for the backward kernels
-            m = self._model()
-            with torch.cuda.device(self.engine.dev):
-                xf_proj, xf_out = m.encode_text(caption, self.device)
-                noise = torch.randn_like(motions)
-                x_t = self.diffusion.q_sample(motions, t, noise=noise)
-                m.reset_all_moe_counters(m)
-                pred, self._saved = self.engine.forward_train(x_t, t, cur_len, xf_proj, xf_out)
-            self.real_noise, self.fake_noise = noise, pred
-            self.moe_loss = 0.0 + m.get_moe_loss(m)
-        else:
-            output = self.diffusion.training_losses(model=self._model(), x_start=motions, t=t,
-                                                    model_kwargs={"text": caption, "length": cur_len})
-            self.real_noise, self.fake_noise = output["target"], output["pred"]
-            self.moe_loss = output.get("moe_loss", 0.0)
-            self._saved = None
+        # training_losses (gaussian_diffusion.py:923-992); with a training engine attached the forward keeps its activations
+        # for the backward kernels (output["saved"])
+        output = self.diffusion.training_losses(model=self._model(), x_start=motions, t=t,
+                                                model_kwargs={"text": caption, "length": cur_len})
+        self.real_noise, self.fake_noise = output["target"], output["pred"]
+        self.moe_loss = output.get("moe_loss", 0.0)
+        self._saved = output.get("saved")
         self.cur_len = cur_len
         self.src_mask = self._model().generate_src_mask(T, cur_len).to(motions.device)
 

@@ -45,6 +45,7 @@ class TrainEngine:
             self._flatten()
             self._build_pack()
             self.refresh()
+        object.__setattr__(model, "_train_engine", self)      # GaussianDiffusion.training_losses keeps activations through it
 
     # ------------------------------------------------------------------ flat parameter storage
     def _groups(self):
