@@ -447,7 +447,8 @@ MDM_API int mdm_seg_colsum(const void* src, int dt, int C, const int* seg_off, c
  * and applies bias-corrected Adam step number `step` (1-based). */
 MDM_API int mdm_grad_clip_coef(const float* g, long n, float max_norm, float* part, int n_part, float* norm_coef, void* stream);
 MDM_API int mdm_adam_step(float* p, float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps, int step,
-                          const float* norm_coef, void* stream);
+                          const float* norm_coef, void* bf16_mirror /* optional: bf16 copy of p, written in the same pass */,
+                          void* stream);
 
 MDM_API int mdm_num_sms(void);
 /* sizeof() of the structs above as this library was compiled: a binding checks its own struct definitions against them

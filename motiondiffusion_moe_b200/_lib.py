@@ -134,7 +134,7 @@ _SIGS = {
     "mdm_transpose_split": [_P, _I, _L, _I, _L, _I, _I, _P, _P],
     "mdm_seg_colsum": [_P, _I, _I, _P, _P, _I, _I, _P, _P],
     "mdm_grad_clip_coef": [_P, _L, _F, _P, _I, _P, _P],
-    "mdm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P, _P],
+    "mdm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P, _P, _P],
     "mdm_num_sms": [],
     "mdm_sizeof_gemm_epi": [],
     "mdm_sizeof_rowop": [],

@@ -1044,7 +1044,8 @@ __global__ void clip_coef_kernel(const float* __restrict__ part, int n, float ma
   out[1] = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
 }
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
-                            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, const float* __restrict__ coef) {
+                            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, const float* __restrict__ coef,
+                            bf16* __restrict__ mirror) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float c = coef ? coef[1] : 1.f;
@@ -1054,7 +1055,9 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
   m[i] = mi; v[i] = vi;
   const float denom = sqrtf(vi) / bc2_sqrt + eps;
-  p[i] -= (lr / bc1) * (mi / denom);
+  const float pn = p[i] - (lr / bc1) * (mi / denom);
+  p[i] = pn;
+  if (mirror) mirror[i] = __float2bfloat16_rn(pn);      // the bf16 operand copy the GEMMs read: refreshed in the same pass
 }
 
 inline unsigned blocks_for(long n, int per) { return (unsigned)((n + per - 1) / per); }
@@ -1352,9 +1355,10 @@ extern "C" MDM_API int mdm_grad_clip_coef(const float* g, long n, float max_norm
   DONE();
 }
 extern "C" MDM_API int mdm_adam_step(float* p, float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
-                                     int step, const float* norm_coef, void* stream) {
+                                     int step, const float* norm_coef, void* bf16_mirror, void* stream) {
   TRY(p && g && m && v && step >= 1);
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = sqrtf(1.f - powf(beta2, (float)step));
-  adam_kernel<<<blocks_for(n, 256), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, norm_coef);
+  adam_kernel<<<blocks_for(n, 256), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, norm_coef,
+                                                          reinterpret_cast<bf16*>(bf16_mirror));
   DONE();
 }

@@ -228,12 +228,13 @@ class TrainEngine:
         m._packed = pk
 
     @torch.no_grad()
-    def refresh(self):
+    def refresh(self, mirror_done=False):
         """Bring the operand-typed weights in line with the fp32 masters (after an optimizer step or a manual edit):
-        one cast of the flat buffer + the few tensors whose kernel layout is a transformation of the parameter."""
+        one cast of the flat buffer (mirror_done: the Adam kernel already wrote it) + the few tensors whose kernel layout is
+        a transformation of the parameter."""
         m, pk = self.m, self.pk
         D = m.latent_dim
-        if self.flat_op is not self.flat:
+        if self.flat_op is not self.flat and not mirror_done:
             T.axpby(self.flat, 1.0, None, 0.0, self.flat_op)
         wdt = self.adt
         pk["je_w"][:, :m.input_feats] = self.P("joint_embed.weight").to(wdt)
@@ -810,8 +811,9 @@ class TrainEngine:
                                           1024, self.norm_coef.data_ptr(), ops._stream()), "mdm_grad_clip_coef")
             T._chk(lib.mdm_adam_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                      self.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
-                                     self.norm_coef.data_ptr(), ops._stream()), "mdm_adam_step")
-            self.refresh()
+                                     self.norm_coef.data_ptr(), self.flat_op.data_ptr() if self.flat_op is not self.flat else None,
+                                     ops._stream()), "mdm_adam_step")
+            self.refresh(mirror_done=True)
 
     # ------------------------------------------------------------------ one training-step evaluation
     def loss_and_grads(self, x_start, t, length, xf_proj, xf_out, noise, diffusion, sd_skip=None, nt=None):

@@ -192,8 +192,10 @@ def test_clip_and_adam_match_torch():
         opt.step()
         gg = gr.clone()
         T._chk(lib.mdm_grad_clip_coef(gg.data_ptr(), n, 1.0, part.data_ptr(), 256, nc.data_ptr(), ops._stream()), "clip")
+        mirror = torch.empty(n, device=DEV, dtype=bf16)
         T._chk(lib.mdm_adam_step(p.data_ptr(), gg.data_ptr(), m.data_ptr(), v.data_ptr(), n, 2e-4, 0.9, 0.999, 1e-8, step, nc.data_ptr(),
-                                 ops._stream()), "adam")
+                                 mirror.data_ptr(), ops._stream()), "adam")
+        assert torch.equal(mirror, p.bfloat16())                       # the bf16 operand mirror written in the same pass
         assert abs(float(nc[0]) - float(norm)) < 1e-4 * float(norm)
         assert rel(gg, ref.grad) < 1e-6                                # clip_grad_norm_ scales .grad in place
         assert rel(p, ref.detach()) < 1e-6
