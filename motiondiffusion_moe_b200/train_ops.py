@@ -3,6 +3,7 @@ torch only provides device memory and the stream; every computation runs in libm
 below (`linear_bwd`, `fastattn_bwd`, `lincross_bwd`, `softmax_cross_bwd`, ...) are the backward twins of the forward
 ops in ops.py; each cites the reference code whose autograd graph it reproduces."""
 import ctypes as C
+import functools
 
 import torch
 
@@ -17,14 +18,12 @@ def _chk(st, what):
     _lib.check(st, what)
 
 
-TENSOR_CORES = [False]      # set by the bf16 training path (fastattn_bwd & co. pass tc=...): see csrc/train.cu bgemm_tc_kernel
-
-
-def bgemm(A, a_str, B, b_str, Cm, c_str, Z1, Z2, M, N, K, alpha=1.0, accumulate=False, tc=None):
+def bgemm(A, a_str, B, b_str, Cm, c_str, Z1, Z2, M, N, K, alpha=1.0, accumulate=False, tc=False):
     """C[z][m][n] (+)= alpha * sum_k A[z][m][k] B[z][k][n]; *_str = (z1, z2, row, col) element strides.
-    tc: True = bf16 tensor-core flavour (operands rounded to bf16 on the fly), False = fp32 FMA, None = TENSOR_CORES[0]."""
+    tc: True = bf16 tensor-core flavour (operands rounded to bf16 while staged, csrc/train.cu bgemm_tc_kernel: what the bf16
+    path's composite functions below pass), False = fp32 FMA (exact; the fp32 parity path)."""
     g = _lib.Bgemm()
-    g.tensor_cores = 1 if (TENSOR_CORES[0] if tc is None else tc) else 0
+    g.tensor_cores = 1 if tc else 0
     g.A, g.a_dt = A.data_ptr(), _dt(A)
     g.a_z1, g.a_z2, g.a_rs, g.a_cs = a_str
     g.B, g.b_dt = B.data_ptr(), _dt(B)
@@ -34,6 +33,9 @@ def bgemm(A, a_str, B, b_str, Cm, c_str, Z1, Z2, M, N, K, alpha=1.0, accumulate=
     g.Z1, g.Z2, g.M, g.N, g.K = Z1, Z2, M, N, K
     g.alpha, g.accumulate = alpha, 1 if accumulate else 0
     _chk(_lib.load().mdm_bgemm(C.byref(g), _stream()), "mdm_bgemm")
+
+
+_bgemm = bgemm
 
 
 def sum_partials(part, S, n, out, accumulate=True):
@@ -176,7 +178,7 @@ def fastattn_bwd(qkv, P, norm_w, norm_b, length, shift, B, H, T, hd, dout, g_nor
     qkv's type (with the reference's [-1, 1] gradient clamp); adds the shared LayerNorm(hd) gradients to g_norm = (dw, db)."""
     lib = _lib.load()
     dev = qkv.device
-    TENSOR_CORES[0] = qkv.dtype == bf16
+    bgemm = functools.partial(_bgemm, tc=qkv.dtype == bf16)      # bf16 operands -> tensor-core flavour
     M = P.shape[1]
     BH, st = B * H, _stream
     z = lambda *s: torch.empty(*s, dtype=f32, device=dev)
@@ -234,7 +236,7 @@ def fastattn_generic(qkv, P, norm_w, norm_b, length, shift, B, H, T, hd, out):
     """FastAttention.forward (models/fast_attention.py:29-92 + the 0.1 pre-scale of :155-157) for any hd in {32 .. 1024}."""
     lib = _lib.load()
     dev = qkv.device
-    TENSOR_CORES[0] = qkv.dtype == bf16
+    bgemm = functools.partial(_bgemm, tc=qkv.dtype == bf16)      # bf16 operands -> tensor-core flavour
     M = P.shape[1]
     BH, st = B * H, _stream
     z = lambda *s: torch.empty(*s, dtype=f32, device=dev)
@@ -261,7 +263,7 @@ def lincross_ctx_generic(k, v, nt, B, Nt, H, hd, ctx):
     """ctx[b, h, d, l] = sum_n softmax_n(k)[n, d] v[n, l], n < nt[b]  (fast_attention.py:249-252)."""
     lib = _lib.load()
     D = H * hd
-    TENSOR_CORES[0] = k.dtype == bf16
+    bgemm = functools.partial(_bgemm, tc=k.dtype == bf16)      # bf16 operands -> tensor-core flavour
     Ks = torch.empty(B, Nt, D, dtype=f32, device=k.device)
     _chk(lib.mdm_col_softmax(k.data_ptr(), _dt(k), _ptr(nt), B, Nt, D, Ks.data_ptr(), _stream()), "mdm_col_softmax")
     bgemm(Ks, (Nt * D, hd, 1, D), v, (Nt * D, hd, D, 1), ctx, (H * hd * hd, hd * hd, hd, 1), B, H, hd, hd, Nt)
@@ -272,7 +274,7 @@ def lincross_apply_generic(q, ctx, B, T, H, hd, y):
     """y[t, h, :] = softmax_hd(q[t, h, :]) @ ctx[b, h]  (fast_attention.py:252-253)."""
     lib = _lib.load()
     D = H * hd
-    TENSOR_CORES[0] = q.dtype == bf16
+    bgemm = functools.partial(_bgemm, tc=q.dtype == bf16)      # bf16 operands -> tensor-core flavour
     Pm = torch.empty(B * H, T, hd, dtype=f32, device=q.device)
     _chk(lib.mdm_head_softmax(q.data_ptr(), _dt(q), B, H, T, hd, Pm.data_ptr(), _stream()), "mdm_head_softmax")
     bgemm(Pm, (H * T * hd, T * hd, hd, 1), ctx, (H * hd * hd, hd * hd, hd, 1), y, (T * D, hd, D, 1), B, H, T, hd, hd)
@@ -283,7 +285,7 @@ def softmax_cross_generic(q, k, v, nt, B, T, Nt, H, hd, o):
     """o = softmax_n(q k^T hd^-0.5) v over the n < nt[b] text tokens  (fast_attention.py:309-322)."""
     lib = _lib.load()
     D = H * hd
-    TENSOR_CORES[0] = q.dtype == bf16
+    bgemm = functools.partial(_bgemm, tc=q.dtype == bf16)      # bf16 operands -> tensor-core flavour
     tok, txt, sm = (T * D, hd, D, 1), (Nt * D, hd, D, 1), (H * T * Nt, T * Nt, Nt, 1)
     S = torch.empty(B * H, T, Nt, dtype=f32, device=q.device)
     bgemm(q, tok, k, (Nt * D, hd, 1, D), S, sm, B, H, T, Nt, hd, alpha=hd ** -0.5)
@@ -297,7 +299,7 @@ def lincross_apply_bwd(q, ctx, B, T, H, hd, dy):
     y = softmax_hd(q) @ ctx[b, h].  Returns (dq [N, D] in q's type, dctx [B, H, hd, hd] fp32)."""
     lib = _lib.load()
     dev, D = q.device, H * hd
-    TENSOR_CORES[0] = q.dtype == bf16
+    bgemm = functools.partial(_bgemm, tc=q.dtype == bf16)      # bf16 operands -> tensor-core flavour
     Pm = torch.empty(B * H, T, hd, dtype=f32, device=dev)
     _chk(lib.mdm_head_softmax(q.data_ptr(), _dt(q), B, H, T, hd, Pm.data_ptr(), _stream()), "mdm_head_softmax")
     hm = (H * T * hd, T * hd, hd, 1)
@@ -317,7 +319,7 @@ def lincross_ctx_bwd(k, v, nt, B, Nt, H, hd, dctx):
     [B*Nt, D] in k's type."""
     lib = _lib.load()
     dev, D = k.device, H * hd
-    TENSOR_CORES[0] = k.dtype == bf16
+    bgemm = functools.partial(_bgemm, tc=k.dtype == bf16)      # bf16 operands -> tensor-core flavour
     Ks = torch.empty(B, Nt, D, dtype=f32, device=dev)
     _chk(lib.mdm_col_softmax(k.data_ptr(), _dt(k), _ptr(nt), B, Nt, D, Ks.data_ptr(), _stream()), "mdm_col_softmax")
     txt = (Nt * D, hd, D, 1)
@@ -336,7 +338,7 @@ def softmax_cross_bwd(q, k, v, nt, B, T, Nt, H, hd, do):
     o = softmax_n(q k^T hd^-0.5) v.  Returns (dq [N, D], dk, dv [B*Nt, D]) in the operand type."""
     lib = _lib.load()
     dev, D = q.device, H * hd
-    TENSOR_CORES[0] = q.dtype == bf16
+    bgemm = functools.partial(_bgemm, tc=q.dtype == bf16)      # bf16 operands -> tensor-core flavour
     scale = hd ** -0.5
     tok, txt = (T * D, hd, D, 1), (Nt * D, hd, D, 1)
     sm = (H * T * Nt, T * Nt, Nt, 1)
