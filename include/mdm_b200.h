@@ -61,6 +61,10 @@ typedef struct MdmGemmEpi {
                          whatever the buffers hold there: pad with zeros).  This is what the weight gradient of an
                          expert needs: dW_e = dY_e^T X_e contracts over the rows of the expert's segment, whose
                          offset and length only exist on the device.  Selects the single-CTA kernel. */
+  int mn_major;       /* mdm_gemm_bf16 only: 1 = "TN" contraction C[M, N] = A^T W over the ROWS of A [K rows, >= M columns] and
+                         W [K rows, >= N columns] (both row-major, read MN-major by TMA / tcgen05: no transposed copies) - the
+                         weight gradient dW = dY^T X of a Linear.  M / N count features, K rows (tokens); a_row0 / w_row0 of a tile
+                         are feature offsets, tile_k a row (token) range; fp32 output only. */
 } MdmGemmEpi;
 
 /* One 128-row tile of a grouped GEMM: rows [a_row0, a_row0+128) of A times the weight rows starting

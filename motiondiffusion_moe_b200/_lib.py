@@ -26,7 +26,7 @@ class GemmEpi(C.Structure):
         ("alpha", C.c_float), ("beta", C.c_float), ("act", C.c_int),
         ("out_f32", C.c_void_p), ("ld_f32", C.c_int),
         ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int), ("bf16_pre_resid", C.c_int), ("pair_tiles", C.c_int),
-        ("tile_k", C.c_void_p),
+        ("tile_k", C.c_void_p), ("mn_major", C.c_int),
     ]
 
 

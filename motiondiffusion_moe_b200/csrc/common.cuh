@@ -197,6 +197,18 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B
   return d;
 }
+// MN-major, 128B-swizzled descriptor: the operand tile lies in shared memory as [K rows][64 MN elements = 128 B] blocks
+// (what a TMA box {64 columns, BK rows} of a row-major [K, MN] tensor produces): 8-row K groups 1024 B apart (SBO),
+// 64-element MN blocks `lbo_bytes` apart (LBO).  Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // LBO, bits [16,30)
+  d |= (uint64_t)(1024u >> 4) << 32;                    // SBO, bits [32,46)
+  d |= (uint64_t)1 << 46;                               // descriptor version = 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B
+  return d;
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4)                    // c_format = F32
@@ -205,3 +217,5 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | ((uint32_t)(N >> 3) << 17) // n_dim
          | ((uint32_t)(M >> 4) << 24);// m_dim
 }
+// the same with both operands MN-major (a_major, b_major = bits 15, 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) { return make_idesc_bf16(M, N) | (1u << 15) | (1u << 16); }

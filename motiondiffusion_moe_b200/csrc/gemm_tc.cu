@@ -41,7 +41,11 @@ namespace {
 // rows of a grouped GEMM's output buffer (TMA-store bound): the caller passes the buffer height as M
 inline long a_rows_out(const GemmEpi*, int M) { return M; }
 
-template <int BN, int STAGES, int EPI, int ACT>
+// MN == true ("TN" contraction, the weight gradient dW = dY^T X of the training step): both operands are read MN-major
+// straight from row-major [tokens, features] tensors - TMA boxes {64 features, BK tokens}, MN-major shared-memory
+// descriptors, a_major / b_major set in the instruction descriptor - so the contraction over the TOKENS needs no
+// transposed copies of dY and X.  a_row0 / w_row0 of a tile are then FEATURE offsets, k indexes tokens.
+template <int BN, int STAGES, int EPI, int ACT, bool MN = false>
 __global__ void __launch_bounds__(num_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -112,14 +116,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_2d(&tmA, &full_bar[stage], sa, k0 + kb * BK, a_row0);
-          tma_load_2d(&tmB, &full_bar[stage], sb, k0 + kb * BK, w_row0 + nt * BN);
+          if constexpr (MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmA, &full_bar[stage], sa + j * (64 * BK * 2), a_row0 + 64 * j, k0 + kb * BK);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(&tmB, &full_bar[stage], sb + j * (64 * BK * 2), w_row0 + nt * BN + 64 * j, k0 + kb * BK);
+          } else {
+            tma_load_2d(&tmA, &full_bar[stage], sa, k0 + kb * BK, a_row0);
+            tma_load_2d(&tmB, &full_bar[stage], sb, k0 + kb * BK, w_row0 + nt * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1 && lane == 0) {
       // ------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = MN ? make_idesc_bf16_mn(BM, BN) : make_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -140,12 +152,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           w_op += PROF_T() - c0;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint64_t adesc = make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc = make_sw128_kmajor_desc(sa + L::A_BYTES);
+          const uint64_t adesc = MN ? make_sw128_mnmajor_desc(sa, 64 * BK * 2) : make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = MN ? make_sw128_mnmajor_desc(sa + L::A_BYTES, 64 * BK * 2) : make_sw128_kmajor_desc(sa + L::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in 16-byte units
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            // K-major: advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in 16-byte units;
+            // MN-major: advance 16 token rows of 128 bytes = 2048 bytes: +128
+            constexpr int step = MN ? (UMMA_K * 128) >> 4 : 2;
+            umma_bf16(d_tmem, adesc + step * k, bdesc + step * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -553,7 +567,7 @@ int num_sms() {
   return g_num_sms[dev];
 }
 
-template <int BN, int STAGES, int EPI, int ACT>
+template <int BN, int STAGES, int EPI, int ACT, bool MN = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
            const CUtensorMap& tf, int M, int N, int K, int num_m_tiles,
            const int* num_m_tiles_dev, const MTile* mtiles, const GemmEpi& epi, int max_ctas,
@@ -563,7 +577,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   static unsigned long long attr_set = 0;   // one bit per device ordinal: the attribute is per (function, device)
   const unsigned long long dev_bit = 1ull << mdm_cur_dev();
   if (!(attr_set & dev_bit)) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI, ACT, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              L::TOTAL) != cudaSuccess)
       return MDM_ERR_CUDA;
     attr_set |= dev_bit;
@@ -573,7 +587,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
   if (num_m_tiles_dev) grid = max_ctas;
   if (grid < 1) grid = 1;
-  gemm_tc_kernel<BN, STAGES, EPI, ACT><<<grid, num_threads(EPI), L::TOTAL, stream>>>(
+  gemm_tc_kernel<BN, STAGES, EPI, ACT, MN><<<grid, num_threads(EPI), L::TOTAL, stream>>>(
       ta, tb, tc, tr, tf, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
@@ -882,6 +896,19 @@ extern "C" MDM_API int mdm_gemm_bf16(const void* A, int lda, long a_rows, const 
   if (num_m_tiles == 0 && !num_m_tiles_dev) return MDM_OK;
   const int sms = num_sms();
   if (max_ctas <= 0 || max_ctas > sms) max_ctas = sms;
+  if (epi->mn_major) {
+    // "TN" contraction over the rows of A and W (tokens): C[M features of A, N features of W] = A^T W, fp32 output only
+    // (partial products of the weight gradients); tiles address FEATURE offsets, tile_k token ranges
+    if (!epi->out_f32 || epi->out_bf16 || epi->resid || epi->bias || epi->rowscale || epi->rowmask || epi->act != MDM_ACT_NONE ||
+        (N & 3) || (epi->ld_f32 & 3) || (reinterpret_cast<uintptr_t>(epi->out_f32) & 15))
+      return MDM_ERR_UNSUPPORTED;
+    CUtensorMap ta, tb;
+    if (!make_map(&ta, A, a_rows, lda, lda, BK) || !make_map(&tb, W, w_rows, ldw, ldw, BK)) return MDM_ERR_CUDA;
+    const MTile* mt = reinterpret_cast<const MTile*>(mtiles);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (N > 128) return launch<256, 4, EPI_F32, MDM_ACT_NONE, true>(ta, tb, ta, ta, ta, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);
+    return launch<128, 6, EPI_F32, MDM_ACT_NONE, true>(ta, tb, ta, ta, ta, M, N, K, num_m_tiles, num_m_tiles_dev, mt, *epi, max_ctas, st);
+  }
   // tile width: 256 columns unless N is small or the 256-wide tiling leaves the last wave mostly idle
   bool wide = N > 128;
   if (wide && !num_m_tiles_dev) {

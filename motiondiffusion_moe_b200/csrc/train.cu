@@ -343,18 +343,27 @@ bgemm_tc_kernel(const MdmBgemm g) {
     }
   }
   if (m0 >= g.M) return;
+  // the two columns a thread holds per accumulator row are adjacent: one 8-byte (fp32) / 4-byte (bf16) store when C is
+  // row-major and aligned (a warp store then fills whole 32-byte sectors instead of half of each)
+  const bool pair_ok = g.c_cs == 1 && !g.accumulate && !(g.c_rs & 1) && !(g.c_z1 & 1) && !(g.c_z2 & 1) &&
+                       !(reinterpret_cast<uintptr_t>(g.C) & (2 * sizeof(TC) - 1));
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int m = m0 + wm + 16 * i + gq + (r >> 1) * 8, n = n0 + wn + 8 * j + 2 * tq + (r & 1);
+      for (int rr = 0; rr < 2; ++rr) {
+        const int m = m0 + wm + 16 * i + gq + rr * 8, n = n0 + wn + 8 * j + 2 * tq;
         if (m >= g.M || n >= g.N) continue;
+        const float v0 = (m < M) ? g.alpha * acc[i][j][2 * rr] : 0.f, v1 = (m < M) ? g.alpha * acc[i][j][2 * rr + 1] : 0.f;
         TC* c = C + (long)m * g.c_rs + (long)n * g.c_cs;
-        float v = (m < M) ? g.alpha * acc[i][j][r] : 0.f;
-        if (g.accumulate) v += ldf<TC>(c);
-        stf<TC>(c, v);
+        if (pair_ok && n + 1 < g.N) {
+          if constexpr (sizeof(TC) == 4) *reinterpret_cast<float2*>(c) = make_float2(v0, v1);
+          else *reinterpret_cast<__nv_bfloat162*>(c) = __floats2bfloat162_rn(v0, v1);
+        } else {
+          stf<TC>(c, g.accumulate ? v0 + ldf<TC>(c) : v0);
+          if (n + 1 < g.N) stf<TC>(c + g.c_cs, g.accumulate ? v1 + ldf<TC>(c + g.c_cs) : v1);
+        }
       }
 }
 

@@ -79,6 +79,22 @@ def transpose_groups(src, rows_per_group, groups=1):
 
 
 _SLAB_TABLES = {}
+USE_TN = [True]      # A/B knob (tests, tools): False = transposed copies + K-major GEMM for the weight gradients
+
+
+def gemm_tn(A, W, out_f32, M, N, tiles, num_tiles, tile_k):
+    """out[c_row0 + m, n] = sum_{k in tile_k range} A[k, a_row0 + m] * W[k, w_row0 + n] per tile: the "TN" contraction of
+    mdm_gemm_bf16 (MdmGemmEpi.mn_major): A [K rows, >= M cols], W [K rows, >= N cols] bf16 row-major, read MN-major by
+    TMA / tcgen05, i.e. the token contraction of a weight gradient without transposed copies of its operands."""
+    _c(tiles, tile_k)
+    lib = _lib.load()
+    e = _lib.GemmEpi()
+    e.alpha, e.beta, e.act = 1.0, 0.0, ACT_NONE
+    e.out_f32, e.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    e.tile_k = tile_k.data_ptr()
+    e.mn_major = 1
+    _chk(lib.mdm_gemm_bf16(A.data_ptr(), A.stride(0), A.shape[0], W.data_ptr(), W.stride(0), W.shape[0], M, N, A.shape[0],
+                           tiles.data_ptr(), num_tiles, None, C.byref(e), 0, _stream()), "mdm_gemm_bf16 (mn_major)")
 
 
 def linear_bwd(x, W_t, dy, *, dx_a=None, dx_f32=None, dx_resid=None, dW=None, db=None, M=None):
@@ -95,7 +111,34 @@ def linear_bwd(x, W_t, dy, *, dx_a=None, dx_f32=None, dx_resid=None, dW=None, db
             ops.gemm(dy, W_t, None, out_f32=dx_f32, resid=dx_resid, alpha=1.0, beta=1.0 if dx_resid is not None else 0.0, M=M)
         else:
             ops.gemm(dy, W_t, None, out_a=dx_a, M=M) if dy.dtype == bf16 else ops.gemm(dy, W_t, None, out_f32=dx_a, M=M)
-    if dW is not None:
+    tn_ok = (x.dtype == bf16 and USE_TN[0] and not (K_in & 3) and not (x.stride(0) & 7) and not (dy.stride(0) & 7) and
+             not ((x.data_ptr() | dy.data_ptr()) & 15))                  # TMA: 16-byte row pitch and base
+    if dW is not None and tn_ok:
+        # bf16 path: the token contraction reads dY and X as they are (MN-major operands), split in S token slabs whose fp32
+        # partial products [S, out, in] are summed in a fixed order
+        tiles_out = (N_out + 127) // 128
+        sms = lib.mdm_num_sms() or 148
+        S = max(1, min(64, (2 * sms) // max(1, tiles_out * ((K_in + 255) // 256)), (M + 255) // 256))
+        Ks = ((M + S - 1) // S + 63) // 64 * 64
+        S = (M + Ks - 1) // Ks                                       # every slab non-empty
+        rows_a = tiles_out * 128
+        key = ("tn", S, Ks, M, tiles_out, rows_a, N_out, str(dev))
+        tt = _SLAB_TABLES.get(key)
+        if tt is None:
+            rows = [[i * 128, s_ * rows_a + i * 128, 0, min(128, N_out - i * 128)] for s_ in range(S) for i in range(tiles_out)]
+            tk = [[s_ * Ks, min(Ks, M - s_ * Ks)] for s_ in range(S) for _ in range(tiles_out)]
+            tt = _SLAB_TABLES[key] = (torch.tensor(rows, dtype=torch.int32).to(dev), torch.tensor(tk, dtype=torch.int32).to(dev))
+        part = torch.empty(S * rows_a, K_in, dtype=f32, device=dev)
+        if rows_a != N_out:
+            part.zero_()
+        gemm_tn(dy, x, part, N_out, K_in, tt[0], S * tiles_out, tt[1])
+        if rows_a == N_out:
+            sum_partials(part, S, N_out * K_in, dW)
+        else:
+            red = torch.empty(rows_a, K_in, dtype=f32, device=dev)
+            sum_partials(part, S, rows_a * K_in, red, accumulate=False)
+            axpby(red[:N_out], 1.0, dW, 1.0, dW)
+    elif dW is not None:
         tiles_out = (N_out + 127) // 128
         sms = lib.mdm_num_sms() or 148
         S = max(1, min(64, (2 * sms) // max(1, tiles_out * ((K_in + 255) // 256)), (M + 255) // 256))
@@ -409,6 +452,18 @@ def expert_ffn_bwd(xp, pre, hp, W1t, W2t, dz, seg_off, idx, N, NB, E, tiles_up, 
                                   tk_up.data_ptr(), tk_dn.data_ptr(), _stream()), "mdm_moe_wgrad_tables")
 
     def wgrad(dy_rows, x_rows, out_dim, in_dim, tk, mt, g_w):
+        if adt == bf16 and USE_TN[0]:          # token contraction on the operands as they are (MN-major), per expert segment
+            key = ("wg_tn", G, out_dim, str(dev))
+            tt = _SLAB_TABLES.get(key)
+            if tt is None:
+                tt = _SLAB_TABLES[key] = torch.tensor([[i * 128, g_ * out_dim + i * 128, 0, min(128, out_dim - i * 128)]
+                                                       for g_ in range(G) for i in range(mt)], dtype=torch.int32).to(dev)
+            part = torch.empty(G * out_dim, in_dim, dtype=f32, device=dev)
+            if out_dim % 128:
+                part.zero_()
+            gemm_tn(dy_rows, x_rows, part, out_dim, in_dim, tt, G * mt, tk)
+            axpby(part, 1.0, g_w, 1.0, g_w)
+            return
         dyT, xT = transpose_groups(dy_rows, rows), transpose_groups(x_rows, rows)      # [out, rows], [in, rows]
         key = ("wg", G, out_dim, str(dev))
         tt = _SLAB_TABLES.get(key)
