@@ -160,7 +160,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 template <typename TA, typename TB, typename TC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)      // <= 85 registers: three CTAs per SM (ncu: 118 registers gave 23 % warps active)
 bgemm_tc_kernel(const MdmBgemm g) {
   __shared__ __align__(16) bf16 As[BT][TPITCH];     // [m][k]
   __shared__ __align__(16) bf16 Bs[BT][TPITCH];     // [n][k]
@@ -185,8 +185,10 @@ bgemm_tc_kernel(const MdmBgemm g) {
   auto al = [](const void* p, long a, long b, long c, int esz) {
     return ((reinterpret_cast<uintptr_t>(p) | (uintptr_t)(a * esz) | (uintptr_t)(b * esz) | (uintptr_t)(c * esz)) & (4 * esz - 1)) == 0;
   };
-  const bool a_vec = VA == 4 && (a_kfast ? al(g.A, g.a_z1, g.a_z2, g.a_rs, sizeof(TA)) : (g.a_rs == 1 && al(g.A, g.a_z1, g.a_z2, g.a_cs, sizeof(TA))));
-  const bool b_vec = VB == 4 && (b_nfast ? al(g.B, g.b_z1, g.b_z2, g.b_rs, sizeof(TB)) : (g.b_rs == 1 && al(g.B, g.b_z1, g.b_z2, g.b_cs, sizeof(TB))));
+  // (only where the shared-memory store is contiguous too, i.e. the operand is k-fast: the transposing cases scatter four
+  //  2-byte stores 4 rows apart - 16-way bank conflicts under ncu - and stay element-wise, lanes along the fast dimension)
+  const bool a_vec = VA == 4 && a_kfast && al(g.A, g.a_z1, g.a_z2, g.a_rs, sizeof(TA));
+  const bool b_vec = VB == 4 && !b_nfast && g.b_rs == 1 && al(g.B, g.b_z1, g.b_z2, g.b_cs, sizeof(TB));
   auto ld4 = [](const auto* p, float (&v)[4]) {
     typedef typename std::remove_cv<typename std::remove_pointer<decltype(p)>::type>::type E;
     if constexpr (sizeof(E) == 4) {
