@@ -120,6 +120,20 @@ MDM_API int mdm_rowop(const MdmRowOp* op, long rows, int D, int out_dt, void* st
 MDM_API int mdm_gemm_rowop(const MdmRowOp* op, long rows, int D, const void* W, int ldw, long w_rows, int N,
                            const MdmGemmEpi* epi, void* stream);
 
+/* The row pipeline fused into the EPILOGUE of the GEMM that produces its input (north_star (3): "StylizationBlock
+ * timestep-FiLM and LayerNorm fused into the adjacent GEMM epilogues"; csrc/gemm_ln.cu):
+ *   y_pre = act(A . W[512, K]^T + bias) * alpha ;  y = y_pre + beta * resid
+ *   epi->out_f32 <- y ;  s = epi->bf16_pre_resid ? y_pre : y ;  epi->out_bf16 <- bf16(s)
+ *   u = L2norm?(LN1(s)) -> op->out1_f32 | op->out1_a ;  z = SiLU?(FiLM?(LN2(u))) -> op->out2_a
+ * (op->in / in_dt / out0_a / out2_f32 are not used: the pipeline's input is the GEMM result, which never leaves the
+ * chip unless out_f32 / out_bf16 ask for it).  N == 512 == the whole row in one 128 x 512 TMEM tile, CTA pairs
+ * (cta_group::2), K % 64 == 0, bf16 operands.  Stage sets built: the five Linear -> LayerNorm chains of
+ * MoEExtendedDecoderLayer (models/fast_attention.py:142,166-176,210-226,248,322-326; models/stylization.py:27-30).
+ * Anything else returns MDM_ERR_UNSUPPORTED (status 3) and the caller uses mdm_gemm_bf16 + mdm_rowop. */
+MDM_API int mdm_gemm_ln(const void* A, int lda, long a_rows, const void* W, int ldw, long w_rows, int M, int N, int K,
+                        const MdmGemmEpi* epi, const MdmRowOp* op, void* stream);
+
+
 /* ---- FastAttention core, models/fast_attention.py:29-92 (PerformerSelfAttention :155-160) ----
  * qkv: [B*T, 3*H*hd] (q | k | v, already multiplied by nothing: the 0.1 pre-scale of :155-157 is
  * applied inside).  P: [hd, M] fp32 projection_matrix.  norm_w/b: the shared LayerNorm(hd).
@@ -455,6 +469,12 @@ MDM_API int mdm_adam_step(float* p, float* g, float* m, float* v, long n, float 
                           void* stream);
 
 MDM_API int mdm_num_sms(void);
+/* Programmatic dependent launch (csrc/common.cuh): the kernels of the hot path are launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization so that the prologue of kernel N+1 overlaps the tail of kernel N
+ * (every kernel executes griddepcontrol.wait before its first global-memory access).  on = 1 / 0 switches the launch
+ * attribute, on < 0 only queries; returns the previous setting.  Default: on (environment MDM_B200_PDL=0 turns it off).
+ * No counterpart in the reference (torch launches every op in plain stream order). */
+MDM_API int mdm_set_pdl(int on);
 /* sizeof() of the structs above as this library was compiled: a binding checks its own struct definitions against them
  * (a short MdmGemmEpi would make the kernel read garbage as the tile_k device pointer). */
 MDM_API int mdm_sizeof_gemm_epi(void);

@@ -66,6 +66,7 @@ _SIGS = {
     "mdm_gemm_f32": [_P, _I, _L, _P, _I, _L, _I, _I, _I, _P, _I, _P, C.POINTER(GemmEpi), _P],
     "mdm_rowop": [C.POINTER(RowOp), _L, _I, _I, _P],
     "mdm_gemm_rowop": [C.POINTER(RowOp), _L, _I, _P, _I, _L, _I, C.POINTER(GemmEpi), _P],
+    "mdm_gemm_ln": [_P, _I, _L, _P, _I, _L, _I, _I, _I, C.POINTER(GemmEpi), C.POINTER(RowOp), _P],
     "mdm_fastattn": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "mdm_fastattn_ordered": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "mdm_lincross_ctx": [_P, _P, _I, _P, _I, _I, _I, _I, _P, _P],
@@ -136,6 +137,7 @@ _SIGS = {
     "mdm_grad_clip_coef": [_P, _L, _F, _P, _I, _P, _P],
     "mdm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P, _P, _P],
     "mdm_num_sms": [],
+    "mdm_set_pdl": [_I],
     "mdm_sizeof_gemm_epi": [],
     "mdm_sizeof_rowop": [],
     "mdm_sizeof_ep_peers": [],

@@ -177,12 +177,7 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);     // kt, q, kv, out
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
-  const int b = seq_order ? seq_order[blockIdx.x / H] : blockIdx.x / H, h = blockIdx.x % H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int D = H * HD;
-  const int len = length ? (int)min((long)T, (long)(length[b] >> length_shift)) : T;
-  const int kc_used = min(KC, (len + 63) / 64);      // frame chunks that contain unmasked keys
-
   FAU_INIT();
   if (tid == 0) {
 #pragma unroll
@@ -190,6 +185,11 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr, NCOLS);
+  pdl_enter();                                       // first global access below
+  const int b = seq_order ? seq_order[blockIdx.x / H] : blockIdx.x / H, h = blockIdx.x % H;
+  const int D = H * HD;
+  const int len = length ? (int)min((long)T, (long)(length[b] >> length_shift)) : T;
+  const int kc_used = min(KC, (len + 63) / 64);      // frame chunks that contain unmasked keys
 
   // ------------------------------------------------------------------ P0: operands
   // Every global load of the CTA is issued before anything waits: v by register prefetch (it is consumed first and
@@ -560,7 +560,7 @@ int launch(const bf16* qkv, const bf16* Pt, const float* nw, const float* nb, co
       return MDM_ERR_CUDA;
     attr |= dev_bit;
   }
-  fastattn_umma_kernel<TP><<<B * H, NTHR, L::TOTAL, st>>>(qkv, Pt, nw, nb, length, shift, H, T, out, seq_order);
+  mdm_launch(fastattn_umma_kernel<TP>, B * H, NTHR, L::TOTAL, st, qkv, Pt, nw, nb, length, shift, H, T, out, seq_order);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -596,6 +596,7 @@ lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, 
   const int D = H * HD;
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(tmem_ptr, TP);
+  pdl_enter();
   const int sub = tid & 7, rr = tid >> 3;
   const unsigned gmask = 0xffu << (lane & 24);
   const bf16* base = q + (long)b * T * D + h * HD;
@@ -746,7 +747,7 @@ int launch_lc(const bf16* q, const bf16* ctxT, int B, int H, int T, bf16* y, cud
       return MDM_ERR_CUDA;
     attr |= dev_bit;
   }
-  lincross_umma_kernel<TP><<<B * H, NTHR, L::TOTAL, st>>>(q, ctxT, H, T, y);
+  mdm_launch(lincross_umma_kernel<TP>, B * H, NTHR, L::TOTAL, st, q, ctxT, H, T, y);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -773,9 +774,10 @@ softmax_cross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = H * HD;
-  const int n_tok = nt ? min(nt[b], Nt_max) : Nt_max;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(tmem_ptr, TP);
+  pdl_enter();
+  const int n_tok = nt ? min(nt[b], Nt_max) : Nt_max;
   const int sub = tid & 7, rr = tid >> 3;
   // v rows -> registers (pairs {2 sub + 16 j, +1} of row n = rr + 32 p)
   uint32_t vraw[3][8];
@@ -977,7 +979,7 @@ int launch_sc(const bf16* q, const bf16* k, const bf16* v, const int* nt, int B,
     attr |= dev_bit;
   }
   const int NK = (Nt_max + 31) / 32 * 32;
-  softmax_cross_umma_kernel<TP><<<B * H, NTHR, L::TOTAL, st>>>(q, k, v, nt, H, T, Nt_max, NK, scale, o);
+  mdm_launch(softmax_cross_umma_kernel<TP>, B * H, NTHR, L::TOTAL, st, q, k, v, nt, H, T, Nt_max, NK, scale, o);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 

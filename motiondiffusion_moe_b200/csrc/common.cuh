@@ -13,6 +13,37 @@ typedef __nv_bfloat16 bf16;
 // current device ordinal (kernel attributes / SM counts are cached per device, not per process)
 inline int mdm_cur_dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The denoiser step is ~550 dependent kernels in one stream / CUDA graph; at batch 8 per GPU (the sharded sampler) each
+// lasts only a few microseconds, so the drain -> launch -> prologue gap between two of them is a large share of the
+// step.  Every kernel of the hot path is therefore launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// (mdm_launch) and follows ONE rule: nothing that touches global memory before pdl_wait().  What runs before it
+// (barrier init, TMEM allocation, tensor-map prefetch, index arithmetic) overlaps the tail of the previous kernel;
+// pdl_wait() returns when ALL prerequisite grids have completed and their writes are visible, so the data flow is the
+// same as with plain stream order (every kernel waits, so completion is transitive along the stream).
+// pdl_trigger() right after the wait lets the NEXT kernel's CTAs be scheduled as soon as every CTA of this grid is
+// resident or done.  Both instructions are no-ops for a kernel launched without the attribute (MDM_B200_PDL=0,
+// mdm_set_pdl(0)): the same binary runs both ways, which is how the A/B in profiles/ was measured.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
+int mdm_pdl_enabled();   // api.cu (host)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t mdm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = mdm_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 typedef MdmGemmEpi GemmEpi;
 typedef MdmMTile MTile;
 typedef MdmRowOp RowOp;

@@ -17,6 +17,8 @@
 #include <stdlib.h>
 #include "gemm_epilogue.cuh"
 #include "rowmath.cuh"
+#include "cluster.cuh"
+#include "tensormap.cuh"
 
 #ifdef MDM_GEMM_PROFILE
 // bring-up instrumentation: per CTA {epilogue wait cycles, epilogue work cycles, MMA-thread cycles waiting
@@ -89,6 +91,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_enter();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
   const int num_m_tiles = num_m_tiles_dev ? *num_m_tiles_dev : num_m_tiles_host;
   const int num_n_tiles = (N + BN - 1) / BN;
@@ -251,55 +254,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   empty[s]      one per CTA, signalled by the leader's multicast tcgen05.commit
 //   tmem_full[a]  one per CTA, multicast commit after the last k-block
 //   tmem_empty[a] leader only, 2 x 8 arrivals (the peer's epilogue warps arrive remotely)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0,
-                                                int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // same smem offset in both CTAs of the pair
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
-      : "memory");
-}
-
 constexpr int BN2 = 256;        // tile width of the pair kernel
 constexpr int HALF_N2 = 128;    // weight rows staged per CTA
 
@@ -357,6 +311,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_enter();
 
   const int num_m_tiles = num_m_tiles_dev ? *num_m_tiles_dev : num_m_tiles_host;
   const int num_pairs = (num_m_tiles + 1) >> 1;
@@ -498,75 +453,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2D bf16 tensor [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols].
-bool make_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld, int box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
-// Output tensor [rows, cols] bf16 with leading dimension ld; box = 32 rows x 32 columns (64-byte rows,
-// SWIZZLE_64B): the staging tile of one epilogue warp.
-bool make_out_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {32, 32};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
-// fp32 tensor [rows, cols] with leading dimension ld; box = 32 rows x 32 columns (128-byte rows, SWIZZLE_128B):
-// one residual / output staging tile of an epilogue warp (EPI_F32T).
-bool make_f32_map(CUtensorMap* map, const void* ptr, long rows, long cols, long ld) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, 32};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
-int g_num_sms[64] = {0};   // per device ordinal
-int num_sms() {
-  const int dev = mdm_cur_dev();
-  if (!g_num_sms[dev]) cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
-  return g_num_sms[dev];
-}
-
 template <int BN, int STAGES, int EPI, int ACT, bool MN = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
            const CUtensorMap& tf, int M, int N, int K, int num_m_tiles,
@@ -587,9 +473,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
   if (num_m_tiles_dev) grid = max_ctas;
   if (grid < 1) grid = 1;
-  gemm_tc_kernel<BN, STAGES, EPI, ACT, MN><<<grid, num_threads(EPI), L::TOTAL, stream>>>(
-      ta, tb, tc, tr, tf, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
-  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+  return mdm_launch(gemm_tc_kernel<BN, STAGES, EPI, ACT, MN>, grid, num_threads(EPI), L::TOTAL, stream,
+                    ta, tb, tc, tr, tf, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi) == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
 template <int STAGES, int EPI, int ACT>
@@ -610,9 +495,8 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
   long clusters = max_ctas / 2;
   if (!num_m_tiles_dev && work < clusters) clusters = work;
   if (clusters < 1) clusters = 1;
-  gemm_tc2_kernel<STAGES, EPI, ACT><<<(unsigned)(2 * clusters), num_threads(EPI), L::TOTAL, stream>>>(
-      ta, tb, tc, tr, tf, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi);
-  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+  return mdm_launch(gemm_tc2_kernel<STAGES, EPI, ACT>, (unsigned)(2 * clusters), num_threads(EPI), L::TOTAL, stream,
+                    ta, tb, tc, tr, tf, M, N, K, num_m_tiles, num_m_tiles_dev, mtiles, epi) == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
 
@@ -690,6 +574,7 @@ gemm_rowop_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_enter();
 
   if (warp < FIRST_EPI_WARP) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -876,10 +761,9 @@ int launch_rowop_gemm(const CUtensorMap& tb, const CUtensorMap& tc, const CUtens
     attr |= dev_bit;
   }
   const int tiles = (M + BM - 1) / BM, sms = num_sms();
-  gemm_rowop_kernel<TI, FLAGS><<<tiles < sms ? tiles : sms, num_threads(EPI_F32T), RowGemmSmem::TOTAL, st>>>(
-      tb, tc, tr, tf, reinterpret_cast<const TI*>(op.in), op.ln1_w, op.ln1_b, op.ln2_w, op.ln2_b, op.film, op.rows_per_seq, M, N,
-      epi);
-  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+  return mdm_launch(gemm_rowop_kernel<TI, FLAGS>, tiles < sms ? tiles : sms, num_threads(EPI_F32T), RowGemmSmem::TOTAL, st,
+                    tb, tc, tr, tf, reinterpret_cast<const TI*>(op.in), op.ln1_w, op.ln1_b, op.ln2_w, op.ln2_b, op.film,
+                    op.rows_per_seq, M, N, epi) == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
 }  // namespace

@@ -7,6 +7,7 @@ namespace {
 
 template <typename T>
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, int B, int D, T* __restrict__ out) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = D / 2;
   if (i >= B * half) return;
@@ -21,6 +22,7 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, int B, 
 
 template <typename T>
 __global__ void gated_mix_kernel(const float* __restrict__ t, const float* __restrict__ x, long n, T* __restrict__ out) {
+  pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float tv = t[i], xv = x[i];
@@ -30,6 +32,7 @@ __global__ void gated_mix_kernel(const float* __restrict__ t, const float* __res
 
 template <typename T>
 __global__ void pad_cast_kernel(const float* __restrict__ x, long rows, int F, T* __restrict__ out, int ld) {
+  pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * ld) return;
   const long r = i / ld;
@@ -46,6 +49,7 @@ __global__ void cfg_update_kernel(const float* x, const float* __restrict__ eps_
                                   const int64_t* __restrict__ t, const float* __restrict__ tables, int n_steps,
                                   float s, int clip, long per_sample, long total, float* x_prev,
                                   float* __restrict__ x0_out) {
+  pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int b = (int)(i / per_sample);
@@ -110,6 +114,7 @@ __global__ void ddim_update_kernel(const float* x /* may alias x_prev */, const 
                                    const int64_t* __restrict__ t, const int64_t* __restrict__ t_prev,
                                    const float* __restrict__ tables, int n_steps, float s, float eta, int clip,
                                    long per_sample, long total, float* x_prev, float* __restrict__ x0_out) {
+  pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int b = (int)(i / per_sample);
@@ -411,8 +416,8 @@ extern "C" MDM_API int mdm_timestep_embedding(const int64_t* t, int B, int D, vo
   if (B == 0) return MDM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long n = (long)B * (D / 2);
-  if (dt == MDM_F32) timestep_embedding_kernel<float><<<blocks(n), 256, 0, st>>>(t, B, D, reinterpret_cast<float*>(out));
-  else timestep_embedding_kernel<bf16><<<blocks(n), 256, 0, st>>>(t, B, D, reinterpret_cast<bf16*>(out));
+  if (dt == MDM_F32) mdm_launch(timestep_embedding_kernel<float>, blocks(n), 256, 0, st, t, B, D, reinterpret_cast<float*>(out));
+  else mdm_launch(timestep_embedding_kernel<bf16>, blocks(n), 256, 0, st, t, B, D, reinterpret_cast<bf16*>(out));
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -420,8 +425,8 @@ extern "C" MDM_API int mdm_gated_mix(const float* t, const float* x, long n, voi
   if (!t || !x || !out) return MDM_ERR_ARG;
   if (n == 0) return MDM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dt == MDM_F32) gated_mix_kernel<float><<<blocks(n), 256, 0, st>>>(t, x, n, reinterpret_cast<float*>(out));
-  else gated_mix_kernel<bf16><<<blocks(n), 256, 0, st>>>(t, x, n, reinterpret_cast<bf16*>(out));
+  if (dt == MDM_F32) mdm_launch(gated_mix_kernel<float>, blocks(n), 256, 0, st, t, x, n, reinterpret_cast<float*>(out));
+  else mdm_launch(gated_mix_kernel<bf16>, blocks(n), 256, 0, st, t, x, n, reinterpret_cast<bf16*>(out));
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -430,8 +435,8 @@ extern "C" MDM_API int mdm_pad_cast(const float* x, long rows, int F, void* out,
   if (rows == 0) return MDM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long n = rows * ld_out;
-  if (dt == MDM_F32) pad_cast_kernel<float><<<blocks(n), 256, 0, st>>>(x, rows, F, reinterpret_cast<float*>(out), ld_out);
-  else pad_cast_kernel<bf16><<<blocks(n), 256, 0, st>>>(x, rows, F, reinterpret_cast<bf16*>(out), ld_out);
+  if (dt == MDM_F32) mdm_launch(pad_cast_kernel<float>, blocks(n), 256, 0, st, x, rows, F, reinterpret_cast<float*>(out), ld_out);
+  else mdm_launch(pad_cast_kernel<bf16>, blocks(n), 256, 0, st, x, rows, F, reinterpret_cast<bf16*>(out), ld_out);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -441,8 +446,7 @@ extern "C" MDM_API int mdm_cfg_update(const float* x, const float* eps_c, const 
   if (!x || !eps_c || !eps_u || !noise || !t || !tables || !x_prev) return MDM_ERR_ARG;
   const long total = (long)B * per_sample;
   if (total == 0) return MDM_OK;
-  cfg_update_kernel<<<blocks(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, eps_c, eps_u, noise, t, tables, n_steps, cfg_scale, clip, per_sample, total, x_prev, x0);
+  mdm_launch(cfg_update_kernel, blocks(total), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, eps_c, eps_u, noise, t, tables, n_steps, cfg_scale, clip, per_sample, total, x_prev, x0);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -474,8 +478,7 @@ extern "C" MDM_API int mdm_ddim_update(const float* x, const float* eps_c, const
   if (!x || !eps_c || !t || !tables4 || !x_prev || (eta != 0.f && !noise)) return MDM_ERR_ARG;
   const long total = (long)B * per_sample;
   if (total == 0) return MDM_OK;
-  ddim_update_kernel<<<blocks(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, eps_c, eps_u, noise, t, t_prev, tables4, n_steps, cfg_scale, eta, clip, per_sample, total, x_prev, x0);
+  mdm_launch(ddim_update_kernel, blocks(total), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, eps_c, eps_u, noise, t, t_prev, tables4, n_steps, cfg_scale, eta, clip, per_sample, total, x_prev, x0);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 

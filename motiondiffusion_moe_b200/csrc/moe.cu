@@ -139,6 +139,7 @@ moe_gate_kernel(const float* __restrict__ x, long N, int D, const float* __restr
     }
     asm volatile("cp.async.commit_group;" ::: "memory");     // always: the group count stays uniform
   };
+  pdl_enter();
   if (PREFETCH) fetch(tok0);
   if (ASYNC) issue(tok0, 0);
   int stage = 0;
@@ -272,6 +273,7 @@ moe_scan_kernel(const int* __restrict__ blk_hist, const float* __restrict__ blk_
                 float* __restrict__ usage, float* __restrict__ importance) {
   __shared__ int total_s[MAX_G];
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_enter();
   if (g < G) {
     const int per = (nblk + 31) / 32, b0 = lane * per, b1 = min(nblk, b0 + per);
     int tot = 0, top1 = 0;
@@ -348,6 +350,7 @@ moe_permute_kernel(const float* __restrict__ x, long N, int D, int NB, int E, co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npairs = TOK_PER_BLK * NBK;           // <= 512
   const int nseg = npairs / 32;                   // <= 16
+  pdl_enter();
   for (int i = threadIdx.x; i < 16 * MAX_G; i += PERM_WARPS * 32) (&seg_cnt[0][0])[i] = 0;
   __syncthreads();
   const long tok_blk0 = (long)blockIdx.x * TOK_PER_BLK;
@@ -420,6 +423,7 @@ moe_combine_film_kernel(const TI* __restrict__ yp, const int* __restrict__ perm,
                         const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                         const float* __restrict__ film, int rows_per_seq, TI* __restrict__ out) {
   const long tok = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  pdl_enter();
   if (tok >= N) return;
   const int lane = threadIdx.x & 31;
   float acc[VPT];
@@ -480,7 +484,7 @@ int launch_gate(const float* x, long N, int D, const float* ln_w, const float* l
     if (smem8 > 48 * 1024 && cudaFuncSetAttribute(moe_gate_kernel<VPT, E, NB, 8, true>,
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8) != cudaSuccess)
       return MDM_ERR_CUDA;
-    moe_gate_kernel<VPT, E, NB, 8, true><<<nblk, 256, smem8, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
+    mdm_launch(moe_gate_kernel<VPT, E, NB, 8, true>, nblk, 256, smem8, st, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
                                                                    blk_hist, blk_imp, forced_idx);
     return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
   }
@@ -492,11 +496,11 @@ int launch_gate(const float* x, long N, int D, const float* ln_w, const float* l
     return MDM_ERR_CUDA;
   const int sms = mdm_num_sms();
   if (nblk <= sms)
-    moe_gate_kernel<VPT, E, NB, 16><<<nblk, 512, smem, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
-                                                             blk_hist, blk_imp);
+    mdm_launch(moe_gate_kernel<VPT, E, NB, 16>, nblk, 512, smem, st, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
+                                                             blk_hist, blk_imp, (const int*)nullptr);
   else
-    moe_gate_kernel<VPT, E, NB, 8><<<nblk, 256, smem8, st>>>(x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
-                                                             blk_hist, blk_imp);
+    mdm_launch(moe_gate_kernel<VPT, E, NB, 8>, nblk, 256, smem8, st, x, N, D, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
+                                                             blk_hist, blk_imp, (const int*)nullptr);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -552,8 +556,7 @@ extern "C" MDM_API int mdm_moe_scan(const int* blk_hist, const float* blk_imp, c
     return MDM_ERR_ARG;
   if (K != 2 || NB * E > MAX_G) return MDM_ERR_UNSUPPORTED;
   const int nblk = (int)((N + TOK_PER_BLK - 1) / TOK_PER_BLK);
-  moe_scan_kernel<<<1, 32 * (NB * E), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      blk_hist, blk_imp, nblk, NB * E, E, F, D, blk_base, seg_offsets, reinterpret_cast<MTile*>(tiles_up),
+  mdm_launch(moe_scan_kernel, 1, 32 * (NB * E), 0, reinterpret_cast<cudaStream_t>(stream), blk_hist, blk_imp, nblk, NB * E, E, F, D, blk_base, seg_offsets, reinterpret_cast<MTile*>(tiles_up),
       reinterpret_cast<MTile*>(tiles_down), num_tiles, usage, importance);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
@@ -569,10 +572,10 @@ extern "C" MDM_API int mdm_moe_permute(const float* x, long N, int D, int NB, in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VPT_SWITCH(D, {
     if (dt == MDM_F32)
-      moe_permute_kernel<V, float><<<nblk, PERM_WARPS * 32, 0, st>>>(x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
+      mdm_launch(moe_permute_kernel<V, float>, nblk, PERM_WARPS * 32, 0, st, x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
                                                           seg_offsets, reinterpret_cast<float*>(xp), perm, rowscale);
     else
-      moe_permute_kernel<V, bf16><<<nblk, PERM_WARPS * 32, 0, st>>>(x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
+      mdm_launch(moe_permute_kernel<V, bf16>, nblk, PERM_WARPS * 32, 0, st, x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
                                                          seg_offsets, reinterpret_cast<bf16*>(xp), perm, rowscale);
   });
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
@@ -588,11 +591,11 @@ extern "C" MDM_API int mdm_moe_combine_film(const void* yp, int dt, const int* p
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VPT_SWITCH(D, {
     if (dt == MDM_F32)
-      moe_combine_film_kernel<V, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(yp), perm, N, D, NBK,
+      mdm_launch(moe_combine_film_kernel<V, float>, grid, 256, 0, st, reinterpret_cast<const float*>(yp), perm, N, D, NBK,
                                                                ln_w, ln_b, film, rows_per_seq,
                                                                reinterpret_cast<float*>(out));
     else
-      moe_combine_film_kernel<V, bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(yp), perm, N, D, NBK,
+      mdm_launch(moe_combine_film_kernel<V, bf16>, grid, 256, 0, st, reinterpret_cast<const bf16*>(yp), perm, N, D, NBK,
                                                               ln_w, ln_b, film, rows_per_seq,
                                                               reinterpret_cast<bf16*>(out));
   });

@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(256, (VPT >= 32 ? 1 : 3)) rowop_kernel(const R
   const bool do_film = FLAGS >= 0 ? (FLAGS & F_FILM) != 0 : op.film != nullptr;
   const bool do_silu = FLAGS >= 0 ? (FLAGS & F_SILU) != 0 : op.silu != 0;
   const TI* in = reinterpret_cast<const TI*>(op.in);
+  pdl_enter();
   // The affine vectors are staged in shared memory rather than registers: the kernel is bound by
   // per-warp dependency latency (ncu: 45 % issue utilisation with 4 warps per scheduler), so the
   // registers buy more resident warps (3 CTAs per SM) instead.
@@ -255,7 +256,8 @@ int dispatch(const RowOp& op, long rows, int D, int out_dt, cudaStream_t st) {
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   const int flags = (op.ln1_w ? F_LN1 : 0) | (op.l2norm ? F_L2 : 0) | (op.ln2_w ? F_LN2 : 0) | (op.film ? F_FILM : 0) |
                     (op.silu ? F_SILU : 0);
-#define ROWOP(TI_, TO_, FAST_, FL_) rowop_kernel<VPT, TI_, TO_, FAST_, FL_><<<grid, 256, 0, st>>>(op, rows, D)
+  cudaError_t err = cudaSuccess;
+#define ROWOP(TI_, TO_, FAST_, FL_) err = mdm_launch(rowop_kernel<VPT, TI_, TO_, FAST_, FL_>, grid, 256, 0, st, op, rows, D)
   if (op.in_dt == MDM_F32 && out_dt == MDM_F32) {
     ROWOP(float, float, false, F_RUNTIME);
   } else if (op.in_dt == MDM_F32 && out_dt == MDM_BF16) {   // stage sets of MotionTransformer._layer
@@ -274,7 +276,7 @@ int dispatch(const RowOp& op, long rows, int D, int out_dt, cudaStream_t st) {
     return MDM_ERR_ARG;
   }
 #undef ROWOP
-  return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+  return err == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
 

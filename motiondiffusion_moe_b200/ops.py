@@ -145,6 +145,45 @@ def gemm_rowop(x, rows, D, W, bias, *, ln1=None, l2norm=False, ln2=None, film=No
     return True
 
 
+def gemm_ln(A, W, bias, *, ln1, act=ACT_NONE, alpha=1.0, beta=0.0, resid=None, out_f32=None, out_a=None, ln_pre_resid=False,
+            l2norm=False, out1_f32=None, out1_a=None, ln2=None, film=None, rows_per_seq=0, silu=False, out2_a=None):
+    """Linear + the row pipeline that follows it in ONE kernel (mdm_gemm_ln, csrc/gemm_ln.cu): N == 512 rows stay in
+    TMEM between the GEMM and the LayerNorm passes.  y = act(A @ W^T + bias) * alpha + beta * resid -> out_f32;
+    s = y (or the pre-residual value with ln_pre_resid) -> out_a (bf16 copy); u = L2norm?(LN1(s)) -> out1_f32 / out1_a;
+    z = SiLU?(FiLM?(LN2(u))) -> out2_a.  Returns False (nothing launched) for shapes / stage sets outside the fused
+    kernel: the caller then runs gemm + rowop."""
+    _req_cuda(A, W, out_f32, out_a, resid)
+    _c(bias, film, out1_f32, out1_a, out2_a)
+    for pair in (ln1, ln2):
+        if pair is not None:
+            _c(*pair)
+    if A.dtype != torch.bfloat16 or W.shape[0] != 512 or A.shape[1] % 64 or A.dim() != 2 or A.stride(1) != 1:
+        return False
+    op = _lib.RowOp()
+    op.ln1_w, op.ln1_b = ln1[0].data_ptr(), ln1[1].data_ptr()
+    op.l2norm = 1 if l2norm else 0
+    op.out1_f32, op.out1_a = _ptr(out1_f32), _ptr(out1_a)
+    if ln2 is not None:
+        op.ln2_w, op.ln2_b = ln2[0].data_ptr(), ln2[1].data_ptr()
+    op.film, op.rows_per_seq, op.silu = _ptr(film), rows_per_seq, 1 if silu else 0
+    op.out2_a = _ptr(out2_a)
+    e = _lib.GemmEpi()
+    e.bias, e.resid = _ptr(bias), _ptr(resid)
+    e.ld_resid = resid.stride(0) if resid is not None else 0
+    e.alpha, e.beta, e.act = alpha, beta, act
+    if out_f32 is not None:
+        e.out_f32, e.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    if out_a is not None:
+        e.out_bf16, e.ld_bf16 = out_a.data_ptr(), out_a.stride(0)
+    e.bf16_pre_resid = 1 if ln_pre_resid else 0
+    st = _lib.load().mdm_gemm_ln(A.data_ptr(), A.stride(0), A.shape[0], W.data_ptr(), W.stride(0), W.shape[0], A.shape[0],
+                                 W.shape[0], A.shape[1], C.byref(e), C.byref(op), _stream())
+    if st == 3:             # MDM_ERR_UNSUPPORTED
+        return False
+    _lib.check(st, "mdm_gemm_ln")
+    return True
+
+
 def fastattn(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out, seq_order=None, Pt=None):
     _c(qkv, P, norm_w, norm_b, length, out, seq_order, Pt)
     if Pt is not None and (Pt.dtype != torch.bfloat16 or tuple(Pt.shape) != (P.shape[1], P.shape[0])):

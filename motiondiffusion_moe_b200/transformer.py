@@ -90,6 +90,9 @@ class MotionTransformer(nn.Module):
         # mdm_gemm_rowop (row pipeline fused into the GEMM's A-operand construction) is correct and tested but slower
         # than rowop + GEMM today (profiles/README.md, step 22): opt-in with MDM_FUSE_ROWOP=1
         self._fuse_rowop = os.environ.get("MDM_FUSE_ROWOP", "0") == "1"
+        # Linear + the LayerNorm chain that follows it in one kernel (ops.gemm_ln: the row stays in TMEM; north_star (3)).
+        # bf16 mode, latent_dim 512; MDM_FUSE_LN=0 keeps the gemm + rowop pairs (A/B runs, parity tests of both).
+        self._fuse_ln = os.environ.get("MDM_FUSE_LN", "1") == "1"
         self._packed = None
         self._ws = {}
         self._film_tiles = {}
@@ -626,8 +629,10 @@ class MotionTransformer(nn.Module):
             out_f32, out_a = out_a, None
         ops.gemm(A, wb[0], wb[1], act=act, out_a=out_a, out_f32=out_f32, **kw)
 
-    def _performer(self, Pk, resid, hh, film, out, Bn, T, length, shift, order=None):
-        """PerformerSelfAttention.forward (fast_attention.py:137-179) after its pre_norm."""
+    def _performer(self, Pk, resid, hh, film, out, Bn, T, length, shift, order=None, next_ln=None, next_out=None):
+        """PerformerSelfAttention.forward (fast_attention.py:137-179) after its pre_norm.  next_ln / next_out: the
+        LayerNorm that consumes this block's output (the next block's pre-norm) and its bf16 destination; returns True
+        when that LayerNorm was computed here (in the epilogue of the output Linear)."""
         adt, D, H = self._adt(), self.latent_dim, self.num_heads
         N = Bn * T
         qkv = self._buf("qkv", (N, 3 * D), adt)
@@ -637,18 +642,34 @@ class MotionTransformer(nn.Module):
         ops.fastattn(qkv, Pk["P"], Pk["fa_norm"][0], Pk["fa_norm"][1], length, shift, Bn, H, T, D // H, a1,
                      seq_order=order, Pt=Pk["Pt"])
         self._lin(a1, Pk["p0"], out_a=a2, act=ACT_GELU)
-        self._lin(a2, Pk["p3"], out_a=a1)
-        # post LN -> L2 norm -> StylizationBlock (LN, FiLM, SiLU) -> its output Linear, + residual: one kernel in bf16
-        # mode (the row pipeline builds the GEMM's A operand in shared memory), rowop + GEMM otherwise
-        if not (self._fuse_rowop and adt == torch.bfloat16 and
-                ops.gemm_rowop(a1, N, D, Pk["s_out"][0], Pk["s_out"][1], ln1=Pk["post"], l2norm=True, ln2=Pk["s_norm"],
-                               film=film, rows_per_seq=T, silu=True, out_f32=out, resid=resid, alpha=0.1, beta=1.0)):
+        fuse = self._fuse_ln and adt == torch.bfloat16
+        # projection Linear -> post LN -> L2 norm -> StylizationBlock (LN, FiLM, SiLU) in the Linear's epilogue
+        if fuse and ops.gemm_ln(a2, Pk["p3"][0], Pk["p3"][1], ln1=Pk["post"], l2norm=True, ln2=Pk["s_norm"], film=film,
+                                rows_per_seq=T, silu=True, out2_a=a1):
+            src = a1
+        else:
+            self._lin(a2, Pk["p3"], out_a=a1)
+            # opt-in alternative: the row pipeline builds the A operand of the output Linear in shared memory
+            if (self._fuse_rowop and adt == torch.bfloat16 and
+                    ops.gemm_rowop(a1, N, D, Pk["s_out"][0], Pk["s_out"][1], ln1=Pk["post"], l2norm=True, ln2=Pk["s_norm"],
+                                   film=film, rows_per_seq=T, silu=True, out_f32=out, resid=resid, alpha=0.1, beta=1.0)):
+                return False
             ops.rowop(a1, N, D, ops._dt(a2), ln1=Pk["post"], l2norm=True, ln2=Pk["s_norm"], film=film,
                       rows_per_seq=T, silu=True, out2_a=a2)
-            self._lin(a2, Pk["s_out"], out_f32=out, resid=resid, alpha=0.1, beta=1.0)
+            src = a2
+        # StylizationBlock output Linear + residual (+ the next block's pre-norm in its epilogue)
+        if (fuse and next_ln is not None and
+                ops.gemm_ln(src, Pk["s_out"][0], Pk["s_out"][1], ln1=next_ln, alpha=0.1, beta=1.0, resid=resid, out_f32=out,
+                            out1_a=next_out)):
+            return True
+        self._lin(src, Pk["s_out"], out_f32=out, resid=resid, alpha=0.1, beta=1.0)
+        return False
 
-    def _layer(self, li, x, ctx, film_all, Bpad, Bn, T, length, shift):
-        """MoEExtendedDecoderLayer.forward (transformer.py:55-64); x [Bn*T, D] fp32 is updated in place."""
+    def _layer(self, li, x, ctx, film_all, Bpad, Bn, T, length, shift, pre_done=False, nxt=None):
+        """MoEExtendedDecoderLayer.forward (transformer.py:55-64); x [Bn*T, D] fp32 is updated in place.
+        pre_done: this layer's two pre-norms (h, a0) and the bf16 copy of x (xa) were already produced by the previous
+        layer's last Linear; nxt: index of the layer that consumes x next (its pre-norms go into this layer's last
+        Linear).  Returns True when the pre-norms of `nxt` were computed here."""
         pk = self._packed
         L = pk["layers"][li]
         adt, D, Fd, E, H = self._adt(), self.latent_dim, self.ff_size, self.moe_num_experts, self.num_heads
@@ -667,13 +688,19 @@ class MotionTransformer(nn.Module):
         a2 = self._buf("a2", (N, D), adt)
         xa = self._buf("xa", (N, D), adt)
         # ---- DualSelfAttentionBlock (fast_attention.py:208-226)
-        ops.rowop(x, N, D, adti, ln1=L["dsa_pre"], out1_f32=h, ln2=L["perf"][0]["pre"], out2_a=a0, out0_a=xa)
-        self._performer(L["perf"][0], h, a0, film[0], loc, Bn, T, length, shift, ctx.seq_order)
-        ops.rowop(loc, N, D, adti, ln1=L["perf"][1]["pre"], out1_a=a0)
+        fuse = self._fuse_ln and adt == torch.bfloat16
+        if not pre_done:
+            ops.rowop(x, N, D, adti, ln1=L["dsa_pre"], out1_f32=h, ln2=L["perf"][0]["pre"], out2_a=a0, out0_a=xa)
+        if not self._performer(L["perf"][0], h, a0, film[0], loc, Bn, T, length, shift, ctx.seq_order,
+                               next_ln=L["perf"][1]["pre"], next_out=a0):
+            ops.rowop(loc, N, D, adti, ln1=L["perf"][1]["pre"], out1_a=a0)
         self._performer(L["perf"][1], loc, a0, film[1], glb, Bn, T, length, shift, ctx.seq_order)
-        pre = h  # h is dead from here on
-        self._lin(xa, L["skip"], out_f32=pre, act=ACT_GELU, resid=glb, alpha=1.0, beta=0.1)
-        ops.rowop(pre, N, D, adti, ln1=L["dsa_post"], out1_f32=x1, ln2=L["ca_norm"], out2_a=a0)
+        # skip Linear + GELU + 0.1 * global branch -> post norm (x1, fp32) -> cross-attention norm (a0)
+        if not (fuse and ops.gemm_ln(xa, L["skip"][0], L["skip"][1], ln1=L["dsa_post"], act=ACT_GELU, alpha=1.0, beta=0.1,
+                                     resid=glb, out1_f32=x1, ln2=L["ca_norm"], out2_a=a0)):
+            pre = h  # h is dead from here on
+            self._lin(xa, L["skip"], out_f32=pre, act=ACT_GELU, resid=glb, alpha=1.0, beta=0.1)
+            ops.rowop(pre, N, D, adti, ln1=L["dsa_post"], out1_f32=x1, ln2=L["ca_norm"], out2_a=a0)
         # ---- GatedCrossAttention (fast_attention.py:242-272)
         self._lin(a0, L["ca_q"], out_a=a1)
         ops.lincross_apply(a1, ctx.lin_ctx[li], Bn, T, H, D // H, a2, ctxT=ctx.lin_ctxT[li])
@@ -700,7 +727,7 @@ class MotionTransformer(nn.Module):
                        importance=pk["importance"][li])
             if self.record_routing:
                 self.last_routing.append((ep.idx.clone(), ep.vals.clone()))
-            return self._layer_tail(li, L, x, x2, None, a1, a2, xa, x1, ctx, Bn, T, N)
+            return self._layer_tail(li, L, x, x2, None, a1, a2, xa, x1, ctx, Bn, T, N, nxt)
         NB, NBK, G = 2, 4, 2 * E
         cap = NBK * N + G * 128
         nblk = (N + 127) // 128
@@ -735,9 +762,9 @@ class MotionTransformer(nn.Module):
         self._lin(hp, (L["w2"], L["b2"]), out_a=yp, N=D, rowscale=rscale, a_rows=cap, w_rows=G * D,
                   **dict(kw, tiles=t_dn))
         ops.moe_combine_film(yp, perm, N, D, NBK, L["ffn_s_norm"][0], L["ffn_s_norm"][1], film[3], T, a1)
-        return self._layer_tail(li, L, x, x2, None, a1, a2, xa, x1, ctx, Bn, T, N)
+        return self._layer_tail(li, L, x, x2, None, a1, a2, xa, x1, ctx, Bn, T, N, nxt)
 
-    def _layer_tail(self, li, L, x, x2, _unused, a1, a2, xa, x1, ctx, Bn, T, N):
+    def _layer_tail(self, li, L, x, x2, _unused, a1, a2, xa, x1, ctx, Bn, T, N, nxt=None):
         """ffn.proj_out Linear + MemoryEfficientCrossAttentionBlock (fast_attention.py:301-330)."""
         adt, D, H = self._adt(), self.latent_dim, self.num_heads
         adti = MDM_BF16 if adt == torch.bfloat16 else MDM_F32
@@ -752,12 +779,28 @@ class MotionTransformer(nn.Module):
         self._lin(x3a, L["sd_q"], out_a=a1)
         ops.softmax_cross(a1, ctx.k2[li], ctx.v2[li], ctx.nt, Bn, T, ctx.nt_max, H, D // H, a2)
         rr = x1  # x1 is dead from here on
-        ops.gemm(a2, L["sd_o"][0], L["sd_o"][1], out_f32=rr, out_a=a1, a_pre_resid=True, resid=x3, alpha=1.0,
-                 beta=1.0)
-        ops.rowop(a1, N, D, adti, ln1=L["sd_ln"], out1_a=a2)
+        fuse = self._fuse_ln and adt == torch.bfloat16
+        # output projection: rr = proj + x3 (fp32), and the LayerNorm of the projection itself in the same kernel
+        if fuse and ops.gemm_ln(a2, L["sd_o"][0], L["sd_o"][1], ln1=L["sd_ln"], alpha=1.0, beta=1.0, resid=x3, out_f32=rr,
+                                ln_pre_resid=True, out1_a=a1):
+            n_in = a1
+        else:
+            ops.gemm(a2, L["sd_o"][0], L["sd_o"][1], out_f32=rr, out_a=a1, a_pre_resid=True, resid=x3, alpha=1.0,
+                     beta=1.0)
+            ops.rowop(a1, N, D, adti, ln1=L["sd_ln"], out1_a=a2)
+            n_in = a2
         f1 = self._buf("f1", (N, 4 * D), adt)
-        self._lin(a2, L["sd_f1"], out_a=f1, act=ACT_GELU)
+        self._lin(n_in, L["sd_f1"], out_a=f1, act=ACT_GELU)
+        if fuse and nxt is not None:
+            # the layer output + the next layer's two pre-norms (h fp32, a0) and the bf16 copy of x (xa): all three
+            # buffers are dead at this point of the layer
+            Ln = self._packed["layers"][nxt]
+            if ops.gemm_ln(f1, L["sd_f3"][0], L["sd_f3"][1], ln1=Ln["dsa_pre"], alpha=1.0, beta=1.0, resid=rr, out_f32=x,
+                           out_a=xa, out1_f32=self._buf("h", (N, D), torch.float32), ln2=Ln["perf"][0]["pre"],
+                           out2_a=self._buf("a0", (N, D), adt)):
+                return True
         self._lin(f1, L["sd_f3"], out_f32=x, resid=rr, alpha=1.0, beta=1.0)
+        return False
 
     def _embeddings(self, timesteps, xf_proj, Bn):
         """fused_emb (transformer.py:313-321) and the FiLM (scale|shift) of all 8L StylizationBlocks
@@ -853,8 +896,10 @@ class MotionTransformer(nn.Module):
         hl = self._buf("x_low", (Nl, D), f32)
         ops.gemm(ha.view(Nl, 2 * D), pk["down_w"], pk["down_b"], out_f32=hl)
         nl = self.num_layers
+        done = False
         for li in range(nl):                                             # transformer.py:341-344
-            self._layer(li, hl, text_ctx, film, Bpad, Bn, T // 2, length, 1)
+            done = self._layer(li, hl, text_ctx, film, Bpad, Bn, T // 2, length, 1, pre_done=done,
+                               nxt=li + 1 if li + 1 < nl else None)
         # upsample ConvTranspose1d(k=2,s=2) + skip (transformer.py:347-353)
         if adt == torch.bfloat16:
             hla = self._buf("x_low_a", (Nl, D), adt)
@@ -864,8 +909,10 @@ class MotionTransformer(nn.Module):
         hc = self._buf("x_high", (N, D), f32)
         ops.gemm(hla, pk["up_w"], pk["up_b"], out_f32=hc.view(Nl, 2 * D), resid=h.view(Nl, 2 * D), alpha=1.0,
                  beta=1.0)
+        done = False
         for li in range(nl, 2 * nl):                                     # transformer.py:356-357
-            self._layer(li, hc, text_ctx, film, Bpad, Bn, T, length, 0)
+            done = self._layer(li, hc, text_ctx, film, Bpad, Bn, T, length, 0, pre_done=done,
+                               nxt=li + 1 if li + 1 < 2 * nl else None)
         if adt == torch.bfloat16:
             hca = self._buf("x_high_a", (N, D), adt)
             ops.rowop(hc, N, D, adti, out0_a=hca)

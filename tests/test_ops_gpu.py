@@ -173,6 +173,74 @@ def test_gemm_rowop_fused(stages, M, T):
     assert not ops.gemm_rowop(x[:, :256].contiguous(), M, 256, W[:, :256].contiguous(), b, out_f32=out[:M], resid=R, **kw)
 
 
+@pytest.mark.parametrize("variant", ["proj_style", "sout_ln", "skip_ln_ln", "sdo_ln_pre", "ffn_ln_ln_copy"])
+@pytest.mark.parametrize("M,K,T", [(196 * 3, 512, 196), (128, 512, 8), (1000, 2048, 100), (25, 512, 5), (1537, 1024, 196)])
+def test_gemm_ln_fused(variant, M, K, T):
+    """mdm_gemm_ln (csrc/gemm_ln.cu): the Linear and the row pipeline that follows it in one kernel (the row stays in
+    TMEM), for the five Linear -> LayerNorm chains of MoEExtendedDecoderLayer, against torch fp32 on the same bf16
+    operands and against the unfused gemm + rowop pair.  Rows past M must stay untouched (TMA clipping), ragged
+    M (not a multiple of the 256-row pair tile), T not dividing 128 (several sequences' FiLM rows in one tile)."""
+    D = N = 512
+    A = randn(M, K, seed=1).bfloat16()
+    W = randn(N, K, seed=2, scale=K ** -0.5).bfloat16()
+    b, R = randn(N, seed=3, scale=0.5), randn(M, N, seed=4, scale=2.0)
+    ln1 = (torch.rand(D, generator=gen(5)).to(DEV) + 0.5, randn(D, seed=6, scale=0.1))
+    ln2 = (torch.rand(D, generator=gen(7)).to(DEV) + 0.5, randn(D, seed=8, scale=0.1))
+    film = randn((M + T - 1) // T, 2 * D, seed=9, scale=0.3)
+    bf = torch.bfloat16
+
+    def buf(dt):
+        return torch.full((M + 8, N), 3.0, device=DEV, dtype=dt)
+
+    acc = A.float() @ W.float().t() + b
+    got, ref = {}, {}
+    if variant == "proj_style":      # Performer p3 -> post LN -> L2 norm -> StylizationBlock LN, FiLM, SiLU
+        o2 = buf(bf)
+        assert ops.gemm_ln(A, W, b, ln1=ln1, l2norm=True, ln2=ln2, film=film, rows_per_seq=T, silu=True, out2_a=o2[:M])
+        v = F.layer_norm(acc, (D,), ln1[0], ln1[1])
+        v = F.normalize(v, dim=-1) * math.sqrt(D)
+        v = F.layer_norm(v, (D,), ln2[0], ln2[1])
+        seq = torch.arange(M, device=DEV) // T
+        ref["out2"] = F.silu(v * (1 + film[seq, :D]) + film[seq, D:])
+        got["out2"] = o2
+    elif variant == "sout_ln":       # s_out + residual -> pre-norm of the next Performer block
+        y, o1 = buf(torch.float32), buf(bf)
+        assert ops.gemm_ln(A, W, b, ln1=ln1, alpha=0.1, beta=1.0, resid=R, out_f32=y[:M], out1_a=o1[:M])
+        ref["y"] = R + 0.1 * acc
+        ref["out1"] = F.layer_norm(ref["y"], (D,), ln1[0], ln1[1])
+        got["y"], got["out1"] = y, o1
+    elif variant == "skip_ln_ln":    # skip Linear + GELU + 0.1 * residual -> post norm (fp32) -> cross-attention norm
+        o1, o2 = buf(torch.float32), buf(bf)
+        assert ops.gemm_ln(A, W, b, ln1=ln1, act=ACT_GELU, alpha=1.0, beta=0.1, resid=R, out1_f32=o1[:M], ln2=ln2, out2_a=o2[:M])
+        pre = F.gelu(acc) + 0.1 * R
+        ref["out1"] = F.layer_norm(pre, (D,), ln1[0], ln1[1])
+        ref["out2"] = F.layer_norm(ref["out1"], (D,), ln2[0], ln2[1])
+        got["out1"], got["out2"] = o1, o2
+    elif variant == "sdo_ln_pre":    # cross-attention output projection: residual sum out, LayerNorm of the projection itself
+        y, o1 = buf(torch.float32), buf(bf)
+        assert ops.gemm_ln(A, W, b, ln1=ln1, alpha=1.0, beta=1.0, resid=R, out_f32=y[:M], ln_pre_resid=True, out1_a=o1[:M])
+        ref["y"] = R + acc
+        ref["out1"] = F.layer_norm(acc, (D,), ln1[0], ln1[1])
+        got["y"], got["out1"] = y, o1
+    else:                            # FFN output Linear + residual = layer output -> next layer's pre-norms + its bf16 copy
+        y, ya, o1, o2 = buf(torch.float32), buf(bf), buf(torch.float32), buf(bf)
+        assert ops.gemm_ln(A, W, b, ln1=ln1, alpha=1.0, beta=1.0, resid=R, out_f32=y[:M], out_a=ya[:M], out1_f32=o1[:M],
+                           ln2=ln2, out2_a=o2[:M])
+        ref["y"] = R + acc
+        ref["ya"] = ref["y"]
+        ref["out1"] = F.layer_norm(ref["y"], (D,), ln1[0], ln1[1])
+        ref["out2"] = F.layer_norm(ref["out1"], (D,), ln2[0], ln2[1])
+        got["y"], got["ya"], got["out1"], got["out2"] = y, ya, o1, o2
+    for k, g in got.items():
+        assert torch.all(g[M:].float() == 3.0), k                       # nothing written past M
+        tol = 1e-4 if g.dtype == torch.float32 else 4e-3                # bf16 outputs: rounding of the output itself
+        if variant == "skip_ln_ln":
+            tol = max(tol, 1e-3)                                        # bf16-grade GELU (gelu_tanh_fit) under the LayerNorm
+        assert rel(g[:M].float(), ref[k]) < tol, (k, rel(g[:M].float(), ref[k]))
+    # shapes outside the fused kernel are declined without launching anything
+    assert not ops.gemm_ln(A, W[:256].contiguous(), b[:256].contiguous(), ln1=ln1, out1_a=buf(bf)[:M])
+
+
 @pytest.mark.parametrize("M,K_in,N_out", [(1000, 512, 512), (25088, 512, 1536), (300, 264, 128), (4097, 1024, 512)])
 def test_linear_backward_building_blocks(M, K_in, N_out):
     """dX = dY W, dW = dY^T X (token slabs as the groups of one grouped GEMM + fp32 partial sums), db = column sums:

@@ -95,6 +95,40 @@ def _unfused(i):
     ops.gemm(ob[i], Wf, bfv, out_f32=of[i], resid=xf[i], alpha=0.1, beta=1.0)
 timeit("rowop31 + gemm s_out (unfused pair)", _unfused, nset, 2.0 * N * D * D, "TFLOP/s")
 
+# ---- Linear + row pipeline in one kernel (mdm_gemm_ln: the row stays in TMEM) against the pairs it replaces
+W2k = (torch.randn(D, 4 * D, device=dev) / (4 * D) ** 0.5).to(bf)
+xb4 = [torch.randn(N, 4 * D, device=dev).to(bf) for _ in range(2)]
+of2 = [torch.empty(N, D, device=dev) for _ in range(nset)]
+timeit("gemm_ln p3 + ln,l2,ln,film,silu", lambda i: ops.gemm_ln(xb[i], Wf, bfv, out2_a=ob[i], **kwf), nset, 2.0 * N * D * D, "TFLOP/s")
+def _pair1(i):
+    ops.gemm(xb[i], Wf, bfv, out_a=ob2[i])
+    ops.rowop(ob2[i], N, D, MDM_BF16, out2_a=ob[i], **kwf)
+timeit("  unfused: gemm p3 + rowop31", _pair1, nset, 2.0 * N * D * D, "TFLOP/s")
+timeit("gemm_ln s_out + resid -> y, ln", lambda i: ops.gemm_ln(xb[i], Wf, bfv, ln1=ln, alpha=0.1, beta=1.0, resid=xf[i], out_f32=of[i], out1_a=ob[i]),
+       nset, 2.0 * N * D * D, "TFLOP/s")
+def _pair2(i):
+    ops.gemm(xb[i], Wf, bfv, out_f32=of[i], resid=xf[i], alpha=0.1, beta=1.0)
+    ops.rowop(of[i], N, D, MDM_BF16, ln1=ln, out1_a=ob[i])
+timeit("  unfused: gemm s_out + rowop ln", _pair2, nset, 2.0 * N * D * D, "TFLOP/s")
+timeit("gemm_ln skip gelu + resid -> ln f32, ln", lambda i: ops.gemm_ln(xb[i], Wf, bfv, ln1=ln, act=ACT_GELU, alpha=1.0, beta=0.1, resid=xf[i],
+       out1_f32=of[i], ln2=ln2, out2_a=ob[i]), nset, 2.0 * N * D * D, "TFLOP/s")
+def _pair3(i):
+    ops.gemm(xb[i], Wf, bfv, act=ACT_GELU, out_f32=of2[i], resid=xf[i], alpha=1.0, beta=0.1)
+    ops.rowop(of2[i], N, D, MDM_BF16, ln1=ln, out1_f32=of[i], ln2=ln2, out2_a=ob[i])
+timeit("  unfused: gemm skip + rowop ln,ln", _pair3, nset, 2.0 * N * D * D, "TFLOP/s")
+timeit("gemm_ln sd_o + resid -> y, ln(pre)", lambda i: ops.gemm_ln(xb[i], Wf, bfv, ln1=ln, alpha=1.0, beta=1.0, resid=xf[i], out_f32=of[i],
+       ln_pre_resid=True, out1_a=ob[i]), nset, 2.0 * N * D * D, "TFLOP/s")
+def _pair4(i):
+    ops.gemm(xb[i], Wf, bfv, out_f32=of[i], out_a=ob2[i], a_pre_resid=True, resid=xf[i], alpha=1.0, beta=1.0)
+    ops.rowop(ob2[i], N, D, MDM_BF16, ln1=ln, out1_a=ob[i])
+timeit("  unfused: gemm sd_o + rowop ln", _pair4, nset, 2.0 * N * D * D, "TFLOP/s")
+timeit("gemm_ln f3 (K 2048) + resid -> y, copy, ln f32, ln", lambda i: ops.gemm_ln(xb4[i % 2], W2k, bfv, ln1=ln, alpha=1.0, beta=1.0, resid=xf[i],
+       out_f32=of[i], out_a=ob2[i], out1_f32=of2[i], ln2=ln2, out2_a=ob[i]), nset, 2.0 * N * D * 4 * D, "TFLOP/s")
+def _pair5(i):
+    ops.gemm(xb4[i % 2], W2k, bfv, out_f32=of[i], resid=xf[i], alpha=1.0, beta=1.0)
+    ops.rowop(of[i], N, D, MDM_BF16, ln1=ln, out1_f32=of2[i], ln2=ln2, out2_a=ob[i], out0_a=ob2[i])
+timeit("  unfused: gemm f3 + rowop ln,ln,copy", _pair5, nset, 2.0 * N * D * 4 * D, "TFLOP/s")
+
 # ---- MoE routing
 E, NB = 8, 2
 G = NB * E
