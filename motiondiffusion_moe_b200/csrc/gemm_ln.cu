@@ -8,20 +8,20 @@
 //
 // Every LayerNorm of MoEExtendedDecoderLayer except the MoE gate's follows a Linear whose output IS the whole row
 // (N = latent_dim = 512: models/fast_attention.py:142,166-176,210,225; models/stylization.py:27-30;
-// models/transformer.py:55-64), so the tile is 128 rows x 512 columns = the whole TMEM (128 lanes x 512 columns of
-// fp32): a row lives in ONE TMEM lane, i.e. in one thread of the epilogue.  Row statistics are therefore plain
-// per-thread sums over tcgen05.ld chunks (no shuffles; the two warps that share a lane quadrant exchange two floats per
-// row through shared memory), and TMEM doubles as the row buffer between the passes (tcgen05.st writes the finished
-// row back over the accumulator):
+// models/transformer.py:55-64).  A cluster of two CTAs owns a 128-row block: CTA r computes columns [256 r, 256 r + 256)
+// of those rows (its own tcgen05 cta_group::1 GEMM: A tile + its half of the weight rows by TMA, 3-stage ring), so a
+// row's 512 values live in ONE TMEM lane of each of the two SMs, i.e. in one epilogue thread per SM.  Row statistics
+// are plain per-thread sums over tcgen05.ld chunks (no shuffles); the two warps of a CTA that share a lane quadrant
+// exchange their partial sums through shared memory, the two CTAs through distributed shared memory + an mbarrier.
+// TMEM doubles as the row buffer between the passes (tcgen05.st writes the finished row back over the accumulator):
 //   pass A  acc -> +bias, activation, alpha, + beta * residual (TMA in) -> y out (TMA) ; sum / sum of squares of s; s -> TMEM
 //   pass B  s -> u = LN1(s) -> out1 (TMA) ; sum / sum of squares of u  (they give |u| for the L2 norm AND the LN2
 //           statistics of u * sqrt(D)/|u| in closed form)
 //   pass C  s -> u -> z -> out2 (TMA)
-// The MMA side is the CTA-pair scheme of gemm_tc2_kernel (cluster of two, tcgen05 cta_group::2, M = 256): each CTA
-// stages its own 128 rows of A and HALF of the weight rows of each 256-column half, so a k-block costs an SM 48 KB of
-// L2 -> shared-memory traffic for 128 x 512 x 64 MACs (the single-CTA 128 x 256 tile pays the same 48 KB for half of
-// that, and is bound by exactly this feed).  One accumulator per CTA: MMA and epilogue of a tile do not overlap, the
-// TMA ring (3 stages) refills during the epilogue.
+// 256 columns per CTA = half of TMEM: two accumulator buffers, the MMAs of the next row block run under the three
+// epilogue passes of the current one.  (First version, commit 1c0bf6d: 128 x 512 tiles = all of TMEM per CTA,
+// cta_group::2 pairs; epilogue and MMA serialised and 196 tiles on 148 SMs left the second wave two thirds empty:
+// 42 us where this layout runs 196 half-size tile pairs in 2.65 waves of 74 clusters.)
 // What it replaces at batch 64 (B200, tools/op_bench.py): p3 GEMM 17.6 us + five-stage rowop 31 us; fp32 + residual
 // GEMM 27 us + LayerNorm rowop 15 us.
 #include <stdlib.h>
@@ -31,21 +31,25 @@
 
 namespace {
 
-constexpr int LN_N = 512;
+constexpr int LN_N = 512;            // row width
+constexpr int LN_NC = 256;           // columns per CTA
 constexpr int LN_STAGES = 3;
 constexpr int LN_EPI_WARPS = 8;
 constexpr int LN_THREADS = (FIRST_EPI_WARP + LN_EPI_WARPS) * 32;
+constexpr int LN_CH = 4;             // 32-column chunks per epilogue warp and pass
 
 struct LnSmem {
-  static constexpr int A_BYTES = BM * BK * 2;                      // this CTA's 128 rows of A
-  static constexpr int BH_BYTES = 128 * BK * 2;                    // this CTA's 128 weight rows of one 256-column half
-  static constexpr int STAGE_BYTES = A_BYTES + 2 * BH_BYTES;       // 48 KB
+  static constexpr int A_BYTES = BM * BK * 2;                      // 128 rows of A
+  static constexpr int B_BYTES = LN_NC * BK * 2;                   // this CTA's 256 weight rows
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;            // 48 KB
   static constexpr int TILE_OFF = LN_STAGES * STAGE_BYTES;         // per epilogue warp 8 KB: 2 fp32 / 4 bf16 staging tiles
-  static constexpr int PRM_OFF = TILE_OFF + LN_EPI_WARPS * 8192;   // bias, ln1_w, ln1_b, ln2_w, ln2_b
-  static constexpr int RED_OFF = PRM_OFF + 5 * LN_N * 4;           // float2 [2 column halves][128 rows]
-  static constexpr int BAR_OFF = RED_OFF + 2 * 128 * 8;
-  // full / empty ring, acc_full, acc_empty, 2 residual barriers per epilogue warp, TMEM pointer; + alignment slack
-  static constexpr int TOTAL = BAR_OFF + (2 * LN_STAGES + 2 + 2 * LN_EPI_WARPS) * 8 + 16 + 1024;
+  static constexpr int PRM_OFF = TILE_OFF + LN_EPI_WARPS * 8192;   // bias, ln1_w, ln1_b, ln2_w, ln2_b of this CTA's columns
+  static constexpr int RED_OFF = PRM_OFF + 5 * LN_NC * 4;          // float2 [2 column halves][128 rows]: inside the CTA
+  static constexpr int XRED_OFF = RED_OFF + 2 * 128 * 8;           // float2 [2 tile parities][2 exchanges][128 rows]: from the peer CTA
+  static constexpr int BAR_OFF = XRED_OFF + 4 * 128 * 8;
+  // full / empty ring, tmem_full[2], tmem_empty[2], 2 residual barriers per epilogue warp, 2 x 2 x 4 exchange barriers,
+  // TMEM pointer; + alignment slack
+  static constexpr int TOTAL = BAR_OFF + (2 * LN_STAGES + 4 + 2 * LN_EPI_WARPS + 16) * 8 + 16 + 1024;
 };
 static_assert(LnSmem::TOTAL <= 227 * 1024, "shared memory budget");
 
@@ -81,6 +85,87 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
 }
+// partial row statistics for the peer CTA: a store into its shared memory, then a release-arrive on its barrier (every
+// thread for itself: the acquire-wait on the other side then sees the value without further fences)
+__device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float2 v) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins == (1u << 22)) __trap();
+  }
+}
+
+// ---- per-chunk (32 columns of one row per thread) helpers, packed fp32 pairs (FFMA2 / FADD2: one issue slot per two
+// elements; the epilogue is issue / latency bound, not bandwidth bound)
+__device__ __forceinline__ void stats_acc(const float (&v)[32], float2 (&s)[2], float2 (&q)[2]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float2 p0 = make_float2(v[j], v[j + 1]), p1 = make_float2(v[j + 2], v[j + 3]);
+    s[0] = add2(s[0], p0);
+    s[1] = add2(s[1], p1);
+    q[0] = fma2(p0, p0, q[0]);
+    q[1] = fma2(p1, p1, q[1]);
+  }
+}
+// v = (v * rstd + nmr) * w + b, nmr = -mean * rstd; w / b: shared-memory vectors (warp-uniform address: broadcast reads)
+__device__ __forceinline__ void ln_apply(float (&v)[32], const float* __restrict__ w_s, const float* __restrict__ b_s, float rstd,
+                                         float nmr) {
+  const float2 r2 = make_float2(rstd, rstd), m2 = make_float2(nmr, nmr);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 w4 = *reinterpret_cast<const float4*>(w_s + 4 * j);
+    const float4 b4 = *reinterpret_cast<const float4*>(b_s + 4 * j);
+    const float2 u0 = fma2(fma2(make_float2(v[4 * j], v[4 * j + 1]), r2, m2), make_float2(w4.x, w4.y), make_float2(b4.x, b4.y));
+    const float2 u1 = fma2(fma2(make_float2(v[4 * j + 2], v[4 * j + 3]), r2, m2), make_float2(w4.z, w4.w), make_float2(b4.z, b4.w));
+    v[4 * j] = u0.x; v[4 * j + 1] = u0.y; v[4 * j + 2] = u1.x; v[4 * j + 3] = u1.y;
+  }
+}
+__device__ __forceinline__ void silu32(float (&v)[32]) {
+  const float2 nl2e = make_float2(-1.4426950408889634f, -1.4426950408889634f), one = make_float2(1.f, 1.f);
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float2 x = make_float2(v[j], v[j + 1]);
+    const float2 t = mul2(x, nl2e);
+    float2 e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+    e = add2(e, one);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(e.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(e.y));
+    const float2 y = mul2(x, r);
+    v[j] = y.x; v[j + 1] = y.y;
+  }
+}
+// row-per-lane staging tiles in the layouts the TMA store expects
+__device__ __forceinline__ void tile_f32(float4* t, int lane, const float (&v)[32]) {       // 32 x 128 B, SWIZZLE_128B
+  float4* t4 = t + lane * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t4[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void tile_bf16(uint4* t, int lane, const float (&v)[32]) {        // 32 x 64 B, SWIZZLE_64B
+  uint4* bt = t + lane * 4;
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    uint4 pk;
+    pk.x = pack2(v[8 * c4], v[8 * c4 + 1]); pk.y = pack2(v[8 * c4 + 2], v[8 * c4 + 3]);
+    pk.z = pack2(v[8 * c4 + 4], v[8 * c4 + 5]); pk.w = pack2(v[8 * c4 + 6], v[8 * c4 + 7]);
+    bt[c4 ^ ((lane >> 1) & 3)] = pk;
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float4 (&q)[8]) {     // 128 contiguous bytes of this lane's row
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q[j].x), "=f"(q[j].y), "=f"(q[j].z), "=f"(q[j].w) : "l"(p + 4 * j));
+}
 
 template <int FLAGS, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LN_THREADS, 1)
@@ -105,16 +190,20 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* prm = reinterpret_cast<float*>(smem + L::PRM_OFF);
   float2* red = reinterpret_cast<float2*>(smem + L::RED_OFF);
+  float2* xred = reinterpret_cast<float2*>(smem + L::XRED_OFF);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + LN_STAGES;
-  uint64_t* acc_full = empty_bar + LN_STAGES;
-  uint64_t* acc_empty = acc_full + 1;
-  uint64_t* res_bar = acc_empty + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * LN_EPI_WARPS);
+  uint64_t* tmem_full = empty_bar + LN_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* res_bar = tmem_empty + 2;
+  // [2 block parities][2 exchanges][4 quadrants], 32 arrivals of the peer CTA each.  One barrier per block PARITY: a
+  // barrier then completes a phase every second block, and the peer cannot be two blocks ahead (it needs this CTA's
+  // totals of the block in between), so a waiter can never be lapped.
+  uint64_t* xbar = res_bar + 2 * LN_EPI_WARPS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xbar + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -124,130 +213,148 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 2 * LN_EPI_WARPS);
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], LN_EPI_WARPS);
+    mbar_init(&tmem_empty[1], LN_EPI_WARPS);
 #pragma unroll
     for (int i = 0; i < 2 * LN_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mbar_init(&xbar[i], 32);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc_2sm(tmem_ptr, LN_N);
+  if (warp == 1) tmem_alloc(tmem_ptr, 2 * LN_NC);
   tc_fence_before();
-  cluster_sync_all();
+  cluster_sync_all();          // the peer's exchange barriers are initialised before anything can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  pdl_enter();   // first global access below
+  pdl_enter();                 // first global access below
 
-  const int num_m_tiles = (M + BM - 1) / BM;
-  const int num_pairs = (num_m_tiles + 1) >> 1;
+  const int num_blocks = (M + BM - 1) / BM;              // 128-row blocks, one per cluster and iteration
   const int num_kb = K / BK;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int ncol0 = (int)rank * LN_NC;                   // this CTA's first column / weight row
 
   if (warp < FIRST_EPI_WARP) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {
-      // ------------------------------------------------------------ TMA producer (both CTAs)
+      // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = cluster_id; w < num_pairs; w += num_clusters) {
-        const int a_row0 = (2 * w + (int)rank) * BM;       // past M for the odd tile out: zero-filled by the TMA
+      for (int w = cluster_id; w < num_blocks; w += num_clusters) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
-          tma_load_2d_2sm(&tmA, fb, sa, kb * BK, a_row0);
-          tma_load_2d_2sm(&tmB, fb, sa + L::A_BYTES, kb * BK, (int)rank * 128);
-          tma_load_2d_2sm(&tmB, fb, sa + L::A_BYTES + L::BH_BYTES, kb * BK, 256 + (int)rank * 128);
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, w * BM);
+          tma_load_2d(&tmB, &full_bar[stage], sa + L::A_BYTES, kb * BK, ncol0);
           if (++stage == LN_STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1 && lane == 0 && leader) {
-      // ------------------------------------------------------------ MMA issuer (leader CTA only)
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 256);
-      int stage = 0;
+    } else if (warp == 1 && lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(BM, LN_NC);
+      int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int w = cluster_id; w < num_pairs; w += num_clusters) {
-        mbar_wait(acc_empty, acc_phase ^ 1);               // the epilogues of both CTAs are done with TMEM
+      for (int w = cluster_id; w < num_blocks; w += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * LN_NC;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t adesc = make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc0 = make_sw128_kmajor_desc(sa + L::A_BYTES);
-          const uint64_t bdesc1 = make_sw128_kmajor_desc(sa + L::A_BYTES + L::BH_BYTES);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + L::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16_2sm(tmem_base, adesc + 2 * k, bdesc0 + 2 * k, idesc, (kb | k) != 0);
-            umma_bf16_2sm(tmem_base + 256, adesc + 2 * k, bdesc1 + 2 * k, idesc, (kb | k) != 0);
-          }
-          umma_commit_2sm(&empty_bar[stage]);
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
           if (++stage == LN_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(acc_full);
-        acc_phase ^= 1;
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // ------------------------------------------------------------ epilogue (8 warps per CTA, own 128 rows)
+    // ------------------------------------------------------------ epilogue (8 warps: lane quadrant x column half)
     const int widx = warp - FIRST_EPI_WARP;
-    const int quad = warp & 3, cpar = widx >> 2;
+    const int quad = warp & 3, ch = widx >> 2;
     uint8_t* wtile = smem + L::TILE_OFF + widx * 8192;
     float4* ftile = reinterpret_cast<float4*>(wtile);          // two 4 KB fp32 tiles (32 rows x 128 B, SWIZZLE_128B)
     uint4* btile = reinterpret_cast<uint4*>(wtile);            // four 2 KB bf16 tiles (32 rows x 64 B, SWIZZLE_64B)
     uint64_t* rbar = res_bar + 2 * widx;
     uint32_t rphase = 0;
-    const float* bias_s = prm;
-    const float* w1_s = prm + LN_N;
-    const float* b1_s = prm + 2 * LN_N;
-    const float* w2_s = prm + 3 * LN_N;
-    const float* b2_s = prm + 4 * LN_N;
+    const float* bias_s = prm + ch * 128;                      // this warp's 128 columns of the CTA's 256
+    const float* w1_s = prm + LN_NC + ch * 128;
+    const float* b1_s = prm + 2 * LN_NC + ch * 128;
+    const float* w2_s = prm + 3 * LN_NC + ch * 128;
+    const float* b2_s = prm + 4 * LN_NC + ch * 128;
     {
-      const int t = threadIdx.x - FIRST_EPI_WARP * 32;         // 0..255: two columns each
-      for (int i = t; i < LN_N; i += LN_EPI_WARPS * 32) {
-        prm[i] = a.bias ? a.bias[i] : 0.f;
-        prm[LN_N + i] = a.ln1_w[i];
-        prm[2 * LN_N + i] = a.ln1_b[i];
-        if (LN2) { prm[3 * LN_N + i] = a.ln2_w[i]; prm[4 * LN_N + i] = a.ln2_b[i]; }
-      }
+      const int t = threadIdx.x - FIRST_EPI_WARP * 32;         // 0..255: one column each
+      prm[t] = a.bias ? a.bias[ncol0 + t] : 0.f;
+      prm[LN_NC + t] = a.ln1_w[ncol0 + t];
+      prm[2 * LN_NC + t] = a.ln1_b[ncol0 + t];
+      if (LN2) { prm[3 * LN_NC + t] = a.ln2_w[ncol0 + t]; prm[4 * LN_NC + t] = a.ln2_b[ncol0 + t]; }
       asm volatile("bar.sync 9, 256;" ::: "memory");            // the epilogue warps only
     }
-    const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int gcol0 = ncol0 + ch * 128;                        // global column of this warp's chunk 0
     const float inv_n = 1.0f / (float)LN_N;
-    uint32_t acc_phase = 0;
-    for (int w = cluster_id; w < num_pairs; w += num_clusters) {
-      const int row0 = (2 * w + (int)rank) * BM + quad * 32;    // first row of this warp's 32-row block
+    int acc = 0;
+    uint32_t acc_phase = 0, it = 0;
+    // row statistics of the whole 512-column row: own 128 columns + the partner warp's (shared memory) + the peer
+    // CTA's 256 (distributed shared memory).  e: exchange index (0 after pass A, 1 after pass B).
+    auto row_total = [&](float& s0, float& s1, int e) {
+      const int row = quad * 32 + lane;
+      red[ch * 128 + row] = make_float2(s0, s1);
+      quad_sync(quad);
+      const float2 o = red[(ch ^ 1) * 128 + row];
+      s0 += o.x;
+      s1 += o.y;
+      quad_sync(quad);
+      const int par = (int)(it & 1);
+      const int slot = ((par * 2 + e) * 128) + row;
+      uint64_t* xb = &xbar[(par * 2 + e) * 4 + quad];
+      if (ch == 0) {                                           // one warp per quadrant sends the CTA's total to the peer
+        st_cluster_f2(mapa_u32(smem_u32(&xred[slot]), rank ^ 1), make_float2(s0, s1));
+        mbar_arrive_cluster(mapa_u32(smem_u32(xb), rank ^ 1));
+      }
+      mbar_wait_cluster(xb, (it >> 1) & 1);
+      const float2 p = xred[slot];
+      s0 += p.x;
+      s1 += p.y;
+    };
+    for (int w = cluster_id; w < num_blocks; w += num_clusters, ++it) {
+      const int row0 = w * BM + quad * 32;                      // first row of this warp's 32-row block
       const int r = row0 + lane;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * LN_NC + ch * 128;
       auto issue_res = [&](int k) {       // lane 0: residual chunk k -> fp32 tile k & 1
         mbar_expect_tx(&rbar[k & 1], 4096);
-        tma_load_2d(&tmR, &rbar[k & 1], ftile + (k & 1) * 256, (cpar + 2 * k) * 32, row0);
+        tma_load_2d(&tmR, &rbar[k & 1], ftile + (k & 1) * 256, gcol0 + 32 * k, row0);
       };
       if (lane == 0) {
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores of the previous tile have left
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores of the previous block have left
         if (RESID) { issue_res(0); issue_res(1); }
       }
       __syncwarp();
-      mbar_wait(acc_full, acc_phase);
+      mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      acc_phase ^= 1;
 
       // ---------------------------------------------------------------- pass A
-      float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-      for (int k = 0; k < 8; ++k) {
-        const int n0 = (cpar + 2 * k) * 32;
-        uint32_t raw[32];
-        tmem_ld32(t_addr + n0, raw);
+      // chunk k: the TMEM load of chunk k + 1 is in flight while chunk k is finished
+      float2 sA[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, qA[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      uint32_t ra[32], rb[32];
+      auto pass_a = [&](int k, uint32_t (&raw)[32], uint32_t (&nraw)[32]) {
+        const int n0 = 32 * k;
         tmem_ld_wait();
+        if (k + 1 < LN_CH) tmem_ld32(t_addr + n0 + 32, nraw);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n0 + 4 * j);
-          v[4 * j] = __uint_as_float(raw[4 * j]) + b4.x;
-          v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4.y;
-          v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4.z;
-          v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4.w;
+          const float2 x0 = add2(make_float2(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1])), make_float2(b4.x, b4.y));
+          const float2 x1 = add2(make_float2(__uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])), make_float2(b4.z, b4.w));
+          v[4 * j] = x0.x; v[4 * j + 1] = x0.y; v[4 * j + 2] = x1.x; v[4 * j + 3] = x1.y;
         }
         if (ACT == MDM_ACT_GELU) {
 #pragma unroll
@@ -257,244 +364,191 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (a.alpha != 1.0f) {
+          const float2 a2 = make_float2(a.alpha, a.alpha);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= a.alpha;
+          for (int j = 0; j < 32; j += 2) {
+            const float2 x = mul2(make_float2(v[j], v[j + 1]), a2);
+            v[j] = x.x; v[j + 1] = x.y;
+          }
         }
         if (LN_PRE) {
+          stats_acc(v, sA, qA);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { sum += v[j]; sq = fmaf(v[j], v[j], sq); raw[j] = __float_as_uint(v[j]); }
+          for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(v[j]);
           tmem_st32(t_addr + n0, raw);
         }
         float4* t4 = ftile + (k & 1) * 256 + lane * 8;
         if (RESID) {
           mbar_wait(&rbar[k & 1], (rphase >> (k & 1)) & 1u);    // residual chunk k has landed
           rphase ^= 1u << (k & 1);
+          const float2 b2 = make_float2(a.beta, a.beta);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int slot = j ^ (lane & 7);
             const float4 r4 = t4[slot];
-            v[4 * j] = fmaf(a.beta, r4.x, v[4 * j]);
-            v[4 * j + 1] = fmaf(a.beta, r4.y, v[4 * j + 1]);
-            v[4 * j + 2] = fmaf(a.beta, r4.z, v[4 * j + 2]);
-            v[4 * j + 3] = fmaf(a.beta, r4.w, v[4 * j + 3]);
-            if (OUT_Y) t4[slot] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            const float2 y0 = fma2(b2, make_float2(r4.x, r4.y), make_float2(v[4 * j], v[4 * j + 1]));
+            const float2 y1 = fma2(b2, make_float2(r4.z, r4.w), make_float2(v[4 * j + 2], v[4 * j + 3]));
+            v[4 * j] = y0.x; v[4 * j + 1] = y0.y; v[4 * j + 2] = y1.x; v[4 * j + 3] = y1.y;
+            if (OUT_Y) t4[slot] = make_float4(y0.x, y0.y, y1.x, y1.y);
           }
         } else if (OUT_Y) {
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // tile k & 1 is free again
           __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) t4[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          tile_f32(ftile + (k & 1) * 256, lane, v);
         }
         if (!LN_PRE) {
+          stats_acc(v, sA, qA);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { sum += v[j]; sq = fmaf(v[j], v[j], sq); raw[j] = __float_as_uint(v[j]); }
+          for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(v[j]);
           tmem_st32(t_addr + n0, raw);
         }
         if (OUT_Y) fence_proxy_async();
         if (OUT_Y || RESID) __syncwarp();                       // every lane is done with the tile
         if (lane == 0) {
           if (OUT_Y) {
-            tma_store_2d(&tmY, ftile + (k & 1) * 256, n0, row0);
+            tma_store_2d(&tmY, ftile + (k & 1) * 256, gcol0 + n0, row0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (RESID && k + 2 < 8) {
+          if (RESID && k + 2 < LN_CH) {
             if (OUT_Y) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store has read the tile
             issue_res(k + 2);
           }
         }
+      };
+      tmem_ld32(t_addr, ra);
+#pragma unroll 1
+      for (int k = 0; k < LN_CH; k += 2) {
+        pass_a(k, ra, rb);
+        pass_a(k + 1, rb, ra);
       }
       tmem_st_wait();
-      // row statistics of s: this warp's 256 columns + the partner warp's
-      red[cpar * 128 + quad * 32 + lane] = make_float2(sum, sq);
-      quad_sync(quad);
-      {
-        const float2 o = red[(cpar ^ 1) * 128 + quad * 32 + lane];
-        sum += o.x;
-        sq += o.y;
-      }
-      quad_sync(quad);
+      float sum = (sA[0].x + sA[0].y) + (sA[1].x + sA[1].y), sq = (qA[0].x + qA[0].y) + (qA[1].x + qA[1].y);
+      row_total(sum, sq, 0);
       const float mean1 = sum * inv_n;
       const float rstd1 = rsqrtf(fmaxf(fmaf(sq, inv_n, -mean1 * mean1), 0.f) + 1e-5f);
+      const float nmr1 = -mean1 * rstd1;
 
       // ---------------------------------------------------------------- pass B
-      float su = 0.f, squ = 0.f;
+      float2 sB[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, qB[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       if (PASS_B) {
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-#pragma unroll 1
-        for (int k = 0; k < 8; ++k) {
-          const int n0 = (cpar + 2 * k) * 32;
-          uint32_t raw[32];
-          tmem_ld32(t_addr + n0, raw);
+        constexpr bool STORE_B = OUT1_F32 || OUT1_A || (COPY_S && !PASS_C);
+        if (STORE_B) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
+        auto pass_b = [&](int k, uint32_t (&raw)[32], uint32_t (&nraw)[32]) {
+          const int n0 = 32 * k;
           tmem_ld_wait();
+          if (k + 1 < LN_CH) tmem_ld32(t_addr + n0 + 32, nraw);
           float u[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 w4 = *reinterpret_cast<const float4*>(w1_s + n0 + 4 * j);
-            const float4 b4 = *reinterpret_cast<const float4*>(b1_s + n0 + 4 * j);
-            u[4 * j] = fmaf((__uint_as_float(raw[4 * j]) - mean1) * rstd1, w4.x, b4.x);
-            u[4 * j + 1] = fmaf((__uint_as_float(raw[4 * j + 1]) - mean1) * rstd1, w4.y, b4.y);
-            u[4 * j + 2] = fmaf((__uint_as_float(raw[4 * j + 2]) - mean1) * rstd1, w4.z, b4.z);
-            u[4 * j + 3] = fmaf((__uint_as_float(raw[4 * j + 3]) - mean1) * rstd1, w4.w, b4.w);
-          }
-          if (STATS2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { su += u[j]; squ = fmaf(u[j], u[j], squ); }
-          }
-          if (OUT1_F32 || OUT1_A || (COPY_S && !PASS_C)) {
+          for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(raw[j]);
+          if (STORE_B) {
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffers of chunk k - 2
             __syncwarp();
-            if (OUT1_F32) {
-              float4* t4 = ftile + (k & 1) * 256 + lane * 8;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) t4[j ^ (lane & 7)] = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
-            }
-            if (OUT1_A) {
-              uint4* bt = btile + ((k & 1) * 2) * 128 + lane * 4;
-#pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) {
-                uint4 pk;
-                pk.x = pack2(u[8 * c4], u[8 * c4 + 1]); pk.y = pack2(u[8 * c4 + 2], u[8 * c4 + 3]);
-                pk.z = pack2(u[8 * c4 + 4], u[8 * c4 + 5]); pk.w = pack2(u[8 * c4 + 6], u[8 * c4 + 7]);
-                bt[c4 ^ ((lane >> 1) & 3)] = pk;
-              }
-            }
-            if (COPY_S && !PASS_C) {
-              uint4* bt = btile + ((k & 1) * 2 + 1) * 128 + lane * 4;
-#pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) {
-                uint4 pk;
-                pk.x = pack2(__uint_as_float(raw[8 * c4]), __uint_as_float(raw[8 * c4 + 1]));
-                pk.y = pack2(__uint_as_float(raw[8 * c4 + 2]), __uint_as_float(raw[8 * c4 + 3]));
-                pk.z = pack2(__uint_as_float(raw[8 * c4 + 4]), __uint_as_float(raw[8 * c4 + 5]));
-                pk.w = pack2(__uint_as_float(raw[8 * c4 + 6]), __uint_as_float(raw[8 * c4 + 7]));
-                bt[c4 ^ ((lane >> 1) & 3)] = pk;
-              }
-            }
+          }
+          if (COPY_S && !PASS_C) tile_bf16(btile + ((k & 1) * 2 + 1) * 128, lane, u);       // bf16 copy of s itself
+          ln_apply(u, w1_s + n0, b1_s + n0, rstd1, nmr1);
+          if (STATS2) stats_acc(u, sB, qB);
+          if (STORE_B) {
+            if (OUT1_F32) tile_f32(ftile + (k & 1) * 256, lane, u);
+            if (OUT1_A) tile_bf16(btile + ((k & 1) * 2) * 128, lane, u);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (OUT1_F32) tma_store_2d(&tmO1F, ftile + (k & 1) * 256, n0, row0);
-              if (OUT1_A) tma_store_2d(&tmO1A, btile + ((k & 1) * 2) * 128, n0, row0);
-              if (COPY_S && !PASS_C) tma_store_2d(&tmS, btile + ((k & 1) * 2 + 1) * 128, n0, row0);
+              if (OUT1_F32) tma_store_2d(&tmO1F, ftile + (k & 1) * 256, gcol0 + n0, row0);
+              if (OUT1_A) tma_store_2d(&tmO1A, btile + ((k & 1) * 2) * 128, gcol0 + n0, row0);
+              if (COPY_S && !PASS_C) tma_store_2d(&tmS, btile + ((k & 1) * 2 + 1) * 128, gcol0 + n0, row0);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
+        };
+        tmem_ld32(t_addr, ra);
+#pragma unroll 1
+        for (int k = 0; k < LN_CH; k += 2) {
+          pass_b(k, ra, rb);
+          pass_b(k + 1, rb, ra);
         }
       }
 
       // ---------------------------------------------------------------- pass C
       if (PASS_C) {
-        float mean_u = 0.f, g = 1.0f;
+        float nmu = 0.f, g = 1.0f;                               // z = (u * g + nmu) * w2 + b2
         if (STATS2) {
-          red[cpar * 128 + quad * 32 + lane] = make_float2(su, squ);
-          quad_sync(quad);
-          const float2 o = red[(cpar ^ 1) * 128 + quad * 32 + lane];
-          su += o.x;
-          squ += o.y;
-          quad_sync(quad);
-          mean_u = su * inv_n;
+          float su = (sB[0].x + sB[0].y) + (sB[1].x + sB[1].y), squ = (qB[0].x + qB[0].y) + (qB[1].x + qB[1].y);
+          row_total(su, squ, 1);
+          const float mean_u = su * inv_n;
           const float var_u = fmaxf(fmaf(squ, inv_n, -mean_u * mean_u), 0.f);
           // F.normalize(u) * sqrt(D): b = u * sc; LayerNorm(b) has mean sc * mean_u and variance sc^2 * var_u
           const float sc = L2N ? sqrtf((float)LN_N) / fmaxf(sqrtf(squ), 1e-12f) : 1.0f;
           g = LN2 ? sc * rsqrtf(sc * sc * var_u + 1e-5f) : sc;
-          if (!LN2) mean_u = 0.f;
+          nmu = LN2 ? -mean_u * g : 0.f;
         }
         const int rc = min(r, M - 1);                            // rows past M only need a valid FiLM address
-        const float* fp = FILM ? a.film + (long)(rc / a.rows_per_seq) * (2 * LN_N) : nullptr;
+        const float* fp = FILM ? a.film + (long)(rc / a.rows_per_seq) * (2 * LN_N) + gcol0 : nullptr;
+        // FiLM (scale | shift) of this lane's row: chunk k + 1 is requested as soon as chunk k's values are consumed
+        float4 fsc[8], fsh[8];
+        if (FILM) { load8(fp, fsc); load8(fp + LN_N, fsh); }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
-#pragma unroll 1
-        for (int k = 0; k < 8; ++k) {
-          const int n0 = (cpar + 2 * k) * 32;
-          uint32_t raw[32];
-          tmem_ld32(t_addr + n0, raw);
+        auto pass_c = [&](int k, uint32_t (&raw)[32], uint32_t (&nraw)[32]) {
+          const int n0 = 32 * k;
           tmem_ld_wait();
+          if (k + 1 < LN_CH) tmem_ld32(t_addr + n0 + 32, nraw);
           float z[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 w4 = *reinterpret_cast<const float4*>(w1_s + n0 + 4 * j);
-            const float4 b4 = *reinterpret_cast<const float4*>(b1_s + n0 + 4 * j);
-            z[4 * j] = fmaf((__uint_as_float(raw[4 * j]) - mean1) * rstd1, w4.x, b4.x);
-            z[4 * j + 1] = fmaf((__uint_as_float(raw[4 * j + 1]) - mean1) * rstd1, w4.y, b4.y);
-            z[4 * j + 2] = fmaf((__uint_as_float(raw[4 * j + 2]) - mean1) * rstd1, w4.z, b4.z);
-            z[4 * j + 3] = fmaf((__uint_as_float(raw[4 * j + 3]) - mean1) * rstd1, w4.w, b4.w);
-          }
+          for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(raw[j]);
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // buffers of chunk k - 2
+          __syncwarp();
+          if (COPY_S) tile_bf16(btile + ((k & 1) * 2 + 1) * 128, lane, z);
+          ln_apply(z, w1_s + n0, b1_s + n0, rstd1, nmr1);
           if (LN2) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 w4 = *reinterpret_cast<const float4*>(w2_s + n0 + 4 * j);
-              const float4 b4 = *reinterpret_cast<const float4*>(b2_s + n0 + 4 * j);
-              z[4 * j] = fmaf((z[4 * j] - mean_u) * g, w4.x, b4.x);
-              z[4 * j + 1] = fmaf((z[4 * j + 1] - mean_u) * g, w4.y, b4.y);
-              z[4 * j + 2] = fmaf((z[4 * j + 2] - mean_u) * g, w4.z, b4.z);
-              z[4 * j + 3] = fmaf((z[4 * j + 3] - mean_u) * g, w4.w, b4.w);
-            }
+            ln_apply(z, w2_s + n0, b2_s + n0, g, nmu);
           } else if (L2N) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) z[j] *= g;
           }
           if (FILM) {
+            const float2 one = make_float2(1.f, 1.f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 sc4 = __ldg(reinterpret_cast<const float4*>(fp + n0 + 4 * j));
-              const float4 sh4 = __ldg(reinterpret_cast<const float4*>(fp + LN_N + n0 + 4 * j));
-              z[4 * j] = fmaf(z[4 * j], 1.f + sc4.x, sh4.x);
-              z[4 * j + 1] = fmaf(z[4 * j + 1], 1.f + sc4.y, sh4.y);
-              z[4 * j + 2] = fmaf(z[4 * j + 2], 1.f + sc4.z, sh4.z);
-              z[4 * j + 3] = fmaf(z[4 * j + 3], 1.f + sc4.w, sh4.w);
+              const float2 y0 = fma2(make_float2(z[4 * j], z[4 * j + 1]), add2(make_float2(fsc[j].x, fsc[j].y), one), make_float2(fsh[j].x, fsh[j].y));
+              const float2 y1 = fma2(make_float2(z[4 * j + 2], z[4 * j + 3]), add2(make_float2(fsc[j].z, fsc[j].w), one), make_float2(fsh[j].z, fsh[j].w));
+              z[4 * j] = y0.x; z[4 * j + 1] = y0.y; z[4 * j + 2] = y1.x; z[4 * j + 3] = y1.y;
             }
+            if (k + 1 < LN_CH) { load8(fp + n0 + 32, fsc); load8(fp + LN_N + n0 + 32, fsh); }
           }
-          if (SILU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) z[j] = silu_fast(z[j]);
-          }
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // buffers of chunk k - 2
-          __syncwarp();
-          {
-            uint4* bt = btile + ((k & 1) * 2) * 128 + lane * 4;
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              uint4 pk;
-              pk.x = pack2(z[8 * c4], z[8 * c4 + 1]); pk.y = pack2(z[8 * c4 + 2], z[8 * c4 + 3]);
-              pk.z = pack2(z[8 * c4 + 4], z[8 * c4 + 5]); pk.w = pack2(z[8 * c4 + 6], z[8 * c4 + 7]);
-              bt[c4 ^ ((lane >> 1) & 3)] = pk;
-            }
-          }
-          if (COPY_S) {
-            uint4* bt = btile + ((k & 1) * 2 + 1) * 128 + lane * 4;
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              uint4 pk;
-              pk.x = pack2(__uint_as_float(raw[8 * c4]), __uint_as_float(raw[8 * c4 + 1]));
-              pk.y = pack2(__uint_as_float(raw[8 * c4 + 2]), __uint_as_float(raw[8 * c4 + 3]));
-              pk.z = pack2(__uint_as_float(raw[8 * c4 + 4]), __uint_as_float(raw[8 * c4 + 5]));
-              pk.w = pack2(__uint_as_float(raw[8 * c4 + 6]), __uint_as_float(raw[8 * c4 + 7]));
-              bt[c4 ^ ((lane >> 1) & 3)] = pk;
-            }
-          }
+          if (SILU) silu32(z);
+          tile_bf16(btile + ((k & 1) * 2) * 128, lane, z);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmO2, btile + ((k & 1) * 2) * 128, n0, row0);
-            if (COPY_S) tma_store_2d(&tmS, btile + ((k & 1) * 2 + 1) * 128, n0, row0);
+            tma_store_2d(&tmO2, btile + ((k & 1) * 2) * 128, gcol0 + n0, row0);
+            if (COPY_S) tma_store_2d(&tmS, btile + ((k & 1) * 2 + 1) * 128, gcol0 + n0, row0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+        };
+        tmem_ld32(t_addr, ra);
+#pragma unroll 1
+        for (int k = 0; k < LN_CH; k += 2) {
+          pass_c(k, ra, rb);
+          pass_c(k + 1, rb, ra);
         }
       }
-      // this warp is done with TMEM: the next tile's MMAs may overwrite its columns
+      // this warp is done with the accumulator buffer: the MMAs of the block after next may overwrite it
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty), 0));
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // TMA stores of this warp have left shared memory
   }
 
   tc_fence_before();
-  cluster_sync_all();
+  cluster_sync_all();          // no CTA exits while its peer may still write into its shared memory
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_2sm(tmem_base, LN_N);
+    tmem_dealloc(tmem_base, 2 * LN_NC);
   }
 }
 
@@ -510,9 +564,9 @@ int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
       return MDM_ERR_CUDA;
     attr_set |= dev_bit;
   }
-  const int pairs = ((M + BM - 1) / BM + 1) / 2;
+  const int blocks = (M + BM - 1) / BM;
   int clusters = num_sms() / 2;
-  if (pairs < clusters) clusters = pairs;
+  if (blocks < clusters) clusters = blocks;
   if (clusters < 1) clusters = 1;
   return mdm_launch(gemm_ln_kernel<FLAGS, ACT>, (unsigned)(2 * clusters), LN_THREADS, LnSmem::TOTAL, st, ta, tb, tr, ty, ts,
                     t1f, t1a, t2, M, K, a) == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
@@ -547,7 +601,7 @@ extern "C" MDM_API int mdm_gemm_ln(const void* A, int lda, long a_rows, const vo
   if (op->silu) flags |= LF_SILU;
   if (op->out2_a) flags |= LF_OUT2;
   CUtensorMap ta, tb;
-  if (!make_map(&ta, A, a_rows, K, lda, BM) || !make_map(&tb, W, w_rows, K, ldw, 128)) return MDM_ERR_CUDA;
+  if (!make_map(&ta, A, a_rows, K, lda, BM) || !make_map(&tb, W, w_rows, K, ldw, LN_NC)) return MDM_ERR_CUDA;
   CUtensorMap tr = ta, ty = ta, ts = ta, t1f = ta, t1a = ta, t2 = ta;
   bool ok = true;
   if (epi->resid) ok = ok && (epi->ld_resid & 3) == 0 && al(epi->resid, 16) && make_f32_map(&tr, epi->resid, M, N, epi->ld_resid);
