@@ -85,23 +85,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
 }
-// partial row statistics for the peer CTA: a store into its shared memory, then a release-arrive on its barrier (every
-// thread for itself: the acquire-wait on the other side then sees the value without further fences)
-__device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float2 v) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (true) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (ok) break;
-    if (++spins == (1u << 22)) __trap();
-  }
+// Partial row statistics for the peer CTA: an asynchronous store into ITS shared memory that signals ITS mbarrier
+// with the byte count (st.async ... mbarrier::complete_tx::bytes): the sender does not wait for anything, and the
+// receiver's ordinary mbarrier wait orders the data (the same mechanism as a TMA multicast from the peer).  The first
+// version used st.shared::cluster + mbarrier.arrive.release.cluster / try_wait.acquire.cluster: a MEMBAR + ERRBAR on the
+// sending warp and an L1 invalidation (CCTL.IVALL) on every waiting warp, 17 % of the epilogue's stall samples.
+__device__ __forceinline__ void st_async_f2(uint32_t cluster_addr, float2 v, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "r"(cluster_bar) : "memory");
 }
 
 // ---- per-chunk (32 columns of one row per thread) helpers, packed fp32 pairs (FFMA2 / FADD2: one issue slot per two
@@ -129,19 +120,18 @@ __device__ __forceinline__ void ln_apply(float (&v)[32], const float* __restrict
     v[4 * j] = u0.x; v[4 * j + 1] = u0.y; v[4 * j + 2] = u1.x; v[4 * j + 3] = u1.y;
   }
 }
+// SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU op per element (ex2 + rcp: two, and the pass that
+// applies it is bound by the 16 MUFU lanes of the SM).  MUFU.TANH: 2^-11 relative, i.e. <= 2.5e-4 of sigmoid: a
+// sixteenth of a bf16 rounding step of the result.
 __device__ __forceinline__ void silu32(float (&v)[32]) {
-  const float2 nl2e = make_float2(-1.4426950408889634f, -1.4426950408889634f), one = make_float2(1.f, 1.f);
+  const float2 half = make_float2(0.5f, 0.5f);
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
-    const float2 x = make_float2(v[j], v[j + 1]);
-    const float2 t = mul2(x, nl2e);
-    float2 e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
-    e = add2(e, one);
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(e.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(e.y));
-    const float2 y = mul2(x, r);
+    const float2 h = mul2(make_float2(v[j], v[j + 1]), half);
+    float2 t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+    const float2 y = fma2(h, t, h);
     v[j] = y.x; v[j + 1] = y.y;
   }
 }
@@ -196,7 +186,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + LN_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;
-  // [2 block parities][2 exchanges][4 quadrants], 32 arrivals of the peer CTA each.  One barrier per block PARITY: a
+  // [2 block parities][2 exchanges][4 quadrants]: one local arrival that expects the 256 bytes the peer warp sends.
+  // One barrier per block PARITY: a
   // barrier then completes a phase every second block, and the peer cannot be two blocks ahead (it needs this CTA's
   // totals of the block in between), so a waiter can never be lapped.
   uint64_t* xbar = res_bar + 2 * LN_EPI_WARPS;
@@ -220,7 +211,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int i = 0; i < 2 * LN_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) mbar_init(&xbar[i], 32);
+    for (int i = 0; i < 16; ++i) mbar_init(&xbar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 2 * LN_NC);
@@ -316,10 +307,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int slot = ((par * 2 + e) * 128) + row;
       uint64_t* xb = &xbar[(par * 2 + e) * 4 + quad];
       if (ch == 0) {                                           // one warp per quadrant sends the CTA's total to the peer
-        st_cluster_f2(mapa_u32(smem_u32(&xred[slot]), rank ^ 1), make_float2(s0, s1));
-        mbar_arrive_cluster(mapa_u32(smem_u32(xb), rank ^ 1));
+        st_async_f2(mapa_u32(smem_u32(&xred[slot]), rank ^ 1), make_float2(s0, s1), mapa_u32(smem_u32(xb), rank ^ 1));
+        if (lane == 0) mbar_expect_tx(xb, 32 * 8);             // own barrier: the peer warp's 32 float2
       }
-      mbar_wait_cluster(xb, (it >> 1) & 1);
+      mbar_wait(xb, (it >> 1) & 1);
       const float2 p = xred[slot];
       s0 += p.x;
       s1 += p.y;
@@ -428,6 +419,13 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float rstd1 = rsqrtf(fmaxf(fmaf(sq, inv_n, -mean1 * mean1), 0.f) + 1e-5f);
       const float nmr1 = -mean1 * rstd1;
 
+      // FiLM (scale | shift) of this lane's row, chunk 0: requested a whole pass before it is needed; chunk k + 1 is
+      // requested as soon as chunk k's values are consumed
+      const int rc = min(r, M - 1);                              // rows past M only need a valid FiLM address
+      const float* fp = FILM ? a.film + (long)(rc / a.rows_per_seq) * (2 * LN_N) + gcol0 : nullptr;
+      float4 fsc[8], fsh[8];
+      if (FILM) { load8(fp, fsc); load8(fp + LN_N, fsh); }
+
       // ---------------------------------------------------------------- pass B
       float2 sB[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, qB[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       if (PASS_B) {
@@ -484,11 +482,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           g = LN2 ? sc * rsqrtf(sc * sc * var_u + 1e-5f) : sc;
           nmu = LN2 ? -mean_u * g : 0.f;
         }
-        const int rc = min(r, M - 1);                            // rows past M only need a valid FiLM address
-        const float* fp = FILM ? a.film + (long)(rc / a.rows_per_seq) * (2 * LN_N) + gcol0 : nullptr;
-        // FiLM (scale | shift) of this lane's row: chunk k + 1 is requested as soon as chunk k's values are consumed
-        float4 fsc[8], fsh[8];
-        if (FILM) { load8(fp, fsc); load8(fp + LN_N, fsh); }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
         auto pass_c = [&](int k, uint32_t (&raw)[32], uint32_t (&nraw)[32]) {
