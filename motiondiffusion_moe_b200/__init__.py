@@ -6,7 +6,8 @@ from .gaussian_diffusion import (GaussianDiffusion, CFGStepper, get_named_beta_s
                                  ModelVarType, LossType)
 
 from .trainer import DDPMTrainer  # noqa: F401
+from .text_encoder import EnhancedTextEncoder  # noqa: F401
 from .postprocess import load_reference_checkpoint, save_reference_checkpoint, recover_from_ric  # noqa: F401
 
-__all__ = ["DDPMTrainer", "load_reference_checkpoint", "save_reference_checkpoint", "recover_from_ric", "MotionTransformer", "TextContext", "GaussianDiffusion", "CFGStepper", "get_named_beta_schedule", "ModelMeanType",
+__all__ = ["DDPMTrainer", "EnhancedTextEncoder", "load_reference_checkpoint", "save_reference_checkpoint", "recover_from_ric", "MotionTransformer", "TextContext", "GaussianDiffusion", "CFGStepper", "get_named_beta_schedule", "ModelMeanType",
            "ModelVarType", "LossType", "MdmError", "load_library"]
