@@ -133,6 +133,20 @@ MDM_API int mdm_gemm_rowop(const MdmRowOp* op, long rows, int D, const void* W, 
 MDM_API int mdm_gemm_ln(const void* A, int lda, long a_rows, const void* W, int ldw, long w_rows, int M, int N, int K,
                         const MdmGemmEpi* epi, const MdmRowOp* op, void* stream);
 
+/* mdm_gemm_ln with the MoE GATE as its second pass: the cross-attention output Linear produces the row the gate reads
+ * (models/fast_attention.py:270-272 -> models/multi_branch.py:52-55 -> models/switch_moe.py:53-57), so
+ *   y = (A . W[512, K]^T + bias) * alpha + beta * resid -> epi->out_f32
+ *   per branch br < 2: softmax(LayerNorm_br(y) . gate_w[br]^T + gate_b[br]) -> top-2
+ * in one kernel: LayerNorm statistics and the 16 dot products per row are per-thread sums (TMEM lane = row), CTA r of
+ * the pair finalises branch r.  Outputs exactly as mdm_moe_gate (idx / vals [M][2][2], stats [M][2] = mean, rstd of the
+ * row, per-128-row-block histograms and importance sums: rows of a block counted in token order).  NB == 2, NB * E == 16,
+ * N == 512; anything else returns MDM_ERR_UNSUPPORTED and the caller runs mdm_gemm_bf16 + mdm_moe_gate. */
+MDM_API int mdm_gemm_gate(const void* A, int lda, long a_rows, const void* W, int ldw, long w_rows, int M, int N, int K,
+                          const MdmGemmEpi* epi, int NB, int E, const float* ln_w, const float* ln_b, const float* gate_w,
+                          const float* gate_b, int* idx, float* vals, float* stats, int* blk_hist, float* blk_imp,
+                          void* stream);
+
+
 
 /* ---- FastAttention core, models/fast_attention.py:29-92 (PerformerSelfAttention :155-160) ----
  * qkv: [B*T, 3*H*hd] (q | k | v, already multiplied by nothing: the 0.1 pre-scale of :155-157 is

@@ -67,6 +67,7 @@ _SIGS = {
     "mdm_rowop": [C.POINTER(RowOp), _L, _I, _I, _P],
     "mdm_gemm_rowop": [C.POINTER(RowOp), _L, _I, _P, _I, _L, _I, C.POINTER(GemmEpi), _P],
     "mdm_gemm_ln": [_P, _I, _L, _P, _I, _L, _I, _I, _I, C.POINTER(GemmEpi), C.POINTER(RowOp), _P],
+    "mdm_gemm_gate": [_P, _I, _L, _P, _I, _L, _I, _I, _I, C.POINTER(GemmEpi), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "mdm_fastattn": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "mdm_fastattn_ordered": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "mdm_lincross_ctx": [_P, _P, _I, _P, _I, _I, _I, _I, _P, _P],

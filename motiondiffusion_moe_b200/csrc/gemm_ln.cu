@@ -28,6 +28,7 @@
 #include "gemm_epilogue.cuh"
 #include "cluster.cuh"
 #include "tensormap.cuh"
+#include "moe_topk.cuh"
 
 namespace {
 
@@ -38,24 +39,35 @@ constexpr int LN_EPI_WARPS = 8;
 constexpr int LN_THREADS = (FIRST_EPI_WARP + LN_EPI_WARPS) * 32;
 constexpr int LN_CH = 4;             // 32-column chunks per epilogue warp and pass
 
-struct LnSmem {
+constexpr int LN_G = 16;             // gate stage: 2 branches x 8 experts (MoEMultiBranchFFN of the default model)
+template <bool GATE>
+struct LnSmemT {
+  // the gate stage keeps its 16 weight rows (16 KB per CTA) and the logit exchange in shared memory and pays for them
+  // with one operand stage: with K = 512 the MMAs of the next block hide under the epilogue either way
+  static constexpr int STAGES = GATE ? 2 : LN_STAGES;
   static constexpr int A_BYTES = BM * BK * 2;                      // 128 rows of A
   static constexpr int B_BYTES = LN_NC * BK * 2;                   // this CTA's 256 weight rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;            // 48 KB
-  static constexpr int TILE_OFF = LN_STAGES * STAGE_BYTES;         // per epilogue warp 8 KB: 2 fp32 / 4 bf16 staging tiles
-  static constexpr int PRM_OFF = TILE_OFF + LN_EPI_WARPS * 8192;   // bias, ln1_w, ln1_b, ln2_w, ln2_b of this CTA's columns
-  static constexpr int RED_OFF = PRM_OFF + 5 * LN_NC * 4;          // float2 [2 column halves][128 rows]: inside the CTA
-  static constexpr int XRED_OFF = RED_OFF + 2 * 128 * 8;           // float2 [2 tile parities][2 exchanges][128 rows]: from the peer CTA
-  static constexpr int BAR_OFF = XRED_OFF + 4 * 128 * 8;
-  // full / empty ring, tmem_full[2], tmem_empty[2], 2 residual barriers per epilogue warp, 2 x 2 x 4 exchange barriers,
-  // TMEM pointer; + alignment slack
-  static constexpr int TOTAL = BAR_OFF + (2 * LN_STAGES + 4 + 2 * LN_EPI_WARPS + 16) * 8 + 16 + 1024;
+  static constexpr int TILE_OFF = STAGES * STAGE_BYTES;            // per epilogue warp 8 KB: 2 fp32 / 4 bf16 staging tiles
+  // this CTA's columns of: bias, ln1_w, ln1_b, ln2_w, ln2_b | gate: bias, ln_w[2], ln_b[2], gate_w[16]
+  static constexpr int PRM_OFF = TILE_OFF + LN_EPI_WARPS * 8192;
+  static constexpr int PRM_FLOATS = GATE ? (1 + 4 + LN_G) * LN_NC : 5 * LN_NC;
+  static constexpr int RED_OFF = PRM_OFF + PRM_FLOATS * 4;         // float2 [2 column halves][128 rows]: inside the CTA
+  static constexpr int XRED_OFF = RED_OFF + 2 * 128 * 8;           // float2 [2 block parities][2 exchanges][128 rows]: from the peer CTA
+  // gate: float [128 rows][16] logit partials of the partner warp | float [2 parities][128 rows][8] from the peer CTA |
+  // {int2 idx, float2 val} [2 parities][128 rows] results of this CTA's branch
+  static constexpr int GATE_OFF = XRED_OFF + 4 * 128 * 8;
+  static constexpr int GATE_BYTES = GATE ? 128 * LN_G * 4 + 2 * 128 * 8 * 4 + 2 * 128 * 16 : 0;
+  static constexpr int BAR_OFF = GATE_OFF + GATE_BYTES;
+  // full / empty ring, tmem_full[2], tmem_empty[2], 2 residual barriers per epilogue warp, 2 x 2 x 4 statistics barriers,
+  // 2 x 4 gate barriers, TMEM pointer; + alignment slack
+  static constexpr int TOTAL = BAR_OFF + (2 * LN_STAGES + 4 + 2 * LN_EPI_WARPS + 16 + 8) * 8 + 16 + 1024;
 };
-static_assert(LnSmem::TOTAL <= 227 * 1024, "shared memory budget");
+static_assert(LnSmemT<true>::TOTAL <= 227 * 1024 && LnSmemT<false>::TOTAL <= 227 * 1024, "shared memory budget");
 
 enum {
   LF_RESID = 1, LF_OUT_Y = 2, LF_COPY_S = 4, LF_LN_PRE = 8, LF_L2 = 16, LF_OUT1_F32 = 32, LF_OUT1_A = 64, LF_LN2 = 128,
-  LF_FILM = 256, LF_SILU = 512, LF_OUT2 = 1024
+  LF_FILM = 256, LF_SILU = 512, LF_OUT2 = 1024, LF_GATE = 2048
 };
 
 struct LnArgs {
@@ -64,6 +76,14 @@ struct LnArgs {
   const float* film;
   float alpha, beta;
   int rows_per_seq;
+  // gate stage (LF_GATE): LayerNorm affine of the two branches [2][512], gate weights [16][512] and bias [16];
+  // outputs of mdm_moe_gate (include/mdm_b200.h): idx / vals [M][2][2], stats [M][2], per-128-row-block histograms
+  const float *gate_ln_w, *gate_ln_b, *gate_w, *gate_b;
+  int* idx;
+  float* vals;
+  float* stats;
+  int* blk_hist;
+  float* blk_imp;
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -93,6 +113,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void st_async_f2(uint32_t cluster_addr, float2 v, uint32_t cluster_bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
                ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "r"(cluster_bar) : "memory");
+}
+
+__device__ __forceinline__ void st_async_f4(uint32_t cluster_addr, float4 v, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(cluster_bar) : "memory");
 }
 
 // ---- per-chunk (32 columns of one row per thread) helpers, packed fp32 pairs (FFMA2 / FADD2: one issue slot per two
@@ -164,7 +189,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmO1F,
                const __grid_constant__ CUtensorMap tmO1A, const __grid_constant__ CUtensorMap tmO2, int M, int K,
                const LnArgs a) {
-  using L = LnSmem;
+  constexpr bool GATE = (FLAGS & LF_GATE) != 0;
+  using L = LnSmemT<GATE>;
+  constexpr int NSTG = L::STAGES;
   constexpr bool RESID = (FLAGS & LF_RESID) != 0, OUT_Y = (FLAGS & LF_OUT_Y) != 0, COPY_S = (FLAGS & LF_COPY_S) != 0;
   constexpr bool LN_PRE = (FLAGS & LF_LN_PRE) != 0, L2N = (FLAGS & LF_L2) != 0, OUT1_F32 = (FLAGS & LF_OUT1_F32) != 0;
   constexpr bool OUT1_A = (FLAGS & LF_OUT1_A) != 0, LN2 = (FLAGS & LF_LN2) != 0, FILM = (FLAGS & LF_FILM) != 0;
@@ -172,6 +199,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr bool PASS_C = OUT2;                          // z is only computed when it has a destination
   constexpr bool STATS2 = PASS_C && (L2N || LN2);        // pass B accumulates the statistics of u
   constexpr bool PASS_B = OUT1_F32 || OUT1_A || STATS2 || (COPY_S && !PASS_C);
+  static_assert(!GATE || !(PASS_B || PASS_C || LN_PRE), "the gate stage is its own second pass");
   static_assert(!(OUT1_F32 && OUT1_A), "out1 has one staging area: fp32 or bf16");
   static_assert(!(OUT1_F32 && COPY_S && !PASS_C), "the bf16 copy of s shares the staging area of out1");
   static_assert(!L2N || !(OUT1_F32 || OUT1_A), "out1 after the L2 norm is not built (no caller)");
@@ -182,7 +210,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float2* red = reinterpret_cast<float2*>(smem + L::RED_OFF);
   float2* xred = reinterpret_cast<float2*>(smem + L::XRED_OFF);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* empty_bar = full_bar + LN_STAGES;
+  uint64_t* empty_bar = full_bar + LN_STAGES;     // (LN_STAGES slots reserved; NSTG of them used)
   uint64_t* tmem_full = empty_bar + LN_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;
@@ -191,7 +219,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // barrier then completes a phase every second block, and the peer cannot be two blocks ahead (it needs this CTA's
   // totals of the block in between), so a waiter can never be lapped.
   uint64_t* xbar = res_bar + 2 * LN_EPI_WARPS;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xbar + 16);
+  uint64_t* gbar = xbar + 16;                            // gate stage: [2 block parities][4 quadrants], same scheme
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(gbar + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -200,7 +229,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
 #pragma unroll
-    for (int s = 0; s < LN_STAGES; ++s) {
+    for (int s = 0; s < NSTG; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -212,6 +241,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2 * LN_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
 #pragma unroll
     for (int i = 0; i < 16; ++i) mbar_init(&xbar[i], 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mbar_init(&gbar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 2 * LN_NC);
@@ -239,7 +270,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, w * BM);
           tma_load_2d(&tmB, &full_bar[stage], sa + L::A_BYTES, kb * BK, ncol0);
-          if (++stage == LN_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NSTG) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1 && lane == 0) {
@@ -260,7 +291,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty_bar[stage]);
-          if (++stage == LN_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NSTG) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -281,12 +312,24 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float* b1_s = prm + 2 * LN_NC + ch * 128;
     const float* w2_s = prm + 3 * LN_NC + ch * 128;
     const float* b2_s = prm + 4 * LN_NC + ch * 128;
+    // gate stage: ln_w[br] at prm + (1 + br) * 256, ln_b[br] at prm + (3 + br) * 256, gate_w[g] at prm + (5 + g) * 256
+    const float* gprm = prm + ch * 128;
     {
       const int t = threadIdx.x - FIRST_EPI_WARP * 32;         // 0..255: one column each
       prm[t] = a.bias ? a.bias[ncol0 + t] : 0.f;
-      prm[LN_NC + t] = a.ln1_w[ncol0 + t];
-      prm[2 * LN_NC + t] = a.ln1_b[ncol0 + t];
-      if (LN2) { prm[3 * LN_NC + t] = a.ln2_w[ncol0 + t]; prm[4 * LN_NC + t] = a.ln2_b[ncol0 + t]; }
+      if (GATE) {
+#pragma unroll
+        for (int br = 0; br < 2; ++br) {
+          prm[(1 + br) * LN_NC + t] = a.gate_ln_w[br * LN_N + ncol0 + t];
+          prm[(3 + br) * LN_NC + t] = a.gate_ln_b[br * LN_N + ncol0 + t];
+        }
+#pragma unroll
+        for (int g = 0; g < LN_G; ++g) prm[(5 + g) * LN_NC + t] = a.gate_w[g * LN_N + ncol0 + t];
+      } else {
+        prm[LN_NC + t] = a.ln1_w[ncol0 + t];
+        prm[2 * LN_NC + t] = a.ln1_b[ncol0 + t];
+        if (LN2) { prm[3 * LN_NC + t] = a.ln2_w[ncol0 + t]; prm[4 * LN_NC + t] = a.ln2_b[ncol0 + t]; }
+      }
       asm volatile("bar.sync 9, 256;" ::: "memory");            // the epilogue warps only
     }
     const int gcol0 = ncol0 + ch * 128;                        // global column of this warp's chunk 0
@@ -418,6 +461,113 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float mean1 = sum * inv_n;
       const float rstd1 = rsqrtf(fmaxf(fmaf(sq, inv_n, -mean1 * mean1), 0.f) + 1e-5f);
       const float nmr1 = -mean1 * rstd1;
+
+      // ---------------------------------------------------------------- gate stage (SwitchMoELayer gate of both branches)
+      // LayerNorm(y) per branch (shared statistics) -> 16 dot products per row, summed per thread over its 128 columns;
+      // partner warp through shared memory, then CTA r finalises branch r: it receives the peer's partial of its 8
+      // logits (st.async), adds the bias, softmax + top-2 per row (one thread per row: no shuffles), writes idx / vals
+      // / stats, and one warp counts the 128 rows of the block in token order (deterministic histograms).
+      if (GATE) {
+        float2 lg[LN_G];
+#pragma unroll
+        for (int g = 0; g < LN_G; ++g) lg[g] = make_float2(0.f, 0.f);
+        auto pass_g = [&](int k, uint32_t (&raw)[32], uint32_t (&nraw)[32]) {
+          const int n0 = 32 * k;
+          tmem_ld_wait();
+          if (k + 1 < LN_CH) tmem_ld32(t_addr + n0 + 32, nraw);
+#pragma unroll
+          for (int br = 0; br < 2; ++br) {
+            float h[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = __uint_as_float(raw[j]);
+            ln_apply(h, gprm + (1 + br) * LN_NC + n0, gprm + (3 + br) * LN_NC + n0, rstd1, nmr1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float* wr = gprm + (5 + br * 8 + e) * LN_NC + n0;
+              float2 acc = lg[br * 8 + e];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * j);
+                acc = fma2(make_float2(h[4 * j], h[4 * j + 1]), make_float2(w4.x, w4.y), acc);
+                acc = fma2(make_float2(h[4 * j + 2], h[4 * j + 3]), make_float2(w4.z, w4.w), acc);
+              }
+              lg[br * 8 + e] = acc;
+            }
+          }
+        };
+        tmem_ld32(t_addr, ra);
+#pragma unroll 1
+        for (int k = 0; k < LN_CH; k += 2) {
+          pass_g(k, ra, rb);
+          pass_g(k + 1, rb, ra);
+        }
+        float lp[LN_G];
+#pragma unroll
+        for (int g = 0; g < LN_G; ++g) lp[g] = lg[g].x + lg[g].y;
+        const int row = quad * 32 + lane;
+        float4* lred = reinterpret_cast<float4*>(smem + L::GATE_OFF);                 // [128 rows][4 float4]
+        const int par = (int)(it & 1);
+        float4* xg = lred + 128 * 4 + par * 128 * 2;                                   // [2 parities][128 rows][2 float4]
+        uint4* resb = reinterpret_cast<uint4*>(lred + 128 * 4 + 2 * 128 * 2) + par * 128;   // [2 parities][128 rows]
+        if (ch == 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) lred[row * 4 + q] = make_float4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
+        }
+        quad_sync(quad);
+        if (ch == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 o = lred[row * 4 + q];
+            lp[4 * q] += o.x; lp[4 * q + 1] += o.y; lp[4 * q + 2] += o.z; lp[4 * q + 3] += o.w;
+          }
+        }
+        quad_sync(quad);
+        if (ch == 0) {
+          const int mine = (int)rank;                            // CTA r finalises branch r
+          float own[8], oth[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { own[e] = mine ? lp[8 + e] : lp[e]; oth[e] = mine ? lp[e] : lp[8 + e]; }
+          uint64_t* gb = &gbar[par * 4 + quad];
+          const uint32_t peer_bar = mapa_u32(smem_u32(gb), rank ^ 1);
+          st_async_f4(mapa_u32(smem_u32(&xg[row * 2]), rank ^ 1), make_float4(oth[0], oth[1], oth[2], oth[3]), peer_bar);
+          st_async_f4(mapa_u32(smem_u32(&xg[row * 2 + 1]), rank ^ 1), make_float4(oth[4], oth[5], oth[6], oth[7]), peer_bar);
+          if (lane == 0) mbar_expect_tx(gb, 32 * 32);              // the peer warp's 32 x 8 floats
+          mbar_wait(gb, (it >> 1) & 1);
+          const float4 p0 = xg[row * 2], p1 = xg[row * 2 + 1];
+          float logits[8], probs[8];
+          logits[0] = own[0] + p0.x; logits[1] = own[1] + p0.y; logits[2] = own[2] + p0.z; logits[3] = own[3] + p0.w;
+          logits[4] = own[4] + p1.x; logits[5] = own[5] + p1.y; logits[6] = own[6] + p1.z; logits[7] = own[7] + p1.w;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) logits[e] += __ldg(a.gate_b + mine * 8 + e);
+          int i0, i1;
+          float v0, v1;
+          softmax_top2<8>(logits, probs, i0, i1, v0, v1);
+          if (r < M) {
+            const long o = ((long)r * 2 + mine) * 2;
+            *reinterpret_cast<int2*>(a.idx + o) = make_int2(i0, i1);
+            *reinterpret_cast<float2*>(a.vals + o) = make_float2(v0, v1);
+            if (mine == 0) *reinterpret_cast<float2*>(a.stats + (long)r * 2) = make_float2(mean1, rstd1);
+          }
+          resb[row] = make_uint4((uint32_t)i0, (uint32_t)i1, __float_as_uint(v0), __float_as_uint(v1));
+          asm volatile("bar.sync 10, 128;" ::: "memory");          // the four finalising warps of this CTA
+          if (quad == 0 && lane < 8) {
+            // group (branch mine, expert lane): rows in token order, slot 0 before slot 1 - the accumulation order of
+            // the reference's per-expert loops (switch_moe.py:72-92); fixed order = deterministic importance sums
+            const int rows_here = min(BM, M - w * BM);
+            int c_all = 0, c_top1 = 0;
+            float imp = 0.f;
+            for (int rr = 0; rr < rows_here; ++rr) {
+              const uint4 q = resb[rr];
+              if ((int)q.x == lane) { ++c_all; ++c_top1; imp += __uint_as_float(q.z); }
+              if ((int)q.y == lane) { ++c_all; imp += __uint_as_float(q.w); }
+            }
+            const int g = mine * 8 + lane;
+            a.blk_hist[((long)w * 2) * LN_G + g] = c_all;
+            a.blk_hist[((long)w * 2 + 1) * LN_G + g] = c_top1;
+            a.blk_imp[(long)w * LN_G + g] = imp;
+          }
+        }
+      }
 
       // FiLM (scale | shift) of this lane's row, chunk 0: requested a whole pass before it is needed; chunk k + 1 is
       // requested as soon as chunk k's values are consumed
@@ -552,7 +702,7 @@ int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   static unsigned long long attr_set = 0;   // one bit per device ordinal
   const unsigned long long dev_bit = 1ull << mdm_cur_dev();
   if (!(attr_set & dev_bit)) {
-    if (cudaFuncSetAttribute(gemm_ln_kernel<FLAGS, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnSmem::TOTAL) !=
+    if (cudaFuncSetAttribute(gemm_ln_kernel<FLAGS, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnSmemT<(FLAGS & LF_GATE) != 0>::TOTAL) !=
         cudaSuccess)
       return MDM_ERR_CUDA;
     attr_set |= dev_bit;
@@ -561,7 +711,7 @@ int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   int clusters = num_sms() / 2;
   if (blocks < clusters) clusters = blocks;
   if (clusters < 1) clusters = 1;
-  return mdm_launch(gemm_ln_kernel<FLAGS, ACT>, (unsigned)(2 * clusters), LN_THREADS, LnSmem::TOTAL, st, ta, tb, tr, ty, ts,
+  return mdm_launch(gemm_ln_kernel<FLAGS, ACT>, (unsigned)(2 * clusters), LN_THREADS, LnSmemT<(FLAGS & LF_GATE) != 0>::TOTAL, st, ta, tb, tr, ty, ts,
                     t1f, t1a, t2, M, K, a) == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -604,7 +754,7 @@ extern "C" MDM_API int mdm_gemm_ln(const void* A, int lda, long a_rows, const vo
   if (op->out1_a) ok = ok && al(op->out1_a, 16) && make_out_map(&t1a, op->out1_a, M, N, N);
   if (op->out2_a) ok = ok && al(op->out2_a, 16) && make_out_map(&t2, op->out2_a, M, N, N);
   if (!ok) return MDM_ERR_UNSUPPORTED;
-  LnArgs a;
+  LnArgs a = {};
   a.bias = epi->bias;
   a.ln1_w = op->ln1_w; a.ln1_b = op->ln1_b; a.ln2_w = op->ln2_w; a.ln2_b = op->ln2_b;
   a.film = op->film;
@@ -627,4 +777,36 @@ extern "C" MDM_API int mdm_gemm_ln(const void* A, int lda, long a_rows, const vo
   MDM_LN(LF_RESID | LF_OUT_Y | LF_COPY_S | LF_OUT1_F32 | LF_LN2 | LF_OUT2, MDM_ACT_NONE);
 #undef MDM_LN
   return MDM_ERR_UNSUPPORTED;
+}
+
+// C-ABI: see include/mdm_b200.h
+extern "C" MDM_API int mdm_gemm_gate(const void* A, int lda, long a_rows, const void* W, int ldw, long w_rows, int M, int N, int K,
+                                     const MdmGemmEpi* epi, int NB, int E, const float* ln_w, const float* ln_b,
+                                     const float* gate_w, const float* gate_b, int* idx, float* vals, float* stats,
+                                     int* blk_hist, float* blk_imp, void* stream) {
+  if (!A || !W || !epi || !ln_w || !ln_b || !gate_w || !gate_b || !idx || !vals || !stats || !blk_hist || !blk_imp || M <= 0 ||
+      K <= 0)
+    return MDM_ERR_ARG;
+  if (N != LN_N || (K % BK) != 0 || w_rows < LN_N || NB != 2 || NB * E != LN_G) return MDM_ERR_UNSUPPORTED;
+  if ((lda & 7) || (ldw & 7)) return MDM_ERR_ARG;
+  auto al = [](const void* p, uintptr_t n) { return (reinterpret_cast<uintptr_t>(p) & (n - 1)) == 0; };
+  if (!al(A, 16) || !al(W, 16)) return MDM_ERR_ARG;
+  if (epi->rowscale || epi->rowmask || epi->tile_k || epi->mn_major || epi->resid_mod > 0 || epi->act != MDM_ACT_NONE ||
+      epi->out_bf16 || !epi->resid || !epi->out_f32)
+    return MDM_ERR_UNSUPPORTED;
+  if ((epi->ld_resid & 3) || (epi->ld_f32 & 3) || !al(epi->resid, 16) || !al(epi->out_f32, 16) || !al(idx, 8) || !al(vals, 8) ||
+      !al(stats, 8))
+    return MDM_ERR_UNSUPPORTED;
+  CUtensorMap ta, tb, tr, ty;
+  if (!make_map(&ta, A, a_rows, K, lda, BM) || !make_map(&tb, W, w_rows, K, ldw, LN_NC)) return MDM_ERR_CUDA;
+  if (!make_f32_map(&tr, epi->resid, M, N, epi->ld_resid) || !make_f32_map(&ty, epi->out_f32, M, N, epi->ld_f32)) return MDM_ERR_CUDA;
+  LnArgs a = {};
+  a.bias = epi->bias;
+  a.alpha = epi->alpha;
+  a.beta = epi->beta;
+  a.rows_per_seq = 1;
+  a.gate_ln_w = ln_w; a.gate_ln_b = ln_b; a.gate_w = gate_w; a.gate_b = gate_b;
+  a.idx = idx; a.vals = vals; a.stats = stats; a.blk_hist = blk_hist; a.blk_imp = blk_imp;
+  return launch_ln<LF_RESID | LF_OUT_Y | LF_GATE, MDM_ACT_NONE>(ta, tb, tr, ty, ta, ta, ta, ta, M, K, a,
+                                                                reinterpret_cast<cudaStream_t>(stream));
 }

@@ -184,6 +184,30 @@ def gemm_ln(A, W, bias, *, ln1, act=ACT_NONE, alpha=1.0, beta=0.0, resid=None, o
     return True
 
 
+def gemm_gate(A, W, bias, *, resid, out_f32, alpha=1.0, beta=1.0, NB, E, ln_w, ln_b, gate_w, gate_b, idx, vals, stats,
+              blk_hist, blk_imp):
+    """Linear + residual AND the MoE gate of the row it produces in one kernel (mdm_gemm_gate): out_f32 = alpha * (A @ W^T +
+    bias) + beta * resid; idx / vals / stats / blk_hist / blk_imp as moe_gate(out_f32, ...) would write them.  Returns
+    False (nothing launched) outside the fused kernel's shapes: the caller then runs gemm + moe_gate."""
+    _req_cuda(A, W, out_f32, resid)
+    _c(bias, ln_w, ln_b, gate_w, gate_b, idx, vals, stats, blk_hist, blk_imp)
+    if (A.dtype != torch.bfloat16 or W.shape[0] != 512 or A.shape[1] % 64 or A.dim() != 2 or A.stride(1) != 1 or NB != 2
+            or NB * E != 16):
+        return False
+    e = _lib.GemmEpi()
+    e.bias, e.resid, e.ld_resid = _ptr(bias), resid.data_ptr(), resid.stride(0)
+    e.alpha, e.beta, e.act = alpha, beta, ACT_NONE
+    e.out_f32, e.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    st = _lib.load().mdm_gemm_gate(A.data_ptr(), A.stride(0), A.shape[0], W.data_ptr(), W.stride(0), W.shape[0], A.shape[0],
+                                   W.shape[0], A.shape[1], C.byref(e), NB, E, ln_w.data_ptr(), ln_b.data_ptr(),
+                                   gate_w.data_ptr(), gate_b.data_ptr(), idx.data_ptr(), vals.data_ptr(), stats.data_ptr(),
+                                   blk_hist.data_ptr(), blk_imp.data_ptr(), _stream())
+    if st == 3:
+        return False
+    _lib.check(st, "mdm_gemm_gate")
+    return True
+
+
 def fastattn(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out, seq_order=None, Pt=None):
     _c(qkv, P, norm_w, norm_b, length, out, seq_order, Pt)
     if Pt is not None and (Pt.dtype != torch.bfloat16 or tuple(Pt.shape) != (P.shape[1], P.shape[0])):

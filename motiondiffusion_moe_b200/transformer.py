@@ -93,6 +93,8 @@ class MotionTransformer(nn.Module):
         # Linear + the LayerNorm chain that follows it in one kernel (ops.gemm_ln: the row stays in TMEM; north_star (3)).
         # bf16 mode, latent_dim 512; MDM_FUSE_LN=0 keeps the gemm + rowop pairs (A/B runs, parity tests of both).
         self._fuse_ln = os.environ.get("MDM_FUSE_LN", "1") == "1"
+        # ... and the MoE gate as the second pass of the cross-attention output Linear (ops.gemm_gate); MDM_FUSE_GATE=0 = off
+        self._fuse_gate = os.environ.get("MDM_FUSE_GATE", "1") == "1"
         self._packed = None
         self._ws = {}
         self._film_tiles = {}
@@ -704,11 +706,13 @@ class MotionTransformer(nn.Module):
         # ---- GatedCrossAttention (fast_attention.py:242-272)
         self._lin(a0, L["ca_q"], out_a=a1)
         ops.lincross_apply(a1, ctx.lin_ctx[li], Bn, T, H, D // H, a2, ctxT=ctx.lin_ctxT[li])
-        if not (self._fuse_rowop and adt == torch.bfloat16 and
+        ca_done = False           # the output Linear of the block may run below, fused with the MoE gate
+        if (self._fuse_rowop and adt == torch.bfloat16 and
                 ops.gemm_rowop(a2, N, D, L["ca_out"][0], L["ca_out"][1], ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T,
                                silu=True, out_f32=x2, resid=x1, alpha=1.0, beta=1.0)):
+            ca_done = True
+        else:
             ops.rowop(a2, N, D, adti, ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T, silu=True, out2_a=a1)
-            self._lin(a1, L["ca_out"], out_f32=x2, resid=x1, alpha=1.0, beta=1.0)
         # ---- MoEMultiBranchFFN (multi_branch.py:52-61, switch_moe.py:44-111)
         forced = None
         if self.force_routing is not None:
@@ -718,6 +722,8 @@ class MotionTransformer(nn.Module):
             if tuple(forced.shape) != (N, 2, 2):
                 raise MdmError("forced routing of layer %d has shape %s, expected %s" % (li, tuple(forced.shape), (N, 2, 2)))
         if self._ep_on:
+            if not ca_done:
+                self._lin(a1, L["ca_out"], out_f32=x2, resid=x1, alpha=1.0, beta=1.0)
             ep = self._ep_for(N)
             if "ep_w" not in L:
                 L["ep_w"] = ep.shard_weights(L["moe_ln_w"], L["moe_ln_b"], L["gate_w"], L["gate_b"], L["w1"], L["b1"],
@@ -748,8 +754,16 @@ class MotionTransformer(nn.Module):
         xp = self._buf("moe_xp", (cap, D), adt)
         hp = self._buf("moe_hp", (cap, Fd), adt)
         yp = self._buf("moe_yp", (cap, D), adt)
-        ops.moe_gate(x2, N, D, NB, E, L["moe_ln_w"], L["moe_ln_b"], L["gate_w"], L["gate_b"], idx, vals, stats,
-                     hist, imp, forced_idx=forced)
+        # cross-attention output Linear + residual (x2) and the gate of both MoE branches on the row it produces: one
+        # kernel in bf16 mode (not with injected routing: the parity hook goes through the stand-alone gate)
+        if not (not ca_done and fuse and self._fuse_gate and forced is None and
+                ops.gemm_gate(a1, L["ca_out"][0], L["ca_out"][1], resid=x1, out_f32=x2, alpha=1.0, beta=1.0, NB=NB, E=E,
+                              ln_w=L["moe_ln_w"], ln_b=L["moe_ln_b"], gate_w=L["gate_w"], gate_b=L["gate_b"], idx=idx,
+                              vals=vals, stats=stats, blk_hist=hist, blk_imp=imp)):
+            if not ca_done:
+                self._lin(a1, L["ca_out"], out_f32=x2, resid=x1, alpha=1.0, beta=1.0)
+            ops.moe_gate(x2, N, D, NB, E, L["moe_ln_w"], L["moe_ln_b"], L["gate_w"], L["gate_b"], idx, vals, stats,
+                         hist, imp, forced_idx=forced)
         ops.moe_scan(hist, imp, idx, N, NB, E, Fd, D, base, seg, t_up, t_dn, ntile, pk["usage"][li],
                      pk["importance"][li])
         ops.moe_permute(x2, N, D, NB, E, L["moe_ln_w"], L["moe_ln_b"], idx, vals, stats, base, seg, xp, perm,

@@ -241,6 +241,67 @@ def test_gemm_ln_fused(variant, M, K, T):
     assert not ops.gemm_ln(A, W[:256].contiguous(), b[:256].contiguous(), ln1=ln1, out1_a=buf(bf)[:M])
 
 
+@pytest.mark.parametrize("M", [196 * 3, 128, 1000, 25, 12544])
+def test_gemm_gate_fused(M):
+    """mdm_gemm_gate: the cross-attention output Linear + residual with the MoE gate of both branches as its second
+    pass, against the unfused pair (mdm_gemm_bf16 + mdm_moe_gate, itself checked against oracle.switch_moe): the same
+    x2, the same routing wherever the decision is not a rounding-level near-tie, the same gate values, per-block
+    histograms / importance sums consistent with the kernel's own routing."""
+    D = N = K = 512
+    NB, E = 2, 8
+    G = NB * E
+    A = randn(M, K, seed=1).bfloat16()
+    W = randn(N, K, seed=2, scale=K ** -0.5).bfloat16()
+    b, R = randn(N, seed=3, scale=0.5), randn(M, N, seed=4, scale=2.0)
+    lnw = torch.rand(NB, D, generator=gen(5)).to(DEV) + 0.5
+    lnb = randn(NB, D, seed=6, scale=0.1)
+    gw = randn(G, D, seed=7, scale=0.08)
+    gb = randn(G, seed=8, scale=0.1)
+    nblk = (M + 127) // 128
+
+    def outs():
+        return (torch.full((M + 8, NB, 2), -7, dtype=torch.int32, device=DEV), torch.full((M + 8, NB, 2), -7.0, device=DEV),
+                torch.full((M + 8, 2), -7.0, device=DEV), torch.zeros(nblk, 2, G, dtype=torch.int32, device=DEV),
+                torch.zeros(nblk, G, device=DEV))
+
+    x2f = torch.full((M + 8, N), 3.0, device=DEV)
+    idx, vals, stats, hist, imp = outs()
+    assert ops.gemm_gate(A, W, b, resid=R, out_f32=x2f[:M], NB=NB, E=E, ln_w=lnw, ln_b=lnb, gate_w=gw, gate_b=gb, idx=idx[:M],
+                         vals=vals[:M], stats=stats[:M], blk_hist=hist, blk_imp=imp)
+    x2u = torch.empty(M, N, device=DEV)
+    ops.gemm(A, W, b, out_f32=x2u, resid=R, alpha=1.0, beta=1.0)
+    idx_u, vals_u, stats_u, hist_u, imp_u = outs()
+    ops.moe_gate(x2u, M, D, NB, E, lnw, lnb, gw, gb, idx_u[:M], vals_u[:M], stats_u[:M], hist_u, imp_u)
+    torch.cuda.synchronize()
+    assert torch.all(x2f[M:] == 3.0) and torch.all(idx[M:] == -7) and torch.all(vals[M:] == -7.0) and torch.all(stats[M:] == -7.0)
+    assert rel(x2f[:M], x2u) < 1e-6
+    # reference probabilities in fp64 from the fused kernel's own x2: decisions with a clear margin must agree
+    y = x2f[:M].double()
+    mu, var = y.mean(-1, keepdim=True), y.var(-1, unbiased=False, keepdim=True)
+    yn = (y - mu) / torch.sqrt(var + 1e-5)
+    for br in range(NB):
+        h = yn * lnw[br].double() + lnb[br].double()
+        p = torch.softmax(h @ gw[br * E:(br + 1) * E].double().t() + gb[br * E:(br + 1) * E].double(), -1)
+        top = torch.sort(p, -1, descending=True)
+        clear = ((top.values[:, 0] - top.values[:, 1]) > 1e-5) & ((top.values[:, 1] - top.values[:, 2]) > 1e-5)
+        assert clear.float().mean() > 0.99
+        assert torch.equal(idx[:M, br][clear].long(), top.indices[:, :2][clear])
+        assert torch.equal(idx[:M, br][clear], idx_u[:M, br][clear])
+        assert (vals[:M, br][clear] - top.values[:, :2][clear].float()).abs().max() < 1e-5
+    assert (stats[:M, 0] - mu[:, 0].float()).abs().max() < 1e-5 and rel(stats[:M, 1], (1 / torch.sqrt(var + 1e-5))[:, 0].float()) < 1e-5
+    # histograms / importance of the kernel's own routing, per 128-row block
+    for blk in range(nblk):
+        sl = slice(blk * 128, min(M, blk * 128 + 128))
+        for br in range(NB):
+            ii, vv = idx[sl, br].long(), vals[sl, br]
+            allc = torch.bincount(ii.reshape(-1), minlength=E)
+            top1 = torch.bincount(ii[:, 0], minlength=E)
+            im = torch.zeros(E, device=DEV).index_add_(0, ii.reshape(-1), vv.reshape(-1))
+            assert torch.equal(hist[blk, 0, br * E:(br + 1) * E].long(), allc)
+            assert torch.equal(hist[blk, 1, br * E:(br + 1) * E].long(), top1)
+            assert (imp[blk, br * E:(br + 1) * E] - im).abs().max() < 1e-4
+
+
 @pytest.mark.parametrize("M,K_in,N_out", [(1000, 512, 512), (25088, 512, 1536), (300, 264, 128), (4097, 1024, 512)])
 def test_linear_backward_building_blocks(M, K_in, N_out):
     """dX = dY W, dW = dY^T X (token slabs as the groups of one grouped GEMM + fp32 partial sums), db = column sums:

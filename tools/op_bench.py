@@ -143,6 +143,14 @@ nblk = (N + 127) // 128
 hist = torch.empty(nblk, 2, G, dtype=torch.int32, device=dev)
 imp = torch.empty(nblk, G, device=dev)
 timeit("moe_gate", lambda i: ops.moe_gate(xf[i], N, D, NB, E, lnw, lnb, gw, gb, idx, vals, stats, hist, imp), nset, N * D * 4, "GB/s")
+def _gg(i):
+    ops.gemm_gate(xb[i], Wf, bfv, resid=xf[i], out_f32=of[i], NB=NB, E=E, ln_w=lnw, ln_b=lnb, gate_w=gw, gate_b=gb, idx=idx, vals=vals,
+                  stats=stats, blk_hist=hist, blk_imp=imp)
+timeit("gemm_gate ca_out + resid -> y, gate (both branches)", _gg, nset, 2.0 * N * D * D, "TFLOP/s")
+def _gu(i):
+    ops.gemm(xb[i], Wf, bfv, out_f32=of[i], resid=xf[i], alpha=1.0, beta=1.0)
+    ops.moe_gate(of[i], N, D, NB, E, lnw, lnb, gw, gb, idx, vals, stats, hist, imp)
+timeit("  unfused: gemm ca_out + moe_gate", _gu, nset, 2.0 * N * D * D, "TFLOP/s")
 
 # ---- FastAttention core
 hd = D // H
