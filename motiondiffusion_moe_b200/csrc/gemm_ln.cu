@@ -481,17 +481,16 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) h[j] = __uint_as_float(raw[j]);
             ln_apply(h, gprm + (1 + br) * LN_NC + n0, gprm + (3 + br) * LN_NC + n0, rstd1, nmr1);
+            // column-outer, expert-inner: eight independent accumulator chains per h value (the expert-outer order is
+            // one 16-long dependent FFMA2 chain per expert)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float* wr = gprm + (5 + br * 8 + e) * LN_NC + n0;
-              float2 acc = lg[br * 8 + e];
+            for (int j = 0; j < 8; ++j) {
+              const float2 h0 = make_float2(h[4 * j], h[4 * j + 1]), h1 = make_float2(h[4 * j + 2], h[4 * j + 3]);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * j);
-                acc = fma2(make_float2(h[4 * j], h[4 * j + 1]), make_float2(w4.x, w4.y), acc);
-                acc = fma2(make_float2(h[4 * j + 2], h[4 * j + 3]), make_float2(w4.z, w4.w), acc);
+              for (int e = 0; e < 8; ++e) {
+                const float4 w4 = *reinterpret_cast<const float4*>(gprm + (5 + br * 8 + e) * LN_NC + n0 + 4 * j);
+                lg[br * 8 + e] = fma2(h1, make_float2(w4.z, w4.w), fma2(h0, make_float2(w4.x, w4.y), lg[br * 8 + e]));
               }
-              lg[br * 8 + e] = acc;
             }
           }
         };
