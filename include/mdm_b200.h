@@ -178,6 +178,15 @@ MDM_API int mdm_lincross_apply(const void* q, int dt, const float* ctx, int B, i
  * per sampling loop: ctx is step-invariant): selects the tcgen05 kernel (hd = 128, T <= 256, bf16). */
 MDM_API int mdm_lincross_apply_ex(const void* q, int dt, const float* ctx, const void* ctxT_bf16, int B, int T, int H,
                                   int hd, void* y, void* stream);
+
+/* mdm_lincross_apply_ex (tcgen05 kernel) with the StylizationBlock that consumes its output in the epilogue
+ * (models/fast_attention.py:248-272 -> models/stylization.py:27-30): y = SiLU(LayerNorm_D(apply(q)) * (1 + scale[b]) + shift[b]),
+ * film = [B, 2 * H * hd] (scale | shift).  The LayerNorm spans the H heads of a row: the H CTAs of a sequence run as a
+ * thread-block cluster and exchange per-row partial sums through distributed shared memory.  hd == 128, T <= 256,
+ * H <= 8, bf16; MDM_ERR_UNSUPPORTED otherwise (the caller then runs mdm_lincross_apply_ex + mdm_rowop). */
+MDM_API int mdm_lincross_apply_style(const void* q, const void* ctxT_bf16, int B, int T, int H, int hd, const float* ln_w,
+                                     const float* ln_b, const float* film, void* y, void* stream);
+
 /* dst[n][c][r] (bf16) = src[n][r][c] (fp32). */
 MDM_API int mdm_transpose_cast_bf16(const float* src, long n, int R, int C, void* dst, void* stream);
 

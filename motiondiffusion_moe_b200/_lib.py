@@ -73,6 +73,7 @@ _SIGS = {
     "mdm_lincross_ctx": [_P, _P, _I, _P, _I, _I, _I, _I, _P, _P],
     "mdm_lincross_apply": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
     "mdm_lincross_apply_ex": [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P],
+    "mdm_lincross_apply_style": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "mdm_transpose_cast_bf16": [_P, _L, _I, _I, _P, _P],
     "mdm_softmax_cross": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P],
     "mdm_moe_gate": [_P, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],

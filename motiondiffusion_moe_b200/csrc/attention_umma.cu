@@ -20,6 +20,7 @@
 // TMEM: K'^T in columns [0, TP), later kv in [0, 128); Q'' / out tiles in [256, 256 + TP).
 #include <stdlib.h>
 #include "common.cuh"
+#include "cluster.cuh"
 
 #ifdef MDM_ATTN_PROFILE
 __device__ unsigned long long g_fau_phase[16];   // cycles per phase summed over CTAs (thread 0): tools/fa_prof.py
@@ -577,12 +578,21 @@ struct SmemLC {
   static constexpr int CT = QS + 2 * TP * 128;        // 2 K-halves x [128 rows x 128 B]
   static constexpr int STG = CT + 2 * 128 * 128;      // staging tail (rows beyond what fits over QS): none needed, see PITCH
   static constexpr int BAR = STG;
-  static constexpr int TOTAL = BAR + 64 + 1024;
+  static constexpr int STY = BAR + 64;                // STYLE: ln_w | ln_b | 1 + scale | shift of this head (4 x 128 floats),
+  static constexpr int RED = STY + 4 * 128 * 4;       //        then float2 [2][TP] partial row statistics (read by the peers)
+  static constexpr int TOTAL = RED + 2 * TP * 8 + 1024;
 };
 
-template <int TP>
+// STYLE: the StylizationBlock that consumes this core's output (models/fast_attention.py:248-272 -> stylization.py:27-30:
+// LayerNorm over the WHOLE row, FiLM, SiLU) in the epilogue.  A row's D = H * 128 values are spread over the H CTAs of
+// one sequence: they form a thread-block cluster, every CTA publishes the partial sum / sum of squares of its 128
+// columns per row in its own shared memory, and after one cluster barrier every thread reads the H partials of its row
+// through distributed shared memory (the same order in every CTA).  TMEM lane = row, so the statistics themselves are
+// per-thread sums.  Replaces the rowop launch (LN, FiLM, SiLU) after the core: the bf16 rounding of y in between is gone.
+template <int TP, bool STYLE>
 __global__ void __launch_bounds__(NTHR, 2)
-lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, int H, int T, bf16* __restrict__ y) {
+lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, int H, int T, bf16* __restrict__ y,
+                     const float* __restrict__ ln_w, const float* __restrict__ ln_b, const float* __restrict__ film) {
   using L = SmemLC<TP>;
   constexpr int MT = TP / 128;
   extern __shared__ uint8_t smem_raw[];
@@ -597,6 +607,13 @@ lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, 
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(tmem_ptr, TP);
   pdl_enter();
+  if (STYLE && tid < HD) {
+    float* sty = reinterpret_cast<float*>(smem + L::STY);
+    sty[tid] = ln_w[h * HD + tid];
+    sty[HD + tid] = ln_b[h * HD + tid];
+    sty[2 * HD + tid] = 1.0f + film[(long)b * 2 * D + h * HD + tid];
+    sty[3 * HD + tid] = film[(long)b * 2 * D + D + h * HD + tid];
+  }
   const int sub = tid & 7, rr = tid >> 3;
   const unsigned gmask = 0xffu << (lane & 24);
   const bf16* base = q + (long)b * T * D + h * HD;
@@ -708,11 +725,72 @@ lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, 
     const int mt = MT == 2 ? hi : 0, c0 = MT == 2 ? 0 : hi * 2;
     const int t = mt * 128 + quad * 32 + lane;
     const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + mt * 128;
+    float mean = 0.f, rstd = 1.f;
+    const float* sty = reinterpret_cast<const float*>(smem + L::STY);
+    if constexpr (STYLE) {
+      // pass 1: partial statistics of this thread's columns -> own shared memory -> cluster barrier -> all H partials
+      float2* red = reinterpret_cast<float2*>(smem + L::RED);
+      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int c = c0; c < c0 + CH; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(t_row + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float2 v = make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));
+          s2 = add2(s2, v);
+          q2 = fma2(v, v, q2);
+        }
+      }
+      red[(MT == 2 ? 0 : hi) * TP + t] = make_float2(s2.x + s2.y, q2.x + q2.y);
+      cluster_sync_all();
+      float S = 0.f, Q = 0.f;
+      for (int rk = 0; rk < H; ++rk) {
+        float2 o;
+        asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(mapa_u32(smem_u32(&red[t]), (uint32_t)rk)));
+        S += o.x; Q += o.y;
+        if (MT == 1) {
+          asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(mapa_u32(smem_u32(&red[TP + t]), (uint32_t)rk)));
+          S += o.x; Q += o.y;
+        }
+      }
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // done with the peers' memory (waited for at exit)
+      const float inv_d = 1.0f / (float)D;
+      mean = S * inv_d;
+      rstd = rsqrtf(fmaxf(fmaf(Q, inv_d, -mean * mean), 0.f) + 1e-5f);
+    }
 #pragma unroll 1
     for (int c = c0; c < c0 + CH; ++c) {
       uint32_t raw[32];
       tmem_ld32(t_row + c * 32, raw);
       tmem_ld_wait();
+      if constexpr (STYLE) {
+        const float2 r2 = make_float2(rstd, rstd), m2 = make_float2(-mean * rstd, -mean * rstd), half = make_float2(0.5f, 0.5f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w4 = *reinterpret_cast<const float4*>(sty + c * 32 + 4 * j);
+          const float4 b4 = *reinterpret_cast<const float4*>(sty + HD + c * 32 + 4 * j);
+          const float4 g4 = *reinterpret_cast<const float4*>(sty + 2 * HD + c * 32 + 4 * j);
+          const float4 h4 = *reinterpret_cast<const float4*>(sty + 3 * HD + c * 32 + 4 * j);
+          float2 z0 = fma2(fma2(make_float2(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1])), r2, m2),
+                           make_float2(w4.x, w4.y), make_float2(b4.x, b4.y));
+          float2 z1 = fma2(fma2(make_float2(__uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])), r2, m2),
+                           make_float2(w4.z, w4.w), make_float2(b4.z, b4.w));
+          z0 = fma2(z0, make_float2(g4.x, g4.y), make_float2(h4.x, h4.y));
+          z1 = fma2(z1, make_float2(g4.z, g4.w), make_float2(h4.z, h4.w));
+          const float2 a0 = mul2(z0, half), a1 = mul2(z1, half);       // SiLU(z) = z/2 + z/2 * tanh(z/2)
+          float2 t0, t1;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t0.x) : "f"(a0.x));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t0.y) : "f"(a0.y));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t1.x) : "f"(a1.x));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t1.y) : "f"(a1.y));
+          z0 = fma2(a0, t0, a0);
+          z1 = fma2(a1, t1, a1);
+          raw[4 * j] = __float_as_uint(z0.x); raw[4 * j + 1] = __float_as_uint(z0.y);
+          raw[4 * j + 2] = __float_as_uint(z1.x); raw[4 * j + 3] = __float_as_uint(z1.y);
+        }
+      }
       if (t < T) {
         uint4* dst = reinterpret_cast<uint4*>(Qs + t * PITCH + c * 64);
 #pragma unroll
@@ -735,19 +813,24 @@ lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, 
     tc_fence_after();
     tmem_dealloc(tmem_base, TP);
   }
+  if (STYLE) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // no peer still reads this CTA's statistics
 }
 
-template <int TP>
-int launch_lc(const bf16* q, const bf16* ctxT, int B, int H, int T, bf16* y, cudaStream_t st) {
+template <int TP, bool STYLE>
+int launch_lc(const bf16* q, const bf16* ctxT, int B, int H, int T, bf16* y, const float* ln_w, const float* ln_b,
+              const float* film, cudaStream_t st) {
   using L = SmemLC<TP>;
   static unsigned long long attr = 0;   // one bit per device ordinal: the attribute is per (function, device)
   const unsigned long long dev_bit = 1ull << mdm_cur_dev();
   if (!(attr & dev_bit)) {
-    if (cudaFuncSetAttribute(lincross_umma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+    if (cudaFuncSetAttribute(lincross_umma_kernel<TP, STYLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
       return MDM_ERR_CUDA;
     attr |= dev_bit;
   }
-  mdm_launch(lincross_umma_kernel<TP>, B * H, NTHR, L::TOTAL, st, q, ctxT, H, T, y);
+  if (STYLE)   // the H head-CTAs of a sequence form a cluster
+    return mdm_launch_cluster(lincross_umma_kernel<TP, STYLE>, B * H, NTHR, L::TOTAL, st, H, q, ctxT, H, T, y, ln_w, ln_b, film) ==
+                   cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
+  mdm_launch(lincross_umma_kernel<TP, STYLE>, B * H, NTHR, L::TOTAL, st, q, ctxT, H, T, y, ln_w, ln_b, film);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -1010,8 +1093,24 @@ int mdm_lincross_apply_umma(const void* q, const void* ctxT_bf16, int B, int T, 
   const bf16* qq = reinterpret_cast<const bf16*>(q);
   const bf16* cc = reinterpret_cast<const bf16*>(ctxT_bf16);
   bf16* yy = reinterpret_cast<bf16*>(y);
-  if (T <= 128) return launch_lc<128>(qq, cc, B, H, T, yy, st);
-  return launch_lc<256>(qq, cc, B, H, T, yy, st);
+  if (T <= 128) return launch_lc<128, false>(qq, cc, B, H, T, yy, nullptr, nullptr, nullptr, st);
+  return launch_lc<256, false>(qq, cc, B, H, T, yy, nullptr, nullptr, nullptr, st);
+}
+
+// C-ABI: see include/mdm_b200.h
+extern "C" MDM_API int mdm_lincross_apply_style(const void* q, const void* ctxT_bf16, int B, int T, int H, int hd,
+                                                const float* ln_w, const float* ln_b, const float* film, void* y, void* stream) {
+  if (!q || !ctxT_bf16 || !ln_w || !ln_b || !film || !y || B <= 0 || T <= 0) return MDM_ERR_ARG;
+  if (hd != HD || T > 256 || H < 1 || H > 8) return MDM_ERR_UNSUPPORTED;     // portable cluster size
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
+      (reinterpret_cast<uintptr_t>(ctxT_bf16) & 15))
+    return MDM_ERR_UNSUPPORTED;
+  const bf16* qq = reinterpret_cast<const bf16*>(q);
+  const bf16* cc = reinterpret_cast<const bf16*>(ctxT_bf16);
+  bf16* yy = reinterpret_cast<bf16*>(y);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (T <= 128) return launch_lc<128, true>(qq, cc, B, H, T, yy, ln_w, ln_b, film, st);
+  return launch_lc<256, true>(qq, cc, B, H, T, yy, ln_w, ln_b, film, st);
 }
 
 // hd == 128, bf16, T <= 256, at most 96 keys; MDM_ERR_UNSUPPORTED otherwise.

@@ -44,6 +44,27 @@ inline cudaError_t mdm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// the same with a run-time thread-block cluster (cluster_x consecutive CTAs of a 1-D grid)
+template <typename... KArgs, typename... Args>
+inline cudaError_t mdm_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                      Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster_x;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = mdm_pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 typedef MdmGemmEpi GemmEpi;
 typedef MdmMTile MTile;
 typedef MdmRowOp RowOp;

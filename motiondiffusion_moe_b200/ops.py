@@ -230,6 +230,20 @@ def lincross_ctx(k, v, nt, B, Nt_max, H, hd, ctx):
                                             ctx.data_ptr(), _stream()), "mdm_lincross_ctx")
 
 
+def lincross_apply_style(q, ctxT, B, T, H, hd, ln, film, y):
+    """lincross_apply + the StylizationBlock's LayerNorm, FiLM and SiLU in its epilogue (mdm_lincross_apply_style: the H
+    head-CTAs of a sequence as a cluster).  Returns False (nothing launched) outside the kernel's shapes."""
+    _c(q, ctxT, y, film, *ln)
+    if q.dtype != torch.bfloat16 or ctxT is None or hd != 128 or T > 256 or H > 8:
+        return False
+    st = _lib.load().mdm_lincross_apply_style(q.data_ptr(), ctxT.data_ptr(), B, T, H, hd, ln[0].data_ptr(), ln[1].data_ptr(),
+                                              film.data_ptr(), y.data_ptr(), _stream())
+    if st == 3:
+        return False
+    _lib.check(st, "mdm_lincross_apply_style")
+    return True
+
+
 def lincross_apply(q, ctx, B, T, H, hd, y, ctxT=None):
     _c(q, ctx, y, ctxT)
     if hd > 128:

@@ -95,6 +95,8 @@ class MotionTransformer(nn.Module):
         self._fuse_ln = os.environ.get("MDM_FUSE_LN", "1") == "1"
         # ... and the MoE gate as the second pass of the cross-attention output Linear (ops.gemm_gate); MDM_FUSE_GATE=0 = off
         self._fuse_gate = os.environ.get("MDM_FUSE_GATE", "1") == "1"
+        # ... and the StylizationBlock after the linear cross-attention core in that core's epilogue; MDM_FUSE_STYLE=0 = off
+        self._fuse_style = os.environ.get("MDM_FUSE_STYLE", "1") == "1"
         self._packed = None
         self._ws = {}
         self._film_tiles = {}
@@ -705,14 +707,20 @@ class MotionTransformer(nn.Module):
             ops.rowop(pre, N, D, adti, ln1=L["dsa_post"], out1_f32=x1, ln2=L["ca_norm"], out2_a=a0)
         # ---- GatedCrossAttention (fast_attention.py:242-272)
         self._lin(a0, L["ca_q"], out_a=a1)
-        ops.lincross_apply(a1, ctx.lin_ctx[li], Bn, T, H, D // H, a2, ctxT=ctx.lin_ctxT[li])
         ca_done = False           # the output Linear of the block may run below, fused with the MoE gate
-        if (self._fuse_rowop and adt == torch.bfloat16 and
-                ops.gemm_rowop(a2, N, D, L["ca_out"][0], L["ca_out"][1], ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T,
-                               silu=True, out_f32=x2, resid=x1, alpha=1.0, beta=1.0)):
-            ca_done = True
+        # linear cross-attention core with the StylizationBlock (LN over the row, FiLM, SiLU) in its epilogue: the H
+        # head-CTAs of a sequence form a cluster (a2 -> a1 directly); otherwise core, then rowop
+        if not (fuse and self._fuse_style and ctx.lin_ctxT[li] is not None and
+                ops.lincross_apply_style(a1, ctx.lin_ctxT[li], Bn, T, H, D // H, L["ca_s_norm"], film[2], a2)):
+            ops.lincross_apply(a1, ctx.lin_ctx[li], Bn, T, H, D // H, a2, ctxT=ctx.lin_ctxT[li])
+            if (self._fuse_rowop and adt == torch.bfloat16 and
+                    ops.gemm_rowop(a2, N, D, L["ca_out"][0], L["ca_out"][1], ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T,
+                                   silu=True, out_f32=x2, resid=x1, alpha=1.0, beta=1.0)):
+                ca_done = True
+            else:
+                ops.rowop(a2, N, D, adti, ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T, silu=True, out2_a=a1)
         else:
-            ops.rowop(a2, N, D, adti, ln2=L["ca_s_norm"], film=film[2], rows_per_seq=T, silu=True, out2_a=a1)
+            a1, a2 = a2, a1       # the styled rows are in a2: it is the A operand of the output Linear below
         # ---- MoEMultiBranchFFN (multi_branch.py:52-61, switch_moe.py:44-111)
         forced = None
         if self.force_routing is not None:

@@ -241,6 +241,37 @@ def test_gemm_ln_fused(variant, M, K, T):
     assert not ops.gemm_ln(A, W[:256].contiguous(), b[:256].contiguous(), ln1=ln1, out1_a=buf(bf)[:M])
 
 
+@pytest.mark.parametrize("B,H,T", [(3, 4, 196), (5, 4, 98), (2, 4, 8), (4, 2, 130), (64, 4, 196)])
+def test_lincross_apply_style_fused(B, H, T):
+    """mdm_lincross_apply_style: the linear cross-attention core with the StylizationBlock (LayerNorm over the whole row =
+    all heads, FiLM, SiLU) in its epilogue (the head-CTAs of a sequence as a cluster, partial row statistics through
+    distributed shared memory) against the core + rowop pair and against torch on the core's fp32 result."""
+    hd = 128
+    D = H * hd
+    N = B * T
+    q = randn(N, D, seed=1).bfloat16()
+    ctx = randn(B, H, hd, hd, seed=2, scale=hd ** -0.5)
+    ctxT = torch.empty(B, H, hd, hd, device=DEV, dtype=torch.bfloat16)
+    ops.transpose_cast_bf16(ctx, ctxT)
+    ln = (torch.rand(D, generator=gen(5)).to(DEV) + 0.5, randn(D, seed=6, scale=0.1))
+    film = randn(B, 2 * D, seed=9, scale=0.3)
+    y = torch.full((N + 4, D), 3.0, device=DEV, dtype=torch.bfloat16)
+    assert ops.lincross_apply_style(q, ctxT, B, T, H, hd, ln, film, y[:N])
+    assert torch.all(y[N:].float() == 3.0)
+    core = torch.empty(N, D, device=DEV, dtype=torch.bfloat16)
+    ops.lincross_apply(q, ctx, B, T, H, hd, core, ctxT=ctxT)
+    unf = torch.empty(N, D, device=DEV, dtype=torch.bfloat16)
+    ops.rowop(core, N, D, ops._dt(unf), ln2=ln, film=film, rows_per_seq=T, silu=True, out2_a=unf)
+    # torch: softmax over the head dimension, times ctx (bf16-rounded operands like the kernel), LN over the row, FiLM, SiLU
+    p = torch.softmax(q.float().view(B, T, H, hd), -1).bfloat16().float()
+    yy = torch.einsum("bthd,bhdl->bthl", p, ctxT.float().transpose(-1, -2)).reshape(N, D)
+    v = F.layer_norm(yy, (D,), ln[0], ln[1])
+    seq = torch.arange(N, device=DEV) // T
+    ref = F.silu(v * (1 + film[seq, :D]) + film[seq, D:])
+    assert rel(y[:N], ref) < 6e-3, rel(y[:N], ref)            # bf16 output + bf16 softmax operand
+    assert rel(y[:N], unf) < 1.2e-2, rel(y[:N], unf)          # the pair rounds the core's output to bf16 in between
+
+
 @pytest.mark.parametrize("M", [196 * 3, 128, 1000, 25, 12544])
 def test_gemm_gate_fused(M):
     """mdm_gemm_gate: the cross-attention output Linear + residual with the MoE gate of both branches as its second

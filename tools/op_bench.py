@@ -168,6 +168,12 @@ ctxT = torch.empty(NSEQ, H, hd, hd, device=dev, dtype=bf)
 ops.transpose_cast_bf16(ctx, ctxT)
 timeit("lincross_apply tcgen05", lambda i: ops.lincross_apply(xb[i], ctx, NSEQ, T, H, hd, ob[i], ctxT=ctxT), nset, N * D * 4, "GB/s")
 timeit("lincross_apply mma.sync", lambda i: ops.lincross_apply(xb[i], ctx, NSEQ, T, H, hd, ob[i]), nset, N * D * 4, "GB/s")
+lnD = (torch.rand(D, device=dev) + 0.5, torch.randn(D, device=dev))
+timeit("lincross_apply_style (core + LN, FiLM, SiLU)", lambda i: ops.lincross_apply_style(xb[i], ctxT, NSEQ, T, H, hd, lnD, film, ob[i]), nset, N * D * 4, "GB/s")
+def _lcu(i):
+    ops.lincross_apply(xb[i], ctx, NSEQ, T, H, hd, ob2[i], ctxT=ctxT)
+    ops.rowop(ob2[i], N, D, MDM_BF16, ln2=lnD, film=film, rows_per_seq=T, silu=True, out2_a=ob[i])
+timeit("  unfused: lincross_apply + rowop ln,film,silu", _lcu, nset, N * D * 4, "GB/s")
 Nt = 20
 k2 = torch.randn(NSEQ * Nt, D, device=dev).to(bf)
 v2 = torch.randn(NSEQ * Nt, D, device=dev).to(bf)
