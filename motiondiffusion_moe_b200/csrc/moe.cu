@@ -17,6 +17,13 @@
 
 namespace {
 
+// A/B knobs (tools/build_variant.sh): MDM_PERM_SPLIT = CTAs per 128-token block of the permute, MDM_SCAN_FAST = single-round-trip scan
+#ifndef MDM_PERM_SPLIT
+#define MDM_PERM_SPLIT 4          // 1 = one CTA per block (A/B builds: tools/build_variant.sh)
+#endif
+#ifndef MDM_SCAN_FAST
+#define MDM_SCAN_FAST 1
+#endif
 constexpr int TOK_PER_BLK = 128;
 constexpr int MAX_G = 32;   // NB * E groups
 constexpr int MAX_E = 16;
@@ -239,10 +246,33 @@ moe_scan_kernel(const int* __restrict__ blk_hist, const float* __restrict__ blk_
     const int per = (nblk + 31) / 32, b0 = lane * per, b1 = min(nblk, b0 + per);
     int tot = 0, top1 = 0;
     float imp = 0.f;
-    for (int b = b0; b < b1; ++b) {
-      tot += blk_hist[((long)b * 2) * G + g];
-      top1 += blk_hist[((long)b * 2 + 1) * G + g];
-      imp += blk_imp[(long)b * G + g];
+    // up to 8 blocks per lane (N <= 32 768 tokens): every load of the lane is issued at once and the histogram stays in
+    // registers for the second pass - one L2 round trip instead of four dependent ones in this single-CTA kernel
+    constexpr int PER_FAST = 8;
+    int hreg[PER_FAST];
+    const bool fast = MDM_SCAN_FAST && per <= PER_FAST;
+    if (fast) {
+      int t1[PER_FAST];
+      float im[PER_FAST];
+#pragma unroll
+      for (int j = 0; j < PER_FAST; ++j) {
+        const int b = b0 + j;
+        const bool ok = j < per && b < b1;
+        hreg[j] = ok ? blk_hist[((long)b * 2) * G + g] : 0;
+        t1[j] = ok ? blk_hist[((long)b * 2 + 1) * G + g] : 0;
+        im[j] = ok ? blk_imp[(long)b * G + g] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < PER_FAST; ++j) {
+        tot += hreg[j]; top1 += t1[j];
+        if (j < per && b0 + j < b1) imp += im[j];      // same additions in the same order as the loop below
+      }
+    } else {
+      for (int b = b0; b < b1; ++b) {
+        tot += blk_hist[((long)b * 2) * G + g];
+        top1 += blk_hist[((long)b * 2 + 1) * G + g];
+        imp += blk_imp[(long)b * G + g];
+      }
     }
     int incl = tot;
 #pragma unroll
@@ -251,9 +281,17 @@ moe_scan_kernel(const int* __restrict__ blk_hist, const float* __restrict__ blk_
       if (lane >= o) incl += n;
     }
     int run = incl - tot;
-    for (int b = b0; b < b1; ++b) {
-      blk_base[(long)b * G + g] = run;
-      run += blk_hist[((long)b * 2) * G + g];
+    if (fast) {
+#pragma unroll
+      for (int j = 0; j < PER_FAST; ++j) {
+        const int b = b0 + j;
+        if (j < per && b < b1) { blk_base[(long)b * G + g] = run; run += hreg[j]; }
+      }
+    } else {
+      for (int b = b0; b < b1; ++b) {
+        blk_base[(long)b * G + g] = run;
+        run += blk_hist[((long)b * 2) * G + g];
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) top1 += __shfl_xor_sync(0xffffffffu, top1, o);
@@ -297,8 +335,12 @@ moe_scan_kernel(const int* __restrict__ blk_hist, const float* __restrict__ blk_
 }
 
 constexpr int PERM_WARPS = 16;
+// A 128-token block of the gate's histogram is moved by PERM_SPLIT CTAs: each recomputes the block's ranks (512 index
+// loads + one match per pair) and moves a quarter of its rows.  One CTA per block was 196 CTAs of 512 threads at
+// N = 25 088, i.e. two waves with the second one third full, and 13 CTAs at 8 sequences per GPU.
+constexpr int PERM_SPLIT = MDM_PERM_SPLIT;
 template <int VPT, typename TO>
-__global__ void __launch_bounds__(PERM_WARPS * 32)
+__global__ void __launch_bounds__(PERM_WARPS * 32, (VPT <= 16 && MDM_PERM_SPLIT > 1) ? 2 : 1)   // two CTAs per SM up to D = 512 (64 registers)
 moe_permute_kernel(const float* __restrict__ x, long N, int D, int NB, int E, const float* __restrict__ ln_w,
                    const float* __restrict__ ln_b, const int* __restrict__ idx, const float* __restrict__ vals,
                    const float* __restrict__ stats, const int* __restrict__ blk_base,
@@ -314,7 +356,9 @@ moe_permute_kernel(const float* __restrict__ x, long N, int D, int NB, int E, co
   pdl_enter();
   for (int i = threadIdx.x; i < 16 * MAX_G; i += PERM_WARPS * 32) (&seg_cnt[0][0])[i] = 0;
   __syncthreads();
-  const long tok_blk0 = (long)blockIdx.x * TOK_PER_BLK;
+  const int blk = blockIdx.x / PERM_SPLIT, part = blockIdx.x % PERM_SPLIT;
+  const long tok_blk0 = (long)blk * TOK_PER_BLK;
+  constexpr int PART_TOK = TOK_PER_BLK / PERM_SPLIT;   // tokens whose rows this CTA moves
   constexpr int SPW = 16 / PERM_WARPS;            // 32-pair segments per warp
   int my_g[SPW], my_rank[SPW];
   for (int r = 0; r < SPW; ++r) {
@@ -342,21 +386,24 @@ moe_permute_kernel(const float* __restrict__ x, long N, int D, int NB, int E, co
       const int p = seg * 32 + lane;
       const long tok = tok_blk0 + p / NBK;
       const int slot = p % NBK;
-      const int pos = seg_offsets[g] + blk_base[(long)blockIdx.x * G + g] + base + my_rank[r];
+      const int pos = seg_offsets[g] + blk_base[(long)blk * G + g] + base + my_rank[r];
       pos_s[p] = pos;
-      perm[tok * NBK + slot] = pos;
-      rowscale[pos] = vals[tok * NBK + slot] / (float)NB;
+      if ((p / NBK) / PART_TOK == part) {          // every pair is published once, by the CTA that moves its row
+        perm[tok * NBK + slot] = pos;
+        rowscale[pos] = vals[tok * NBK + slot] / (float)NB;
+      }
     }
   }
   __syncthreads();
-  constexpr int TPW = TOK_PER_BLK / PERM_WARPS, UNR = 4;   // tokens per warp; rows in flight per warp
+  constexpr int TPW = PART_TOK / PERM_WARPS, UNR = TPW < 4 ? TPW : 4;   // tokens per warp; rows in flight per warp
+  static_assert(TPW >= 1 && TPW * PERM_WARPS * PERM_SPLIT == TOK_PER_BLK, "token split");
 #pragma unroll 1
   for (int it = 0; it < TPW; it += UNR) {
     float v[UNR][VPT];
     float2 ms[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const long tok = tok_blk0 + warp * TPW + it + u;
+      const long tok = tok_blk0 + part * PART_TOK + warp * TPW + it + u;
       if (tok < N) {
         load_row<VPT, float>(x + tok * D, lane, v[u]);
         ms[u] = *reinterpret_cast<const float2*>(stats + tok * 2);
@@ -364,7 +411,7 @@ moe_permute_kernel(const float* __restrict__ x, long N, int D, int NB, int E, co
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const int tl = warp * TPW + it + u;
+      const int tl = part * PART_TOK + warp * TPW + it + u;
       if (tok_blk0 + tl >= N) break;
       for (int br = 0; br < NB; ++br) {
         float hrow[VPT];
@@ -533,10 +580,10 @@ extern "C" MDM_API int mdm_moe_permute(const float* x, long N, int D, int NB, in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VPT_SWITCH(D, {
     if (dt == MDM_F32)
-      mdm_launch(moe_permute_kernel<V, float>, nblk, PERM_WARPS * 32, 0, st, x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
+      mdm_launch(moe_permute_kernel<V, float>, nblk * PERM_SPLIT, PERM_WARPS * 32, 0, st, x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
                                                           seg_offsets, reinterpret_cast<float*>(xp), perm, rowscale);
     else
-      mdm_launch(moe_permute_kernel<V, bf16>, nblk, PERM_WARPS * 32, 0, st, x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
+      mdm_launch(moe_permute_kernel<V, bf16>, nblk * PERM_SPLIT, PERM_WARPS * 32, 0, st, x, N, D, NB, E, ln_w, ln_b, idx, vals, stats, blk_base,
                                                          seg_offsets, reinterpret_cast<bf16*>(xp), perm, rowscale);
   });
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;

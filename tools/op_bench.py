@@ -152,6 +152,29 @@ def _gu(i):
     ops.moe_gate(of[i], N, D, NB, E, lnw, lnb, gw, gb, idx, vals, stats, hist, imp)
 timeit("  unfused: gemm ca_out + moe_gate", _gu, nset, 2.0 * N * D * D, "TFLOP/s")
 
+# scan / permute / combine on the routing the gate above produced (Fd = 1024 per expert)
+if not ONLY or "moe" in ONLY:
+    Fd, NBK = 1024, 2 * NB
+    ops.moe_gate(xf[0], N, D, NB, E, lnw, lnb, gw, gb, idx, vals, stats, hist, imp)
+    cap = NBK * N + G * 128
+    base = torch.empty(nblk, G, dtype=torch.int32, device=dev)
+    seg = torch.empty(G + 1, dtype=torch.int32, device=dev)
+    t_up = torch.empty(cap // 128, 4, dtype=torch.int32, device=dev)
+    t_dn = torch.empty(cap // 128, 4, dtype=torch.int32, device=dev)
+    ntile = torch.empty(1, dtype=torch.int32, device=dev)
+    perm = torch.empty(N, NBK, dtype=torch.int32, device=dev)
+    rscale = torch.empty(cap, device=dev)
+    usage, importance = torch.zeros(G, device=dev), torch.zeros(G, device=dev)
+    xps = [torch.empty(cap, D, device=dev, dtype=bf) for _ in range(2)]
+    yps = [torch.randn(cap, D, device=dev).to(bf) for _ in range(2)]
+    filmm = torch.randn(NSEQ, 2 * D, device=dev) * 0.1
+    timeit("moe_scan", lambda i: ops.moe_scan(hist, imp, idx, N, NB, E, Fd, D, base, seg, t_up, t_dn, ntile, usage, importance),
+           nset, N * 4, "GB/s")
+    timeit("moe_permute (LN both branches, 4 rows out)", lambda i: ops.moe_permute(xf[i], N, D, NB, E, lnw, lnb, idx, vals, stats, base,
+           seg, xps[i % 2], perm, rscale), nset, N * D * (4 + 4 * 2), "GB/s")
+    timeit("moe_combine_film (4 rows in, LN, FiLM, SiLU)", lambda i: ops.moe_combine_film(yps[i % 2], perm, N, D, NBK, ln[0], ln[1],
+           filmm, T, ob[i]), nset, N * D * (4 * 2 + 2), "GB/s")
+
 # ---- FastAttention core
 hd = D // H
 qkv = [(torch.randn(N, 3 * D, device=dev)).to(bf) for _ in range(nset)]
