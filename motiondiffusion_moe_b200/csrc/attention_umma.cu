@@ -19,8 +19,10 @@
 // bf16 rounding points are those of the mma.sync kernels in attention_tc.cu (normalised q / k / v, q', k', kv).
 // TMEM: K'^T in columns [0, TP), later kv in [0, 128); Q'' / out tiles in [256, 256 + TP).
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "cluster.cuh"
+#include "tensormap.cuh"
 
 #ifdef MDM_ATTN_PROFILE
 __device__ unsigned long long g_fau_phase[16];   // cycles per phase summed over CTAs (thread 0): tools/fa_prof.py
@@ -55,6 +57,29 @@ __device__ __forceinline__ float expfeat_u(float x) {
 // byte offset of element (row r, column c) in a K-major SWIZZLE_128B tile whose rows are 64 bf16 (128 B)
 __device__ __forceinline__ uint32_t sw_off(int r, int c) {
   return (uint32_t)(r * 128 + ((((c >> 3) ^ r) & 7) << 4) + ((c & 7) << 1));
+}
+
+// TMA 3D tile load: coordinates (c0 = innermost element, c1 = row inside the sequence, c2 = sequence)
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// bf16 tensor [B][T][cols] (row pitch ld elements) as a 3D map with boxes of {64 columns, box_rows frames, 1 sequence},
+// SWIZZLE_128B: a box lands as one K-half of an operand tile ([box_rows] x 128 B, 16-byte chunk ^ (row & 7)), and the
+// frames beyond T are zero-filled by the TMA unit (a 2D map over [B * T] rows would read the next sequence instead).
+bool make_seq_map(CUtensorMap* map, const void* ptr, int B, int T, long cols, long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * (cuuint64_t)ld * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
 }
 
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {      // packed bf16 pair -> two fp32 (exact)
@@ -161,7 +186,8 @@ template <int TP>
 __global__ void __launch_bounds__(NTHR, TP == 128 ? 2 : 1)
 fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg, const float* __restrict__ nw,
                      const float* __restrict__ nb, const int64_t* __restrict__ length, int length_shift, int H, int T,
-                     bf16* __restrict__ out, const int* __restrict__ seq_order) {
+                     bf16* __restrict__ out, const int* __restrict__ seq_order,
+                     const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmPt, int use_tma) {
   using L = Smem<TP>;
   constexpr int MT = TP / 128;        // 128-row tiles of the query side
   constexpr int KC = TP / 64;         // 64-frame chunks (K of the kv product)
@@ -177,15 +203,19 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   float* nb_s = nw_s + HD;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);     // kt, q, kv, out
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* load_bar = bars + 5;                                   // q, k, P^T tiles by TMA
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   FAU_INIT();
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    mbar_init(load_bar, 1);
     fence_mbar_init();
+    if (use_tma) { tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmPt); }
   }
   if (warp == 0) tmem_alloc(tmem_ptr, NCOLS);
+  if (use_tma) __syncthreads();                      // load_bar is polled before the first block-wide barrier below
   pdl_enter();                                       // first global access below
   const int b = seq_order ? seq_order[blockIdx.x / H] : blockIdx.x / H, h = blockIdx.x % H;
   const int D = H * HD;
@@ -210,6 +240,20 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
       for (int j = 0; j < 8; ++j) vraw[p][j] = __ldg(src + 8 * j);
     }
   }
+  // q, k, P^T: six TMA boxes (one K-half of an operand tile each: [TP frames] x 64 columns, SWIZZLE_128B = sw_off; the
+  // frames beyond T arrive as zeros; key rows in [len, T) arrive raw and are masked in P2).  As cp.async these were 40
+  // 16-byte copies per thread: the load phase was bound by LSU issue (6 k of the CTA's 34 k cycles, tools/fa_prof.py).
+  if (use_tma) {
+    if (tid == 0) {
+      mbar_expect_tx(load_bar, 4 * TP * 128 + 2 * 128 * 128);
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh) {
+        tma_load_3d(&tmQKV, load_bar, Ks + kh * (TP * 128), D + h * HD + kh * 64, 0, b);
+        tma_load_2d(&tmPt, load_bar, Pt + kh * (128 * 128), kh * 64, 0);
+        tma_load_3d(&tmQKV, load_bar, Qs + kh * (TP * 128), h * HD + kh * 64, 0, b);
+      }
+    }
+  } else {
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
     uint8_t* dst = (which == 0 ? Qs : Ks) + (sub >> 2) * (TP * 128);
@@ -234,6 +278,7 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
                  ::"r"(smem_u32(Pt + (c >> 3) * (128 * 128) + sw_off(m, (c & 7) * 8))), "l"(Ptg + m * HD + c * 8) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int i = tid; i < HD; i += NTHR) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }   // read again after the barrier below
   FAU_MARK(0);
   // v: LayerNorm, transposed 2-byte stores (the pair ownership costs a 2-way bank conflict, the loads are 4 bytes)
@@ -270,7 +315,8 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   FAU_MARK(1);
   // q and k in place: thread owns columns [16 sub, 16 sub + 16) of its rows (the chunks it requested itself);
   // two rows per iteration so that the shuffle / rsqrt latencies of one row hide behind the other's arithmetic
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (use_tma) mbar_wait(load_bar, 0);
+  else asm volatile("cp.async.wait_group 0;" ::: "memory");
   {
     float2 w2[8], b2[8];
 #pragma unroll
@@ -561,7 +607,13 @@ int launch(const bf16* qkv, const bf16* Pt, const float* nw, const float* nb, co
       return MDM_ERR_CUDA;
     attr |= dev_bit;
   }
-  mdm_launch(fastattn_umma_kernel<TP>, B * H, NTHR, L::TOTAL, st, qkv, Pt, nw, nb, length, shift, H, T, out, seq_order);
+  // MDM_FA_TMA=0: q / k / P^T by cp.async instead of TMA (A/B runs; also the path taken if a tensor map cannot be built)
+  static const int tma_env = [] { const char* e = getenv("MDM_FA_TMA"); return e ? atoi(e) : 1; }();
+  CUtensorMap tq, tp;
+  memset(&tq, 0, sizeof(tq)); memset(&tp, 0, sizeof(tp));
+  const int use_tma = tma_env && make_seq_map(&tq, qkv, B, T, 3L * H * HD, 3L * H * HD, TP) && make_map(&tp, Pt, HD, HD, HD, 128);
+  mdm_launch(fastattn_umma_kernel<TP>, B * H, NTHR, L::TOTAL, st, qkv, Pt, nw, nb, length, shift, H, T, out, seq_order, tq, tp,
+             use_tma);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
