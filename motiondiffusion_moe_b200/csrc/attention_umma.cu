@@ -39,22 +39,6 @@ extern "C" MDM_API int mdm_debug_read_fau_phase(unsigned long long* host, int re
 #define FAU_INIT() do { } while (0)
 #endif
 
-// A/B knobs (tools/build_variant.sh).  At TP = 256 the kernel runs one CTA of 256 threads per SM, i.e. it may use 255
-// registers per thread: NR4 = four rows per iteration in the q / k normalisation pass; WIDE2 / WIDE3 / WIDE6 = all
-// tcgen05.ld of a thread's P2 / P3 / P6 row issued before the first wait (128 live registers) instead of chunk by chunk.
-#ifndef MDM_FA_NR4
-#define MDM_FA_NR4 1
-#endif
-#ifndef MDM_FA_WIDE2
-#define MDM_FA_WIDE2 1
-#endif
-#ifndef MDM_FA_WIDE3
-#define MDM_FA_WIDE3 1
-#endif
-#ifndef MDM_FA_WIDE6
-#define MDM_FA_WIDE6 1
-#endif
-
 namespace {
 
 constexpr int HD = 128;
@@ -136,67 +120,53 @@ __device__ __forceinline__ void norm_slice(float2 (&x)[8], const float2 (&w2)[8]
   }
 }
 
-// norm_slice<true> on NR rows at once: the NR dependency chains (three 8-lane reductions, rsqrt, sqrt + division each)
-// are independent, so the shuffle / MUFU latencies of one row hide behind the arithmetic of the others.
-template <int NR>
-__device__ __forceinline__ void norm_slice_n(float2 (&x)[NR][8], const float2 (&w2)[8], const float2 (&b2)[8], unsigned gmask) {
+// norm_slice<true> on two rows at once (independent dependency chains interleaved by hand)
+__device__ __forceinline__ void norm_slice2(float2 (&x)[8], float2 (&y)[8], const float2 (&w2)[8], const float2 (&b2)[8],
+                                            unsigned gmask) {
   const float2 tenth = make_float2(0.1f, 0.1f);
-  float a[NR];
+  float2 sx = make_float2(0.f, 0.f), sy = sx;
 #pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    float2 s = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { x[r][i] = mul2(x[r][i], tenth); s = add2(s, x[r][i]); }
-    a[r] = s.x + s.y;
+  for (int i = 0; i < 8; ++i) {
+    x[i] = mul2(x[i], tenth); y[i] = mul2(y[i], tenth);
+    sx = add2(sx, x[i]); sy = add2(sy, y[i]);
   }
+  float ax = sx.x + sx.y, ay = sy.x + sy.y;
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) {
-    float t[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) t[r] = __shfl_xor_sync(gmask, a[r], o);
-#pragma unroll
-    for (int r = 0; r < NR; ++r) a[r] += t[r];
+    const float tx = __shfl_xor_sync(gmask, ax, o), ty = __shfl_xor_sync(gmask, ay, o);
+    ax += tx; ay += ty;
   }
+  const float2 nmx = make_float2(-ax / (float)HD, -ax / (float)HD), nmy = make_float2(-ay / (float)HD, -ay / (float)HD);
+  float2 qx = make_float2(0.f, 0.f), qy = qx;
 #pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const float2 nm = make_float2(-a[r] / (float)HD, -a[r] / (float)HD);
-    float2 q = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { x[r][i] = add2(x[r][i], nm); q = fma2(x[r][i], x[r][i], q); }
-    a[r] = q.x + q.y;
+  for (int i = 0; i < 8; ++i) {
+    x[i] = add2(x[i], nmx); y[i] = add2(y[i], nmy);
+    qx = fma2(x[i], x[i], qx); qy = fma2(y[i], y[i], qy);
   }
+  ax = qx.x + qx.y; ay = qy.x + qy.y;
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) {
-    float t[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) t[r] = __shfl_xor_sync(gmask, a[r], o);
-#pragma unroll
-    for (int r = 0; r < NR; ++r) a[r] += t[r];
+    const float tx = __shfl_xor_sync(gmask, ax, o), ty = __shfl_xor_sync(gmask, ay, o);
+    ax += tx; ay += ty;
   }
+  const float rx = rsqrtf(ax / (float)HD + 1e-5f), ry = rsqrtf(ay / (float)HD + 1e-5f);
+  const float2 rx2 = make_float2(rx, rx), ry2 = make_float2(ry, ry);
+  float2 nx = make_float2(0.f, 0.f), ny = nx;
 #pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const float rs = rsqrtf(a[r] / (float)HD + 1e-5f);
-    const float2 r2 = make_float2(rs, rs);
-    float2 n = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { x[r][i] = fma2(x[r][i], mul2(w2[i], r2), b2[i]); n = fma2(x[r][i], x[r][i], n); }
-    a[r] = n.x + n.y;
+  for (int i = 0; i < 8; ++i) {
+    x[i] = fma2(x[i], mul2(w2[i], rx2), b2[i]); y[i] = fma2(y[i], mul2(w2[i], ry2), b2[i]);
+    nx = fma2(x[i], x[i], nx); ny = fma2(y[i], y[i], ny);
   }
+  ax = nx.x + nx.y; ay = ny.x + ny.y;
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) {
-    float t[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) t[r] = __shfl_xor_sync(gmask, a[r], o);
-#pragma unroll
-    for (int r = 0; r < NR; ++r) a[r] += t[r];
+    const float tx = __shfl_xor_sync(gmask, ax, o), ty = __shfl_xor_sync(gmask, ay, o);
+    ax += tx; ay += ty;
   }
+  const float ix = 1.0f / fmaxf(sqrtf(ax), 1e-12f), iy = 1.0f / fmaxf(sqrtf(ay), 1e-12f);
+  const float2 ix2 = make_float2(ix, ix), iy2 = make_float2(iy, iy);
 #pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const float inv = 1.0f / fmaxf(sqrtf(a[r]), 1e-12f);
-    const float2 i2 = make_float2(inv, inv);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[r][i] = mul2(x[r][i], i2);
-  }
+  for (int i = 0; i < 8; ++i) { x[i] = mul2(x[i], ix2); y[i] = mul2(y[i], iy2); }
 }
 
 template <int TP>   // padded frames: 128 or 256
@@ -370,17 +340,15 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
     for (int which = 0; which < 2; ++which) {
       uint8_t* dst = (which == 0 ? Qs : Ks) + (sub >> 2) * (TP * 128);
       const int rows_live = which == 0 ? T : len;
-      // NR rows per iteration: four where the register file allows it (one CTA per SM at TP = 256), else two
-      constexpr int NR = (TP == 256 && MDM_FA_NR4) ? 4 : 2;
 #pragma unroll 1
-      for (int t = rr; t < rows_live; t += 32 * NR) {
-        float2 xr[NR][8];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) load8(dst, (t + 32 * r < rows_live) ? t + 32 * r : t, xr[r]);   // uniform over a row's lanes
-        norm_slice_n<NR>(xr, w2, b2, gmask);
-#pragma unroll
-        for (int r = 0; r < NR; ++r)
-          if (t + 32 * r < rows_live) store8(dst, t + 32 * r, xr[r]);
+      for (int t = rr; t < rows_live; t += 64) {
+        const bool two = t + 32 < rows_live;           // uniform over the 8 lanes of a row
+        float2 xa[8], xb[8];
+        load8(dst, t, xa);
+        load8(dst, two ? t + 32 : t, xb);
+        norm_slice2(xa, xb, w2, b2, gmask);
+        store8(dst, t, xa);
+        if (two) store8(dst, t + 32, xb);
       }
     }
   }
@@ -425,15 +393,7 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
     tc_fence_after();
     const int m = quad * 32 + lane;
     constexpr int CH = TP / 64;                        // 32-column chunks per warp: columns [hi * TP/2, +TP/2)
-    constexpr bool WIDE2 = TP == 256 && MDM_FA_WIDE2;
-    uint32_t rawall[WIDE2 ? CH : 1][32];
-    if constexpr (WIDE2) {
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-        if (hi * (TP / 2) + c * 32 < len) tmem_ld32(t_lane + hi * (TP / 2) + c * 32, rawall[c]);   // warp-uniform
-      tmem_ld_wait();
-    }
-#pragma unroll(WIDE2 ? CH : 1)
+#pragma unroll 1
     for (int c = 0; c < CH; ++c) {
       const int t0 = hi * (TP / 2) + c * 32;
       uint8_t* dst = Ks + (t0 >> 6) * (128 * 128);
@@ -443,12 +403,9 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
           *reinterpret_cast<uint4*>(dst + sw_off(m, (t0 & 63) + 8 * j)) = make_uint4(0u, 0u, 0u, 0u);
         continue;
       }
-      uint32_t rawc[32];
-      if constexpr (!WIDE2) {
-        tmem_ld32(t_lane + t0, rawc);
-        tmem_ld_wait();
-      }
-      const uint32_t (&raw)[32] = WIDE2 ? rawall[WIDE2 ? c : 0] : rawc;
+      uint32_t raw[32];
+      tmem_ld32(t_lane + t0, raw);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float f[8];
@@ -488,21 +445,11 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   if (hi < MT) {
     const int t = hi * 128 + quad * 32 + lane;
     float den = 0.f;
-    constexpr bool WIDE3 = TP == 256 && MDM_FA_WIDE3;
-    uint32_t rawall[WIDE3 ? 4 : 1][32];
-    if constexpr (WIDE3) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(t_lane + QCOL + hi * 128 + c * 32, rawall[c]);
-      tmem_ld_wait();
-    }
-#pragma unroll(WIDE3 ? 4 : 1)
+#pragma unroll 1
     for (int c = 0; c < 4; ++c) {
-      uint32_t rawc[32];
-      if constexpr (!WIDE3) {
-        tmem_ld32(t_lane + QCOL + hi * 128 + c * 32, rawc);
-        tmem_ld_wait();
-      }
-      const uint32_t (&raw)[32] = WIDE3 ? rawall[WIDE3 ? c : 0] : rawc;
+      uint32_t raw[32];
+      tmem_ld32(t_lane + QCOL + hi * 128 + c * 32, raw);
+      tmem_ld_wait();
       uint32_t pk[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) pk[e] = pack2u(expfeat_u(__uint_as_float(raw[2 * e])), expfeat_u(__uint_as_float(raw[2 * e + 1])));
@@ -585,23 +532,12 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
     const float sc = 0.1f / den_r;
     const float2 sc2 = make_float2(sc, sc);
     const uint32_t t_row = t_lane + QCOL + hi * 128;
-    // WIDE6: the whole row (128 accumulator columns) is read from TMEM once and stays in registers for the three passes
-    constexpr bool WIDE6 = TP == 256 && MDM_FA_WIDE6;
-    uint32_t rawall[WIDE6 ? 4 : 1][32];
-    if constexpr (WIDE6) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(t_row + c * 32, rawall[c]);
-      tmem_ld_wait();
-    }
     float2 s2 = make_float2(0.f, 0.f);
-#pragma unroll(WIDE6 ? 4 : 1)
+#pragma unroll 1
     for (int c = 0; c < 4; ++c) {
-      uint32_t rawc[32];
-      if constexpr (!WIDE6) {
-        tmem_ld32(t_row + c * 32, rawc);
-        tmem_ld_wait();
-      }
-      const uint32_t (&raw)[32] = WIDE6 ? rawall[WIDE6 ? c : 0] : rawc;
+      uint32_t raw[32];
+      tmem_ld32(t_row + c * 32, raw);
+      tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 16; ++e)
         s2 = fma2(make_float2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1])), sc2, s2);
@@ -609,14 +545,11 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
     const float mean = (s2.x + s2.y) / (float)HD;
     const float2 nm = make_float2(-mean, -mean);
     float2 q2 = make_float2(0.f, 0.f);
-#pragma unroll(WIDE6 ? 4 : 1)
+#pragma unroll 1
     for (int c = 0; c < 4; ++c) {
-      uint32_t rawc[32];
-      if constexpr (!WIDE6) {
-        tmem_ld32(t_row + c * 32, rawc);
-        tmem_ld_wait();
-      }
-      const uint32_t (&raw)[32] = WIDE6 ? rawall[WIDE6 ? c : 0] : rawc;
+      uint32_t raw[32];
+      tmem_ld32(t_row + c * 32, raw);
+      tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const float2 d = fma2(make_float2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1])), sc2, nm);
@@ -625,14 +558,11 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
     }
     const float rstd = rsqrtf((q2.x + q2.y) / (float)HD + 1e-5f);
     const float2 r2 = make_float2(rstd, rstd);
-#pragma unroll(WIDE6 ? 4 : 1)
+#pragma unroll 1
     for (int c = 0; c < 4; ++c) {
-      uint32_t rawc[32];
-      if constexpr (!WIDE6) {
-        tmem_ld32(t_row + c * 32, rawc);
-        tmem_ld_wait();
-      }
-      const uint32_t (&raw)[32] = WIDE6 ? rawall[WIDE6 ? c : 0] : rawc;
+      uint32_t raw[32];
+      tmem_ld32(t_row + c * 32, raw);
+      tmem_ld_wait();
       if (t < T) {
         uint4* dst = reinterpret_cast<uint4*>(stage + t * PITCH + c * 64);
 #pragma unroll
