@@ -186,7 +186,7 @@ ep_combine_film_kernel(MdmEpPeers peers, const int* __restrict__ perm, long N, i
   layernorm_row<VPT>(acc, ln_w, ln_b, lane, D);
   film_row<VPT>(acc, film + (tok / rows_per_seq) * 2 * D, lane, D);
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) acc[i] = silu_f(acc[i]);
+  for (int i = 0; i < VPT; ++i) acc[i] = silu_out<TI>(acc[i]);
   store_row<VPT, TI>(out + tok * D, lane, acc);
 }
 

@@ -499,7 +499,7 @@ moe_combine_film_kernel(const TI* __restrict__ yp, const int* __restrict__ perm,
   layernorm_row<VPT>(acc, ln_w, ln_b, lane, D);
   film_row<VPT>(acc, film + (tok / rows_per_seq) * 2 * D, lane, D);
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) acc[i] = silu_f(acc[i]);
+  for (int i = 0; i < VPT; ++i) acc[i] = silu_out<TI>(acc[i]);
   store_row<VPT, TI>(out + tok * D, lane, acc);
 }
 
