@@ -439,7 +439,8 @@ def expert_ffn_bwd(xp, pre, hp, W1t, W2t, dz, seg_off, idx, N, NB, E, tiles_up, 
     out = lambda t: dict(out_a=t) if adt == bf16 else dict(out_f32=t)
     d_hp = torch.empty(rows, F, dtype=adt, device=dev)
     ops.gemm(dz, W2t, None, N=F, tiles=tiles_up, w_rows=G * F, **out(d_hp), **kw)           # d_hp = dz W2_g  (tiles_up: w_row0 = g*F)
-    d_pre = torch.zeros(rows, F, dtype=adt, device=dev)
+    d_pre = torch.empty(rows, F, dtype=adt, device=dev)      # rows < cap are written below; [cap, rows) is the zero region
+    d_pre[cap:].zero_()
     _chk(lib.mdm_act_bwd(pre.data_ptr(), d_hp.data_ptr(), _dt(pre), cap * F, ACT_GELU, d_pre.data_ptr(), _stream()), "mdm_act_bwd")
     d_xp = torch.empty(rows, D, dtype=adt, device=dev)
     ops.gemm(d_pre, W1t, None, N=D, tiles=tiles_dn, w_rows=G * D, **out(d_xp), **kw)        # d_xp = d_pre W1_g (tiles_dn: w_row0 = g*D)
