@@ -160,7 +160,10 @@ MDM_API int mdm_fastattn(const void* qkv, int dt, const float* P, const float* n
  *     unmasked key windows) are started first, which shortens the tail of the 2-wave grid.  `length` is fixed over
  *     a sampling loop, so the host sorts once per loop (CFGStepper), not per step.
  *   Pt_bf16 [M, hd] bf16: the projection matrix already transposed and rounded (== what the bf16 kernel builds from
- *     P in every CTA); packed once per model. */
+ *     P in every CTA); packed once per model.  It selects the tcgen05 kernel (hd == M == 128, T <= 256).  For
+ *     hd == M == 64 with an even head count pass the block-diagonal diag(P^T, P^T) [128, 128] instead: one CTA then takes
+ *     two adjacent heads through the same 128-wide tcgen05 products (row statistics per 64-column half, the cross-head
+ *     blocks of the key-value state zeroed); the [64, 64] matrix selects the mma.sync kernel as before. */
 MDM_API int mdm_fastattn_ordered(const void* qkv, int dt, const float* P, const float* norm_w,
                                  const float* norm_b, const int64_t* length, int length_shift, int B, int H,
                                  int T, int hd, int M, void* out, const int* seq_order, const void* Pt_bf16,

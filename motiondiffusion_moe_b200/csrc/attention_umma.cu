@@ -17,6 +17,11 @@
 //   P6  out epilogue: x 0.1 / den -> LayerNorm(hd) (lane == row: the row statistics need no shuffles) -> bf16 -> global
 //
 // bf16 rounding points are those of the mma.sync kernels in attention_tc.cu (normalised q / k / v, q', k', kv).
+//
+// hd = M = 64 (HPC = 2): one CTA takes TWO adjacent heads, i.e. the same 128 contiguous columns of q / k / v.  P^T is
+// passed as the block-diagonal [128 x 128] matrix diag(P^T, P^T), so K'^T and Q'' come out per head from the same
+// 128-wide products; the row statistics (LayerNorm / L2 norm over 64, the denominators) are taken per 64-column half;
+// the cross-head blocks of kv are zeroed when kv^T is written, which makes the apply product block-diagonal as well.
 // TMEM: K'^T in columns [0, TP), later kv in [0, 128); Q'' / out tiles in [256, 256 + TP).
 #include <stdlib.h>
 #include <string.h>
@@ -85,14 +90,39 @@ bool make_seq_map(CUtensorMap* map, const void* ptr, int B, int T, long cols, lo
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {      // packed bf16 pair -> two fp32 (exact)
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
+template <int HPC = 1>
 __device__ __forceinline__ float group8_sum(float v, unsigned gmask) {
   v += __shfl_xor_sync(gmask, v, 1);
   v += __shfl_xor_sync(gmask, v, 2);
-  v += __shfl_xor_sync(gmask, v, 4);
+  if (HPC == 1) v += __shfl_xor_sync(gmask, v, 4);      // HPC == 2: lanes 0-3 / 4-7 of the row hold different heads
   return v;
 }
 // The slice of one row owned by a thread (16 elements as 8 packed pairs; 8 threads per row): 0.1 x -> LayerNorm(128)
 // with the affine pairs w2 / b2 -> optional L2 normalisation of the whole row.  FFMA2 / FMUL2 / FADD2 throughout.
+// v rows at HPC == 2: the thread's pairs j < 4 belong to the first head, j >= 4 to the second (columns 2 sub + 16 j), and all
+// eight lanes of the row contribute to both: two sums per reduction.
+__device__ __forceinline__ void norm_slice_v2(float2 (&x)[8], const float2 (&w2)[8], const float2 (&b2)[8], unsigned gmask) {
+  const float2 tenth = make_float2(0.1f, 0.1f);
+  float2 sa = make_float2(0.f, 0.f), sb = sa;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { x[i] = mul2(x[i], tenth); sa = add2(sa, x[i]); x[i + 4] = mul2(x[i + 4], tenth); sb = add2(sb, x[i + 4]); }
+  const float ma = group8_sum<1>(sa.x + sa.y, gmask) / 64.f, mb = group8_sum<1>(sb.x + sb.y, gmask) / 64.f;
+  const float2 na = make_float2(-ma, -ma), nb2 = make_float2(-mb, -mb);
+  float2 qa = make_float2(0.f, 0.f), qb = qa;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[i] = add2(x[i], na); qa = fma2(x[i], x[i], qa);
+    x[i + 4] = add2(x[i + 4], nb2); qb = fma2(x[i + 4], x[i + 4], qb);
+  }
+  const float ra = rsqrtf(group8_sum<1>(qa.x + qa.y, gmask) / 64.f + 1e-5f), rb = rsqrtf(group8_sum<1>(qb.x + qb.y, gmask) / 64.f + 1e-5f);
+  const float2 ra2 = make_float2(ra, ra), rb2 = make_float2(rb, rb);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[i] = fma2(x[i], mul2(w2[i], ra2), b2[i]);
+    x[i + 4] = fma2(x[i + 4], mul2(w2[i + 4], rb2), b2[i + 4]);
+  }
+}
+
 template <bool L2>
 __device__ __forceinline__ void norm_slice(float2 (&x)[8], const float2 (&w2)[8], const float2 (&b2)[8], unsigned gmask) {
   const float2 tenth = make_float2(0.1f, 0.1f);
@@ -121,6 +151,7 @@ __device__ __forceinline__ void norm_slice(float2 (&x)[8], const float2 (&w2)[8]
 }
 
 // norm_slice<true> on two rows at once (independent dependency chains interleaved by hand)
+template <int HPC>
 __device__ __forceinline__ void norm_slice2(float2 (&x)[8], float2 (&y)[8], const float2 (&w2)[8], const float2 (&b2)[8],
                                             unsigned gmask) {
   const float2 tenth = make_float2(0.1f, 0.1f);
@@ -132,11 +163,11 @@ __device__ __forceinline__ void norm_slice2(float2 (&x)[8], float2 (&y)[8], cons
   }
   float ax = sx.x + sx.y, ay = sy.x + sy.y;
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
+  for (int o = 1; o < 8 / HPC; o <<= 1) {
     const float tx = __shfl_xor_sync(gmask, ax, o), ty = __shfl_xor_sync(gmask, ay, o);
     ax += tx; ay += ty;
   }
-  const float2 nmx = make_float2(-ax / (float)HD, -ax / (float)HD), nmy = make_float2(-ay / (float)HD, -ay / (float)HD);
+  const float2 nmx = make_float2(-ax / (float)(HD / HPC), -ax / (float)(HD / HPC)), nmy = make_float2(-ay / (float)(HD / HPC), -ay / (float)(HD / HPC));
   float2 qx = make_float2(0.f, 0.f), qy = qx;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -145,11 +176,11 @@ __device__ __forceinline__ void norm_slice2(float2 (&x)[8], float2 (&y)[8], cons
   }
   ax = qx.x + qx.y; ay = qy.x + qy.y;
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
+  for (int o = 1; o < 8 / HPC; o <<= 1) {
     const float tx = __shfl_xor_sync(gmask, ax, o), ty = __shfl_xor_sync(gmask, ay, o);
     ax += tx; ay += ty;
   }
-  const float rx = rsqrtf(ax / (float)HD + 1e-5f), ry = rsqrtf(ay / (float)HD + 1e-5f);
+  const float rx = rsqrtf(ax / (float)(HD / HPC) + 1e-5f), ry = rsqrtf(ay / (float)(HD / HPC) + 1e-5f);
   const float2 rx2 = make_float2(rx, rx), ry2 = make_float2(ry, ry);
   float2 nx = make_float2(0.f, 0.f), ny = nx;
 #pragma unroll
@@ -159,7 +190,7 @@ __device__ __forceinline__ void norm_slice2(float2 (&x)[8], float2 (&y)[8], cons
   }
   ax = nx.x + nx.y; ay = ny.x + ny.y;
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
+  for (int o = 1; o < 8 / HPC; o <<= 1) {
     const float tx = __shfl_xor_sync(gmask, ax, o), ty = __shfl_xor_sync(gmask, ay, o);
     ax += tx; ay += ty;
   }
@@ -182,7 +213,7 @@ struct Smem {
   static constexpr int TOTAL = BAR + 64 + 1024;       // + alignment slack
 };
 
-template <int TP>
+template <int TP, int HPC>    // HPC heads per CTA: 1 (hd = 128) or 2 (hd = 64, block-diagonal P^T)
 __global__ void __launch_bounds__(NTHR, TP == 128 ? 2 : 1)
 fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg, const float* __restrict__ nw,
                      const float* __restrict__ nb, const int64_t* __restrict__ length, int length_shift, int H, int T,
@@ -193,6 +224,7 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   constexpr int KC = TP / 64;         // 64-frame chunks (K of the kv product)
   constexpr int QCOL = TP;            // TMEM: K'^T / kv in columns [0, TP), Q'' / out tiles from QCOL on
   constexpr int NCOLS = 2 * TP;       // 256 columns per CTA at TP = 128 (two CTAs per SM), 512 at TP = 256
+  constexpr int HW = HD / HPC;        // columns of one head: the width of every row statistic
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* Qs = smem + L::QS;
@@ -279,15 +311,15 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  for (int i = tid; i < HD; i += NTHR) { nw_s[i] = nw[i]; nb_s[i] = nb[i]; }   // read again after the barrier below
+  for (int i = tid; i < HD; i += NTHR) { nw_s[i] = nw[i % HW]; nb_s[i] = nb[i % HW]; }   // read again after the barrier below
   FAU_MARK(0);
   // v: LayerNorm, transposed 2-byte stores (the pair ownership costs a 2-way bank conflict, the loads are 4 bytes)
   auto v_pass = [&]() {
     float2 w2[8], b2[8];                               // straight from global: no barrier before this pass
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      w2[j] = __ldg(reinterpret_cast<const float2*>(nw + 2 * sub + 16 * j));
-      b2[j] = __ldg(reinterpret_cast<const float2*>(nb + 2 * sub + 16 * j));
+      w2[j] = __ldg(reinterpret_cast<const float2*>(nw + (2 * sub + 16 * j) % HW));
+      b2[j] = __ldg(reinterpret_cast<const float2*>(nb + (2 * sub + 16 * j) % HW));
     }
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -302,7 +334,8 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
       float2 x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = bf2_to_f2(vraw[p][j]);
-      norm_slice<false>(x, w2, b2, gmask);
+      if constexpr (HPC == 2) norm_slice_v2(x, w2, b2, gmask);
+      else norm_slice<false>(x, w2, b2, gmask);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint32_t pk = pack2u(x[j].x, x[j].y);
@@ -321,8 +354,8 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
     float2 w2[8], b2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      w2[i] = __ldg(reinterpret_cast<const float2*>(nw + sub * 16 + 2 * i));
-      b2[i] = __ldg(reinterpret_cast<const float2*>(nb + sub * 16 + 2 * i));
+      w2[i] = __ldg(reinterpret_cast<const float2*>(nw + (sub * 16 + 2 * i) % HW));
+      b2[i] = __ldg(reinterpret_cast<const float2*>(nb + (sub * 16 + 2 * i) % HW));
     }
     auto load8 = [&](uint8_t* dst, int t, float2 (&x)[8]) {
       const uint4 r0 = *reinterpret_cast<const uint4*>(dst + sw_off(t, (sub & 3) * 16));
@@ -346,7 +379,7 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
         float2 xa[8], xb[8];
         load8(dst, t, xa);
         load8(dst, two ? t + 32 : t, xb);
-        norm_slice2(xa, xb, w2, b2, gmask);
+        norm_slice2<HPC>(xa, xb, w2, b2, gmask);
         store8(dst, t, xa);
         if (two) store8(dst, t + 32, xb);
       }
@@ -441,10 +474,12 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   }
   mbar_wait(&bars[1], 0);
   tc_fence_after();
-  float den_r = 1.f;                                   // denominator of this thread's frame (same thread in P6)
+  float den_r[HPC];                                    // denominator(s) of this thread's frame (same thread in P6)
+#pragma unroll
+  for (int i = 0; i < HPC; ++i) den_r[i] = 1.f;
   if (hi < MT) {
     const int t = hi * 128 + quad * 32 + lane;
-    float den = 0.f;
+    float den = 0.f, den_b = 0.f;                      // den_b: second head (columns 64..127) at HPC == 2
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t raw[32];
@@ -461,8 +496,13 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
           const int m = c * 32 + 2 * e;
           const float k0 = __bfloat162float(*reinterpret_cast<const bf16*>(kt + sw_off(m, t & 63)));
           const float k1 = __bfloat162float(*reinterpret_cast<const bf16*>(kt + sw_off(m + 1, t & 63)));
-          den = fmaf(__low2float(q2), k0, den);
-          den = fmaf(__high2float(q2), k1, den);
+          if (HPC == 2 && c >= 2) {
+            den_b = fmaf(__low2float(q2), k0, den_b);
+            den_b = fmaf(__high2float(q2), k1, den_b);
+          } else {
+            den = fmaf(__low2float(q2), k0, den);
+            den = fmaf(__high2float(q2), k1, den);
+          }
         }
       }
       uint8_t* dst = Qs + (c >> 1) * (TP * 128);
@@ -470,7 +510,8 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(dst + sw_off(t, (c & 1) * 32 + 8 * j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     }
-    den_r = fmaxf(den, 1e-6f);
+    den_r[0] = fmaxf(den, 1e-6f);
+    if (HPC == 2) den_r[HPC - 1] = fmaxf(den_b, 1e-6f);
   }
 
   FAU_MARK(4);
@@ -490,6 +531,10 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
       } else {
 #pragma unroll
         for (int e = 0; e < 32; ++e) raw[e] = 0u;     // no unmasked key: no MMA was issued, kv == 0
+      }
+      if (HPC == 2 && (quad >> 1) != hi) {             // kv[m of one head][l of the other]: not part of the op
+#pragma unroll
+        for (int e = 0; e < 32; ++e) raw[e] = 0u;
       }
 #pragma unroll
       for (int e = 0; e < 32; ++e)
@@ -527,55 +572,60 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   static_assert((TP == 128 ? 128 : 256) * PITCH <= L::NW - L::KS - (TP == 128 ? 0 : (TP / 64) * 128 * 128), "staging area");
   uint8_t* stage = Ks;
   if (hi < MT) {
-    // three passes over the thread's TMEM row (mean, variance, normalise) instead of 128 live registers
+    // three passes over the thread's TMEM row (mean, variance, normalise) instead of 128 live registers; at HPC == 2 once
+    // per head (64-column half, its own denominator and statistics)
     const int t = hi * 128 + quad * 32 + lane;
-    const float sc = 0.1f / den_r;
-    const float2 sc2 = make_float2(sc, sc);
     const uint32_t t_row = t_lane + QCOL + hi * 128;
-    float2 s2 = make_float2(0.f, 0.f);
+    constexpr int CPH = 4 / HPC;                       // 32-column chunks per head
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t raw[32];
-      tmem_ld32(t_row + c * 32, raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 16; ++e)
-        s2 = fma2(make_float2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1])), sc2, s2);
-    }
-    const float mean = (s2.x + s2.y) / (float)HD;
-    const float2 nm = make_float2(-mean, -mean);
-    float2 q2 = make_float2(0.f, 0.f);
+    for (int hf = 0; hf < HPC; ++hf) {
+      const float sc = 0.1f / den_r[hf];
+      const float2 sc2 = make_float2(sc, sc);
+      float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t raw[32];
-      tmem_ld32(t_row + c * 32, raw);
-      tmem_ld_wait();
+      for (int c = hf * CPH; c < (hf + 1) * CPH; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(t_row + c * 32, raw);
+        tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float2 d = fma2(make_float2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1])), sc2, nm);
-        q2 = fma2(d, d, q2);
+        for (int e = 0; e < 16; ++e)
+          s2 = fma2(make_float2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1])), sc2, s2);
       }
-    }
-    const float rstd = rsqrtf((q2.x + q2.y) / (float)HD + 1e-5f);
-    const float2 r2 = make_float2(rstd, rstd);
+      const float mean = (s2.x + s2.y) / (float)HW;
+      const float2 nm = make_float2(-mean, -mean);
+      float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t raw[32];
-      tmem_ld32(t_row + c * 32, raw);
-      tmem_ld_wait();
-      if (t < T) {
-        uint4* dst = reinterpret_cast<uint4*>(stage + t * PITCH + c * 64);
+      for (int c = hf * CPH; c < (hf + 1) * CPH; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(t_row + c * 32, raw);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t pk[4];
+        for (int e = 0; e < 16; ++e) {
+          const float2 d = fma2(make_float2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1])), sc2, nm);
+          q2 = fma2(d, d, q2);
+        }
+      }
+      const float rstd = rsqrtf((q2.x + q2.y) / (float)HW + 1e-5f);
+      const float2 r2 = make_float2(rstd, rstd);
+#pragma unroll 1
+      for (int c = hf * CPH; c < (hf + 1) * CPH; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(t_row + c * 32, raw);
+        tmem_ld_wait();
+        if (t < T) {
+          uint4* dst = reinterpret_cast<uint4*>(stage + t * PITCH + c * 64);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = c * 32 + 8 * j + 2 * e;
-            const float2 d = fma2(make_float2(__uint_as_float(raw[8 * j + 2 * e]), __uint_as_float(raw[8 * j + 2 * e + 1])), sc2, nm);
-            const float2 y = fma2(d, mul2(make_float2(nw_s[col], nw_s[col + 1]), r2), make_float2(nb_s[col], nb_s[col + 1]));
-            pk[e] = pack2u(y.x, y.y);
+          for (int j = 0; j < 4; ++j) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = c * 32 + 8 * j + 2 * e;
+              const float2 d = fma2(make_float2(__uint_as_float(raw[8 * j + 2 * e]), __uint_as_float(raw[8 * j + 2 * e + 1])), sc2, nm);
+              const float2 y = fma2(d, mul2(make_float2(nw_s[col], nw_s[col + 1]), r2), make_float2(nb_s[col], nb_s[col + 1]));
+              pk[e] = pack2u(y.x, y.y);
+            }
+            dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
-          dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
     }
@@ -595,7 +645,8 @@ fastattn_umma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ Ptg,
   }
 }
 
-template <int TP>
+// H counts the CTAs per sequence: heads of 128, or pairs of heads of 64 (HPC = 2)
+template <int TP, int HPC>
 int launch(const bf16* qkv, const bf16* Pt, const float* nw, const float* nb, const int64_t* length, int shift, int B,
            int H, int T, bf16* out, const int* seq_order, cudaStream_t st) {
   using L = Smem<TP>;
@@ -603,7 +654,7 @@ int launch(const bf16* qkv, const bf16* Pt, const float* nw, const float* nb, co
   static unsigned long long attr = 0;   // one bit per device ordinal: the attribute is per (function, device)
   const unsigned long long dev_bit = 1ull << mdm_cur_dev();
   if (!(attr & dev_bit)) {
-    if (cudaFuncSetAttribute(fastattn_umma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+    if (cudaFuncSetAttribute(fastattn_umma_kernel<TP, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
       return MDM_ERR_CUDA;
     attr |= dev_bit;
   }
@@ -612,7 +663,7 @@ int launch(const bf16* qkv, const bf16* Pt, const float* nw, const float* nb, co
   CUtensorMap tq, tp;
   memset(&tq, 0, sizeof(tq)); memset(&tp, 0, sizeof(tp));
   const int use_tma = tma_env && make_seq_map(&tq, qkv, B, T, 3L * H * HD, 3L * H * HD, TP) && make_map(&tp, Pt, HD, HD, HD, 128);
-  mdm_launch(fastattn_umma_kernel<TP>, B * H, NTHR, L::TOTAL, st, qkv, Pt, nw, nb, length, shift, H, T, out, seq_order, tq, tp,
+  mdm_launch(fastattn_umma_kernel<TP, HPC>, B * H, NTHR, L::TOTAL, st, qkv, Pt, nw, nb, length, shift, H, T, out, seq_order, tq, tp,
              use_tma);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
@@ -1120,20 +1171,26 @@ int launch_sc(const bf16* q, const bf16* k, const bf16* v, const int* nt, int B,
 
 }  // namespace
 
-// hd == M == 128, bf16, T <= 256, with the pre-transposed bf16 projection matrix; MDM_ERR_UNSUPPORTED otherwise
+// hd == M == 128 (P^T [128 x 128] in bf16) or hd == M == 64 with an even head count (diag(P^T, P^T) [128 x 128] in bf16),
+// bf16, T <= 256; MDM_ERR_UNSUPPORTED otherwise
 // (the caller falls back to the mma.sync kernels of attention_tc.cu).
 int mdm_fastattn_umma(const void* qkv, const void* Pt_bf16, const float* norm_w, const float* norm_b,
                       const int64_t* length, int length_shift, int B, int H, int T, int hd, int M, void* out,
                       const int* seq_order, cudaStream_t st) {
-  if (hd != HD || M != HD || T > 256 || !Pt_bf16) return MDM_ERR_UNSUPPORTED;
+  const bool two = hd == 64 && M == 64 && (H & 1) == 0;      // two heads of 64 per CTA: Pt_bf16 is diag(P^T, P^T) [128 x 128]
+  if (!((hd == HD && M == HD) || two) || T > 256 || !Pt_bf16) return MDM_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
       (reinterpret_cast<uintptr_t>(Pt_bf16) & 15))
     return MDM_ERR_UNSUPPORTED;
   const bf16* q = reinterpret_cast<const bf16*>(qkv);
   const bf16* p = reinterpret_cast<const bf16*>(Pt_bf16);
   bf16* o = reinterpret_cast<bf16*>(out);
-  if (T <= 128) return launch<128>(q, p, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order, st);
-  return launch<256>(q, p, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order, st);
+  if (two) {
+    if (T <= 128) return launch<128, 2>(q, p, norm_w, norm_b, length, length_shift, B, H / 2, T, o, seq_order, st);
+    return launch<256, 2>(q, p, norm_w, norm_b, length, length_shift, B, H / 2, T, o, seq_order, st);
+  }
+  if (T <= 128) return launch<128, 1>(q, p, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order, st);
+  return launch<256, 1>(q, p, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order, st);
 }
 
 // hd == 128, bf16, T <= 256, with ctx^T in bf16 ([B, H, l, d]); MDM_ERR_UNSUPPORTED otherwise.

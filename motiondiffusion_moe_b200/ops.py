@@ -208,10 +208,24 @@ def gemm_gate(A, W, bias, *, resid, out_f32, alpha=1.0, beta=1.0, NB, E, ln_w, l
     return True
 
 
+def pack_fastattn_pt(P):
+    """The bf16 operand that selects the tcgen05 FastAttention kernel: P^T for head size 128; for head size 64 the
+    block-diagonal diag(P^T, P^T) [128, 128] (one CTA takes two heads); None where only the other kernels apply."""
+    hd, M = P.shape
+    Pt = P.float().t().contiguous().to(torch.bfloat16)
+    if hd == 128 and M == 128:
+        return Pt
+    if hd == 64 and M == 64:
+        return torch.block_diag(Pt, Pt).contiguous()
+    return None
+
+
 def fastattn(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out, seq_order=None, Pt=None):
     _c(qkv, P, norm_w, norm_b, length, out, seq_order, Pt)
-    if Pt is not None and (Pt.dtype != torch.bfloat16 or tuple(Pt.shape) != (P.shape[1], P.shape[0])):
-        raise _lib.MdmError("Pt must be P^T in bf16")
+    if Pt is not None:
+        two = tuple(P.shape) == (64, 64) and tuple(Pt.shape) == (128, 128)      # diag(P^T, P^T): pack_fastattn_pt
+        if Pt.dtype != torch.bfloat16 or not (two or tuple(Pt.shape) == (P.shape[1], P.shape[0])):
+            raise _lib.MdmError("Pt must be P^T in bf16 (pack_fastattn_pt)")
     if hd > 128:       # head sizes outside the fused kernels (model_size="big": 4 heads of 256): the composed generic path
         from . import train_ops
         return train_ops.fastattn_generic(qkv, P, norm_w, norm_b, length, length_shift, B, H, T, hd, out)

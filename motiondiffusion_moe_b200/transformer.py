@@ -503,7 +503,7 @@ class MotionTransformer(nn.Module):
                       "qkv_b": torch.cat([g(p + ".query.bias"), g(p + ".key.bias"),
                                           g(p + ".value.bias")]).float().contiguous(),
                       "P": g(p + ".fast_attention.projection_matrix").float().contiguous(),
-                      "Pt": (g(p + ".fast_attention.projection_matrix").float().t().contiguous().to(torch.bfloat16)
+                      "Pt": (ops.pack_fastattn_pt(g(p + ".fast_attention.projection_matrix"))
                              if wdt == torch.bfloat16 else None),
                       "fa_norm": LN(p + ".fast_attention.norm"),
                       "p0": (W(p + ".proj_out.0"), Bf(p + ".proj_out.0")),

@@ -467,7 +467,7 @@ def _attn_params(hd, seed):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,H,T,hd", [(3, 4, 196, 128), (2, 4, 98, 128), (3, 4, 60, 64), (2, 2, 8, 32)])
+@pytest.mark.parametrize("B,H,T,hd", [(3, 4, 196, 128), (2, 4, 98, 128), (3, 4, 60, 64), (3, 8, 196, 64), (2, 2, 8, 32)])
 def test_fastattn(dtype, B, H, T, hd):
     D = H * hd
     P, nw, nb = _attn_params(hd, 1)
@@ -479,10 +479,13 @@ def test_fastattn(dtype, B, H, T, hd):
     p = {"fa.projection_matrix": P, "fa.norm.weight": nw, "fa.norm.bias": nb}
     ref = mo.fast_attention(p, "fa", q, k, v, mo.src_mask(T, length)).permute(0, 2, 1, 3).reshape(B * T, D)
     assert rel(out, ref) < TOL[dtype]
-    if dtype == torch.bfloat16 and hd == 128:
-        # with the packed bf16 P^T the tcgen05 kernel (attention_umma.cu) runs instead of the mma.sync one
+    if dtype == torch.bfloat16 and hd in (128, 64):
+        # with the packed bf16 P^T the tcgen05 kernel (attention_umma.cu) runs instead of the mma.sync one; head size 64:
+        # two heads per CTA with the block-diagonal diag(P^T, P^T)
+        Pt = ops.pack_fastattn_pt(P)
+        assert Pt is not None and tuple(Pt.shape) == (128, 128)
         out2 = torch.full_like(out, float("nan"))
-        ops.fastattn(qkv, P, nw, nb, length, 0, B, H, T, hd, out2, Pt=P.t().contiguous().to(torch.bfloat16))
+        ops.fastattn(qkv, P, nw, nb, length, 0, B, H, T, hd, out2, Pt=Pt)
         assert rel(out2, ref) < TOL[dtype]
         assert rel(out2, out) < 1e-2
 

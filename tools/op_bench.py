@@ -186,6 +186,15 @@ order = torch.argsort(length, descending=True).to(torch.int32)
 timeit("fastattn tcgen05 (Pt, longest first)", lambda i: ops.fastattn(qkv[i], P, nw, nb_, length, 0, NSEQ, H, T, hd, ob[i], seq_order=order, Pt=Pt), nset, N * D * 8, "GB/s")
 timeit("fastattn tcgen05 (Pt)", lambda i: ops.fastattn(qkv[i], P, nw, nb_, length, 0, NSEQ, H, T, hd, ob[i], Pt=Pt), nset, N * D * 8, "GB/s")
 timeit("fastattn mma.sync", lambda i: ops.fastattn(qkv[i], P, nw, nb_, length, 0, NSEQ, H, T, hd, ob[i], seq_order=order), nset, N * D * 8, "GB/s")
+
+# head size 64 (the as-shipped tools/train.py shape: D 512, 8 heads): two heads per CTA on the tcgen05 kernel vs mma.sync
+if not ONLY or "fastattn" in ONLY:
+    H8, hd8 = 8, 64
+    P8 = torch.randn(hd8, hd8, device=dev) * hd8 ** -0.5
+    Pt8 = ops.pack_fastattn_pt(P8)
+    nw8, nb8 = torch.rand(hd8, device=dev) + 0.5, torch.randn(hd8, device=dev) * 0.1
+    timeit("fastattn hd 64 tcgen05 (2 heads / CTA)", lambda i: ops.fastattn(qkv[i], P8, nw8, nb8, length, 0, NSEQ, H8, T, hd8, ob[i], seq_order=order, Pt=Pt8), nset, N * D * 8, "GB/s")
+    timeit("fastattn hd 64 mma.sync", lambda i: ops.fastattn(qkv[i], P8, nw8, nb8, length, 0, NSEQ, H8, T, hd8, ob[i], seq_order=order), nset, N * D * 8, "GB/s")
 ctx = torch.randn(NSEQ, H, hd, hd, device=dev)
 ctxT = torch.empty(NSEQ, H, hd, hd, device=dev, dtype=bf)
 ops.transpose_cast_bf16(ctx, ctxT)
