@@ -186,7 +186,9 @@ MDM_API int mdm_lincross_apply_ex(const void* q, int dt, const float* ctx, const
  * (models/fast_attention.py:248-272 -> models/stylization.py:27-30): y = SiLU(LayerNorm_D(apply(q)) * (1 + scale[b]) + shift[b]),
  * film = [B, 2 * H * hd] (scale | shift).  The LayerNorm spans the H heads of a row: the H CTAs of a sequence run as a
  * thread-block cluster and exchange per-row partial sums through distributed shared memory.  hd == 128, T <= 256,
- * H <= 8, bf16; MDM_ERR_UNSUPPORTED otherwise (the caller then runs mdm_lincross_apply_ex + mdm_rowop). */
+ * H <= 8, bf16; or hd == 64 with an even H <= 16: ctxT_bf16 is then [B, H / 2, 128, 128], the block-diagonal ctx^T of each
+ * pair of adjacent heads (one CTA takes two heads; the same layout selects the tcgen05 kernel in mdm_lincross_apply_ex).
+ * MDM_ERR_UNSUPPORTED otherwise (the caller then runs mdm_lincross_apply_ex + mdm_rowop). */
 MDM_API int mdm_lincross_apply_style(const void* q, const void* ctxT_bf16, int B, int T, int H, int hd, const float* ln_w,
                                      const float* ln_b, const float* film, void* y, void* stream);
 

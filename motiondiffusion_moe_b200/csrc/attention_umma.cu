@@ -692,7 +692,9 @@ struct SmemLC {
 // columns per row in its own shared memory, and after one cluster barrier every thread reads the H partials of its row
 // through distributed shared memory (the same order in every CTA).  TMEM lane = row, so the statistics themselves are
 // per-thread sums.  Replaces the rowop launch (LN, FiLM, SiLU) after the core: the bf16 rounding of y in between is gone.
-template <int TP, bool STYLE>
+// HPC = 2 (head size 64): the CTA takes two adjacent heads, ctx^T is the block-diagonal [128 x 128] of the pair, the
+// softmax runs over each 64-column half (four lanes of a row instead of eight).
+template <int TP, bool STYLE, int HPC>
 __global__ void __launch_bounds__(NTHR, 2)
 lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, int H, int T, bf16* __restrict__ y,
                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, const float* __restrict__ film) {
@@ -767,7 +769,7 @@ lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, 
 #pragma unroll
       for (int i = 1; i < 8; ++i) { ma = fmaxf(ma, fmaxf(xa[i].x, xa[i].y)); mb = fmaxf(mb, fmaxf(xb[i].x, xb[i].y)); }
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
+      for (int o = 1; o < 8 / HPC; o <<= 1) {
         ma = fmaxf(ma, __shfl_xor_sync(gmask, ma, o));
         mb = fmaxf(mb, __shfl_xor_sync(gmask, mb, o));
       }
@@ -785,7 +787,7 @@ lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, 
         sb += xb[i].x + xb[i].y;
       }
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
+      for (int o = 1; o < 8 / HPC; o <<= 1) {
         sa += __shfl_xor_sync(gmask, sa, o);
         sb += __shfl_xor_sync(gmask, sb, o);
       }
@@ -919,21 +921,21 @@ lincross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ ctxT, 
   if (STYLE) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // no peer still reads this CTA's statistics
 }
 
-template <int TP, bool STYLE>
+template <int TP, bool STYLE, int HPC = 1>    // H counts the CTAs per sequence (heads of 128 or pairs of heads of 64)
 int launch_lc(const bf16* q, const bf16* ctxT, int B, int H, int T, bf16* y, const float* ln_w, const float* ln_b,
               const float* film, cudaStream_t st) {
   using L = SmemLC<TP>;
   static unsigned long long attr = 0;   // one bit per device ordinal: the attribute is per (function, device)
   const unsigned long long dev_bit = 1ull << mdm_cur_dev();
   if (!(attr & dev_bit)) {
-    if (cudaFuncSetAttribute(lincross_umma_kernel<TP, STYLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+    if (cudaFuncSetAttribute(lincross_umma_kernel<TP, STYLE, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
       return MDM_ERR_CUDA;
     attr |= dev_bit;
   }
   if (STYLE)   // the H head-CTAs of a sequence form a cluster
-    return mdm_launch_cluster(lincross_umma_kernel<TP, STYLE>, B * H, NTHR, L::TOTAL, st, H, q, ctxT, H, T, y, ln_w, ln_b, film) ==
+    return mdm_launch_cluster(lincross_umma_kernel<TP, STYLE, HPC>, B * H, NTHR, L::TOTAL, st, H, q, ctxT, H, T, y, ln_w, ln_b, film) ==
                    cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
-  mdm_launch(lincross_umma_kernel<TP, STYLE>, B * H, NTHR, L::TOTAL, st, q, ctxT, H, T, y, ln_w, ln_b, film);
+  mdm_launch(lincross_umma_kernel<TP, STYLE, HPC>, B * H, NTHR, L::TOTAL, st, q, ctxT, H, T, y, ln_w, ln_b, film);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -1193,15 +1195,20 @@ int mdm_fastattn_umma(const void* qkv, const void* Pt_bf16, const float* norm_w,
   return launch<256, 1>(q, p, norm_w, norm_b, length, length_shift, B, H, T, o, seq_order, st);
 }
 
-// hd == 128, bf16, T <= 256, with ctx^T in bf16 ([B, H, l, d]); MDM_ERR_UNSUPPORTED otherwise.
+// hd == 128, bf16, T <= 256, with ctx^T in bf16 ([B, H, l, d]), or hd == 64 with an even head count and the block-diagonal
+// ctx^T of each pair of heads ([B, H / 2, 128, 128]); MDM_ERR_UNSUPPORTED otherwise.
 int mdm_lincross_apply_umma(const void* q, const void* ctxT_bf16, int B, int T, int H, int hd, void* y, cudaStream_t st) {
-  if (hd != HD || T > 256 || !ctxT_bf16) return MDM_ERR_UNSUPPORTED;
+  if (!(hd == HD || (hd == 64 && (H & 1) == 0)) || T > 256 || !ctxT_bf16) return MDM_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
       (reinterpret_cast<uintptr_t>(ctxT_bf16) & 15))
     return MDM_ERR_UNSUPPORTED;
   const bf16* qq = reinterpret_cast<const bf16*>(q);
   const bf16* cc = reinterpret_cast<const bf16*>(ctxT_bf16);
   bf16* yy = reinterpret_cast<bf16*>(y);
+  if (hd == 64) {     // ctxT_bf16: [B, H / 2, 128, 128], the block-diagonal ctx^T of each pair of heads
+    if (T <= 128) return launch_lc<128, false, 2>(qq, cc, B, H / 2, T, yy, nullptr, nullptr, nullptr, st);
+    return launch_lc<256, false, 2>(qq, cc, B, H / 2, T, yy, nullptr, nullptr, nullptr, st);
+  }
   if (T <= 128) return launch_lc<128, false>(qq, cc, B, H, T, yy, nullptr, nullptr, nullptr, st);
   return launch_lc<256, false>(qq, cc, B, H, T, yy, nullptr, nullptr, nullptr, st);
 }
@@ -1210,7 +1217,8 @@ int mdm_lincross_apply_umma(const void* q, const void* ctxT_bf16, int B, int T, 
 extern "C" MDM_API int mdm_lincross_apply_style(const void* q, const void* ctxT_bf16, int B, int T, int H, int hd,
                                                 const float* ln_w, const float* ln_b, const float* film, void* y, void* stream) {
   if (!q || !ctxT_bf16 || !ln_w || !ln_b || !film || !y || B <= 0 || T <= 0) return MDM_ERR_ARG;
-  if (hd != HD || T > 256 || H < 1 || H > 8) return MDM_ERR_UNSUPPORTED;     // portable cluster size
+  const bool two = hd == 64 && (H & 1) == 0;      // pairs of heads of 64: ctxT_bf16 is [B, H / 2, 128, 128] block-diagonal
+  if (!(hd == HD || two) || T > 256 || H < 1 || H / (two ? 2 : 1) > 8) return MDM_ERR_UNSUPPORTED;     // portable cluster size
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
       (reinterpret_cast<uintptr_t>(ctxT_bf16) & 15))
     return MDM_ERR_UNSUPPORTED;
@@ -1218,6 +1226,10 @@ extern "C" MDM_API int mdm_lincross_apply_style(const void* q, const void* ctxT_
   const bf16* cc = reinterpret_cast<const bf16*>(ctxT_bf16);
   bf16* yy = reinterpret_cast<bf16*>(y);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (hd == 64) {
+    if (T <= 128) return launch_lc<128, true, 2>(qq, cc, B, H / 2, T, yy, ln_w, ln_b, film, st);
+    return launch_lc<256, true, 2>(qq, cc, B, H / 2, T, yy, ln_w, ln_b, film, st);
+  }
   if (T <= 128) return launch_lc<128, true>(qq, cc, B, H, T, yy, ln_w, ln_b, film, st);
   return launch_lc<256, true>(qq, cc, B, H, T, yy, ln_w, ln_b, film, st);
 }

@@ -244,11 +244,36 @@ def lincross_ctx(k, v, nt, B, Nt_max, H, hd, ctx):
                                             ctx.data_ptr(), _stream()), "mdm_lincross_ctx")
 
 
+def pack_lincross_ctxT(ctx):
+    """The bf16 B operand of the tcgen05 linear cross-attention kernel from the fp32 state ctx [B, H, d, l]: ctx^T
+    [B, H, l, d] for head size 128; for head size 64 (even head count) the block-diagonal [B, H / 2, 128, 128] of each pair
+    of heads (one CTA takes two heads); None where only the other kernels apply."""
+    B, H, hd, _ = ctx.shape
+    if hd == 128:
+        cT = torch.empty(B, H, hd, hd, dtype=torch.bfloat16, device=ctx.device)
+        transpose_cast_bf16(ctx, cT)
+        return cT
+    if hd == 64 and H % 2 == 0:
+        ct = ctx.transpose(-1, -2).to(torch.bfloat16)                    # [B, H, l, d]
+        out = torch.zeros(B, H // 2, 128, 128, dtype=torch.bfloat16, device=ctx.device)
+        out[:, :, :64, :64] = ct[:, 0::2]
+        out[:, :, 64:, 64:] = ct[:, 1::2]
+        return out
+    return None
+
+
+def _lincross_ctxT_ok(ctxT, B, H, hd):
+    if ctxT is None:
+        return False
+    want = (B, H, 128, 128) if hd == 128 else ((B, H // 2, 128, 128) if (hd == 64 and H % 2 == 0) else None)
+    return want is not None and tuple(ctxT.shape) == want and ctxT.dtype == torch.bfloat16
+
+
 def lincross_apply_style(q, ctxT, B, T, H, hd, ln, film, y):
     """lincross_apply + the StylizationBlock's LayerNorm, FiLM and SiLU in its epilogue (mdm_lincross_apply_style: the H
     head-CTAs of a sequence as a cluster).  Returns False (nothing launched) outside the kernel's shapes."""
     _c(q, ctxT, y, film, *ln)
-    if q.dtype != torch.bfloat16 or ctxT is None or hd != 128 or T > 256 or H > 8:
+    if q.dtype != torch.bfloat16 or not _lincross_ctxT_ok(ctxT, B, H, hd) or T > 256 or H // (128 // hd) > 8:
         return False
     st = _lib.load().mdm_lincross_apply_style(q.data_ptr(), ctxT.data_ptr(), B, T, H, hd, ln[0].data_ptr(), ln[1].data_ptr(),
                                               film.data_ptr(), y.data_ptr(), _stream())
@@ -263,6 +288,8 @@ def lincross_apply(q, ctx, B, T, H, hd, y, ctxT=None):
     if hd > 128:
         from . import train_ops
         return train_ops.lincross_apply_generic(q, ctx, B, T, H, hd, y)
+    if not _lincross_ctxT_ok(ctxT, B, H, hd):        # (a [B, H, 64, 64] transpose is not what the two-head kernel reads)
+        ctxT = None
     _lib.check(_lib.load().mdm_lincross_apply_ex(q.data_ptr(), _dt(q), ctx.data_ptr(), _ptr(ctxT), B, T, H, hd,
                                                  y.data_ptr(), _stream()), "mdm_lincross_apply")
 

@@ -617,11 +617,7 @@ class MotionTransformer(nn.Module):
             self._lin(xa, L["sd_k"], out_a=k2)
             self._lin(xa, L["sd_v"], out_a=v2)
             ctx.lin_ctx.append(c)
-            cT = None
-            if adt == torch.bfloat16:
-                cT = torch.empty(B, H, hd, hd, dtype=torch.bfloat16, device=dev)
-                ops.transpose_cast_bf16(c, cT)
-            ctx.lin_ctxT.append(cT)
+            ctx.lin_ctxT.append(ops.pack_lincross_ctxT(c) if adt == torch.bfloat16 else None)
             ctx.k2.append(k2)
             ctx.v2.append(v2)
         return ctx

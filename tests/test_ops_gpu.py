@@ -241,18 +241,17 @@ def test_gemm_ln_fused(variant, M, K, T):
     assert not ops.gemm_ln(A, W[:256].contiguous(), b[:256].contiguous(), ln1=ln1, out1_a=buf(bf)[:M])
 
 
-@pytest.mark.parametrize("B,H,T", [(3, 4, 196), (5, 4, 98), (2, 4, 8), (4, 2, 130), (64, 4, 196)])
-def test_lincross_apply_style_fused(B, H, T):
+@pytest.mark.parametrize("B,H,T,hd", [(3, 4, 196, 128), (5, 4, 98, 128), (2, 4, 8, 128), (4, 2, 130, 128), (64, 4, 196, 128),
+                                      (3, 8, 196, 64), (5, 4, 98, 64)])
+def test_lincross_apply_style_fused(B, H, T, hd):
     """mdm_lincross_apply_style: the linear cross-attention core with the StylizationBlock (LayerNorm over the whole row =
     all heads, FiLM, SiLU) in its epilogue (the head-CTAs of a sequence as a cluster, partial row statistics through
     distributed shared memory) against the core + rowop pair and against torch on the core's fp32 result."""
-    hd = 128
     D = H * hd
     N = B * T
     q = randn(N, D, seed=1).bfloat16()
     ctx = randn(B, H, hd, hd, seed=2, scale=hd ** -0.5)
-    ctxT = torch.empty(B, H, hd, hd, device=DEV, dtype=torch.bfloat16)
-    ops.transpose_cast_bf16(ctx, ctxT)
+    ctxT = ops.pack_lincross_ctxT(ctx)          # head size 64: block-diagonal pairs of heads, two heads per CTA
     ln = (torch.rand(D, generator=gen(5)).to(DEV) + 0.5, randn(D, seed=6, scale=0.1))
     film = randn(B, 2 * D, seed=9, scale=0.3)
     y = torch.full((N + 4, D), 3.0, device=DEV, dtype=torch.bfloat16)
@@ -264,7 +263,7 @@ def test_lincross_apply_style_fused(B, H, T):
     ops.rowop(core, N, D, ops._dt(unf), ln2=ln, film=film, rows_per_seq=T, silu=True, out2_a=unf)
     # torch: softmax over the head dimension, times ctx (bf16-rounded operands like the kernel), LN over the row, FiLM, SiLU
     p = torch.softmax(q.float().view(B, T, H, hd), -1).bfloat16().float()
-    yy = torch.einsum("bthd,bhdl->bthl", p, ctxT.float().transpose(-1, -2)).reshape(N, D)
+    yy = torch.einsum("bthd,bhdl->bthl", p, ctx.bfloat16().float()).reshape(N, D)
     v = F.layer_norm(yy, (D,), ln[0], ln[1])
     seq = torch.arange(N, device=DEV) // T
     ref = F.silu(v * (1 + film[seq, :D]) + film[seq, D:])
@@ -556,11 +555,16 @@ def test_linear_cross_attention(dtype, B, H, T, hd, Nt):
     qs = F.softmax(q.float().view(B, T, H, hd), dim=-1)
     ref = torch.einsum("bnhd,bhdl->bnhl", qs, att).reshape(B * T, D)
     assert rel(y, ref) < TOL[dtype]
-    if dtype == torch.bfloat16 and hd == 128:
-        # with ctx^T packed as bf16 the tcgen05 kernel (attention_umma.cu) runs; also at the half resolution
-        ctxT = torch.empty(B, H, hd, hd, device=DEV, dtype=torch.bfloat16)
-        ops.transpose_cast_bf16(ctx, ctxT)
-        assert torch.equal(ctxT, ctx.transpose(-1, -2).contiguous().to(torch.bfloat16))
+    if dtype == torch.bfloat16 and hd in (128, 64):
+        # with ctx^T packed as bf16 the tcgen05 kernel (attention_umma.cu) runs; also at the half resolution.  Head size
+        # 64: two heads per CTA, ctx^T as the block-diagonal [128, 128] of each pair of heads
+        ctxT = ops.pack_lincross_ctxT(ctx)
+        if hd == 128:
+            assert torch.equal(ctxT, ctx.transpose(-1, -2).contiguous().to(torch.bfloat16))
+        else:
+            assert tuple(ctxT.shape) == (B, H // 2, 128, 128)
+            assert torch.equal(ctxT[:, :, 64:, 64:], ctx.transpose(-1, -2)[:, 1::2].to(torch.bfloat16))
+            assert float(ctxT[:, :, :64, 64:].abs().max()) == 0.0
         y2 = torch.full_like(y, float("nan"))
         ops.lincross_apply(q, ctx, B, T, H, hd, y2, ctxT=ctxT)
         assert rel(y2, ref) < TOL[dtype]
