@@ -946,13 +946,18 @@ int launch_lc(const bf16* q, const bf16* ctxT, int B, int H, int T, bf16* y, con
 // rows brought by cp.async straight into operand layout (K = head dim); the softmax over the keys is lane-local in
 // TMEM (lane == frame) and its bf16 result P overwrites Q as the A operand of O = P V (K = keys, only the NK/16
 // k-steps that hold keys); v waits in registers and is stored transposed over K once S has retired.
-template <int TP>
+// HDIM = head size: 128, or 64 (one K-half of the Q / K tiles, HDIM / 16 lanes per row in the copies, a 64-wide O product)
+template <int TP, int HDIM>
 __global__ void __launch_bounds__(NTHR, 2)
 softmax_cross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                           const int* __restrict__ nt, int H, int T, int Nt_max, int NK, float scale,
                           bf16* __restrict__ o) {
   using L = SmemLC<TP>;                  // Qs (later P, later staging) + a 32 KB operand region (K, later V^T)
   constexpr int MT = TP / 128;
+  constexpr int KH = HDIM / 64;          // 64-column K-halves of the Q / K operand tiles
+  constexpr int LPR = HDIM / 16;         // lanes per row in the q / k / v copies (16 columns each)
+  constexpr int RPP = NTHR / LPR;        // rows per pass
+  constexpr int NPV = (96 + RPP - 1) / RPP;   // passes over the (at most 96) value rows
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* Qs = smem + L::QS;
@@ -961,28 +966,28 @@ softmax_cross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int D = H * HD;
+  const int D = H * HDIM;
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(tmem_ptr, TP);
   pdl_enter();
   const int n_tok = nt ? min(nt[b], Nt_max) : Nt_max;
-  const int sub = tid & 7, rr = tid >> 3;
-  // v rows -> registers (pairs {2 sub + 16 j, +1} of row n = rr + 32 p)
-  uint32_t vraw[3][8];
-  const bf16* vb = v + (long)b * Nt_max * D + h * HD;
+  const int sub = tid & (LPR - 1), rr = tid / LPR;
+  // v rows -> registers (pairs {2 sub + 2 LPR j, +1} of row n = rr + RPP p)
+  uint32_t vraw[NPV][8];
+  const bf16* vb = v + (long)b * Nt_max * D + h * HDIM;
 #pragma unroll
-  for (int p = 0; p < 3; ++p) {
-    const int n = rr + 32 * p;
+  for (int p = 0; p < NPV; ++p) {
+    const int n = rr + RPP * p;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      vraw[p][j] = n < n_tok ? __ldg(reinterpret_cast<const uint32_t*>(vb + (long)n * D) + sub + 8 * j) : 0u;
+      vraw[p][j] = n < n_tok ? __ldg(reinterpret_cast<const uint32_t*>(vb + (long)n * D) + sub + LPR * j) : 0u;
   }
   // raw q -> A tiles, raw k -> B tiles (rows = keys; keys >= n_tok are zero rows, masked in the softmax)
   {
-    const bf16* qb = q + (long)b * T * D + h * HD;
+    const bf16* qb = q + (long)b * T * D + h * HDIM;
     uint8_t* dstq = Qs + (sub >> 2) * (TP * 128);
 #pragma unroll 1
-    for (int t = rr; t < TP; t += 32) {
+    for (int t = rr; t < TP; t += RPP) {
       uint8_t* d0 = dstq + sw_off(t, (sub & 3) * 16);
       uint8_t* d1 = dstq + sw_off(t, (sub & 3) * 16 + 8);
       if (t < T) {
@@ -994,10 +999,10 @@ softmax_cross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
         *reinterpret_cast<uint4*>(d1) = make_uint4(0u, 0u, 0u, 0u);
       }
     }
-    const bf16* kb = k + (long)b * Nt_max * D + h * HD;
+    const bf16* kb = k + (long)b * Nt_max * D + h * HDIM;
     uint8_t* dstk = Kv + (sub >> 2) * (128 * 128);
 #pragma unroll 1
-    for (int n = rr; n < NK; n += 32) {
+    for (int n = rr; n < NK; n += RPP) {
       uint8_t* d0 = dstk + sw_off(n, (sub & 3) * 16);
       uint8_t* d1 = dstk + sw_off(n, (sub & 3) * 16 + 8);
       if (n < n_tok) {
@@ -1023,7 +1028,7 @@ softmax_cross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-      for (int kc = 0; kc < 2; ++kc) {
+      for (int kc = 0; kc < KH; ++kc) {
         const uint64_t ad = make_sw128_kmajor_desc(qs_a + kc * (TP * 128) + mt * (128 * 128));
         const uint64_t bd = make_sw128_kmajor_desc(kv_a + kc * (128 * 128));
 #pragma unroll
@@ -1036,14 +1041,14 @@ softmax_cross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
   tc_fence_after();
   // v^T over the K region (S has retired): V^T[l][n], zero columns for the masked keys
 #pragma unroll
-  for (int p = 0; p < 3; ++p) {
-    const int n = rr + 32 * p;
+  for (int p = 0; p < NPV; ++p) {
+    const int n = rr + RPP * p;
     if (n < NK) {
       uint8_t* dcol = Kv + (n >> 6) * (128 * 128);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        *reinterpret_cast<uint16_t*>(dcol + sw_off(2 * sub + 16 * j, n & 63)) = (uint16_t)(vraw[p][j] & 0xffffu);
-        *reinterpret_cast<uint16_t*>(dcol + sw_off(2 * sub + 16 * j + 1, n & 63)) = (uint16_t)(vraw[p][j] >> 16);
+        *reinterpret_cast<uint16_t*>(dcol + sw_off(2 * sub + 2 * LPR * j, n & 63)) = (uint16_t)(vraw[p][j] & 0xffffu);
+        *reinterpret_cast<uint16_t*>(dcol + sw_off(2 * sub + 2 * LPR * j + 1, n & 63)) = (uint16_t)(vraw[p][j] >> 16);
       }
     }
   }
@@ -1104,7 +1109,7 @@ softmax_cross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
   __syncthreads();
   tc_fence_after();
   if (tid == 0) {                        // O[mt] = P[mt] . V   (K = NK keys)
-    constexpr uint32_t id = make_idesc_bf16(128, 128);
+    constexpr uint32_t id = make_idesc_bf16(128, HDIM);
     const int ksteps = NK / 16;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
@@ -1121,8 +1126,9 @@ softmax_cross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
   tc_fence_after();
   constexpr int PITCH = 272;
   {
-    constexpr int CH = MT == 2 ? 4 : 2;
-    const int mt = MT == 2 ? hi : 0, c0 = MT == 2 ? 0 : hi * 2;
+    constexpr int NCH = HDIM / 32;                     // 32-column chunks of an output row
+    constexpr int CH = MT == 2 ? NCH : NCH / 2;
+    const int mt = MT == 2 ? hi : 0, c0 = MT == 2 ? 0 : hi * CH;
     const int t = mt * 128 + quad * 32 + lane;
     const uint32_t t_row = t_lane + mt * 128;
 #pragma unroll 1
@@ -1143,9 +1149,10 @@ softmax_cross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
   }
   tc_fence_before();
   __syncthreads();
-  for (int i = tid; i < T * 16; i += NTHR) {
-    const int r = i >> 4, c = i & 15;
-    *reinterpret_cast<uint4*>(o + ((long)(b * T + r)) * D + h * HD + c * 8) =
+  constexpr int CPR = HDIM / 8;                        // 16-byte pieces of an output row
+  for (int i = tid; i < T * CPR; i += NTHR) {
+    const int r = i / CPR, c = i % CPR;
+    *reinterpret_cast<uint4*>(o + ((long)(b * T + r)) * D + h * HDIM + c * 8) =
         *reinterpret_cast<const uint4*>(Qs + r * PITCH + c * 16);
   }
   if (warp == 0) {
@@ -1154,20 +1161,20 @@ softmax_cross_umma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
   }
 }
 
-template <int TP>
+template <int TP, int HDIM = 128>
 int launch_sc(const bf16* q, const bf16* k, const bf16* v, const int* nt, int B, int H, int T, int Nt_max, float scale,
               bf16* o, cudaStream_t st) {
   using L = SmemLC<TP>;
   static unsigned long long attr = 0;   // one bit per device ordinal: the attribute is per (function, device)
   const unsigned long long dev_bit = 1ull << mdm_cur_dev();
   if (!(attr & dev_bit)) {
-    if (cudaFuncSetAttribute(softmax_cross_umma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+    if (cudaFuncSetAttribute(softmax_cross_umma_kernel<TP, HDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
         cudaSuccess)
       return MDM_ERR_CUDA;
     attr |= dev_bit;
   }
   const int NK = (Nt_max + 31) / 32 * 32;
-  mdm_launch(softmax_cross_umma_kernel<TP>, B * H, NTHR, L::TOTAL, st, q, k, v, nt, H, T, Nt_max, NK, scale, o);
+  mdm_launch(softmax_cross_umma_kernel<TP, HDIM>, B * H, NTHR, L::TOTAL, st, q, k, v, nt, H, T, Nt_max, NK, scale, o);
   return cudaGetLastError() == cudaSuccess ? MDM_OK : MDM_ERR_CUDA;
 }
 
@@ -1234,16 +1241,20 @@ extern "C" MDM_API int mdm_lincross_apply_style(const void* q, const void* ctxT_
   return launch_lc<256, true>(qq, cc, B, H, T, yy, ln_w, ln_b, film, st);
 }
 
-// hd == 128, bf16, T <= 256, at most 96 keys; MDM_ERR_UNSUPPORTED otherwise.
+// hd == 128 or 64, bf16, T <= 256, at most 96 keys; MDM_ERR_UNSUPPORTED otherwise.
 int mdm_softmax_cross_umma(const void* q, const void* k, const void* v, const int* nt, int B, int T, int Nt_max, int H,
                            int hd, float scale, void* o, cudaStream_t st) {
-  if (hd != HD || T > 256 || Nt_max > 96 || Nt_max < 1) return MDM_ERR_UNSUPPORTED;
+  if ((hd != HD && hd != 64) || T > 256 || Nt_max > 96 || Nt_max < 1) return MDM_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) ||
       (reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(o) & 15))
     return MDM_ERR_UNSUPPORTED;
   const bf16 *qq = reinterpret_cast<const bf16*>(q), *kk = reinterpret_cast<const bf16*>(k),
              *vv = reinterpret_cast<const bf16*>(v);
   bf16* oo = reinterpret_cast<bf16*>(o);
+  if (hd == 64) {
+    if (T <= 128) return launch_sc<128, 64>(qq, kk, vv, nt, B, H, T, Nt_max, scale, oo, st);
+    return launch_sc<256, 64>(qq, kk, vv, nt, B, H, T, Nt_max, scale, oo, st);
+  }
   if (T <= 128) return launch_sc<128>(qq, kk, vv, nt, B, H, T, Nt_max, scale, oo, st);
   return launch_sc<256>(qq, kk, vv, nt, B, H, T, Nt_max, scale, oo, st);
 }

@@ -577,7 +577,7 @@ def test_linear_cross_attention(dtype, B, H, T, hd, Nt):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,T,hd,Nt", [(3, 4, 196, 128, 20), (2, 4, 60, 64, 85), (2, 2, 8, 32, 10), (3, 4, 98, 128, 85),
-                                         (2, 4, 196, 128, 40), (2, 2, 130, 128, 96)])
+                                         (2, 4, 196, 128, 40), (2, 2, 130, 128, 96), (3, 8, 196, 64, 40), (2, 3, 98, 64, 96)])
 def test_softmax_cross_attention(dtype, B, H, T, hd, Nt):
     D = H * hd
     q = randn(B * T, D, seed=1, scale=2.0).to(dtype)
