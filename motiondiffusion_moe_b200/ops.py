@@ -273,7 +273,7 @@ def lincross_apply_style(q, ctxT, B, T, H, hd, ln, film, y):
     """lincross_apply + the StylizationBlock's LayerNorm, FiLM and SiLU in its epilogue (mdm_lincross_apply_style: the H
     head-CTAs of a sequence as a cluster).  Returns False (nothing launched) outside the kernel's shapes."""
     _c(q, ctxT, y, film, *ln)
-    if q.dtype != torch.bfloat16 or not _lincross_ctxT_ok(ctxT, B, H, hd) or T > 256 or H // (128 // hd) > 8:
+    if q.dtype != torch.bfloat16 or not _lincross_ctxT_ok(ctxT, B, H, hd) or T > 256 or H // (2 if hd == 64 else 1) > 8:
         return False
     st = _lib.load().mdm_lincross_apply_style(q.data_ptr(), ctxT.data_ptr(), B, T, H, hd, ln[0].data_ptr(), ln[1].data_ptr(),
                                               film.data_ptr(), y.data_ptr(), _stream())

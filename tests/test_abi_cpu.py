@@ -172,3 +172,29 @@ def test_ddim_schedule_and_trainer_host_logic():
         tr.update()
     with pytest.raises(ValueError):
         mdm.DDPMTrainer(types.SimpleNamespace(device="cpu", diffusion_steps=100, is_train=False), net, sampler="euler")
+
+
+def test_packed_attention_operands_for_head_size_64():
+    """Host-side packing of the operands that select the tcgen05 attention kernels at head size 64 (two heads per CTA):
+    the block-diagonal diag(P^T, P^T) of FastAttention and the block-diagonal ctx^T of each pair of heads of the linear
+    cross-attention (pure torch: no GPU needed)."""
+    from motiondiffusion_moe_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    P = torch.randn(64, 64, generator=g)
+    Pt = ops.pack_fastattn_pt(P)
+    assert Pt.dtype == torch.bfloat16 and tuple(Pt.shape) == (128, 128)
+    ref = P.t().contiguous().to(torch.bfloat16)
+    assert torch.equal(Pt[:64, :64], ref) and torch.equal(Pt[64:, 64:], ref)
+    assert float(Pt[:64, 64:].abs().max()) == 0.0 and float(Pt[64:, :64].abs().max()) == 0.0
+    P128 = torch.randn(128, 128, generator=g)
+    assert torch.equal(ops.pack_fastattn_pt(P128), P128.t().contiguous().to(torch.bfloat16))
+    assert ops.pack_fastattn_pt(torch.randn(32, 32, generator=g)) is None
+    ctx = torch.randn(3, 6, 64, 64, generator=g)                       # [B, H, d, l]
+    cT = ops.pack_lincross_ctxT(ctx)
+    assert tuple(cT.shape) == (3, 3, 128, 128) and cT.dtype == torch.bfloat16
+    for hp in range(3):
+        assert torch.equal(cT[:, hp, :64, :64], ctx[:, 2 * hp].transpose(-1, -2).to(torch.bfloat16))
+        assert torch.equal(cT[:, hp, 64:, 64:], ctx[:, 2 * hp + 1].transpose(-1, -2).to(torch.bfloat16))
+    assert float(cT[:, :, :64, 64:].abs().max()) == 0.0 and float(cT[:, :, 64:, :64].abs().max()) == 0.0
+    assert ops.pack_lincross_ctxT(torch.randn(2, 3, 64, 64, generator=g)) is None       # odd head count: mma.sync kernels
+    assert ops.pack_lincross_ctxT(torch.randn(2, 2, 32, 32, generator=g)) is None
