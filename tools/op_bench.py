@@ -212,6 +212,15 @@ v2 = torch.randn(NSEQ * Nt, D, device=dev).to(bf)
 nt = torch.full((NSEQ,), Nt, dtype=torch.int32, device=dev)
 timeit("softmax_cross", lambda i: ops.softmax_cross(xb[i], k2, v2, nt, NSEQ, T, Nt, H, hd, ob[i]), nset, N * D * 4, "GB/s")
 
+# head size 64 (8 heads): the two cross-attention cores (MDM_LC_UMMA=0 / MDM_SC_UMMA=0 select the mma.sync kernels)
+if not ONLY or "hd 64" in ONLY:
+    H8, hd8 = 8, 64
+    ctx8 = torch.randn(NSEQ, H8, hd8, hd8, device=dev)
+    ctxT8 = ops.pack_lincross_ctxT(ctx8)
+    timeit("lincross_apply hd 64 (packed ctx^T)", lambda i: ops.lincross_apply(xb[i], ctx8, NSEQ, T, H8, hd8, ob[i], ctxT=ctxT8), nset, N * D * 4, "GB/s")
+    timeit("lincross_apply_style hd 64", lambda i: ops.lincross_apply_style(xb[i], ctxT8, NSEQ, T, H8, hd8, lnD, film, ob[i]), nset, N * D * 4, "GB/s")
+    timeit("softmax_cross hd 64", lambda i: ops.softmax_cross(xb[i], k2, v2, nt, NSEQ, T, Nt, H8, hd8, ob[i]), nset, N * D * 4, "GB/s")
+
 # ---- backward building blocks of a Linear (dX, dW with token slabs, db)
 xg = torch.randn(N, D, device=dev).to(bf)
 Wg = (torch.randn(D, D, device=dev) / D ** 0.5).to(bf)
